@@ -1,0 +1,146 @@
+"""The CPU oracle (oracle/pylc_oracle.py) against vectors produced by the unmodified reference
+(oracle/gen_golden.py).  This is what pins the oracle: the reference ships no tests of its own."""
+import json
+
+import numpy as np
+import pytest
+
+import pylc_oracle as orc
+
+
+@pytest.mark.parametrize("name", ["gray_s32", "gray_s16", "rgb_s32", "rgb_s16"])
+def test_split(golden, name):
+    g = golden("split")
+    T, S = g["split_%s_TS" % name]
+    assert np.array_equal(orc.split_tiles(g["split_%s_img" % name], int(T), int(S)), g["split_%s_tiles" % name])
+
+
+@pytest.mark.parametrize("name", ["a", "b", "dup"])
+def test_class_encode(golden, name):
+    g = golden("encode")
+    pal = g["palette_%s" % name].tolist()
+    assert np.array_equal(orc.class_encode_port(g["encode_%s_in" % name], pal), g["encode_%s_out" % name])
+    assert np.array_equal(orc.class_encode(g["encode_%s_in" % name], pal), g["encode_%s_out" % name])
+    # off-palette pixels exist in the fixture and land in class 1
+    assert (g["encode_%s_out" % name] == 1).any()
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_colourize(golden, palettes, name):
+    g = golden("colourize")
+    pal = palettes[name]
+    lab = g["colourize_%s_in" % name]
+    assert np.array_equal(orc.colourize_port(lab, len(pal), pal), g["colourize_%s_out" % name])
+    assert np.array_equal(orc.colourize(lab, len(pal), pal), g["colourize_%s_out" % name])
+
+
+def test_colourize_grey_chain():
+    # a palette whose class-0 colour is the grey [2,2,2] is re-mapped by the later pass i=2
+    pal = [[2, 2, 2], [9, 9, 9], [50, 60, 70]]
+    lab = np.array([[[0, 1, 2]]])
+    assert np.array_equal(orc.colourize_port(lab, 3, pal), orc.colourize(lab, 3, pal))
+    assert orc.colourize(lab, 3, pal)[0, 0, 0].tolist() == [50, 60, 70]
+
+
+@pytest.mark.parametrize("name,ch,pk", [("gray_a", 1, "a"), ("rgb_b", 3, "b")])
+def test_extract_profile(golden, palettes, name, ch, pk):
+    g = golden("extract_profile")
+    pal = palettes[pk]
+    C = len(pal)
+    imgs, masks = [], []
+    for k in g["exprof_%s_order" % name]:
+        imgs.append(orc.split_tiles(g["exprof_%s_img%d" % (name, k)], 32, 32))
+        mt = orc.split_tiles(g["exprof_%s_mask%d" % (name, k)], 32, 32)
+        masks.append(orc.class_encode(mt, pal))
+    imgs = np.concatenate(imgs)
+    masks = np.concatenate(masks)
+    assert np.array_equal(imgs, g["exprof_%s_tiles_img" % name])
+    assert np.array_equal(masks, g["exprof_%s_tiles_mask" % name])
+    for prof in (orc.profile_port(imgs, masks, C, 32), orc.profile(imgs, masks, C, 32)):
+        assert np.array_equal(prof["px_dist"], g["exprof_%s_px_dist" % name])
+        assert np.array_equal(prof["dset_px_dist"], g["exprof_%s_dset_px_dist" % name])
+        assert prof["dset_px_count"] == int(g["exprof_%s_dset_px_count" % name])
+        np.testing.assert_allclose(prof["probs"], g["exprof_%s_probs" % name], rtol=0, atol=0)
+        np.testing.assert_allclose(prof["weights"], g["exprof_%s_weights" % name], rtol=1e-15)
+        np.testing.assert_allclose([prof["m2"], prof["jsd"]], g["exprof_%s_m2jsd" % name], rtol=1e-14)
+        np.testing.assert_allclose(prof["px_mean"], g["exprof_%s_px_mean" % name], rtol=1e-5)
+        np.testing.assert_allclose(prof["px_std"], g["exprof_%s_px_std" % name], rtol=1e-5)
+
+
+def test_fit_dims(golden):
+    for W, H, w_fit, h_fit, off in golden("fit")["fit_dims"]:
+        assert orc.fit_dims(int(W), int(H), 512) == (w_fit, h_fit)
+        assert off == 0
+
+
+def test_nn_index_map(golden):
+    g = golden("fit")
+    for src, dst in g["nn_pairs"]:
+        assert np.array_equal(orc.nn_index_map(int(src), int(dst)), g["nn_map_%d_%d" % (src, dst)]), (src, dst)
+
+
+def _recon_cases(golden):
+    return [str(c) for c in golden("reconstruct")["recon_cases"]]
+
+
+@pytest.mark.parametrize("case", ["a_2x3", "a_3x2", "a_3x3", "a_2x1", "b_4x5", "a_s32_2x3"])
+def test_reconstruct(golden, palettes, case):
+    g = golden("reconstruct")
+    nr, nc, T, S, h, w, w_full, h_full, C = [int(v) for v in g["recon_%s_geom" % case]]
+    pal = palettes["b" if case.startswith("b") else "a"]
+    tiles = g["recon_%s_tiles" % case]
+    ref_map = g["recon_%s_map" % case]
+    assert orc.stitch_grid(h, w, T, S) == (nr, nc)
+    # the step-by-step port is bit-equal to the reference
+    port = orc.stitch_map_port(tiles, h, w, T, S)
+    assert np.array_equal(port, ref_map)
+    # and so is the closed form
+    closed = orc.stitch_map(tiles, nr, nc, T, S)
+    assert np.array_equal(closed, ref_map)
+    # labels -> NN resample -> colourise == reference RGB output
+    labels = orc.stitch_labels(closed)
+    full = orc.resample_labels(labels, w_full, h_full)
+    rgb = orc.colourize(full[None], C, pal)[0].astype(np.float32)
+    assert np.array_equal(rgb, g["recon_%s_rgb" % case])
+    batches = [tiles[i:i + 4] for i in range(0, len(tiles), 4)]
+    assert np.array_equal(orc.reconstruct_port(batches, h, w, w_full, h_full, T, S, pal, C), g["recon_%s_rgb" % case])
+
+
+def test_evaluate(golden, palettes):
+    g = golden("evaluate")
+    pal = palettes["a"]
+    C = len(pal)
+    y_pred = orc.class_encode_hwc(g["eval_pred_rgb"].astype(np.uint8), pal).ravel()
+    y_true = orc.class_encode_hwc(g["eval_gt_rgb"], pal).ravel()
+    assert np.array_equal(y_pred, g["eval_y_pred_raw"])
+    assert np.array_equal(y_true, g["eval_y_true_raw"])
+    yt, yp = orc.inject_coverage(y_true, y_pred, C)
+    assert np.array_equal(yt, g["eval_y_true"]) and np.array_equal(yp, g["eval_y_pred"])
+    labels = [str(s) for s in g["eval_labels"]]
+    M = orc.confusion_counts(yt, yp, C)
+    assert M.sum() == yt.size
+    ref_report = json.loads(str(g["eval_report_json"]))
+    for res in (orc.metrics_from_confusion(M, labels), orc.metrics_port(yt, yp, labels)):
+        np.testing.assert_allclose([res["f1"], res["iou"], res["mcc"]], g["eval_scalars"], rtol=1e-12)
+        np.testing.assert_allclose(res["cmatrix"], g["eval_cmatrix"], rtol=1e-15)
+        for key, val in ref_report.items():
+            if isinstance(val, dict):
+                for k2, v2 in val.items():
+                    assert res["report"][key][k2] == pytest.approx(v2, rel=1e-12), (key, k2)
+            else:
+                assert res["report"][key] == pytest.approx(val, rel=1e-12)
+
+
+@pytest.mark.parametrize("name,C,weighted", [("a_unw", 9, False), ("a_w", 9, True), ("b_w", 11, True)])
+def test_multiloss(golden, name, C, weighted):
+    g = golden("loss")
+    z, t, w = g["loss_%s_z" % name], g["loss_%s_t" % name], g["loss_%s_w" % name]
+    ref_vals, ref_grad = g["loss_%s_vals" % name], g["loss_%s_grad" % name]
+    port = orc.multiloss_port(z, t, C, weights=w, weighted=weighted)
+    np.testing.assert_allclose(port[:4], ref_vals, rtol=1e-6)
+    np.testing.assert_allclose(port[4], ref_grad, rtol=1e-5, atol=1e-9)
+    loss, ce, dice, focal, grad, partials = orc.multiloss(z, t, C, weights=w, weighted=weighted)
+    # north_star tolerance: loss values within 1e-4 relative
+    np.testing.assert_allclose([loss, ce, dice, focal], ref_vals, rtol=1e-5)
+    np.testing.assert_allclose(grad, ref_grad, rtol=2e-4, atol=2e-9)
+    assert partials.shape == (2 * C + 3,)
