@@ -1,0 +1,208 @@
+/*
+ * pylc_b200 -- C ABI of the sm_100a kernel library for PyLC's tiled-segmentation hot path.
+ *
+ * This is the drop-in boundary.  The PyLC reference has no FFI layer (it is pure Python); each
+ * entry point below replaces the NumPy / Torch-CPU / scikit-learn body of one reference function
+ * (cited per function, paths relative to the PyLC source root).  The Python host layer
+ * (pylc_b200/utils/*.py, pylc_b200/models/modules/loss.py) binds these with ctypes and keeps the
+ * reference's own signatures; INTEGRATION.md shows the stub a PyLC maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - Every pointer is a DEVICE pointer owned by the caller unless marked HOST.
+ *   - `stream` is a cudaStream_t passed as void*; NULL = legacy default stream.
+ *   - Nothing allocates, synchronises or calls back; a call returns once the launch is enqueued.
+ *   - Return value: 0 = ok, > 0 = cudaError_t of the failed launch, < 0 = PYLC_ERR_* below.
+ *   - Accumulator outputs (stat, px_dist, conf, partials) are ADDED INTO; the caller zeroes them.
+ *     Integer accumulators make every result independent of launch geometry and GPU count.
+ *   - Pitches are in bytes.  Sources whose base and pitch are 16-byte aligned take the vectorised
+ *     path; anything else takes a slower byte-wise path with identical results.
+ */
+#ifndef PYLC_B200_H
+#define PYLC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYLC_ABI_VERSION 1
+#define PYLC_MAX_CLASSES 32
+
+#define PYLC_OK 0
+#define PYLC_ERR_ARG (-1)         /* null pointer / non-positive size                        */
+#define PYLC_ERR_CLASSES (-2)     /* n_classes outside [1, PYLC_MAX_CLASSES]                 */
+#define PYLC_ERR_GEOMETRY (-3)    /* tile/stride combination the kernels do not implement    */
+#define PYLC_ERR_ALIGN (-4)       /* destination pointer not 16-byte aligned                 */
+#define PYLC_ERR_PALETTE (-5)     /* no collision-free hash found for the palette            */
+
+#if defined(__GNUC__)
+#define PYLC_API __attribute__((visibility("default")))
+#else
+#define PYLC_API
+#endif
+
+typedef void *pylc_stream_t;
+
+/* ---- library ------------------------------------------------------------------------------ */
+
+PYLC_API int pylc_abi_version(void);
+/* Human-readable text for any return code of this library (never NULL). */
+PYLC_API const char *pylc_error_string(int code);
+/* Device the calling thread is bound to: SM count and compute capability (major*10+minor). */
+PYLC_API int pylc_device_info(int *sm_count, int *compute_capability);
+/* Counts kernel launches issued through this library since load (bench.py's gpu_launches). */
+PYLC_API int64_t pylc_launch_count(void);
+
+/* ---- tile extraction ---------------------------------------------------------------------- */
+
+/* Number of tiles Tensor.unfold(0,T,S).unfold(1,T,S) yields (utils/extract.py:302-305). */
+PYLC_API int pylc_tile_grid(int H, int W, int T, int S, int *nH, int *nW);
+
+/*
+ * Overlapping tile gather, replaces Extractor.__split + np.copyto (utils/extract.py:279-310,182).
+ *   src   [H, W] (ch=1) or [H, W, 3] interleaved (ch=3) u8, row pitch `src_pitch` bytes
+ *   dst   [nH*nW, ch, T, T] u8, tile k = r*nW + c covers rows [rS, rS+T), cols [cS, cS+T)
+ *   stat  nullable [nH*nW, ch, 2] u64: per tile/channel sum(x), sum(x*x) (exact integers; the
+ *         host derives torch.mean / torch.std of utils/profile.py:101-106 from them)
+ * Requires T % 16 == 0, S % 16 == 0, T % S == 0 (vector path) -- otherwise PYLC_ERR_GEOMETRY.
+ */
+PYLC_API int pylc_tile_gather_u8(const uint8_t *src, int H, int W, int ch, size_t src_pitch, int T, int S,
+                        uint8_t *dst, uint64_t *stat, pylc_stream_t stream);
+
+/*
+ * Fused mask tile gather + palette encode + per-tile class histogram; replaces
+ * Extractor.__split + tools.class_encode + the one_hot/np.sum histogram
+ * (utils/extract.py:195-214, utils/tools.py:412-449, utils/profile.py:109-111).
+ *   src      [H, W, 3] RGB u8, pitch bytes
+ *   palette  HOST [C, 3] u8.  Unmatched colours encode to class 1, later duplicates win.
+ *   dst      [nH*nW, T, T] u8 class indices
+ *   px_dist  nullable [nH*nW, C] i64
+ */
+PYLC_API int pylc_mask_gather_encode_hist(const uint8_t *src, int H, int W, size_t src_pitch, int T, int S,
+                                 const uint8_t *palette, int C, uint8_t *dst, int64_t *px_dist,
+                                 pylc_stream_t stream);
+
+/*
+ * Standalone tools.class_encode (utils/tools.py:412-449).
+ *   layout 0: rgb is [n_img, rows, cols, 3] interleaved with row pitch `pitch` (n_img images
+ *             stored back to back, rows*pitch bytes each)          -> out [n_img, rows, cols]
+ *   layout 1: rgb is [n_img, 3, rows*cols] planar (the reference's NCHW argument); pitch ignored
+ *   hist     nullable [C] i64, histogram of the encoded output
+ */
+PYLC_API int pylc_class_encode(const uint8_t *rgb, int n_img, int rows, int cols, size_t pitch, int layout,
+                      const uint8_t *palette, int C, uint8_t *out, int64_t *hist,
+                      pylc_stream_t stream);
+
+/*
+ * Profiling sweep over already extracted tiles (utils/profile.py:98-111): per-tile class
+ * histograms and per-tile/channel sum(x), sum(x*x).  Either input may be NULL.
+ *   imgs [n, ch, tile_px] u8 -> stat [n, ch, 2] u64 ;  masks [n, tile_px] u8 -> px_dist [n, C] i64
+ */
+PYLC_API int pylc_profile_tiles(const uint8_t *imgs, int ch, const uint8_t *masks, int n, int64_t tile_px,
+                       int C, uint64_t *stat, int64_t *px_dist, pylc_stream_t stream);
+
+/*
+ * Tile gather fused with Model.normalize_image (models/model.py:416-445) and the grayscale
+ * x3 channel replicate (models/model.py:376-377): writes network-ready f32 tiles.
+ *   dst [nH*nW, out_ch, T, T] f32, value = ((x - mean[c]) / std[c]) / post_div in IEEE f32, the
+ *       reference's operation order (post_div 255, or 1 for the grayscale `default` branch)
+ *   mean / std: HOST [3] f32 (index 0 used for ch=1).  out_ch is 3 (ch=1 replicates) or ch.
+ */
+PYLC_API int pylc_tile_gather_norm_f32(const uint8_t *src, int H, int W, int ch, size_t src_pitch, int T,
+                              int S, const float *mean, const float *std, float post_div,
+                              int out_ch, float *dst, pylc_stream_t stream);
+
+/* ---- stitching ---------------------------------------------------------------------------- */
+
+/*
+ * Fused stitch + softmax + argmax + colourise, replaces tools.reconstruct up to and including
+ * colourize (utils/tools.py:239-313, 322-358) with the reference's exact band semantics
+ * (raw logits at the borders, one softmax-average on edges, double softmax in the interior).
+ *   logits        one contiguous [nr*nc, C, T, T] f32 buffer, row-major tile order, or NULL
+ *   tile_batches  (used when logits == NULL) device array of pointers, batch b =
+ *                 [tiles_per_batch, C, T, T] f32 holding tiles b*tiles_per_batch ... -- the list of
+ *                 per-batch network outputs the reference concatenates (utils/tools.py:221-222)
+ *   S             T/2 (output (nr+1)S x (nc+1)S) or T (pure scatter, output nr*T x nc*T)
+ *   lut_rgb       HOST [C, 3] u8 colour per label (colourize's final mapping); needed iff rgb
+ *   labels        [h, w] u8 first-maximum argmax     (nullable)
+ *   rgb           [h, w, 3] u8                       (nullable)
+ *   stitched      [C, h, w] f32 merged map           (nullable; parity tests / save_logits)
+ */
+PYLC_API int pylc_stitch_argmax_colour(const float *logits, const float *const *tile_batches,
+                              int tiles_per_batch, int nr, int nc, int C, int T, int S,
+                              const uint8_t *lut_rgb, uint8_t *labels, uint8_t *rgb,
+                              float *stitched, pylc_stream_t stream);
+
+/* tools.colourize (utils/tools.py:322-358) on a flat u8 label array: rgb[i] = lut_rgb[labels[i]]. */
+PYLC_API int pylc_colourise_u8(const uint8_t *labels, int64_t n_px, const uint8_t *lut_rgb, int C,
+                      uint8_t *rgb, pylc_stream_t stream);
+
+/* ---- evaluation --------------------------------------------------------------------------- */
+
+/*
+ * Nearest-neighbour resample of the fitted label map to full resolution + ground-truth palette
+ * encode + confusion matrix; replaces cv2.resize(INTER_NEAREST) of the colourised map,
+ * Evaluator.load's two class_encode passes, Evaluator.validate's coverage injection and every
+ * scikit-learn confusion matrix (utils/tools.py:316-317, utils/evaluate.py:87-119,150-176,
+ * utils/metrics.py:45-87).
+ *   labels    [h, w] u8 fitted-resolution labels
+ *   x_ofs     [w_full] i32, y_ofs [h_full] i32: OpenCV nearest source index per destination index
+ *   gt_rgb    nullable [h_full, w_full, 3] u8 ground truth, pitch bytes (NULL: no confusion)
+ *   palette   HOST [C, 3] u8 (class_encode rules as above) ; lut_rgb HOST [C,3] (for pred_rgb)
+ *   n_inject  flat pixels i < n_inject count as (i, i)  (utils/evaluate.py:172-174)
+ *   conf      nullable [C, C] i64, conf[t*C + p] += 1
+ *   pred_full nullable [h_full, w_full] u8 ; pred_rgb nullable [h_full, w_full, 3] u8
+ *   gt_full   nullable [h_full, w_full] u8 encoded ground truth
+ */
+PYLC_API int pylc_resample_encode_confusion(const uint8_t *labels, int h, int w, const int32_t *x_ofs,
+                                   const int32_t *y_ofs, int h_full, int w_full,
+                                   const uint8_t *gt_rgb, size_t gt_pitch, const uint8_t *palette,
+                                   const uint8_t *lut_rgb, int C, int n_inject, int64_t *conf,
+                                   uint8_t *pred_full, uint8_t *pred_rgb, uint8_t *gt_full,
+                                   pylc_stream_t stream);
+
+/* Confusion matrix of two flat u8 label vectors (aggregate mode, utils/evaluate.py:158-174). */
+PYLC_API int pylc_confusion_u8(const uint8_t *y_true, const uint8_t *y_pred, int64_t n, int C, int n_inject,
+                      int64_t *conf, pylc_stream_t stream);
+
+/* ---- multi-loss --------------------------------------------------------------------------- */
+
+/*
+ * MultiLoss = ce_w*CE + dice_w*Dice + focal_w*Focal (models/modules/loss.py:71-194), computed in
+ * two passes because Dice needs batch-global sums before any gradient exists:
+ *
+ *   pylc_multiloss_reduce    logits + target -> partials[2C+3] f64 (ADDED INTO):
+ *                            [0,C) I_c = sum p_c [t=c]; [C,2C) K_c = sum (p_c + [t=c]);
+ *                            2C: sum w_t (-ln p_t); 2C+1: sum w_t; 2C+2: sum focal_px
+ *                            (data-parallel ranks all-reduce `partials` here)
+ *   pylc_multiloss_finalize  partials -> out[4] f32 = {loss, ce, dice, focal}
+ *   pylc_multiloss_grad      logits + target + partials -> grad[B,C,HW] f32 = grad_scale * dL/dz
+ *
+ *   logits  [B, C, HW] f32 ; target [B, HW], target_is_i64 ? int64 (the reference dtype) : u8
+ *   class_w nullable [C] f32 device (CrossEntropyLoss weights; NULL = unweighted)
+ *   n_px_total: pixels over ALL ranks (= B*HW on one GPU)
+ */
+typedef struct pylc_loss_cfg {
+    float ce_weight, dice_weight, focal_weight; /* config.py:201-203, defaults 0.5 each */
+    float dice_smooth;                          /* config.py:204, 1.0                   */
+    float fl_gamma, fl_alpha;                   /* config.py:206-207, 2 and 0.25        */
+    float eps;                                  /* models/modules/loss.py:51, 1e-8      */
+} pylc_loss_cfg;
+
+PYLC_API int pylc_multiloss_reduce(const float *logits, const void *target, int target_is_i64, int B, int C,
+                          int64_t HW, const float *class_w, const pylc_loss_cfg *cfg,
+                          double *partials, pylc_stream_t stream);
+PYLC_API int pylc_multiloss_finalize(const double *partials, int C, int64_t n_px_total,
+                            const pylc_loss_cfg *cfg, float *out4, pylc_stream_t stream);
+PYLC_API int pylc_multiloss_grad(const float *logits, const void *target, int target_is_i64, int B, int C,
+                        int64_t HW, const float *class_w, const pylc_loss_cfg *cfg,
+                        const double *partials, int64_t n_px_total, float grad_scale, float *grad,
+                        pylc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYLC_B200_H */

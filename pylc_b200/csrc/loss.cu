@@ -1,0 +1,349 @@
+// MultiLoss = ce_w*CE + dice_w*Dice + focal_w*Focal (models/modules/loss.py:71-194), forward and
+// backward, as two streaming passes over the logits:
+//
+//   reduce : softmax once per pixel, accumulate I_c, K_c, the CE numerator/denominator and the
+//            focal sum (2C+3 numbers) -- Dice needs these batch-global sums before any gradient
+//            exists, and under data parallelism they are all-reduced between the two passes.
+//   grad   : softmax again, closed-form gradient written with 128-bit stores.
+//
+// Logits are [B, C, HW]; a thread handles PX consecutive pixels and reads one 16-byte vector per
+// class plane, so every warp-level load is a contiguous 512-byte segment.
+#include "common.cuh"
+
+namespace pylc {
+
+struct LossArgs {
+    const float *logits;
+    const void *target;
+    const float *class_w;  // device, nullable
+    int target_is_i64;
+    int B, C;
+    long long HW, units_per_img, total_units;
+    pylc_loss_cfg cfg;
+};
+
+template <int PX>
+struct PxVec;
+template <>
+struct PxVec<4> {
+    static __device__ __forceinline__ void load(const float *p, float (&o)[4]) {
+        const float4 t = ld_stream_f4(p);
+        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float *p, const float (&v)[4]) {
+        st_stream_f4(p, make_float4(v[0], v[1], v[2], v[3]));
+    }
+    static __device__ __forceinline__ void load_target(const void *t, int is_i64, long long idx, int (&o)[4]) {
+        if (is_i64) {
+            const longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(static_cast<const long long *>(t) + idx));
+            const longlong2 b = __ldg(reinterpret_cast<const longlong2 *>(static_cast<const long long *>(t) + idx + 2));
+            o[0] = (int)a.x; o[1] = (int)a.y; o[2] = (int)b.x; o[3] = (int)b.y;
+        } else {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(t) + idx));
+            o[0] = w & 0xFF; o[1] = (w >> 8) & 0xFF; o[2] = (w >> 16) & 0xFF; o[3] = w >> 24;
+        }
+    }
+};
+template <>
+struct PxVec<1> {
+    static __device__ __forceinline__ void load(const float *p, float (&o)[1]) { o[0] = __ldg(p); }
+    static __device__ __forceinline__ void store(float *p, const float (&v)[1]) { *p = v[0]; }
+    static __device__ __forceinline__ void load_target(const void *t, int is_i64, long long idx, int (&o)[1]) {
+        o[0] = is_i64 ? (int)__ldg(static_cast<const long long *>(t) + idx)
+                      : (int)__ldg(static_cast<const uint8_t *>(t) + idx);
+    }
+};
+
+__device__ __forceinline__ float pow_gamma(float base, float gamma) {
+    if (gamma == 2.f) return base * base;
+    if (gamma == 1.f) return base;
+    if (gamma == 0.f) return 1.f;
+    return powf(base, gamma);
+}
+
+// softmax of one pixel column; returns max and sum, leaves exp(z - max) in e[]
+template <int CMAX>
+__device__ __forceinline__ void softmax_px(const float (&z)[CMAX], int C, float (&e)[CMAX], float &m, float &s) {
+    m = z[0];
+#pragma unroll
+    for (int c = 1; c < CMAX; ++c)
+        if (c < C) m = fmaxf(m, z[c]);
+    s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+            e[c] = expf(z[c] - m);
+            s += e[c];
+        }
+}
+
+template <int C_T, int CMAX, int PX>
+__global__ void __launch_bounds__(kThreads, 2) loss_reduce_kernel(LossArgs a, double *__restrict__ partials) {
+    const int C = C_T > 0 ? C_T : a.C;
+    __shared__ float s_w[PYLC_MAX_CLASSES];
+    __shared__ double s_part[2 * PYLC_MAX_CLASSES + 3];
+    if (threadIdx.x < PYLC_MAX_CLASSES) s_w[threadIdx.x] = (a.class_w && threadIdx.x < C) ? a.class_w[threadIdx.x] : 1.f;
+    if (threadIdx.x < 2 * PYLC_MAX_CLASSES + 3) s_part[threadIdx.x] = 0.0;
+    __syncthreads();
+
+    float accI[CMAX], accP[CMAX];
+    uint32_t accN[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        accI[c] = 0.f;
+        accP[c] = 0.f;
+        accN[c] = 0;
+    }
+    float ce_num = 0.f, ce_den = 0.f, focal = 0.f;
+    const float eps = a.cfg.eps, gamma = a.cfg.fl_gamma, alpha = a.cfg.fl_alpha;
+
+    for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < a.total_units;
+         u += (long long)gridDim.x * kThreads) {
+        const long long b = u / a.units_per_img;
+        const long long off = (u - b * a.units_per_img) * PX;
+        const float *p = a.logits + ((size_t)b * C) * a.HW + off;
+        float z[CMAX][PX];
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+            if (c < C) PxVec<PX>::load(p + (size_t)c * a.HW, z[c]);
+        int t[PX];
+        PxVec<PX>::load_target(a.target, a.target_is_i64, b * a.HW + off, t);
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            float zc[CMAX], e[CMAX], m, s;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) zc[c] = z[c][j];
+            softmax_px<CMAX>(zc, C, e, m, s);
+            const float r = __frcp_rn(s);
+            float zt = 0.f, pt = 0.f, wt = 0.f;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c)
+                if (c < C) {
+                    const float pc = e[c] * r;
+                    const bool hit = t[j] == c;
+                    accP[c] += pc;
+                    accI[c] += hit ? pc : 0.f;
+                    accN[c] += hit ? 1u : 0u;
+                    zt = hit ? zc[c] : zt;
+                    pt = hit ? pc : pt;
+                    wt = hit ? s_w[c] : wt;
+                }
+            ce_num += wt * (m + logf(s) - zt);
+            ce_den += wt;
+            const float q = pt + eps;
+            focal += -alpha * pow_gamma(1.f - q, gamma) * logf(q);
+        }
+    }
+
+    // block reduction: warp shuffles in f32, cross-warp in f64 shared atomics
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+            float vi = accI[c], vp = accP[c];
+            uint32_t vn = __reduce_add_sync(0xFFFFFFFFu, accN[c]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                vi += __shfl_xor_sync(0xFFFFFFFFu, vi, o);
+                vp += __shfl_xor_sync(0xFFFFFFFFu, vp, o);
+            }
+            if (lane == 0) {
+                atomicAdd(&s_part[c], (double)vi);
+                atomicAdd(&s_part[C + c], (double)vp + (double)vn);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ce_num += __shfl_xor_sync(0xFFFFFFFFu, ce_num, o);
+        ce_den += __shfl_xor_sync(0xFFFFFFFFu, ce_den, o);
+        focal += __shfl_xor_sync(0xFFFFFFFFu, focal, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&s_part[2 * C], (double)ce_num);
+        atomicAdd(&s_part[2 * C + 1], (double)ce_den);
+        atomicAdd(&s_part[2 * C + 2], (double)focal);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * C + 3) atomicAdd(&partials[threadIdx.x], s_part[threadIdx.x]);
+}
+
+template <int C_T, int CMAX, int PX>
+__global__ void __launch_bounds__(kThreads, 2)
+    loss_grad_kernel(LossArgs a, const double *__restrict__ partials, long long n_px_total, float grad_scale,
+                     float *__restrict__ grad) {
+    const int C = C_T > 0 ? C_T : a.C;
+    __shared__ float s_w[PYLC_MAX_CLASSES], s_a[PYLC_MAX_CLASSES], s_b[PYLC_MAX_CLASSES];
+    __shared__ float s_inv_den;
+    if (threadIdx.x < PYLC_MAX_CLASSES) {
+        const int c = threadIdx.x;
+        s_w[c] = (a.class_w && c < C) ? a.class_w[c] : 1.f;
+        float av = 0.f, bv = 0.f;
+        if (c < C) {
+            const double I = partials[c], K = partials[C + c], sm = (double)a.cfg.dice_smooth;
+            av = (float)(-2.0 / ((K + sm) * C));
+            bv = (float)((2.0 * I + sm) / ((K + sm) * (K + sm) * C));
+        }
+        s_a[c] = av;
+        s_b[c] = bv;
+    }
+    if (threadIdx.x == 0) s_inv_den = (float)(1.0 / partials[2 * C + 1]);
+    __syncthreads();
+    const float eps = a.cfg.eps, gamma = a.cfg.fl_gamma;
+    const float lce = a.cfg.ce_weight * s_inv_den, ld = a.cfg.dice_weight;
+    const float lf = a.cfg.focal_weight * a.cfg.fl_alpha / (float)n_px_total;
+    float bb[CMAX], aa[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        bb[c] = c < C ? s_b[c] : 0.f;
+        aa[c] = c < C ? s_a[c] : 0.f;
+    }
+
+    for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < a.total_units;
+         u += (long long)gridDim.x * kThreads) {
+        const long long b = u / a.units_per_img;
+        const long long off = (u - b * a.units_per_img) * PX;
+        const size_t base = ((size_t)b * C) * a.HW + off;
+        float z[CMAX][PX];
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+            if (c < C) PxVec<PX>::load(a.logits + base + (size_t)c * a.HW, z[c]);
+        int t[PX];
+        PxVec<PX>::load_target(a.target, a.target_is_i64, b * a.HW + off, t);
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            float zc[CMAX], e[CMAX], m, s;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) zc[c] = z[c][j];
+            softmax_px<CMAX>(zc, C, e, m, s);
+            const float r = __frcp_rn(s);
+            float pt = 0.f, wt = 0.f, at = 0.f, sb = 0.f;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c)
+                if (c < C) {
+                    e[c] *= r;  // p_c
+                    const bool hit = t[j] == c;
+                    pt = hit ? e[c] : pt;
+                    wt = hit ? s_w[c] : wt;
+                    at = hit ? aa[c] : at;
+                    sb = fmaf(bb[c], e[c], sb);
+                }
+            const float q = pt + eps, omq = 1.f - q;
+            const float dq = gamma * pow_gamma(omq, gamma - 1.f) * logf(q) - pow_gamma(omq, gamma) / q;
+            const float f = lf * dq * pt;
+            const float ca = lce * wt;
+            const float common = ca - f - ld * (at * pt + sb);
+            const float hitk = f - ca;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c)
+                if (c < C) {
+                    float g = e[c] * fmaf(ld, bb[c], common);
+                    if (t[j] == c) g += fmaf(ld * e[c], aa[c], hitk);
+                    z[c][j] = g * grad_scale;
+                }
+        }
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+            if (c < C) PxVec<PX>::store(grad + base + (size_t)c * a.HW, z[c]);
+    }
+}
+
+__global__ void loss_finalize_kernel(const double *__restrict__ partials, int C, long long n_px_total, pylc_loss_cfg cfg,
+                                     float *__restrict__ out4) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double ce = partials[2 * C] / partials[2 * C + 1];
+    double dice = 0.0;
+    for (int c = 0; c < C; ++c)
+        dice += 1.0 - (2.0 * partials[c] + cfg.dice_smooth) / (partials[C + c] + cfg.dice_smooth);
+    dice /= C;
+    const double focal = partials[2 * C + 2] / (double)n_px_total;
+    out4[0] = (float)(cfg.ce_weight * ce + cfg.dice_weight * dice + cfg.focal_weight * focal);
+    out4[1] = (float)ce;
+    out4[2] = (float)dice;
+    out4[3] = (float)focal;
+}
+
+static int fill_args(const float *logits, const void *target, int target_is_i64, int B, int C, int64_t HW,
+                     const float *class_w, const pylc_loss_cfg *cfg, LossArgs *a, int *px) {
+    if (!logits || !target || !cfg || B < 1 || HW < 1) return PYLC_ERR_ARG;
+    if (C < 1 || C > PYLC_MAX_CLASSES) return PYLC_ERR_CLASSES;
+    const uintptr_t talign = target_is_i64 ? 16 : 4;
+    const bool vec = (HW % 4 == 0) && ((uintptr_t)logits % 16 == 0) && ((uintptr_t)target % talign == 0) && C <= 16;
+    *px = vec ? 4 : 1;
+    a->logits = logits;
+    a->target = target;
+    a->class_w = class_w;
+    a->target_is_i64 = target_is_i64;
+    a->B = B;
+    a->C = C;
+    a->HW = HW;
+    a->units_per_img = HW / *px;
+    a->total_units = a->units_per_img * B;
+    a->cfg = *cfg;
+    return PYLC_OK;
+}
+
+static unsigned loss_grid(long long units) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long want = (units + kThreads - 1) / kThreads;
+    const long long cap = (long long)sms * 4;
+    return (unsigned)(want < cap ? want : cap);
+}
+
+}  // namespace pylc
+
+using namespace pylc;
+
+#define DISPATCH_LOSS(KERNEL, ...)                                                                      \
+    do {                                                                                                \
+        if (px == 4) {                                                                                  \
+            if (C == 9) KERNEL<9, 9, 4><<<grid, kThreads, 0, st>>>(__VA_ARGS__);                        \
+            else if (C == 11) KERNEL<11, 11, 4><<<grid, kThreads, 0, st>>>(__VA_ARGS__);                \
+            else if (C <= 4) KERNEL<0, 4, 4><<<grid, kThreads, 0, st>>>(__VA_ARGS__);                   \
+            else if (C <= 8) KERNEL<0, 8, 4><<<grid, kThreads, 0, st>>>(__VA_ARGS__);                   \
+            else if (C <= 12) KERNEL<0, 12, 4><<<grid, kThreads, 0, st>>>(__VA_ARGS__);                 \
+            else KERNEL<0, 16, 4><<<grid, kThreads, 0, st>>>(__VA_ARGS__);                              \
+        } else {                                                                                        \
+            if (C <= 12) KERNEL<0, 12, 1><<<grid, kThreads, 0, st>>>(__VA_ARGS__);                      \
+            else KERNEL<0, 32, 1><<<grid, kThreads, 0, st>>>(__VA_ARGS__);                              \
+        }                                                                                               \
+    } while (0)
+
+extern "C" int pylc_multiloss_reduce(const float *logits, const void *target, int target_is_i64, int B, int C,
+                                     int64_t HW, const float *class_w, const pylc_loss_cfg *cfg, double *partials,
+                                     pylc_stream_t stream) {
+    if (!partials) return PYLC_ERR_ARG;
+    LossArgs a;
+    int px;
+    int rc = fill_args(logits, target, target_is_i64, B, C, HW, class_w, cfg, &a, &px);
+    if (rc) return rc;
+    const unsigned grid = loss_grid(a.total_units);
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_LOSS(loss_reduce_kernel, a, partials);
+    return finish_launch();
+}
+
+extern "C" int pylc_multiloss_grad(const float *logits, const void *target, int target_is_i64, int B, int C,
+                                   int64_t HW, const float *class_w, const pylc_loss_cfg *cfg, const double *partials,
+                                   int64_t n_px_total, float grad_scale, float *grad, pylc_stream_t stream) {
+    if (!partials || !grad || n_px_total < 1) return PYLC_ERR_ARG;
+    if ((uintptr_t)grad % 16) return PYLC_ERR_ALIGN;
+    LossArgs a;
+    int px;
+    int rc = fill_args(logits, target, target_is_i64, B, C, HW, class_w, cfg, &a, &px);
+    if (rc) return rc;
+    const unsigned grid = loss_grid(a.total_units);
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_LOSS(loss_grad_kernel, a, partials, (long long)n_px_total, grad_scale, grad);
+    return finish_launch();
+}
+
+extern "C" int pylc_multiloss_finalize(const double *partials, int C, int64_t n_px_total, const pylc_loss_cfg *cfg,
+                                       float *out4, pylc_stream_t stream) {
+    if (!partials || !cfg || !out4 || n_px_total < 1) return PYLC_ERR_ARG;
+    if (C < 1 || C > PYLC_MAX_CLASSES) return PYLC_ERR_CLASSES;
+    loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partials, C, (long long)n_px_total, *cfg, out4);
+    return finish_launch();
+}

@@ -1,0 +1,312 @@
+"""
+Torch-tensor front end of the C ABI: allocates outputs with the PyTorch caching allocator,
+passes raw device pointers + the current CUDA stream to libpylc_b200.so, never synchronises.
+
+PyTorch is plumbing here (device memory, streams); every per-pixel operation is a hand-written
+sm_100a kernel behind include/pylc_b200.h.  No function in this module has a CPU path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LossCfg, PylcError, check
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise PylcError("pylc_b200 ops take CUDA tensors (there is no CPU fallback)")
+
+
+def pitch_for(width_bytes):
+    """Row pitch (bytes) that keeps every row 16-byte aligned for the vectorised kernels."""
+    return (width_bytes + 15) // 16 * 16
+
+
+def tile_grid(H, W, T, S):
+    nH, nW = ctypes.c_int(0), ctypes.c_int(0)
+    check(_lib.load().pylc_tile_grid(H, W, T, S, ctypes.byref(nH), ctypes.byref(nW)), "pylc_tile_grid")
+    return nH.value, nW.value
+
+
+def pinned_pitched(img):
+    """Host staging: copy an [H,W] / [H,W,3] u8 array into pinned memory with 16-byte-aligned
+    rows.  Returns (tensor [H, pitch] u8 pinned, pitch)."""
+    img = np.asarray(img)
+    H = img.shape[0]
+    row = img.shape[1] * (img.shape[2] if img.ndim == 3 else 1)
+    pitch = pitch_for(row)
+    buf = torch.empty((H, pitch), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    buf.numpy()[:, :row] = img.reshape(H, row)
+    return buf, pitch
+
+
+def upload_image(img, device=None):
+    """u8 image -> device tensor [H, pitch] with aligned rows (one async H2D copy)."""
+    buf, pitch = pinned_pitched(img)
+    return buf.to(device or torch.device("cuda"), non_blocking=True), pitch
+
+
+# ---- extraction ---------------------------------------------------------------------------------
+
+
+def tile_gather_u8(src, H, W, ch, pitch, T, S, stats=False, out=None):
+    """pylc_tile_gather_u8: returns tiles [n,ch,T,T] u8 (and stat [n,ch,2] i64 = sum x, sum x^2)."""
+    _need_cuda(src)
+    nH, nW = tile_grid(H, W, T, S)
+    n = nH * nW
+    tiles = out if out is not None else torch.empty((n, ch, T, T), dtype=torch.uint8, device=src.device)
+    stat = torch.zeros((n, ch, 2), dtype=torch.int64, device=src.device) if stats else None
+    check(_lib.load().pylc_tile_gather_u8(_p(src), H, W, ch, pitch, T, S, _p(tiles), _p(stat), _stream()),
+          "pylc_tile_gather_u8")
+    return (tiles, stat) if stats else tiles
+
+
+def mask_gather_encode_hist(src, H, W, pitch, T, S, palette, hist=True, out=None):
+    """pylc_mask_gather_encode_hist: returns (tiles [n,T,T] u8, px_dist [n,C] i64 or None)."""
+    _need_cuda(src)
+    pal, C = _lib.palette_array(palette)
+    nH, nW = tile_grid(H, W, T, S)
+    n = nH * nW
+    tiles = out if out is not None else torch.empty((n, T, T), dtype=torch.uint8, device=src.device)
+    px_dist = torch.zeros((n, C), dtype=torch.int64, device=src.device) if hist else None
+    check(_lib.load().pylc_mask_gather_encode_hist(_p(src), H, W, pitch, T, S, pal, C, _p(tiles), _p(px_dist),
+                                                   _stream()), "pylc_mask_gather_encode_hist")
+    return tiles, px_dist
+
+
+def tile_gather_norm_f32(src, H, W, ch, pitch, T, S, mean, std, post_div=255.0, out_ch=3, out=None):
+    """pylc_tile_gather_norm_f32: network-ready f32 tiles [n,out_ch,T,T]."""
+    _need_cuda(src)
+    nH, nW = tile_grid(H, W, T, S)
+    n = nH * nW
+    tiles = out if out is not None else torch.empty((n, out_ch, T, T), dtype=torch.float32, device=src.device)
+    check(_lib.load().pylc_tile_gather_norm_f32(_p(src), H, W, ch, pitch, T, S, _lib.float3(mean), _lib.float3(std),
+                                                float(post_div), out_ch, _p(tiles), _stream()),
+          "pylc_tile_gather_norm_f32")
+    return tiles
+
+
+def class_encode_nchw(rgb, palette, hist=False):
+    """tools.class_encode on a CUDA [N,3,H,W] u8 tensor -> [N,H,W] u8 (+ [C] i64 histogram)."""
+    _need_cuda(rgb)
+    if rgb.dim() != 4 or rgb.shape[1] != 3:
+        raise PylcError("Input data must be 3 channel (RGB)")
+    rgb = rgb.contiguous()
+    pal, C = _lib.palette_array(palette)
+    n, _, h, w = rgb.shape
+    out = torch.empty((n, h, w), dtype=torch.uint8, device=rgb.device)
+    hs = torch.zeros((C,), dtype=torch.int64, device=rgb.device) if hist else None
+    check(_lib.load().pylc_class_encode(_p(rgb), n, h, w, 0, 1, pal, C, _p(out), _p(hs), _stream()),
+          "pylc_class_encode")
+    return (out, hs) if hist else out
+
+
+def class_encode_hwc(rgb, rows, cols, pitch, palette, n_img=1, hist=False):
+    """class_encode on interleaved RGB rows (pitch bytes per row) -> [n_img, rows, cols] u8."""
+    _need_cuda(rgb)
+    pal, C = _lib.palette_array(palette)
+    out = torch.empty((n_img, rows, cols), dtype=torch.uint8, device=rgb.device)
+    hs = torch.zeros((C,), dtype=torch.int64, device=rgb.device) if hist else None
+    check(_lib.load().pylc_class_encode(_p(rgb), n_img, rows, cols, pitch, 0, pal, C, _p(out), _p(hs), _stream()),
+          "pylc_class_encode")
+    return (out, hs) if hist else out
+
+
+def profile_tiles(imgs, masks, n_classes):
+    """pylc_profile_tiles: (stat [n,ch,2] i64 or None, px_dist [n,C] i64 or None)."""
+    _need_cuda(imgs, masks)
+    stat = px_dist = None
+    n = (imgs if imgs is not None else masks).shape[0]
+    ch = 1
+    tile_px = 0
+    if imgs is not None:
+        imgs = imgs.contiguous()
+        ch = imgs.shape[1]
+        tile_px = imgs.shape[2] * imgs.shape[3]
+        stat = torch.zeros((n, ch, 2), dtype=torch.int64, device=imgs.device)
+    if masks is not None:
+        masks = masks.contiguous()
+        tile_px = masks.shape[1] * masks.shape[2]
+        px_dist = torch.zeros((n, n_classes), dtype=torch.int64, device=masks.device)
+    check(_lib.load().pylc_profile_tiles(_p(imgs), ch, _p(masks), n, tile_px, n_classes, _p(stat), _p(px_dist),
+                                         _stream()), "pylc_profile_tiles")
+    return stat, px_dist
+
+
+# ---- stitching ----------------------------------------------------------------------------------
+
+
+def stitch_dims(nr, nc, T, S):
+    return ((nr + 1) * S, (nc + 1) * S) if S < T else (nr * S, nc * S)
+
+
+def stitch_argmax_colour(logits, nr, nc, T, S, lut_rgb=None, want_labels=True, want_rgb=False,
+                         want_stitched=False, tiles_per_batch=None):
+    """pylc_stitch_argmax_colour.  `logits` is one contiguous CUDA [nr*nc,C,T,T] f32 tensor, or a list
+    of per-batch tensors [<=b,C,T,T] (the reference's `model_outputs` list).
+    Returns (labels [h,w] u8 | None, rgb [h,w,3] u8 | None, stitched [C,h,w] f32 | None)."""
+    lib = _lib.load()
+    batch_table = None
+    if isinstance(logits, (list, tuple)):
+        _need_cuda(*logits)
+        C = logits[0].shape[1]
+        dev = logits[0].device
+        tpb = tiles_per_batch or logits[0].shape[0]
+        for i, t in enumerate(logits):
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise PylcError("tile batches must be contiguous float32")
+            if i < len(logits) - 1 and t.shape[0] != tpb:
+                raise PylcError("all tile batches but the last must hold tiles_per_batch tiles")
+        if sum(t.shape[0] for t in logits) != nr * nc:
+            raise PylcError("expected %d tiles, got %d" % (nr * nc, sum(t.shape[0] for t in logits)))
+        ptrs = torch.tensor([t.data_ptr() for t in logits], dtype=torch.int64)
+        batch_table = ptrs.to(dev, non_blocking=True)
+        lp, bp = ctypes.c_void_p(0), _p(batch_table)
+    else:
+        _need_cuda(logits)
+        if logits.dtype != torch.float32 or not logits.is_contiguous():
+            raise PylcError("logits must be contiguous float32")
+        if logits.shape[0] != nr * nc:
+            raise PylcError("expected %d tiles, got %d" % (nr * nc, logits.shape[0]))
+        C = logits.shape[1]
+        dev = logits.device
+        tpb = nr * nc
+        lp, bp = _p(logits), ctypes.c_void_p(0)
+    h, w = stitch_dims(nr, nc, T, S)
+    labels = torch.empty((h, w), dtype=torch.uint8, device=dev) if want_labels else None
+    rgb = torch.empty((h, w, 3), dtype=torch.uint8, device=dev) if want_rgb else None
+    stitched = torch.empty((C, h, w), dtype=torch.float32, device=dev) if want_stitched else None
+    pal = None
+    if lut_rgb is not None:
+        pal, c2 = _lib.palette_array(lut_rgb)
+        if c2 != C:
+            raise PylcError("lut_rgb has %d colours, logits have %d classes" % (c2, C))
+    check(lib.pylc_stitch_argmax_colour(lp, bp, tpb, nr, nc, C, T, S, pal, _p(labels), _p(rgb), _p(stitched),
+                                        _stream()), "pylc_stitch_argmax_colour")
+    if batch_table is not None:
+        batch_table.record_stream(torch.cuda.current_stream())
+    return labels, rgb, stitched
+
+
+def colourise_u8(labels, lut_rgb):
+    _need_cuda(labels)
+    labels = labels.contiguous()
+    pal, C = _lib.palette_array(lut_rgb)
+    rgb = torch.empty(tuple(labels.shape) + (3,), dtype=torch.uint8, device=labels.device)
+    check(_lib.load().pylc_colourise_u8(_p(labels), labels.numel(), pal, C, _p(rgb), _stream()), "pylc_colourise_u8")
+    return rgb
+
+
+# ---- evaluation ---------------------------------------------------------------------------------
+
+
+def nn_index_map(n_src, n_dst):
+    """OpenCV INTER_NEAREST source index per destination index (resizeNN's x_ofs table):
+    min(floor(x * (1 / (n_dst / n_src))), n_src - 1) in double precision."""
+    scale = 1.0 / (n_dst / n_src)
+    idx = np.floor(np.arange(n_dst, dtype=np.float64) * scale).astype(np.int64)
+    return np.minimum(idx, n_src - 1).astype(np.int32)
+
+
+def resample_encode_confusion(labels, w_full, h_full, gt_rgb=None, gt_pitch=0, palette=None, lut_rgb=None,
+                              n_classes=None, n_inject=0, conf=None, want_pred=False, want_rgb=False,
+                              want_gt=False, maps=None):
+    """pylc_resample_encode_confusion.  Returns dict(conf, pred_full, pred_rgb, gt_full)."""
+    _need_cuda(labels, gt_rgb)
+    h, w = labels.shape
+    dev = labels.device
+    if maps is None:
+        maps = (torch.from_numpy(nn_index_map(w, w_full)).to(dev, non_blocking=True),
+                torch.from_numpy(nn_index_map(h, h_full)).to(dev, non_blocking=True))
+    x_ofs, y_ofs = maps
+    pal = lut = None
+    C = n_classes
+    if palette is not None:
+        pal, C = _lib.palette_array(palette)
+    if lut_rgb is not None:
+        lut, C = _lib.palette_array(lut_rgb)
+    if gt_rgb is not None and conf is None:
+        conf = torch.zeros((C, C), dtype=torch.int64, device=dev)
+    pred_full = torch.empty((h_full, w_full), dtype=torch.uint8, device=dev) if want_pred else None
+    pred_rgb = torch.empty((h_full, w_full, 3), dtype=torch.uint8, device=dev) if want_rgb else None
+    gt_full = torch.empty((h_full, w_full), dtype=torch.uint8, device=dev) if want_gt else None
+    check(_lib.load().pylc_resample_encode_confusion(
+        _p(labels), h, w, _p(x_ofs), _p(y_ofs), h_full, w_full, _p(gt_rgb), gt_pitch, pal, lut, C, n_inject,
+        _p(conf if gt_rgb is not None else None), _p(pred_full), _p(pred_rgb), _p(gt_full), _stream()),
+        "pylc_resample_encode_confusion")
+    return {"conf": conf, "pred_full": pred_full, "pred_rgb": pred_rgb, "gt_full": gt_full}
+
+
+def confusion_u8(y_true, y_pred, n_classes, n_inject=0, conf=None):
+    _need_cuda(y_true, y_pred)
+    y_true = y_true.contiguous().view(-1)
+    y_pred = y_pred.contiguous().view(-1)
+    if y_true.numel() != y_pred.numel():
+        raise PylcError("Input dimensions %s not same as target %s." % (tuple(y_pred.shape), tuple(y_true.shape)))
+    if conf is None:
+        conf = torch.zeros((n_classes, n_classes), dtype=torch.int64, device=y_true.device)
+    check(_lib.load().pylc_confusion_u8(_p(y_true), _p(y_pred), y_true.numel(), n_classes, n_inject, _p(conf),
+                                        _stream()), "pylc_confusion_u8")
+    return conf
+
+
+# ---- multi-loss ---------------------------------------------------------------------------------
+
+
+def loss_cfg(ce=0.5, dice=0.5, focal=0.5, smooth=1.0, gamma=2.0, alpha=0.25, eps=1e-8):
+    return LossCfg(ce, dice, focal, smooth, gamma, alpha, eps)
+
+
+def _loss_inputs(logits, target):
+    _need_cuda(logits, target)
+    if logits.dtype != torch.float32:
+        raise PylcError("logits must be float32")
+    logits = logits.contiguous()
+    target = target.contiguous()
+    if target.dtype == torch.int64:
+        is_i64 = 1
+    elif target.dtype == torch.uint8:
+        is_i64 = 0
+    else:
+        raise PylcError("target must be int64 or uint8")
+    B, C = logits.shape[0], logits.shape[1]
+    HW = logits.numel() // (B * C)
+    if target.numel() != B * HW:
+        raise PylcError("pred/target shape mismatch")
+    return logits, target, is_i64, B, C, HW
+
+
+def multiloss_reduce(logits, target, cfg, class_w=None, partials=None):
+    logits, target, is_i64, B, C, HW = _loss_inputs(logits, target)
+    if partials is None:
+        partials = torch.zeros((2 * C + 3,), dtype=torch.float64, device=logits.device)
+    check(_lib.load().pylc_multiloss_reduce(_p(logits), _p(target), is_i64, B, C, HW, _p(class_w), ctypes.byref(cfg),
+                                            _p(partials), _stream()), "pylc_multiloss_reduce")
+    return partials
+
+
+def multiloss_finalize(partials, n_classes, n_px_total, cfg):
+    out = torch.empty((4,), dtype=torch.float32, device=partials.device)
+    check(_lib.load().pylc_multiloss_finalize(_p(partials), n_classes, n_px_total, ctypes.byref(cfg), _p(out),
+                                              _stream()), "pylc_multiloss_finalize")
+    return out
+
+
+def multiloss_grad(logits, target, cfg, partials, n_px_total, class_w=None, grad_scale=1.0, out=None):
+    logits, target, is_i64, B, C, HW = _loss_inputs(logits, target)
+    grad = out if out is not None else torch.empty_like(logits)
+    check(_lib.load().pylc_multiloss_grad(_p(logits), _p(target), is_i64, B, C, HW, _p(class_w), ctypes.byref(cfg),
+                                          _p(partials), n_px_total, float(grad_scale), _p(grad), _stream()),
+          "pylc_multiloss_grad")
+    return grad

@@ -1,0 +1,408 @@
+"""Parity of every CUDA kernel (through the C ABI) against the CPU oracle on identical seeded
+inputs, plus the reference-generated golden fixtures.  Integer / byte outputs are bit-exact;
+floating point carries the north_star tolerances written next to each assert."""
+import numpy as np
+import pytest
+import torch
+
+import pylc_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+STITCH_RTOL = 1e-5     # north_star: stitched probabilities within 1e-5 relative (fp32)
+LOSS_RTOL = 1e-4       # north_star: loss values within 1e-4 relative
+ARGMAX_MARGIN = 1e-6   # labels must agree wherever the reference's top-1 beats top-2 by more than this
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from pylc_b200 import ops as _ops
+    _ops._lib.load()
+    return _ops
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ---------------------------------------------------------------------------------------------
+# tile gather
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("H,W,ch,T,S", [
+    (1100, 1300, 1, 512, 512), (1100, 1300, 3, 512, 512), (1536, 1024, 1, 512, 256), (1024, 1536, 3, 512, 256),
+    (75, 101, 1, 32, 32), (80, 96, 3, 32, 16), (70, 200, 1, 64, 16), (512, 512, 3, 512, 512),
+    (300, 300, 1, 512, 512),
+])
+def test_tile_gather(ops, H, W, ch, T, S):
+    img = orc.synth_image(3, W, H, ch)
+    d, pitch = ops.upload_image(img)
+    tiles, stat = ops.tile_gather_u8(d, H, W, ch, pitch, T, S, stats=True)
+    ref = orc.split_tiles(img, T, S)
+    assert tuple(tiles.shape) == ref.shape
+    assert np.array_equal(tiles.cpu().numpy(), ref)
+    if ref.shape[0]:
+        x = ref.astype(np.int64).reshape(ref.shape[0], ch, -1)
+        want = np.stack([x.sum(-1), (x * x).sum(-1)], axis=-1)
+        assert np.array_equal(stat.cpu().numpy(), want)
+
+
+def test_tile_gather_unaligned_source(ops):
+    # contiguous rows of 1001 bytes: base/pitch not 16-byte aligned -> byte-wise path, same result
+    img = orc.synth_image(4, 1001, 700, 1)
+    d = dev(img)
+    tiles = ops.tile_gather_u8(d, 700, 1001, 1, 1001, 512, 256)
+    assert np.array_equal(tiles.cpu().numpy(), orc.split_tiles(img, 512, 256))
+    img3 = orc.synth_image(5, 601, 600, 3)
+    tiles = ops.tile_gather_u8(dev(img3), 600, 601, 3, 601 * 3, 512, 512)
+    assert np.array_equal(tiles.cpu().numpy(), orc.split_tiles(img3, 512, 512))
+
+
+def test_tile_gather_rejects_bad_geometry(ops):
+    d, pitch = ops.upload_image(orc.synth_image(0, 640, 640, 1))
+    with pytest.raises(ops.PylcError):
+        ops.tile_gather_u8(d, 640, 640, 1, pitch, 500, 250)   # T % 16 != 0
+    with pytest.raises(ops.PylcError):
+        ops.tile_gather_u8(d, 640, 640, 1, pitch, 512, 384)   # T % S != 0
+
+
+def test_split_golden(ops, golden):
+    g = golden("split")
+    for name in ("gray_s32", "gray_s16", "rgb_s32", "rgb_s16"):
+        img = g["split_%s_img" % name]
+        T, S = [int(v) for v in g["split_%s_TS" % name]]
+        ch = 3 if img.ndim == 3 else 1
+        d, pitch = ops.upload_image(img)
+        tiles = ops.tile_gather_u8(d, img.shape[0], img.shape[1], ch, pitch, T, S)
+        assert np.array_equal(tiles.cpu().numpy(), g["split_%s_tiles" % name])
+
+
+@pytest.mark.parametrize("ch", [1, 3])
+def test_gather_norm_bit_exact(ops, ch):
+    H, W, T, S = 1024, 1536, 512, 256
+    img = orc.synth_image(6, W, H, ch)
+    mean = [127.3, 131.9, 120.1][:ch]
+    std = [61.2, 58.7, 63.3][:ch]
+    d, pitch = ops.upload_image(img)
+    got = ops.tile_gather_norm_f32(d, H, W, ch, pitch, T, S, mean, std, 255.0, out_ch=3).cpu()
+    tiles = torch.from_numpy(orc.split_tiles(img, T, S)).float()
+    # models/model.py:434-445 in f32
+    m = torch.tensor(mean, dtype=torch.float32)[None, :, None, None]
+    s = torch.tensor(std, dtype=torch.float32)[None, :, None, None]
+    want = ((tiles - m) / s) / 255
+    if ch == 1:
+        want = torch.cat((want, want, want), 1)   # models/model.py:376-377
+    assert torch.equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------
+# mask gather + encode + histogram
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("pk,H,W,T,S,skew", [
+    ("a", 1100, 1300, 512, 512, False), ("b", 1100, 1300, 512, 512, True), ("a", 1024, 1536, 512, 256, True),
+    ("b", 80, 96, 32, 16, False), ("a", 2000, 3000, 512, 512, True),
+])
+def test_mask_gather_encode_hist(ops, palettes, pk, H, W, T, S, skew):
+    pal = palettes[pk]
+    C = len(pal)
+    mask = orc.synth_mask(7, W, H, pal, skew=skew, off_palette=0.002)
+    d, pitch = ops.upload_image(mask)
+    tiles, px_dist = ops.mask_gather_encode_hist(d, H, W, pitch, T, S, pal)
+    ref = orc.class_encode(orc.split_tiles(mask, T, S), pal)
+    assert np.array_equal(tiles.cpu().numpy(), ref)
+    assert np.array_equal(px_dist.cpu().numpy(), orc.tile_histograms(ref, C))
+    assert int(px_dist.sum()) == ref.size                       # utils/profile.py:125-126
+    assert (ref == 1).sum() > 0
+
+
+def test_mask_gather_wide_palette_duplicates_unaligned(ops):
+    rng = np.random.default_rng(8)
+    pal = rng.integers(0, 256, size=(20, 3)).tolist()
+    pal[7] = pal[3]      # duplicate colour: the later index (7) wins
+    mask = orc.synth_mask(9, 1001, 600, pal, off_palette=0.01)
+    ref = orc.class_encode(orc.split_tiles(mask, 512, 512), pal)
+    assert (ref == 7).any() and not (ref == 3).any()
+    d, pitch = ops.upload_image(mask)
+    tiles, px_dist = ops.mask_gather_encode_hist(d, 600, 1001, pitch, 512, 512, pal)
+    assert np.array_equal(tiles.cpu().numpy(), ref)
+    assert np.array_equal(px_dist.cpu().numpy(), orc.tile_histograms(ref, 20))
+    # unpitched source -> byte-wise loads
+    tiles2, px2 = ops.mask_gather_encode_hist(dev(mask), 600, 1001, 1001 * 3, 512, 512, pal)
+    assert torch.equal(tiles, tiles2) and torch.equal(px_dist, px2)
+
+
+def test_class_encode_golden_and_layouts(ops, golden, palettes):
+    g = golden("encode")
+    for name in ("a", "b", "dup"):
+        pal = g["palette_%s" % name].tolist()
+        x = g["encode_%s_in" % name]
+        out, hist = ops.class_encode_nchw(dev(x), pal, hist=True)
+        assert np.array_equal(out.cpu().numpy(), g["encode_%s_out" % name])
+        assert np.array_equal(hist.cpu().numpy(), np.bincount(g["encode_%s_out" % name].ravel(), minlength=len(pal)))
+    pal = palettes["b"]
+    for (h, w) in [(37, 53), (64, 48), (1500, 2000)]:
+        mask = orc.synth_mask(h, w, h, pal, off_palette=0.01)
+        want = orc.class_encode_hwc(mask, pal)
+        # planar (the reference's NCHW argument), arbitrary size
+        out = ops.class_encode_nchw(dev(np.moveaxis(mask, 2, 0)[None]), pal)
+        assert np.array_equal(out.cpu().numpy()[0], want)
+        # interleaved, pitched and unpitched
+        d, pitch = ops.upload_image(mask)
+        out, hist = ops.class_encode_hwc(d, h, w, pitch, pal, hist=True)
+        assert np.array_equal(out.cpu().numpy()[0], want)
+        assert np.array_equal(hist.cpu().numpy(), np.bincount(want.ravel(), minlength=len(pal)))
+        out = ops.class_encode_hwc(dev(mask), h, w, w * 3, pal)
+        assert np.array_equal(out.cpu().numpy()[0], want)
+
+
+def test_class_encode_rejects_non_rgb(ops):
+    with pytest.raises(ops.PylcError):   # utils/tools.py:433
+        ops.class_encode_nchw(torch.zeros((1, 4, 8, 8), dtype=torch.uint8, device="cuda"), [[0, 0, 0]])
+
+
+@pytest.mark.parametrize("ch,C,T", [(1, 9, 512), (3, 11, 512), (1, 20, 64), (3, 9, 32)])
+def test_profile_tiles(ops, ch, C, T):
+    rng = np.random.default_rng(10)
+    n = 5
+    imgs = rng.integers(0, 256, size=(n, ch, T, T), dtype=np.uint8)
+    masks = rng.integers(0, C, size=(n, T, T), dtype=np.uint8)
+    masks[0] = 0
+    stat, px_dist = ops.profile_tiles(dev(imgs), dev(masks), C)
+    assert np.array_equal(px_dist.cpu().numpy(), orc.tile_histograms(masks, C))
+    x = imgs.astype(np.int64).reshape(n, ch, -1)
+    assert np.array_equal(stat.cpu().numpy(), np.stack([x.sum(-1), (x * x).sum(-1)], axis=-1))
+
+
+def test_extract_profile_golden(ops, golden, palettes):
+    """extract + profile of the reference run in gen_golden.py, reproduced through the kernels."""
+    g = golden("extract_profile")
+    for name, ch, pk in (("gray_a", 1, "a"), ("rgb_b", 3, "b")):
+        pal = palettes[pk]
+        imgs, masks, dists = [], [], []
+        for k in g["exprof_%s_order" % name]:
+            img, mask = g["exprof_%s_img%d" % (name, k)], g["exprof_%s_mask%d" % (name, k)]
+            d, p = ops.upload_image(img)
+            imgs.append(ops.tile_gather_u8(d, img.shape[0], img.shape[1], ch, p, 32, 32))
+            d, p = ops.upload_image(mask)
+            t, pd = ops.mask_gather_encode_hist(d, mask.shape[0], mask.shape[1], p, 32, 32, pal)
+            masks.append(t)
+            dists.append(pd)
+        assert np.array_equal(torch.cat(imgs).cpu().numpy(), g["exprof_%s_tiles_img" % name])
+        assert np.array_equal(torch.cat(masks).cpu().numpy(), g["exprof_%s_tiles_mask" % name])
+        assert np.array_equal(torch.cat(dists).cpu().numpy(), g["exprof_%s_px_dist" % name])
+
+
+# ---------------------------------------------------------------------------------------------
+# stitch + softmax + argmax + colourise
+# ---------------------------------------------------------------------------------------------
+
+def check_stitch(ops, tiles, nr, nc, T, S, pal, ref_map=None, batches=None):
+    C = tiles.shape[1]
+    lut = orc.colourize_lut(C, pal).tolist()
+    if ref_map is None:
+        ref_map = orc.stitch_map(tiles, nr, nc, T, S)
+    if batches:
+        src = [dev(tiles[i:i + batches]) for i in range(0, len(tiles), batches)]
+    else:
+        src = dev(tiles)
+    labels, rgb, stitched = ops.stitch_argmax_colour(src, nr, nc, T, S, lut_rgb=lut, want_rgb=True, want_stitched=True)
+    got = stitched.cpu().numpy()
+    np.testing.assert_allclose(got, ref_map, rtol=STITCH_RTOL, atol=1e-7)
+    lab = labels.cpu().numpy()
+    # our labels are the exact first-argmax of our own map ...
+    assert np.array_equal(lab, np.argmax(got, axis=0))
+    # ... and agree with the reference wherever its top-1 is separated from top-2
+    ref_lab = orc.stitch_labels(ref_map)
+    margin = orc.top2_margin(ref_map)
+    mism = lab != ref_lab
+    assert not (mism & (margin > ARGMAX_MARGIN)).any(), "argmax mismatch above margin"
+    assert np.array_equal(rgb.cpu().numpy(), np.asarray(lut, dtype=np.uint8)[lab])
+    return int(mism.sum()), lab.size
+
+
+@pytest.mark.parametrize("case", ["a_2x3", "a_3x2", "a_3x3", "a_2x1", "b_4x5", "a_s32_2x3"])
+def test_stitch_golden(ops, golden, palettes, case):
+    g = golden("reconstruct")
+    nr, nc, T, S, h, w, w_full, h_full, C = [int(v) for v in g["recon_%s_geom" % case]]
+    pal = palettes["b" if case.startswith("b") else "a"]
+    tiles = g["recon_%s_tiles" % case]
+    check_stitch(ops, tiles, nr, nc, T, S, pal, ref_map=g["recon_%s_map" % case])
+    check_stitch(ops, tiles, nr, nc, T, S, pal, ref_map=g["recon_%s_map" % case], batches=4)
+    # end of tools.reconstruct: NN-resample to (w_full, h_full) and colourise == reference RGB
+    labels, _, _ = ops.stitch_argmax_colour(dev(tiles), nr, nc, T, S)
+    res = ops.resample_encode_confusion(labels, w_full, h_full, lut_rgb=orc.colourize_lut(C, pal).tolist(), want_rgb=True)
+    ref_rgb = g["recon_%s_rgb" % case]
+    ours = res["pred_rgb"].cpu().numpy().astype(np.float32)
+    ref_map = g["recon_%s_map" % case]
+    near_tie = orc.resample_labels((orc.top2_margin(ref_map) <= ARGMAX_MARGIN).astype(np.uint8), w_full, h_full) > 0
+    assert np.array_equal(ours[~near_tie], ref_rgb[~near_tie])
+
+
+@pytest.mark.parametrize("C,nr,nc,T,S", [(9, 2, 3, 512, 256), (11, 3, 2, 512, 256), (9, 2, 2, 512, 512),
+                                        (5, 3, 3, 64, 32), (12, 2, 2, 64, 32), (20, 2, 3, 64, 32), (2, 1, 1, 32, 16),
+                                        (9, 3, 1, 32, 16), (16, 2, 2, 32, 32)])
+def test_stitch_vs_oracle(ops, C, nr, nc, T, S):
+    g = torch.Generator().manual_seed(C * 100 + nr * 10 + nc)
+    tiles = (torch.randn(nr * nc, C, T, T, generator=g) * 3).numpy()
+    pal = np.random.default_rng(C).integers(0, 256, size=(C, 3)).tolist()
+    check_stitch(ops, tiles, nr, nc, T, S, pal)
+    if nr * nc > 2:
+        check_stitch(ops, tiles, nr, nc, T, S, pal, batches=2)
+
+
+def test_stitch_exact_ties_pick_first_class(ops):
+    # identical logits in every class: every softmax is uniform, np.argmax returns class 0
+    tiles = np.zeros((4, 9, 32, 32), dtype=np.float32)
+    labels, _, _ = ops.stitch_argmax_colour(dev(tiles), 2, 2, 32, 16)
+    assert int(labels.max()) == 0
+    tiles[:, 4] = 1.0
+    labels, _, _ = ops.stitch_argmax_colour(dev(tiles), 2, 2, 32, 16)
+    assert int(labels.min()) == 4 and int(labels.max()) == 4
+
+
+def test_stitch_fitted_3000x2000(ops, palettes):
+    """BASELINE config 2 geometry: 3000x2000 fits to 2560x1536 -> 5 x 9 tiles, C = 9."""
+    nr, nc, T, S, C = 5, 9, 512, 256, 9
+    g = torch.Generator().manual_seed(2)
+    tiles = (torch.randn(nr * nc, C, T, T, generator=g) * 3).numpy()
+    mism, total = check_stitch(ops, tiles, nr, nc, T, S, palettes["a"], batches=8)
+    assert mism <= total * 1e-5
+
+
+def test_colourise(ops, golden, palettes):
+    g = golden("colourize")
+    for name in ("a", "b"):
+        pal = palettes[name]
+        lab = g["colourize_%s_in" % name].astype(np.uint8)
+        lut = orc.colourize_lut(len(pal), pal).tolist()
+        rgb = ops.colourise_u8(dev(lab), lut)
+        assert np.array_equal(rgb.cpu().numpy().astype(np.int64), g["colourize_%s_out" % name])
+
+
+# ---------------------------------------------------------------------------------------------
+# resample + encode + confusion
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("pk,h,w,h_full,w_full", [("a", 1024, 1536, 1500, 2000), ("a", 1536, 2560, 2000, 3000),
+                                                  ("b", 64, 96, 70, 100), ("a", 512, 512, 512, 512),
+                                                  ("a", 96, 64, 131, 77)])
+def test_resample_encode_confusion(ops, palettes, pk, h, w, h_full, w_full):
+    pal = palettes[pk]
+    C = len(pal)
+    rng = np.random.default_rng(h + w)
+    labels = orc.synth_labels(11, w, h, C, block=37)
+    gt = orc.synth_mask(12, w_full, h_full, pal, skew=True, off_palette=0.003)
+    d_gt, pitch = ops.upload_image(gt)
+    lut = orc.colourize_lut(C, pal).tolist()
+    res = ops.resample_encode_confusion(dev(labels), w_full, h_full, gt_rgb=d_gt, gt_pitch=pitch, palette=pal,
+                                        lut_rgb=lut, n_inject=C, want_pred=True, want_rgb=True, want_gt=True)
+    pred_full = orc.resample_labels(labels, w_full, h_full)
+    gt_lab = orc.class_encode_hwc(gt, pal)
+    yt, yp = orc.inject_coverage(gt_lab, pred_full, C)
+    assert np.array_equal(res["pred_full"].cpu().numpy().ravel(), yp)
+    assert np.array_equal(res["gt_full"].cpu().numpy().ravel(), yt)
+    assert np.array_equal(res["conf"].cpu().numpy(), orc.confusion_counts(yt, yp, C))
+    assert int(res["conf"].sum()) == h_full * w_full
+    assert np.array_equal(res["pred_rgb"].cpu().numpy().reshape(-1, 3), np.asarray(lut, dtype=np.uint8)[yp])
+    # aggregate path: flat vectors
+    conf2 = ops.confusion_u8(dev(gt_lab), dev(pred_full), C, n_inject=C)
+    assert torch.equal(conf2, res["conf"])
+    # random (incoherent) labels stress the run-length path
+    a = rng.integers(0, C, size=100003, dtype=np.uint8)
+    b = rng.integers(0, C, size=100003, dtype=np.uint8)
+    assert np.array_equal(ops.confusion_u8(dev(a), dev(b), C).cpu().numpy(), orc.confusion_counts(a, b, C))
+
+
+def test_evaluate_golden(ops, golden, palettes):
+    g = golden("evaluate")
+    pal = palettes["a"]
+    C = len(pal)
+    gt = g["eval_gt_rgb"]
+    pred_rgb = g["eval_pred_rgb"].astype(np.uint8)
+    h, w = gt.shape[:2]
+    # Evaluator.load class-encodes the predicted RGB mask back to labels (utils/evaluate.py:104-107)
+    d_pred, pp = ops.upload_image(pred_rgb)
+    pred_lab = ops.class_encode_hwc(d_pred, h, w, pp, pal)[0]
+    assert np.array_equal(pred_lab.cpu().numpy().ravel(), g["eval_y_pred_raw"])
+    d_gt, gp = ops.upload_image(gt)
+    res = ops.resample_encode_confusion(pred_lab, w, h, gt_rgb=d_gt, gt_pitch=gp, palette=pal, n_inject=C,
+                                        want_pred=True, want_gt=True)
+    assert np.array_equal(res["gt_full"].cpu().numpy().ravel(), g["eval_y_true"])
+    assert np.array_equal(res["pred_full"].cpu().numpy().ravel(), g["eval_y_pred"])
+    M = res["conf"].cpu().numpy()
+    m = orc.metrics_from_confusion(M)
+    np.testing.assert_allclose([m["f1"], m["iou"], m["mcc"]], g["eval_scalars"], rtol=1e-12)
+    np.testing.assert_allclose(m["cmatrix"], g["eval_cmatrix"], rtol=1e-15)
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-loss
+# ---------------------------------------------------------------------------------------------
+
+def run_loss(ops, z, t, C, w=None, weighted=False, **kw):
+    cfg = ops.loss_cfg(**kw)
+    dz, dt = dev(z), dev(t)
+    cw = dev(np.asarray(w, dtype=np.float32)) if weighted else None
+    part = ops.multiloss_reduce(dz, dt, cfg, class_w=cw)
+    vals = ops.multiloss_finalize(part, C, t.size, cfg)
+    grad = ops.multiloss_grad(dz, dt, cfg, part, t.size, class_w=cw)
+    return vals.cpu().numpy(), grad.cpu().numpy(), part.cpu().numpy()
+
+
+@pytest.mark.parametrize("name,C,weighted", [("a_unw", 9, False), ("a_w", 9, True), ("b_w", 11, True)])
+def test_multiloss_golden(ops, golden, name, C, weighted):
+    g = golden("loss")
+    z, t, w = g["loss_%s_z" % name], g["loss_%s_t" % name], g["loss_%s_w" % name]
+    vals, grad, _ = run_loss(ops, z, t, C, w, weighted)
+    np.testing.assert_allclose(vals, g["loss_%s_vals" % name], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(grad, g["loss_%s_grad" % name], rtol=1e-3, atol=2e-9)
+    # u8 targets take the same path
+    vals8, grad8, _ = run_loss(ops, z, t.astype(np.uint8), C, w, weighted)
+    assert np.array_equal(vals, vals8) or np.allclose(vals, vals8, rtol=1e-6)
+    np.testing.assert_allclose(grad8, grad, rtol=1e-5, atol=1e-10)
+
+
+@pytest.mark.parametrize("B,C,H,W,weighted", [(4, 9, 128, 128, False), (2, 11, 64, 96, True), (3, 5, 17, 23, True),
+                                              (2, 20, 32, 32, False), (1, 12, 64, 64, True), (2, 2, 16, 16, False)])
+def test_multiloss_vs_oracle(ops, B, C, H, W, weighted):
+    rng = np.random.default_rng(B * 1000 + C)
+    z = (rng.standard_normal((B, C, H, W)) * 3).astype(np.float32)
+    t = rng.integers(0, C, size=(B, H, W)).astype(np.int64)
+    w = (rng.random(C) * 0.9 + 0.1).astype(np.float32)
+    vals, grad, part = run_loss(ops, z, t, C, w, weighted)
+    loss, ce, dice, focal, ref_grad, ref_part = orc.multiloss(z, t, C, weights=w, weighted=weighted)
+    np.testing.assert_allclose(vals, [loss, ce, dice, focal], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(part, ref_part, rtol=1e-5)
+    np.testing.assert_allclose(grad, ref_grad, rtol=1e-3, atol=1e-9)
+    # the port (torch autograd, what the reference runs) agrees too
+    port = orc.multiloss_port(z, t, C, weights=w, weighted=weighted)
+    np.testing.assert_allclose(vals, port[:4], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(grad, port[4], rtol=1e-3, atol=2e-9)
+
+
+def test_multiloss_other_hyperparameters(ops):
+    rng = np.random.default_rng(77)
+    z = (rng.standard_normal((2, 9, 32, 32)) * 2).astype(np.float32)
+    t = rng.integers(0, 9, size=(2, 32, 32)).astype(np.int64)
+    kw = dict(ce=0.3, dice=1.2, focal=0.7, smooth=0.5, gamma=3.0, alpha=0.4)
+    vals, grad, _ = run_loss(ops, z, t, 9, **kw)
+    ref = orc.multiloss(z, t, 9, **kw)
+    np.testing.assert_allclose(vals, ref[:4], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(grad, ref[4], rtol=1e-3, atol=1e-9)
+
+
+def test_multiloss_partials_are_additive_across_shards(ops):
+    """Data-parallel contract: partials of two half-batches add up to the full-batch partials,
+    so an all-reduce between the two passes reproduces the single-GPU loss and gradient."""
+    rng = np.random.default_rng(5)
+    z = (rng.standard_normal((4, 9, 64, 64)) * 3).astype(np.float32)
+    t = rng.integers(0, 9, size=(4, 64, 64)).astype(np.int64)
+    cfg = ops.loss_cfg()
+    full = ops.multiloss_reduce(dev(z), dev(t), cfg)
+    part = ops.multiloss_reduce(dev(z[:2]), dev(t[:2]), cfg)
+    part = ops.multiloss_reduce(dev(z[2:]), dev(t[2:]), cfg, partials=part)
+    np.testing.assert_allclose(part.cpu().numpy(), full.cpu().numpy(), rtol=1e-12)
+    g_full = ops.multiloss_grad(dev(z), dev(t), cfg, full, t.size)
+    g_half = ops.multiloss_grad(dev(z[2:]), dev(t[2:]), cfg, part, t.size)
+    np.testing.assert_allclose(g_half.cpu().numpy(), g_full.cpu().numpy()[2:], rtol=1e-6, atol=1e-12)

@@ -1,0 +1,161 @@
+"""Per-kernel micro-benchmark: achieved algorithmic HBM GB/s of every custom kernel at the
+BASELINE sizes, against the measured peak in MEASURED_PEAKS.json.  CUDA events around each
+launch on the launching stream, L2 flushed between launches.  Writes one JSON line per kernel.
+
+    python tools/kbench.py [--iters 20] [--out gpurun_out/kbench.jsonl] [--only stitch,loss]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+from pylc_b200 import ops  # noqa: E402
+from pylc_b200.config import Parameters  # noqa: E402
+
+
+def peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class Timer:
+    def __init__(self, iters, warmup=3):
+        self.iters, self.warmup = iters, warmup
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def run(self, fn):
+        for _ in range(self.warmup):
+            fn()
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(self.iters):
+            self.flush.zero_()                      # evict L2 (126 MB) between timed launches
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            e.synchronize()
+            times.append(s.elapsed_time(e))
+        return float(np.median(times)), float(np.min(times))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    only = set(filter(None, args.only.split(",")))
+    import pylc_oracle as orc
+    peak, peak_kind = peak_gbs()
+    tm = Timer(args.iters)
+    meta = Parameters()
+    pal, C = meta.palette_rgb, meta.n_classes
+    T = 512
+    rows = []
+
+    def report(name, alg_bytes, fn, note=""):
+        if only and not any(o in name for o in only):
+            return
+        med, best = tm.run(fn)
+        gbs = alg_bytes / (med * 1e-3) / 1e9
+        row = {"kernel": name, "ms_median": round(med, 4), "ms_min": round(best, 4), "alg_MB": round(alg_bytes / 1e6, 2),
+               "achieved_gbs": round(gbs, 1), "peak_gbs": peak, "peak_kind": peak_kind, "frac": round(gbs / peak, 4),
+               "note": note}
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+
+    # ---- extraction ------------------------------------------------------------------------
+    W, H = 6000, 4000
+    mask = orc.synth_mask(0, W, H, pal, skew=True)
+    d_mask, mp = ops.upload_image(mask)
+    nH, nW = ops.tile_grid(H, W, T, 512)
+    m_out = torch.empty((nH * nW, T, T), dtype=torch.uint8, device="cuda")
+    tile_px = nH * nW * T * T
+    report("mask_gather_encode_hist 6000x4000 S512 C9", tile_px * 4,
+           lambda: ops.mask_gather_encode_hist(d_mask, H, W, mp, T, 512, pal, out=m_out), "3 B in + 1 B out per tile px")
+    Wf, Hf = 5632, 3584
+    img1 = orc.synth_image(0, Wf, Hf, 1)
+    d_img1, ip1 = ops.upload_image(img1)
+    nH2, nW2 = ops.tile_grid(Hf, Wf, T, 256)
+    g_out = torch.empty((nH2 * nW2, 1, T, T), dtype=torch.uint8, device="cuda")
+    report("tile_gather_u8 gray 5632x3584 S256", nH2 * nW2 * T * T * 1.25,
+           lambda: ops.tile_gather_u8(d_img1, Hf, Wf, 1, ip1, T, 256, out=g_out), "1.25 B per tile px")
+    img3 = orc.synth_image(1, Wf, Hf, 3)
+    d_img3, ip3 = ops.upload_image(img3)
+    g3_out = torch.empty((nH2 * nW2, 3, T, T), dtype=torch.uint8, device="cuda")
+    report("tile_gather_u8 rgb 5632x3584 S256", nH2 * nW2 * T * T * 3.75,
+           lambda: ops.tile_gather_u8(d_img3, Hf, Wf, 3, ip3, T, 256, out=g3_out), "3.75 B per tile px")
+    n_out = torch.empty((nH2 * nW2, 3, T, T), dtype=torch.float32, device="cuda")
+    report("tile_gather_norm_f32 rgb 5632x3584 S256", nH2 * nW2 * T * T * (0.75 + 12),
+           lambda: ops.tile_gather_norm_f32(d_img3, Hf, Wf, 3, ip3, T, 256, [128.0] * 3, [60.0] * 3, out=n_out),
+           "0.75 B in + 12 B out per tile px")
+    report("profile_tiles hist 273 tiles", m_out.numel() * 1.0,
+           lambda: ops.profile_tiles(None, m_out, C), "1 B per px")
+    report("profile_tiles moments 273x3 planes", g3_out.numel() * 1.0,
+           lambda: ops.profile_tiles(g3_out, None, C), "1 B per px")
+    del g3_out, n_out, g_out
+
+    # ---- stitch ------------------------------------------------------------------------------
+    nr, nc = Hf // 256 - 1, Wf // 256 - 1
+    g = torch.Generator(device="cuda").manual_seed(0)
+    logits = torch.randn((nr * nc, C, T, T), generator=g, device="cuda") * 3
+    lut = pal
+    hw = Hf * Wf
+    report("stitch_argmax_colour 273 tiles C9 labels", logits.numel() * 4 + hw,
+           lambda: ops.stitch_argmax_colour(logits, nr, nc, T, 256), "every logit once + 1 B label")
+    report("stitch_argmax_colour 273 tiles C9 labels+rgb", logits.numel() * 4 + hw * 4,
+           lambda: ops.stitch_argmax_colour(logits, nr, nc, T, 256, lut_rgb=lut, want_rgb=True))
+    labels, _, _ = ops.stitch_argmax_colour(logits, nr, nc, T, 256)
+    del logits
+
+    # ---- evaluation --------------------------------------------------------------------------
+    maps = (torch.from_numpy(ops.nn_index_map(Wf, W)).cuda(), torch.from_numpy(ops.nn_index_map(Hf, H)).cuda())
+    conf = torch.zeros((C, C), dtype=torch.int64, device="cuda")
+    report("resample_encode_confusion 6000x4000 C9", H * W * 4,
+           lambda: ops.resample_encode_confusion(labels, W, H, gt_rgb=d_mask, gt_pitch=mp, palette=pal, n_inject=C,
+                                                 conf=conf, maps=maps), "3 B GT + 1 B label per full-res px")
+
+    # ---- multi-loss --------------------------------------------------------------------------
+    B = 64
+    z = torch.randn((B, C, T, T), generator=g, device="cuda") * 3
+    t64 = torch.randint(0, C, (B, T, T), generator=g, device="cuda")
+    t8 = t64.to(torch.uint8)
+    cfg = ops.loss_cfg()
+    npx = B * T * T
+    part = torch.zeros((2 * C + 3,), dtype=torch.float64, device="cuda")
+    report("multiloss_reduce B64 C9 i64 target", npx * (4 * C + 8),
+           lambda: ops.multiloss_reduce(z, t64, cfg, partials=part), "fwd only: 4C + 8 B/px")
+    report("multiloss_reduce B64 C9 u8 target", npx * (4 * C + 1),
+           lambda: ops.multiloss_reduce(z, t8, cfg, partials=part), "fwd only: 4C + 1 B/px")
+    part = ops.multiloss_reduce(z, t64, cfg)
+    grad = torch.empty_like(z)
+    report("multiloss_grad B64 C9 i64 target", npx * (8 * C + 8),
+           lambda: ops.multiloss_grad(z, t64, cfg, part, npx, out=grad), "8C + 8 B/px physically moved")
+
+    def fwd_bwd():
+        p = torch.zeros((2 * C + 3,), dtype=torch.float64, device="cuda")
+        ops.multiloss_reduce(z, t64, cfg, partials=p)
+        ops.multiloss_grad(z, t64, cfg, p, npx, out=grad)
+    report("multiloss fwd+bwd B64 C9 (algorithmic 8C+8)", npx * (8 * C + 8), fwd_bwd,
+           "two passes physically move 12C + 16 B/px")
+
+    if args.out:
+        os.makedirs(os.path.dirname(args.out), exist_ok=True)
+        with open(args.out, "w") as f:
+            for r in rows:
+                f.write(json.dumps(r) + "\n")
+
+
+if __name__ == "__main__":
+    main()
