@@ -332,13 +332,14 @@ extern "C" int pylc_tile_grid(int H, int W, int T, int S, int *nH, int *nW) {
 
 extern "C" int pylc_tile_gather_u8(const uint8_t *src, int H, int W, int ch, size_t src_pitch, int T, int S,
                                    uint8_t *dst, uint64_t *stat, pylc_stream_t stream) {
-    if (!dst || (ch != 1 && ch != 3)) return PYLC_ERR_ARG;
-    if ((uintptr_t)dst % 16) return PYLC_ERR_ALIGN;
+    if (ch != 1 && ch != 3) return PYLC_ERR_ARG;
     GatherGeom g;
     int rc = make_geom(src, H, W, ch, src_pitch, T, S, &g);
     if (rc) return rc;
     const long long ctas = (long long)g.nbx * g.nby * g.slabs;
-    if (ctas == 0) return PYLC_OK;
+    if (ctas == 0) return PYLC_OK;  // source smaller than one tile: nothing to write
+    if (!dst) return PYLC_ERR_ARG;
+    if ((uintptr_t)dst % 16) return PYLC_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     const bool al = aligned16(src, src_pitch);
     auto *sp = reinterpret_cast<unsigned long long *>(stat);
@@ -357,9 +358,8 @@ extern "C" int pylc_tile_gather_u8(const uint8_t *src, int H, int W, int ch, siz
 extern "C" int pylc_mask_gather_encode_hist(const uint8_t *src, int H, int W, size_t src_pitch, int T, int S,
                                             const uint8_t *palette, int C, uint8_t *dst, int64_t *px_dist,
                                             pylc_stream_t stream) {
-    if (!dst || !palette) return PYLC_ERR_ARG;
+    if (!palette) return PYLC_ERR_ARG;
     if (C < 1 || C > PYLC_MAX_CLASSES) return PYLC_ERR_CLASSES;
-    if ((uintptr_t)dst % 16) return PYLC_ERR_ALIGN;
     GatherGeom g;
     int rc = make_geom(src, H, W, 3, src_pitch, T, S, &g);
     if (rc) return rc;
@@ -368,6 +368,8 @@ extern "C" int pylc_mask_gather_encode_hist(const uint8_t *src, int H, int W, si
     if (rc) return rc;
     const long long ctas = (long long)g.nbx * g.nby * g.slabs;
     if (ctas == 0) return PYLC_OK;
+    if (!dst) return PYLC_ERR_ARG;
+    if ((uintptr_t)dst % 16) return PYLC_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     const bool al = aligned16(src, src_pitch);
     auto *pd = reinterpret_cast<long long *>(px_dist);
@@ -382,12 +384,14 @@ extern "C" int pylc_mask_gather_encode_hist(const uint8_t *src, int H, int W, si
 extern "C" int pylc_tile_gather_norm_f32(const uint8_t *src, int H, int W, int ch, size_t src_pitch, int T, int S,
                                          const float *mean, const float *std, float post_div, int out_ch,
                                          float *dst, pylc_stream_t stream) {
-    if (!dst || !mean || !std || (ch != 1 && ch != 3)) return PYLC_ERR_ARG;
+    if (!mean || !std || (ch != 1 && ch != 3)) return PYLC_ERR_ARG;
     if (!((ch == 1 && (out_ch == 1 || out_ch == 3)) || (ch == 3 && out_ch == 3))) return PYLC_ERR_ARG;
-    if ((uintptr_t)dst % 16) return PYLC_ERR_ALIGN;
     GatherGeom g;
     int rc = make_geom(src, H, W, ch, src_pitch, T, S, &g);
     if (rc) return rc;
+    if ((long long)g.nbx * g.nby == 0) return PYLC_OK;
+    if (!dst) return PYLC_ERR_ARG;
+    if ((uintptr_t)dst % 16) return PYLC_ERR_ALIGN;
     NormParams np;
     for (int k = 0; k < 3; ++k) {
         np.mean[k] = mean[ch == 1 ? 0 : k];
