@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""
+bench.py -- end-to-end tiled inference + evaluation throughput (BASELINE.json metric:
+megapixels/s at 1/2/4/8 B200, kernel HBM GB/s as a fraction of the measured peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): a DST.A-shaped colour batch of 64 synthetic 3000x2000
+image/mask pairs per GPU, schema_a (9 classes), DeepLabv3+/ResNet-101 random-init, 512x512 tiles
+with 50 % overlap (45 tiles per image after the fit-resize to 2560x1536), stitch + argmax,
+nearest-neighbour resample to full resolution, confusion matrix -> weighted IoU / F1 / MCC.
+One "step" = one pass over the 64 images of a rank.  Weak scaling: every rank owns 64 images; the
+only collective is the all-reduce of the [9,9] i64 confusion matrix.
+
+    value   Mpx/s with the fitted images and ground truths already resident in HBM
+    e2e     Mpx/s through pylc_b200.pipeline.TiledSegmenter.run_host: decoded images in pinned
+            host memory -> host fit-resize (OpenCV, as the reference) -> H2D -> GPU -> D2H of the
+            confusion matrix; every byte of every step's input crosses PCIe inside the timed region
+    roofline   the dominant custom kernel (fused stitch+softmax+argmax), timed live with CUDA
+            events on its stream inside the timed steps
+    cpu_baseline / --impl reference   the reference's CPU path (oracle port: same per-class
+            passes, band-merge loops, scikit-learn calls; torch CPU network) on the host cores
+"""
+import argparse
+import concurrent.futures as cf
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_IMAGES, W_FULL, H_FULL, CH = 64, 3000, 2000, 3
+WORKLOAD = "configs[1]: 64 synthetic 3000x2000 colour image/mask pairs per GPU, schema_a, DeepLabv3+ " \
+           "ResNet-101 random-init, 512px tiles stride 256, stitch+argmax+resample+confusion/mIoU"
+METRIC = "megapixels/sec end-to-end tiled inference"
+
+
+def peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        reasons = []
+        for k, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_inputs(rank, palette):
+    """64 decoded image / RGB-mask pairs per rank in pinned host memory (global image index =
+    rank * 64 + i, so ranks hold different images)."""
+    from pylc_b200 import synth
+
+    def one(i):
+        g = rank * N_IMAGES + i
+        return synth.image(g, W_FULL, H_FULL, CH), synth.mask(g, W_FULL, H_FULL, palette)
+    with cf.ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 4)) as ex:
+        pairs = list(ex.map(one, range(N_IMAGES)))
+    imgs = [p[0] for p in pairs]
+    masks = [p[1] for p in pairs]
+    return imgs, masks
+
+
+def build_model(device, seed=0):
+    from pylc_b200.config import defaults
+    from pylc_b200.models.model import Model
+    torch.manual_seed(seed)
+    model = Model()
+    model.track = False
+    model.device = device
+    model.update_meta({"ch": CH, "arch": "deeplab", "backbone": "resnet", "pretrained": False,
+                       "px_mean": list(defaults.px_rgb_mean), "px_std": list(defaults.px_rgb_std),
+                       "weights": [1.0] * defaults.n_classes, "normalize_default": False})
+    model.build()
+    model.net.eval()
+    return model
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's CPU path on a bounded sample
+# ---------------------------------------------------------------------------------------------
+
+def reference_sample():
+    """Bounded sample of the workload: the top-left 2000x1500 crop of image 0 and its mask
+    (fitted 1536x1024 -> 15 of the image's 45 tiles); every phase of the path scales with pixels."""
+    from pylc_b200 import synth
+    from pylc_b200.config import defaults
+    img = synth.image(0, W_FULL, H_FULL, CH)[:1500, :2000].copy()
+    gt = synth.mask(0, W_FULL, H_FULL, defaults.palette_rgb)[:1500, :2000].copy()
+    return img, gt, "top-left 2000x1500 crop of image 0 (+mask): 15 of its 45 tiles, all phases incl. CPU network"
+
+
+class ReferenceCPU(object):
+    """pylc.py test on the CPU as the reference runs it (test.py:52-115), via the oracle port."""
+
+    def __init__(self):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pylc_oracle as orc                       # allowed here: cpu_baseline / reference leg
+        from pylc_b200.config import defaults
+        from pylc_b200.models.deeplab import DeepLab    # stock torch ops; state_dict == reference's
+        self.orc, self.meta = orc, defaults
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        torch.manual_seed(0)
+        self.net = DeepLab(n_classes=defaults.n_classes).eval()
+        self.mean = torch.tensor(defaults.px_rgb_mean)[None, :, None, None]
+        self.std = torch.tensor(defaults.px_rgb_std)[None, :, None, None]
+
+    def step(self, img, gt):
+        import cv2
+        orc, meta, T, S = self.orc, self.meta, 512, 256
+        ph = {}
+        t0 = time.perf_counter()
+        w_fit, h_fit = orc.fit_dims(img.shape[1], img.shape[0], T)
+        fitted = cv2.resize(img, (w_fit, h_fit), interpolation=cv2.INTER_AREA)      # tools.py:194
+        tiles = orc.split_tiles(fitted, T, S)                                       # extract.py:296-310
+        ph["fit+split"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        outs = []
+        with torch.no_grad():
+            for lo in range(0, len(tiles), 8):                                       # test.py:68-83, batch 8
+                x = torch.tensor(tiles[lo:lo + 8]).float()
+                x = ((x - self.mean) / self.std) / 255                               # model.py:443-445
+                outs.append(self.net(x).numpy())
+        ph["network_cpu"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        rgb = orc.reconstruct_port(outs, h_fit, w_fit, img.shape[1], img.shape[0], T, S, meta.palette_rgb,
+                                   meta.n_classes)                                   # tools.py:209-319
+        ph["reconstruct"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        y_pred = orc.class_encode_port(np.moveaxis(rgb.astype(np.uint8), 2, 0)[None], meta.palette_rgb).ravel()
+        y_true = orc.class_encode_port(np.moveaxis(gt, 2, 0)[None], meta.palette_rgb).ravel()  # evaluate.py:103-108
+        ph["class_encode x2"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        y_true, y_pred = orc.inject_coverage(y_true, y_pred, len(meta.class_codes))  # evaluate.py:172-174
+        res = orc.metrics_port(y_true, y_pred, meta.class_codes)                     # metrics.py:45-87
+        ph["sklearn_metrics"] = time.perf_counter() - t0
+        return res, ph
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    img, gt, desc = reference_sample()
+    ref = ReferenceCPU()
+    mpx = img.shape[0] * img.shape[1] / 1e6
+    for _ in range(args.warmup):
+        ref.step(img, gt)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, phases = ref.step(img, gt)
+    dt = time.perf_counter() - t0
+    v = mpx * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mpx/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample_per_step": desc},
+            "cpu_baseline": {"value": v, "unit": "Mpx/s", "cores": ref.cores, "kind": "port", "sample": desc,
+                             "phases_s": {k: round(x, 3) for k, x in phases.items()}},
+            "e2e": {"value": v, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline():
+    img, gt, desc = reference_sample()
+    ref = ReferenceCPU()
+    t0 = time.perf_counter()
+    _, phases = ref.step(img, gt)
+    dt = time.perf_counter() - t0
+    return {"value": img.shape[0] * img.shape[1] / 1e6 / dt, "unit": "Mpx/s", "cores": ref.cores, "kind": "port",
+            "sample": desc + "; 1 pass, no warm-up", "phases_s": {k: round(x, 3) for k, x in phases.items()}}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+
+class StitchTimer(object):
+    """Wraps ops.stitch_argmax_colour with CUDA events on the launching stream."""
+
+    def __init__(self, ops):
+        self.ops, self.orig, self.pairs, self.bytes, self.on = ops, ops.stitch_argmax_colour, [], 0, False
+
+    def __enter__(self):
+        def timed(logits, nr, nc, T, S, **kw):
+            if not self.on:
+                return self.orig(logits, nr, nc, T, S, **kw)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = self.orig(logits, nr, nc, T, S, **kw)
+            e.record()
+            self.pairs.append((s, e))
+            n_logit = sum(t.numel() for t in logits) if isinstance(logits, (list, tuple)) else logits.numel()
+            self.bytes += n_logit * 4 + out[0].numel()          # every logit once + 1 B label per output px
+            return out
+        self.ops.stitch_argmax_colour = timed
+        return self
+
+    def __exit__(self, *a):
+        self.ops.stitch_argmax_colour = self.orig
+
+    def reset(self):
+        self.pairs, self.bytes = [], 0
+
+    def result(self):
+        ms = [s.elapsed_time(e) for s, e in self.pairs]
+        return (sum(ms) / len(ms), self.bytes / len(ms)) if ms else (None, None)
+
+
+def run_ours(args, rank, world, local_rank):
+    from pylc_b200 import _lib, ops
+    from pylc_b200 import dist as pdist
+    from pylc_b200.pipeline import TiledSegmenter
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    _lib.load()
+    torch.backends.cudnn.benchmark = True
+    dtype = {"fp32": None, "bf16": torch.bfloat16, "fp16": torch.float16}[args.backbone_dtype]
+
+    model = build_model(device)
+    seg = TiledSegmenter(model, batch_tiles=args.batch_tiles, channels_last=not args.no_channels_last,
+                         autocast_dtype=dtype, host_workers=args.host_workers)
+    imgs, masks = make_inputs(rank, model.meta.palette_rgb)
+    mpx_step = N_IMAGES * W_FULL * H_FULL / 1e6
+    d2h = seg.C * seg.C * 8
+
+    def barrier_sync():
+        torch.cuda.synchronize()
+        pdist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM -------------------------------------------------------
+    resident = [seg.stage(imgs[i], masks[i], index=rank * N_IMAGES + i) for i in range(N_IMAGES)]
+    torch.cuda.synchronize()
+    h2d = sum(f.img.numel() + f.gt.numel() for f in resident)     # bytes run_host copies per step
+    clocks = ClockSampler(local_rank)
+    with StitchTimer(ops) as st:
+        for _ in range(args.warmup):
+            seg.reset()
+            seg.run_resident(resident)
+        barrier_sync()
+        st.on = True
+        clocks.start()
+        launches0 = _lib.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            seg.reset()
+            seg.run_resident(resident)
+            conf_dev = pdist.all_reduce_(seg.conf.clone()) if world > 1 else seg.conf
+        ev1.record()
+        barrier_sync()
+        st.on = False
+        launches = _lib.launch_count() - launches0
+        ms = pdist.max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+        k_ms, k_bytes = st.result()
+    conf_resident = conf_dev.cpu().numpy()
+    del resident
+
+    # ---- e2e: host buffers, copies inside the timed region -------------------------------------
+    for _ in range(max(1, min(args.warmup, 2))):
+        seg.reset()
+        seg.run_host(imgs, masks, distributed=world > 1)
+    barrier_sync()
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        seg.reset()
+        conf_host, _ = seg.run_host(imgs, masks, distributed=world > 1)
+    ev1.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = pdist.max_over_ranks(max(ev0.elapsed_time(ev1), wall_ms)) / args.steps
+    barrier_sync()
+    clk = clocks.summary()
+
+    if rank != 0:
+        return
+    peak, peak_kind = peak_gbs()
+    scores = seg.scores(conf_host)
+    line = {
+        "metric": METRIC, "value": mpx_step * world / (ms * 1e-3), "unit": "Mpx/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 hot-path kernels (u8/i64 integer paths); network %s" % (
+            "fp32 with cuDNN TF32 (PyTorch default, as the reference would run)" if dtype is None else args.backbone_dtype),
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "images_per_gpu": N_IMAGES, "tiles_per_image": 45, "batch_tiles": args.batch_tiles,
+                   "l2": "inputs larger than L2 (each step streams > 20 GB of logits per GPU)",
+                   "parallelism": "dp%d, images sharded, one [9,9] i64 all-reduce per step" % world,
+                   "value_region": "fitted u8 images + RGB ground truth resident in HBM -> all-reduced confusion matrix",
+                   "weighted_iou": scores["iou"], "confusion_sum": int(conf_host.sum()),
+                   "resident_equals_e2e": bool(np.array_equal(conf_resident, conf_host))},
+        "e2e": {"value": mpx_step * world / (e2e_ms * 1e-3), "unit": "Mpx/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "api": "pylc_b200.pipeline.TiledSegmenter.run_host"},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {"kernel": "stitch_kernel (pylc_stitch_argmax_colour)", "bound": "hbm",
+                     "achieved": (k_bytes / (k_ms * 1e-3) / 1e9) if k_ms else None, "peak": peak, "peak_kind": peak_kind,
+                     "unit": "GB/s", "frac": (k_bytes / (k_ms * 1e-3) / 1e9 / peak) if k_ms else None,
+                     "avg_launch_ms": k_ms, "algorithmic_bytes_per_launch": k_bytes, "traffic": None,
+                     "share_of_step": (k_ms * N_IMAGES / ms) if k_ms else None},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--backbone-dtype", default="fp32", choices=["fp32", "bf16", "fp16"])
+    ap.add_argument("--batch-tiles", type=int, default=45)
+    ap.add_argument("--host-workers", type=int, default=6)
+    ap.add_argument("--no-channels-last", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args, int(os.environ.get("RANK", "0")))
+        return
+    from pylc_b200 import dist as pdist
+    rank, world, local_rank = pdist.init_from_env()
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus %d needs torchrun (one process per GPU); WORLD_SIZE is 1" % args.gpus)
+    run_ours(args, rank, world, local_rank)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,142 @@
+"""
+MultiLoss -- host-side mirror of PyLC's models/modules/loss.py (reference loss.py:23-215).
+
+    L = ce_weight * CE + dice_weight * Dice + focal_weight * Focal        (loss.py:107-112)
+
+The reference evaluates this with ~10 torch kernels forward (2 softmax, 2 one_hot to int64
+[B,H,W,C], CE, pow/log/sum ...) plus autograd backward.  Here the forward is ONE streaming pass
+over the logits (pylc_multiloss_reduce -> 2C+3 partial sums) and the backward ONE more
+(pylc_multiloss_grad, closed-form gradient of all three terms); Dice needs the
+batch-global sums before any gradient exists, so two passes is the minimum.  Under data
+parallelism the partials are all-reduced between the passes (`distributed=True`), which makes the
+loss and gradient those of the single large batch.
+
+Interface kept: MultiLoss(loss_weights, schema); .forward(pred, target); .ce_loss / .dice_loss /
+.focal_loss callable on their own (models/model.py:360-362); .ce / .dsc / .fl hold the last
+component values; .print_settings().
+"""
+import numpy as np
+import torch
+
+from ... import dist as pdist
+from ... import ops
+from ...config import defaults
+
+
+class _MultiLossFn(torch.autograd.Function):
+    """pred [B,C,H,W] f32, target [B,H,W] i64/u8 -> out[4] = (loss, ce, dice, focal)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, class_w, cfg, distributed):
+        pred = pred.contiguous()
+        target = target.contiguous()
+        C = pred.shape[1]
+        partials = ops.multiloss_reduce(pred, target, cfg, class_w)
+        n_px = target.numel()
+        if distributed and pdist.world_size() > 1:
+            pdist.all_reduce_(partials)
+            n_px *= pdist.world_size()
+        out = ops.multiloss_finalize(partials, C, n_px, cfg)
+        ctx.save_for_backward(pred, target, partials)
+        ctx.class_w, ctx.cfg, ctx.n_px = class_w, cfg, n_px
+        ctx.mark_non_differentiable(target)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        pred, target, partials = ctx.saved_tensors
+        # dL/dz from the kernel, scaled by the upstream gradient of out[0] (the weighted loss).
+        # The component outputs out[1:4] are reporting values; gradients through them are dropped.
+        grad = ops.multiloss_grad(pred, target, ctx.cfg, partials, ctx.n_px, ctx.class_w)
+        g0 = grad_out[0]
+        grad.mul_(g0)
+        return grad, None, None, None, None
+
+
+class MultiLoss(torch.nn.Module):
+    def __init__(self, loss_weights, schema, distributed=False):
+        super(MultiLoss, self).__init__()
+        self.n_classes = schema['n_classes']
+        self.codes = schema['class_codes']
+        self.categories = schema['class_labels']
+        self.weighted = loss_weights['weighted']
+        self.dsc_weight = loss_weights['dice']
+        self.ce_weight = loss_weights['ce']
+        self.fl_weight = loss_weights['focal']
+        self.eps = 1e-8
+        self.ce = 0.
+        self.dsc = 0.
+        self.fl = 0.
+        self.distributed = distributed
+        self.device = torch.device(defaults.device)
+        w = loss_weights.get('weights')
+        if w is not None:
+            self.weights = torch.tensor(np.array(w)).float().to(self.device)
+        else:
+            self.weights = torch.ones(self.n_classes).to(self.device)
+
+    # -- kernel plumbing ---------------------------------------------------------------------
+    def _cfg(self, ce, dice, focal):
+        return ops.loss_cfg(ce=ce, dice=dice, focal=focal, smooth=defaults.dice_smooth, gamma=defaults.fl_gamma,
+                            alpha=defaults.fl_alpha, eps=self.eps)
+
+    def _class_w(self, pred):
+        return self.weights.to(pred.device) if self.weighted else None
+
+    def _check(self, pred, target):
+        if not torch.is_tensor(pred):
+            raise TypeError("Input type is not a torch.Tensor. Got {}".format(type(pred)))
+        if not len(pred.shape) >= 2:
+            raise ValueError("Invalid input shape, we expect BxCx*. Got: {}".format(pred.shape))
+        assert pred.size(0) == target.size(0)
+        assert pred.size(2) == target.size(1)
+        assert pred.size(3) == target.size(2)
+        if not pred.device == target.device:
+            raise ValueError("input and target must be in the same device. Got: {} and {}".format(
+                pred.device, target.device))
+        if defaults.fl_reduction != 'mean':
+            raise NotImplementedError("Invalid reduction mode: {}".format(defaults.fl_reduction))
+
+    def _run(self, pred, target, ce, dice, focal):
+        self._check(pred, target)
+        return _MultiLossFn.apply(pred.float(), target, self._class_w(pred), self._cfg(ce, dice, focal),
+                                  self.distributed)
+
+    # -- reference API -----------------------------------------------------------------------
+    def forward(self, pred, target):
+        out = self._run(pred, target, self.ce_weight, self.dsc_weight, self.fl_weight)
+        vals = out.detach()
+        self.ce, self.dsc, self.fl = vals[1], vals[2], vals[3]
+        self.last = vals            # (loss, ce, dice, focal): one D2H copy reads all four
+        return out[0]
+
+    def ce_loss(self, pred, target):
+        return self._run(pred, target, 1.0, 0.0, 0.0)[0]
+
+    def dice_loss(self, pred, target):
+        return self._run(pred, target, 0.0, 1.0, 0.0)[0]
+
+    def focal_loss(self, pred, target):
+        return self._run(pred, target, 0.0, 0.0, 1.0)[0]
+
+    def components(self, pred, target):
+        """(ce, dice, focal) from ONE pass -- what Model.eval needs (models/model.py:360-362 makes
+        three separate calls)."""
+        with torch.no_grad():
+            out = self._run(pred, target, self.ce_weight, self.dsc_weight, self.fl_weight)
+        return out[1], out[2], out[3]
+
+    def print_settings(self):
+        hline = '_' * 40
+        print('{:30s}{:<10s}'.format('Loss', 'Weight'))
+        print(hline)
+        print('{:30s}{:<10f}'.format('Cross-entropy', self.ce_weight))
+        print('\tCE losses weighted by class.' if self.weighted else '\tCE losses not weighted by class.')
+        print('{:30s}{:<10f}'.format('Dice Coefficient', self.dsc_weight))
+        print('{:30s}{:<10f}'.format('Focal Loss', self.fl_weight))
+        print()
+        print('{:8s}{:22s}{:<10s}'.format('Class', 'Label', 'Weight'))
+        print(hline)
+        for i, w in enumerate(self.weights):
+            print('{:8s}{:22s}{:<10f}'.format(self.codes[i], self.categories[i], w))
+        print()

@@ -219,6 +219,21 @@ def nn_index_map(n_src, n_dst):
     return np.minimum(idx, n_src - 1).astype(np.int32)
 
 
+_MAP_CACHE = {}
+
+
+def device_index_maps(w, h, w_full, h_full, device):
+    """(x_ofs [w_full] i32, y_ofs [h_full] i32) on `device`, cached per geometry."""
+    key = (w, h, w_full, h_full, str(device))
+    maps = _MAP_CACHE.get(key)
+    if maps is None:
+        if len(_MAP_CACHE) > 64:
+            _MAP_CACHE.clear()
+        maps = (torch.from_numpy(nn_index_map(w, w_full)).to(device), torch.from_numpy(nn_index_map(h, h_full)).to(device))
+        _MAP_CACHE[key] = maps
+    return maps
+
+
 def resample_encode_confusion(labels, w_full, h_full, gt_rgb=None, gt_pitch=0, palette=None, lut_rgb=None,
                               n_classes=None, n_inject=0, conf=None, want_pred=False, want_rgb=False,
                               want_gt=False, maps=None):
@@ -227,8 +242,7 @@ def resample_encode_confusion(labels, w_full, h_full, gt_rgb=None, gt_pitch=0, p
     h, w = labels.shape
     dev = labels.device
     if maps is None:
-        maps = (torch.from_numpy(nn_index_map(w, w_full)).to(dev, non_blocking=True),
-                torch.from_numpy(nn_index_map(h, h_full)).to(dev, non_blocking=True))
+        maps = device_index_maps(w, h, w_full, h_full, dev)
     x_ofs, y_ofs = maps
     pal = lut = None
     C = n_classes

@@ -1,0 +1,170 @@
+"""
+Tiled inference + evaluation pipeline: the GPU-resident form of the loop in PyLC's test.py
+(reference test.py:52-115).
+
+Per image, the reference does (host unless noted): fit-resize -> unfold tiles -> float + normalise
+-> H2D per 8 tiles -> network (device) -> D2H of ALL logits -> band-merge loops -> argmax ->
+colourise -> NN resize -> class_encode(pred), class_encode(GT) -> five scikit-learn passes.
+
+Here, per image:
+    host   cv2 fit-resize (same OpenCV call => same bytes), staged in pinned memory
+    copy   one H2D of the fitted image and one of the RGB ground truth (copy stream, overlapped)
+    GPU    pylc_tile_gather_norm_f32     tiles, normalised, grayscale replicated   (1 launch)
+           DeepLabv3+/ResNet-101         stock PyTorch / cuDNN, batches of `batch_tiles`
+           pylc_stitch_argmax_colour     logits -> label map, reference band semantics (1 launch)
+           pylc_resample_encode_confusion  NN resample + GT encode + [C,C] counts    (1 launch)
+    D2H    nothing per image; the [C,C] i64 matrix (and optional masks) at the end
+Logits never leave the device.  Images are independent, so data-parallel ranks take images
+round-robin and all-reduce only the [C,C] matrix (pylc_b200.dist).
+"""
+import concurrent.futures as cf
+
+import cv2
+import numpy as np
+import torch
+
+from . import dist as pdist
+from . import ops
+from .config import defaults
+from .utils import tools
+from .utils.metrics import scores_from_confusion
+
+
+class FittedImage(object):
+    """A fitted u8 image (and optional RGB ground truth) resident on the device."""
+    __slots__ = ("img", "pitch", "h", "w", "gt", "gt_pitch", "h_full", "w_full", "index", "ready")
+
+
+class TiledSegmenter(object):
+    def __init__(self, model, batch_tiles=32, channels_last=True, autocast_dtype=None, host_workers=4,
+                 n_inject=None, keep_masks=False):
+        self.model = model
+        self.meta = model.meta
+        self.net = model.net.eval()
+        self.device = next(self.net.parameters()).device
+        self.T = self.meta.tile_size
+        self.S = self.T // 2                      # test.py:63: stride = tile_size // 2
+        self.C = self.meta.n_classes
+        self.ch = self.meta.ch
+        self.batch_tiles = batch_tiles
+        self.autocast_dtype = autocast_dtype
+        self.channels_last = channels_last
+        if channels_last:
+            self.net = self.net.to(memory_format=torch.channels_last)
+        self.mean, self.std, self.post_div, self.out_ch = model.norm_params()
+        self.palette = self.meta.palette_rgb
+        self.lut = tools.colourize_lut(self.C, self.palette)
+        self.n_inject = min(len(defaults.class_codes), self.C) if n_inject is None else n_inject
+        self.keep_masks = keep_masks
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.pool = cf.ThreadPoolExecutor(max_workers=host_workers)
+        self.conf = torch.zeros((self.C, self.C), dtype=torch.int64, device=self.device)
+
+    # ---- host stage ---------------------------------------------------------------------------
+    def fit_host(self, img):
+        """adjust_to_tile on the host into pinned, 16-byte-pitched memory."""
+        fitted, w, h, offset = tools.adjust_to_tile(img, self.T, self.S, self.ch)
+        assert offset == 0
+        buf, pitch = ops.pinned_pitched(fitted)
+        return buf, pitch, h, w
+
+    def stage(self, img, gt=None, index=0):
+        """Host fit + async H2D on the copy stream.  Returns a FittedImage; the compute stream must
+        wait on `f.ready` before touching its tensors."""
+        buf, pitch, h, w = self.fit_host(img)
+        f = FittedImage()
+        f.index = index
+        f.h, f.w, f.pitch = h, w, pitch
+        f.h_full, f.w_full = img.shape[0], img.shape[1]
+        with torch.cuda.stream(self.copy_stream):
+            f.img = buf.to(self.device, non_blocking=True)
+            if gt is not None:
+                if torch.is_tensor(gt):
+                    gbuf, f.gt_pitch = gt, gt.shape[1]
+                else:
+                    gbuf, f.gt_pitch = ops.pinned_pitched(gt)
+                f.gt = gbuf.to(self.device, non_blocking=True)
+            else:
+                f.gt, f.gt_pitch = None, 0
+            f.ready = torch.cuda.Event()
+            f.ready.record(self.copy_stream)
+        return f
+
+    # ---- device stage -------------------------------------------------------------------------
+    def forward_tiles(self, tiles):
+        """Network forward over [n,3,T,T] f32 tiles in batches; returns the list of logit batches."""
+        outs = []
+        with torch.no_grad():
+            for lo in range(0, tiles.shape[0], self.batch_tiles):
+                x = tiles[lo:lo + self.batch_tiles]
+                if self.channels_last:
+                    x = x.contiguous(memory_format=torch.channels_last)
+                if self.autocast_dtype is not None:
+                    with torch.autocast("cuda", dtype=self.autocast_dtype):
+                        y = self.net(x)
+                    y = y.float()
+                else:
+                    y = self.net(x)
+                outs.append(y.contiguous())
+        return outs
+
+    def segment_fitted(self, f, inject=None):
+        """All device work for one fitted image; accumulates into self.conf when f.gt is set.
+        Returns the fitted-resolution label map (and full-res masks when keep_masks)."""
+        tiles = ops.tile_gather_norm_f32(f.img, f.h, f.w, self.ch, f.pitch, self.T, self.S, self.mean, self.std,
+                                         self.post_div, self.out_ch)
+        nr, nc = f.h // self.S - 1, f.w // self.S - 1
+        logits = self.forward_tiles(tiles)
+        labels, _, _ = ops.stitch_argmax_colour(logits if len(logits) > 1 else logits[0], nr, nc, self.T, self.S,
+                                                tiles_per_batch=self.batch_tiles)
+        n_inject = self.n_inject if inject is None else inject
+        res = ops.resample_encode_confusion(
+            labels, f.w_full, f.h_full, gt_rgb=f.gt, gt_pitch=f.gt_pitch, palette=self.palette, lut_rgb=self.lut,
+            n_classes=self.C, n_inject=n_inject if f.gt is not None else 0, conf=self.conf if f.gt is not None else None,
+            want_pred=self.keep_masks, want_rgb=self.keep_masks)
+        res["labels"] = labels
+        return res
+
+    # ---- drivers ------------------------------------------------------------------------------
+    def reset(self):
+        self.conf.zero_()
+
+    def run_resident(self, fitted_images):
+        """Device-only pass over images already staged in HBM (bench.py `value`)."""
+        out = None
+        for f in fitted_images:
+            out = self.segment_fitted(f, inject=self.n_inject if f.index == 0 else 0)
+        return out
+
+    def run_host(self, images, masks=None, indices=None, distributed=False):
+        """End-to-end pass from decoded host arrays (bench.py `e2e`, test.py's loop): host fit and
+        H2D of image k+1 overlap the device work of image k.  Returns (conf ndarray, results)."""
+        idx = list(range(len(images))) if indices is None else list(indices)
+        compute = torch.cuda.current_stream(self.device)
+        prefetch = 3
+
+        def submit(k):
+            i = idx[k]
+            return self.pool.submit(self.stage, images[i], None if masks is None else masks[i], i)
+
+        pending = [submit(k) for k in range(min(prefetch, len(idx)))]
+        results = []
+        for k in range(len(idx)):
+            f = pending.pop(0).result()
+            if k + prefetch < len(idx):
+                pending.append(submit(k + prefetch))
+            compute.wait_event(f.ready)
+            res = self.segment_fitted(f, inject=self.n_inject if f.index == 0 else 0)
+            f.img.record_stream(compute)
+            if f.gt is not None:
+                f.gt.record_stream(compute)
+            if self.keep_masks:
+                results.append(res)
+        conf = self.conf
+        if distributed:
+            conf = pdist.all_reduce_(conf.clone())
+        return conf.cpu().numpy(), results           # the step's only D2H: C*C*8 bytes
+
+    def scores(self, conf):
+        labels = defaults.class_codes if self.C == len(defaults.class_codes) else self.meta.class_codes
+        return scores_from_confusion(conf, labels)

@@ -1,0 +1,250 @@
+"""
+Host-side mirror of PyLC's utils/tools.py for the tiled-segmentation path: same function names,
+argument meaning, return types and error behaviour (print + exit(1) / assert), with every
+per-pixel body replaced by an sm_100a kernel call through the C ABI (pylc_b200.ops).
+
+    get_image / adjust_to_tile   host (OpenCV decode + INTER_AREA fit), reference tools.py:77-206
+    class_encode                 pylc_class_encode,            reference tools.py:412-449
+    colourize                    pylc_colourise_u8,            reference tools.py:322-358
+    reconstruct                  pylc_stitch_argmax_colour +
+                                 pylc_resample_encode_confusion, reference tools.py:209-319
+    coshuffle / collate / load_files / mk_path / confirm_write_file   host, unchanged semantics
+
+There is no CPU path for the kernels: without a CUDA device these functions raise PylcError.
+"""
+import os
+from math import ceil
+
+import cv2
+import numpy as np
+import torch
+
+from .. import ops
+from .._lib import PylcError
+from ..config import defaults
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise PylcError("pylc_b200 needs a CUDA device (B200); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def is_grayscale(img):
+    """True when all three channels are identical (reference tools.py:27-43)."""
+    if img.ndim < 3 or img.shape[2] == 1:
+        return True
+    return bool(np.array_equal(img[:, :, 0], img[:, :, 1]) and np.array_equal(img[:, :, 1], img[:, :, 2]))
+
+
+def get_image(img_path, ch=3, scale=None, tile_size=None, interpolate=cv2.INTER_AREA):
+    """Decode an image to u8 [H,W] (ch=1) or RGB [H,W,3] (ch=3), optionally rescaled
+    (reference tools.py:77-148).  Returns (img, w, h, w_resized, h_resized).
+    Unlike the reference a colour image given with ch=1 is not prompted about: it is decoded with
+    IMREAD_GRAYSCALE exactly as the reference does after the prompt."""
+    assert ch == 3 or ch == 1, 'Invalid number of input channels:\t{}.'.format(ch)
+    assert os.path.exists(img_path), 'Image path {} does not exist.'.format(img_path)
+    if not tile_size:
+        tile_size = defaults.tile_size
+    if ch == 3:
+        img = cv2.imread(img_path, cv2.IMREAD_COLOR)
+        if is_grayscale(img):
+            print('\nInput image is grayscale but process expects colour (RGB).\n\tApplication stopped.')
+            exit(1)
+        img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+    else:
+        img = cv2.imread(img_path, cv2.IMREAD_GRAYSCALE)
+    height, width = img.shape[:2]
+    height_resized, width_resized = height, width
+    if scale:
+        min_dim = min(height, width)
+        if min_dim < tile_size:
+            scale = tile_size / min_dim
+        dim = (int(scale * width), int(scale * height))
+        img = cv2.resize(img, dim, interpolation=interpolate)
+        height_resized, width_resized = img.shape[:2]
+    return img, width, height, width_resized, height_resized
+
+
+def fit_dims(w, h, tile_size):
+    """Target size of adjust_to_tile (reference tools.py:178-192)."""
+    aspect = w / h
+    w_fit = (w // tile_size) * tile_size
+    h_fit = (ceil(w_fit / aspect) // tile_size) * tile_size
+    return w_fit, h_fit
+
+
+def adjust_to_tile(img, tile_size, stride, ch, interpolate=cv2.INTER_AREA):
+    """Resize an image to a whole number of tiles (reference tools.py:151-206).  Stays on the host:
+    the same OpenCV call gives the same bytes.  Returns (img, w_fitted, h_fitted, offset)."""
+    h, w = img.shape[:2]
+    assert tile_size % stride == 0 and stride <= tile_size, "Tile size must be multiple of stride."
+    w_fit, h_fit = fit_dims(w, h, tile_size)
+    img_resized = cv2.resize(img, (w_fit, h_fit), interpolation=interpolate)
+    h_resized = img_resized.shape[0]
+    h_crop = h_resized - int(h_resized / tile_size) * tile_size
+    img_cropped = img_resized[h_crop:h_resized]
+    return img_cropped, img_cropped.shape[1], img_cropped.shape[0], h_crop
+
+
+def class_encode(img_array, palette):
+    """RGB mask [N,3,H,W] u8 -> class indices [N,H,W] u8 (reference tools.py:412-449): unmatched
+    colours become class 1, later palette duplicates win.  CUDA tensors stay on the device; CPU
+    tensors / arrays are uploaded and the result is returned on the CPU like the reference's."""
+    assert img_array.shape[1] == 3, "Input data must be 3 channel (RGB)"
+    on_host = not (torch.is_tensor(img_array) and img_array.is_cuda)
+    t = torch.as_tensor(img_array)
+    if t.dtype != torch.uint8:
+        t = t.to(torch.uint8)
+    if on_host:
+        t = t.contiguous().pin_memory().to(_device(), non_blocking=True)
+    try:
+        out = ops.class_encode_nchw(t, palette)
+    except PylcError as inst:
+        print(inst)
+        print('Mask cannot be encoded by selected palette. Please check schema settings.')
+        exit(1)
+    return out.cpu() if on_host else out
+
+
+def colourize_lut(n_classes, palette):
+    """Final colour of each label under the reference's sequential in-place passes
+    (tools.py:352-356): label i takes palette[i]; a grey palette colour [k,k,k] with i < k < C is
+    re-mapped by pass k.  For both shipped schemas this is the palette itself."""
+    lut = []
+    for i in range(n_classes):
+        cur = [int(v) for v in palette[i]]
+        for j in range(i + 1, n_classes):
+            if cur == [j, j, j]:
+                cur = [int(v) for v in palette[j]]
+        lut.append(cur)
+    return lut
+
+
+def colourize(img, n_classes, palette=None):
+    """Label map [n,h,w] -> RGB [n,h,w,3] (reference tools.py:322-358).  Returns the reference's
+    dtype (int64 ndarray) for host input, a u8 CUDA tensor for CUDA input."""
+    palette = palette if palette is not None else defaults.palette_rgb
+    lut = colourize_lut(n_classes, palette)
+    on_host = not (torch.is_tensor(img) and img.is_cuda)
+    t = torch.as_tensor(np.ascontiguousarray(img) if on_host else img)
+    if on_host:
+        if t.numel() and (int(t.min()) < 0 or int(t.max()) >= n_classes):
+            raise PylcError("colourize: label outside [0, n_classes)")
+        t = t.to(torch.uint8).pin_memory().to(_device(), non_blocking=True)
+    elif t.dtype != torch.uint8:
+        t = t.to(torch.uint8)
+    rgb = ops.colourise_u8(t, lut)
+    return rgb.cpu().numpy().astype(np.int64) if on_host else rgb
+
+
+def stitch_geometry(meta):
+    """(nr, nc, T, S, h, w, w_full, h_full) for reconstruct, from meta.extract (tools.py:224-236)."""
+    ex = meta.extract
+    T, S = meta.tile_size, meta.stride
+    w, h = ex['w_fitted'], ex['h_fitted']
+    nc = w // S - 1 if S < T else w // S
+    nr = h // S - 1 if S < T else h // S
+    return nr, nc, T, S, h, w, ex['w_scaled'], ex['h_scaled']
+
+
+def reconstruct_device(logits, meta, want_rgb=True, want_labels=True):
+    """Device half of reconstruct: fused stitch + softmax + argmax (+ colourise) at fitted
+    resolution, then nearest-neighbour resample to (w_scaled, h_scaled).  Returns a dict of CUDA
+    tensors: labels [h,w] u8, pred_full [h_full,w_full] u8, pred_rgb [h_full,w_full,3] u8."""
+    nr, nc, T, S, h, w, w_full, h_full = stitch_geometry(meta)
+    if meta.extract.get('offset', 0):
+        raise PylcError("non-zero crop offset is outside the reference's contract (always 0)")
+    if isinstance(logits, (list, tuple)):
+        logits = [t if t.is_cuda else t.to(_device(), non_blocking=True) for t in logits]
+        if len(logits) == 1:
+            logits = logits[0]
+    elif not logits.is_cuda:
+        logits = logits.to(_device(), non_blocking=True)
+    lut = colourize_lut(meta.n_classes, meta.palette_rgb)
+    labels, _, _ = ops.stitch_argmax_colour(logits, nr, nc, T, S)
+    res = ops.resample_encode_confusion(labels, w_full, h_full, lut_rgb=lut, n_classes=meta.n_classes,
+                                        want_pred=want_labels, want_rgb=want_rgb)
+    res["labels"] = labels
+    return res
+
+
+def reconstruct(logits, meta):
+    """Tile logits (list of [b,C,T,T] f32 batches) -> full-sized RGB mask, np.float32
+    [h_scaled, w_scaled, 3] (reference tools.py:209-319), with the reference's band semantics
+    (SURVEY.md A.3).  Logits never leave the device; only the RGB mask is copied back."""
+    res = reconstruct_device(logits, meta, want_rgb=True, want_labels=False)
+    return res["pred_rgb"].cpu().numpy().astype(np.float32)
+
+
+def coshuffle(img_array, mask_array, permutation=None):
+    """Shuffle images and masks with one permutation (reference tools.py:361-385).  `permutation`
+    (extension) injects the index order for reproducible parity tests."""
+    idx_arr = np.arange(len(img_array)) if permutation is None else np.asarray(permutation)
+    if permutation is None:
+        np.random.shuffle(idx_arr)
+    if torch.is_tensor(img_array):
+        idx = torch.as_tensor(idx_arr, device=img_array.device)
+        return img_array[idx], mask_array[idx.to(mask_array.device)]
+    return img_array[idx_arr], mask_array[idx_arr]
+
+
+def load_files(path, exts):
+    """File path(s) with the given extension(s) (reference tools.py:597-626)."""
+    if not os.path.exists(path):
+        print('File not found:\n\t{} .'.format(path))
+        exit(1)
+    files = []
+    if os.path.isfile(path):
+        ext = os.path.splitext(os.path.basename(path))[1]
+        assert ext in exts, "File {} of type {} is invalid.".format(path, ext)
+        files.append(path)
+    elif os.path.isdir(path):
+        files.extend(sorted(os.path.join(path, f) for f in os.listdir(path) if any(ext in f for ext in exts)))
+    return files
+
+
+def collate(img_dir, mask_dir=None):
+    """Match image / mask files by base name (reference tools.py:629-680)."""
+    img_files = load_files(img_dir, ['.tif', '.tiff', '.jpg', '.jpeg'])
+    if not mask_dir:
+        return img_files
+    img_paths = {os.path.splitext(os.path.basename(f))[0]: f for f in img_files}
+    mask_files = load_files(mask_dir, ['.png'])
+    mask_paths = {os.path.splitext(os.path.basename(f))[0]: f for f in mask_files}
+    files = []
+    for name, img_path in img_paths.items():
+        if name not in mask_paths:
+            print('\nMask not found for image {}.'.format(name))
+            exit(1)
+        files.append({'img': img_path, 'mask': mask_paths.pop(name)})
+    if mask_paths:
+        print('\nImage not found for mask(s):\n\t{}.'.format("\n\t".join(mask_paths.values())))
+        exit(1)
+    return files
+
+
+def get_fname(path):
+    if os.path.isfile(path):
+        return os.path.splitext(os.path.basename(path))[0]
+    return path
+
+
+def mk_path(path, check=True):
+    """Create a directory if missing (reference tools.py:697-723)."""
+    if os.path.exists(path):
+        return path
+    if check or input("\nRequested directory does not exist:\n\t{}"
+                      "\n\nCreate?  (Enter 'Y' or 'y' for yes): ".format(path)) in ['Y', 'y']:
+        os.makedirs(path, exist_ok=True)
+        print('\nDirectory created:\n\t{}.'.format(path))
+        return path
+    print('Application stopped.')
+    exit(0)
+
+
+def confirm_write_file(file_path):
+    """Ask before overwriting (reference tools.py:726-743)."""
+    return True if not os.path.exists(file_path) or \
+        input("\nFile {} exists.\n\tOverwrite?  (Enter 'Y' or 'y' for yes): ".format(file_path)) in ['Y', 'y'] \
+        else False

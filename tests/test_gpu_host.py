@@ -1,0 +1,309 @@
+"""GPU parity of the host-side mirror (Extractor, tools.*, Evaluator, MultiLoss, Model, the tiled
+pipeline) against the CPU oracle's *_port functions -- the reference's own call sequences.
+These tests read like PyLC's call sites: same object chains, same argument meaning."""
+import numpy as np
+import pytest
+import torch
+
+import pylc_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+T = 512
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from pylc_b200 import ops as _ops
+    _ops._lib.load()
+    return _ops
+
+
+def _params(**kw):
+    from pylc_b200.config import Parameters
+    p = Parameters()
+    p.update(kw)
+    return p
+
+
+# ---------------------------------------------------------------------------------------------
+# Extractor: extract -> profile  (preprocess.py:37-38)
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("ch,schema", [(1, "a"), (3, "b")])
+def test_extractor_extract_profile(ops, palettes, ch, schema):
+    from pylc_b200.config import Parameters
+    from pylc_b200.utils.extract import Extractor
+    pal = palettes[schema]
+    meta = Parameters({"schema": "./schemas/schema_%s.json" % schema})
+    meta.update({"ch": ch})
+    imgs = [orc.synth_image(i, 1300 + 40 * i, 1100, ch) for i in range(3)]
+    masks = [orc.synth_mask(i, 1300 + 40 * i, 1100, pal, skew=(i == 1)) for i in range(3)]
+    ex = Extractor(meta)
+    ex.verbose = False
+    ex.load_arrays(imgs, masks).extract().profile()
+    ref_i = np.concatenate([orc.split_tiles(im, T, T) for im in imgs])
+    ref_m = np.concatenate([orc.class_encode_port(orc.split_tiles(m, T, T), pal) for m in masks])
+    got_i, got_m = ex.host()
+    assert np.array_equal(got_i, ref_i)                      # bit-exact tiles
+    assert np.array_equal(got_m, ref_m)                      # bit-exact encoded masks
+    want = orc.profile_port(ref_i, ref_m, len(pal), T)
+    m = ex.get_meta()
+    assert m.n_samples == len(ref_i) == 12
+    assert np.array_equal(np.array(m.px_dist), want["px_dist"])          # bit-exact histograms
+    assert np.array_equal(np.array(m.dset_px_dist), want["dset_px_dist"])
+    assert m.dset_px_count == want["dset_px_count"]
+    np.testing.assert_allclose(m.px_mean, want["px_mean"], rtol=1e-5)
+    np.testing.assert_allclose(m.px_std, want["px_std"], rtol=1e-5)
+    np.testing.assert_allclose(m.probs, want["probs"], rtol=0, atol=0)
+    np.testing.assert_allclose(m.weights, want["weights"], rtol=1e-15)
+    assert m.m2 == pytest.approx(want["m2"], rel=1e-15) and m.jsd == pytest.approx(want["jsd"], rel=1e-15)
+    # get_profile over the dataset object (the `profile --db` route) gives the same metadata
+    from pylc_b200.utils.profile import get_profile
+    m2 = get_profile(ex.get_data())
+    assert np.array_equal(np.array(m2.px_dist), want["px_dist"])
+    np.testing.assert_allclose(m2.px_std, want["px_std"], rtol=1e-5)
+
+
+def test_extractor_coshuffle_is_one_permutation(ops, palettes):
+    from pylc_b200.utils.extract import Extractor
+    meta = _params(ch=1)
+    img = orc.synth_image(7, 1600, 1100, 1)
+    mask = orc.synth_mask(7, 1600, 1100, palettes["a"])
+    ex = Extractor(meta)
+    ex.verbose = False
+    ex.load_arrays([img], [mask]).extract()
+    i0, m0 = ex.host()
+    ex.coshuffle()
+    i1, m1 = ex.host()
+    perm = ex._perm
+    assert sorted(perm.tolist()) == list(range(len(i0)))
+    assert np.array_equal(i1, i0[perm]) and np.array_equal(m1, m0[perm])
+    ex.profile()                                             # per-tile rows follow the permutation
+    assert np.array_equal(np.array(ex.get_meta().px_dist), orc.tile_histograms(m1, 9))
+
+
+def test_extractor_fit_matches_reference_geometry(ops):
+    from pylc_b200.utils.extract import Extractor
+    img = orc.synth_image(2, 2000, 1500, 1)
+    ex = Extractor(_params(ch=1))
+    ex.verbose = False
+    ex.load_arrays([img]).extract(fit=True, stride=256)
+    e = ex.get_meta().extract
+    assert (e["w_fitted"], e["h_fitted"], e["offset"], e["n"]) == (1536, 1024, 0, 15)
+    import cv2
+    fitted = cv2.resize(img, (1536, 1024), interpolation=cv2.INTER_AREA)
+    assert np.array_equal(ex.host()[0], orc.split_tiles(fitted, T, 256))
+
+
+# ---------------------------------------------------------------------------------------------
+# tools.class_encode / colourize / reconstruct
+# ---------------------------------------------------------------------------------------------
+
+def test_tools_class_encode_and_colourize(ops, palettes):
+    from pylc_b200.utils import tools
+    pal = palettes["a"]
+    mask = orc.synth_mask(3, 640, 512, pal, off_palette=0.01)
+    nchw = torch.from_numpy(np.moveaxis(mask, 2, 0)[None].copy())
+    enc = tools.class_encode(nchw, pal)
+    assert enc.dtype == torch.uint8 and not enc.is_cuda
+    assert np.array_equal(enc.numpy(), orc.class_encode_port(nchw.numpy(), pal))
+    rgb = tools.colourize(enc.numpy().astype(np.int64), 9, palette=pal)
+    assert rgb.dtype == np.int64
+    assert np.array_equal(rgb, orc.colourize_port(enc.numpy().astype(np.int64), 9, pal))
+    with pytest.raises(AssertionError):
+        tools.class_encode(torch.zeros((1, 4, 8, 8), dtype=torch.uint8), pal)
+
+
+@pytest.mark.parametrize("w_full,h_full", [(2000, 1500), (1700, 1100)])
+def test_tools_reconstruct_matches_port(ops, palettes, w_full, h_full):
+    """tools.reconstruct(list of batches of 8, meta) == the reference's loops (tools.py:209-319)."""
+    from pylc_b200.utils import tools
+    meta = _params(ch=1, stride=256)
+    w_fit, h_fit = orc.fit_dims(w_full, h_full, T)
+    nr, nc = h_fit // 256 - 1, w_fit // 256 - 1
+    meta.extract = {"fid": "x", "n": nr * nc, "w_full": w_full, "h_full": h_full, "w_scaled": w_full,
+                    "h_scaled": h_full, "w_fitted": w_fit, "h_fitted": h_fit, "offset": 0}
+    g = torch.Generator().manual_seed(5)
+    logits = torch.randn(nr * nc, 9, T, T, generator=g) * 3
+    batches = [logits[i:i + 8].cuda() for i in range(0, nr * nc, 8)]
+    got = tools.reconstruct(batches, meta)
+    want = orc.reconstruct_port([b.cpu().numpy() for b in batches], h_fit, w_fit, w_full, h_full, T, 256,
+                                palettes["a"], 9)
+    assert got.dtype == np.float32 and got.shape == want.shape == (h_full, w_full, 3)
+    bad = np.any(got != want, axis=2)
+    if bad.any():   # only where the reference's own top-1 is a near tie
+        margin = orc.resample_labels(orc.top2_margin(orc.stitch_map(logits.numpy(), nr, nc, T, 256)), w_full, h_full)
+        assert not (bad & (margin > 1e-6)).any()
+    assert bad.mean() < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# Evaluator
+# ---------------------------------------------------------------------------------------------
+
+def _eval_case(palettes, seed, w_full=1000, h_full=760):
+    pal = palettes["a"]
+    gt = orc.synth_mask(seed, w_full, h_full, pal, skew=True)
+    pred_lab = orc.synth_labels(seed + 50, w_full, h_full, 9, skew=False, block=37)
+    pred_rgb = np.asarray(pal, dtype=np.uint8)[pred_lab].astype(np.float32)
+    meta = _params(ch=1)
+    meta.extract = {"fid": "img_%d" % seed, "n": 0, "w_full": w_full, "h_full": h_full, "w_scaled": w_full,
+                    "h_scaled": h_full, "w_fitted": 0, "h_fitted": 0, "offset": 0}
+    return gt, pred_lab, pred_rgb, meta
+
+
+def test_evaluator_matches_sklearn_port(ops, palettes, tmp_path, monkeypatch):
+    from pylc_b200.utils.evaluate import Evaluator
+    monkeypatch.chdir(tmp_path)
+    gt, pred_lab, pred_rgb, meta = _eval_case(palettes, 1)
+    ev = Evaluator(meta)
+    ev.load(pred_rgb, meta, mask_true=gt).evaluate()
+    yt, yp = orc.inject_coverage(orc.class_encode_hwc(gt, palettes["a"]), pred_lab, 9)
+    want = orc.metrics_port(yt, yp, meta.class_codes)
+    assert np.array_equal(ev.conf.cpu().numpy(), orc.confusion_counts(yt, yp, 9))    # bit-exact
+    r = ev.metrics.results
+    assert r["f1"] == want["f1"] and r["iou"] == want["iou"] and r["mcc"] == want["mcc"]
+    assert np.array_equal(ev.metrics.cmatrix, want["cmatrix"])
+    for k, v in want["report"].items():
+        assert r["report"][k] == pytest.approx(v, rel=0, abs=0) if not isinstance(v, dict) else r["report"][k] == v
+    files = ev.save_metrics()
+    assert all(f.endswith(s) for f, s in zip(files, ("_eval.json", "_cmap.pdf", "_cmap.npy")))
+    assert np.array_equal(np.load(files[2]), want["cmatrix"])
+    assert ev.save_image().endswith("img_1.png")
+
+
+def test_evaluator_aggregate_equals_concatenation(ops, palettes, tmp_path, monkeypatch):
+    from pylc_b200.utils.evaluate import Evaluator
+    monkeypatch.chdir(tmp_path)
+    ev = None
+    yts, yps = [], []
+    for seed in (1, 2, 3):
+        gt, pred_lab, pred_rgb, meta = _eval_case(palettes, seed, 900 + 16 * seed, 700)
+        ev = ev or Evaluator(meta)
+        ev.load(pred_rgb, meta, mask_true=gt)
+        ev.reset()
+        yts.append(orc.class_encode_hwc(gt, palettes["a"]).ravel())
+        yps.append(pred_lab.ravel())
+    ev.evaluate(aggregate=True)
+    yt, yp = orc.inject_coverage(np.concatenate(yts), np.concatenate(yps), 9)       # evaluate.py:158-174
+    assert np.array_equal(ev.metrics.counts, orc.confusion_counts(yt, yp, 9))
+    want = orc.metrics_port(yt, yp, ev.labels)
+    assert ev.metrics.results["iou"] == want["iou"] and ev.fid == "aggregate_metrics"
+
+
+# ---------------------------------------------------------------------------------------------
+# MultiLoss (autograd Function) and Model
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_multiloss_module_forward_backward(ops, weighted):
+    from pylc_b200.models.modules.loss import MultiLoss
+    from pylc_b200.config import defaults
+    C = 9
+    g = torch.Generator().manual_seed(11)
+    z = (torch.randn(3, C, 96, 80, generator=g) * 2)
+    t = torch.randint(0, C, (3, 96, 80), generator=g)
+    w = (torch.rand(C, generator=g) + 0.2).tolist()
+    crit = MultiLoss({"weighted": weighted, "weights": w, "ce": 0.5, "dice": 0.5, "focal": 0.5},
+                     {"n_classes": C, "class_codes": defaults.class_codes, "class_labels": defaults.class_labels})
+    zc = z.cuda().requires_grad_(True)
+    loss = crit.forward(zc, t.cuda())
+    (loss * 2.0).backward()
+    ref = orc.multiloss_port(z.numpy(), t.numpy(), C, weights=w, weighted=weighted)
+    assert loss.item() == pytest.approx(ref[0], rel=1e-4)
+    assert crit.ce.item() == pytest.approx(ref[1], rel=1e-4)
+    assert crit.dsc.item() == pytest.approx(ref[2], rel=1e-4)
+    assert crit.fl.item() == pytest.approx(ref[3], rel=1e-4)
+    np.testing.assert_allclose(zc.grad.cpu().numpy(), 2.0 * ref[4], rtol=2e-3, atol=1e-9)
+    # component calls used by Model.eval (model.py:360-362)
+    assert crit.ce_loss(zc.detach(), t.cuda()).item() == pytest.approx(ref[1], rel=1e-4)
+    assert crit.dice_loss(zc.detach(), t.cuda()).item() == pytest.approx(ref[2], rel=1e-4)
+    assert crit.focal_loss(zc.detach(), t.cuda()).item() == pytest.approx(ref[3], rel=1e-4)
+    with pytest.raises(AssertionError):
+        crit.forward(zc, t[:, :50].cuda())
+
+
+def _tiny_model(ch):
+    from pylc_b200.config import defaults
+    from pylc_b200.models.model import Model
+    torch.manual_seed(0)
+    model = Model()
+    model.track = False
+    stats = ([120.0], [40.0]) if ch == 1 else ([130.0, 140.0, 150.0], [25.0, 22.0, 19.0])
+    model.update_meta({"ch": ch, "arch": "deeplab", "backbone": "resnet", "pretrained": False, "px_mean": stats[0],
+                       "px_std": stats[1], "weights": [1.0] * 9, "normalize_default": False, "weighted": False,
+                       "schema": defaults.schema})
+    model.build()
+    model.net.eval()
+    return model
+
+
+@pytest.mark.parametrize("ch", [1, 3])
+def test_model_test_equals_fused_tile_path(ops, ch):
+    """Model.test(u8 tiles) (reference route: float -> normalize -> cat x3 -> net) and
+    Model.test_tiles(pylc_tile_gather_norm_f32 output) see bit-identical network inputs."""
+    model = _tiny_model(ch)
+    img = orc.synth_image(1, 1024, 1024, ch)
+    d, pitch = ops.upload_image(img)
+    mean, std, post, out_ch = model.norm_params()
+    fused = ops.tile_gather_norm_f32(d, 1024, 1024, ch, pitch, T, 256, mean, std, post, out_ch)
+    tiles = torch.from_numpy(orc.split_tiles(img, T, 256)).float()
+    x_ref = model._prepare(tiles)
+    assert torch.equal(fused, x_ref)
+    assert torch.equal(model.test_tiles(fused[:2])[0], model.test(tiles[:2])[0])
+
+
+def test_model_train_step_runs_and_reports(ops):
+    model = _tiny_model(3)
+    model.net.train()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(0, 256, (2, 3, 128, 128), generator=g).float()
+    y = torch.randint(0, 9, (2, 128, 128), generator=g)
+    before = [p.detach().clone() for p in list(model.net.parameters())[:3]]
+    loss = model.train(x, y)
+    assert torch.isfinite(loss) and model.iter == 1
+    assert any(not torch.equal(a, b) for a, b in zip(before, list(model.net.parameters())[:3]))
+    model.eval(x, y)
+
+
+# ---------------------------------------------------------------------------------------------
+# Tiled pipeline (test.py's loop, GPU-resident)
+# ---------------------------------------------------------------------------------------------
+
+def test_pipeline_matches_reference_sequence(ops, palettes):
+    """TiledSegmenter on a 1600x1200 colour image == reference sequence evaluated by the oracle on
+    the very logits the network produced (network is stock torch, so it is not under test)."""
+    import cv2
+    from pylc_b200.pipeline import TiledSegmenter
+    model = _tiny_model(3)
+    pal = palettes["a"]
+    W, H = 1600, 1200
+    img = orc.synth_image(9, W, H, 3)
+    gt = orc.synth_mask(9, W, H, pal, skew=True)
+    seg = TiledSegmenter(model, batch_tiles=8, channels_last=False, keep_masks=True)
+    conf, results = seg.run_host([img], [gt])
+    res = results[0]
+    # oracle on the same network outputs
+    w_fit, h_fit = orc.fit_dims(W, H, T)
+    fitted = cv2.resize(img, (w_fit, h_fit), interpolation=cv2.INTER_AREA)
+    tiles = torch.from_numpy(orc.split_tiles(fitted, T, 256))
+    outs = [model.test(tiles[i:i + 8])[0] for i in range(0, len(tiles), 8)]
+    logits = torch.cat(outs).cpu().numpy()
+    nr, nc = h_fit // 256 - 1, w_fit // 256 - 1
+    ref_map = orc.stitch_map(logits, nr, nc, T, 256)
+    ref_lab = orc.stitch_labels(ref_map)
+    near_tie = orc.top2_margin(ref_map) <= 1e-6
+    got_lab = res["labels"].cpu().numpy()
+    assert not ((got_lab != ref_lab) & ~near_tie).any()
+    pred_full = orc.resample_labels(got_lab, W, H)
+    assert np.array_equal(res["pred_full"].cpu().numpy(), pred_full)
+    assert np.array_equal(res["pred_rgb"].cpu().numpy(), np.asarray(pal, dtype=np.uint8)[pred_full])
+    yt, yp = orc.inject_coverage(orc.class_encode_hwc(gt, pal), pred_full, 9)
+    assert np.array_equal(conf, orc.confusion_counts(yt, yp, 9))
+    # resident route gives the same matrix
+    seg.reset()
+    seg.run_resident([seg.stage(img, gt, index=0)])
+    assert np.array_equal(seg.conf.cpu().numpy(), conf)
+    s = seg.scores(conf)
+    assert s["iou"] == orc.metrics_port(yt, yp, model.meta.class_codes)["iou"]

@@ -1,0 +1,199 @@
+"""CPU-side tests of the host logic: metrics from one confusion matrix vs scikit-learn, the tile
+dataset, geometry helpers, config/schema handling and the data-parallel plumbing (gloo, 2 ranks).
+No CUDA kernel is executed here."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import pylc_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- metrics --------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("C,seed,missing", [(9, 0, None), (11, 1, None), (9, 2, 4), (3, 3, None)])
+def test_scores_from_confusion_equal_sklearn(C, seed, missing):
+    from pylc_b200.utils.metrics import scores_from_confusion
+    rng = np.random.default_rng(seed)
+    yt = rng.integers(0, C, 50000).astype(np.uint8)
+    yp = np.where(rng.random(50000) < 0.7, yt, rng.integers(0, C, 50000)).astype(np.uint8)
+    if missing is not None:                       # a class present in neither vector is dropped (unique_labels)
+        yt[yt == missing] = 0
+        yp[yp == missing] = 0
+    labels = ["c%d" % i for i in range(C)]
+    present = sorted(set(yt.tolist()) | set(yp.tolist()))
+    want = orc.metrics_port(yt, yp, [labels[i] for i in present])
+    got = scores_from_confusion(orc.confusion_counts(yt, yp, C), labels)
+    assert got["f1"] == want["f1"] and got["iou"] == want["iou"] and got["mcc"] == want["mcc"]
+    assert np.array_equal(got["cmatrix"], want["cmatrix"])
+    assert got["report"] == want["report"]
+
+
+def test_metrics_object_from_counts():
+    from pylc_b200.utils.metrics import Metrics, format_report
+    M = np.array([[5, 1, 0], [2, 7, 1], [0, 0, 4]])
+    m = Metrics().set_counts(M, ["a", "b", "c"])
+    m.f1_score(None, None)
+    m.jaccard(None, None)
+    m.mcc(None, None)
+    m.confusion_matrix(None, None, labels=["a", "b", "c"])
+    m.report(None, None, labels=["a", "b", "c"])
+    assert set(m.results) == {"f1", "iou", "mcc", "report"}
+    assert np.allclose(m.cmatrix.sum(axis=1), 1.0)
+    assert "weighted avg" in format_report(m.results["report"])
+    json.dumps(m.results)                          # what save_metrics writes
+
+
+def test_jsd_m2_match_oracle():
+    from pylc_b200.utils.metrics import jsd, m2
+    p = np.array([0.55, 0.0, 0.22, 0.08, 0.1, 0.001, 0.001, 0.035, 0.013])
+    q = np.full(9, 1 / 9)
+    assert jsd(p, q) == orc.jsd(p, q) and m2(p, 9) == orc.m2(p, 9)
+    with pytest.raises(AssertionError):
+        m2(p, 1)
+
+
+# ---- geometry / host tools -------------------------------------------------------------------
+
+def test_fit_dims_and_nn_maps_match_reference_golden(golden):
+    """tests/golden/fit.npz was produced by the reference's adjust_to_tile / cv2.resize."""
+    from pylc_b200.ops import nn_index_map
+    from pylc_b200.utils import tools
+    g = golden("fit")
+    for W, H, w_fit, h_fit, off in g["fit_dims"]:
+        assert tools.fit_dims(int(W), int(H), 512) == (w_fit, h_fit) and off == 0
+    for n_src, n_dst in g["nn_pairs"]:
+        assert np.array_equal(nn_index_map(int(n_src), int(n_dst)), g["nn_map_%d_%d" % (n_src, n_dst)])
+    img = orc.synth_image(0, 1300, 900, 3)
+    out, w, h, off = tools.adjust_to_tile(img, 512, 256, 3)
+    assert (w, h, off) == (1024, 512, 0) and out.shape == (512, 1024, 3)
+    with pytest.raises(AssertionError):
+        tools.adjust_to_tile(np.zeros((600, 600), np.uint8), 512, 300, 1)
+
+
+def test_colourize_lut_follows_sequential_passes(palettes):
+    from pylc_b200.utils.tools import colourize_lut
+    for pal in palettes.values():
+        assert colourize_lut(len(pal), pal) == [list(c) for c in pal]
+    chain = [[2, 2, 2], [9, 9, 9], [7, 7, 7]]       # label 0 -> grey 2 -> re-mapped by pass 2
+    assert colourize_lut(3, chain) == orc.colourize_lut(3, chain).tolist() == [[7, 7, 7], [9, 9, 9], [7, 7, 7]]
+
+
+def test_nn_index_map_equals_opencv():
+    import cv2
+    from pylc_b200.ops import nn_index_map
+    for n_src, n_dst in [(2560, 3000), (1536, 2000), (5632, 6000), (1024, 1500), (512, 512), (1536, 1100)]:
+        ramp = np.arange(n_src, dtype=np.float32)[None, :]
+        want = cv2.resize(ramp, (n_dst, 1), interpolation=cv2.INTER_NEAREST)[0].astype(np.int32)
+        assert np.array_equal(nn_index_map(n_src, n_dst), want)
+
+
+def test_collate_pairs_by_basename(tmp_path):
+    from pylc_b200.utils import tools
+    (tmp_path / "img").mkdir()
+    (tmp_path / "mask").mkdir()
+    for n in ("b", "a"):
+        (tmp_path / "img" / (n + ".tif")).write_bytes(b"x")
+        (tmp_path / "mask" / (n + ".png")).write_bytes(b"x")
+    files = tools.collate(str(tmp_path / "img"), str(tmp_path / "mask"))
+    assert [os.path.basename(f["img"]) for f in files] == ["a.tif", "b.tif"]
+    assert all(os.path.basename(f["mask"])[0] == os.path.basename(f["img"])[0] for f in files)
+    (tmp_path / "mask" / "c.png").write_bytes(b"x")
+    with pytest.raises(SystemExit):
+        tools.collate(str(tmp_path / "img"), str(tmp_path / "mask"))
+
+
+# ---- config / dataset ------------------------------------------------------------------------
+
+def test_parameters_schema_b_and_update():
+    from pylc_b200.config import Parameters
+    p = Parameters({"schema": "./schemas/schema_b.json", "ch": 1})
+    assert p.n_classes == 11 and len(p.palette_rgb) == 11 and p.ch_label == "grayscale"
+    p.update({"px_mean": np.array([1.0, 2.0]), "not_a_field": 3})
+    assert p.px_mean == [1.0, 2.0] and not hasattr(p, "not_a_field")
+    assert p.tiles_per_image == 700
+    json.dumps({k: v for k, v in vars(p).items()})   # the HDF5 `meta` attribute must stay JSON-serialisable
+
+
+def test_dataset_partition_iteration_and_npz_roundtrip(tmp_path):
+    from pylc_b200.config import Parameters
+    from pylc_b200.db.dataset import MLPDataset
+    rng = np.random.default_rng(0)
+    imgs = rng.integers(0, 256, (10, 1, 16, 16), dtype=np.uint8)
+    masks = rng.integers(0, 9, (10, 16, 16), dtype=np.uint8)
+    meta = Parameters({"ch": 1})
+    meta.id, meta.output_dir = "unit_db", str(tmp_path)
+    full = MLPDataset(input_data={"img": imgs, "mask": masks, "meta": meta})
+    train = MLPDataset(input_data={"img": imgs, "mask": masks, "meta": meta}, partition=(0, 0.8))
+    valid = MLPDataset(input_data={"img": imgs, "mask": masks, "meta": meta}, partition=(0.8, 1.0))
+    assert (full.size, train.size, valid.size) == (10, 8, 2)
+    items = list(valid)
+    assert items[0][0].dtype == torch.float32 and items[0][1].dtype == torch.int64
+    assert torch.equal(items[1][1], torch.from_numpy(masks[9]).long())
+    loader, n_batches = train.loader(batch_size=4, drop_last=True)
+    assert n_batches == 2 and [b[0].shape[0] for b in loader] == [4, 4]
+    path = full.save()
+    assert path.endswith(".npz") or path.endswith(".h5")
+    back = MLPDataset(db_path=path)
+    assert np.array_equal(back.get_data("img"), imgs) and np.array_equal(back.get_data("mask"), masks)
+    assert back.get_meta().id == "unit_db" and back.get_meta().n_classes == 9
+
+
+# ---- data-parallel plumbing (gloo, world_size 2) ----------------------------------------------
+
+_WORKER = r"""
+import os, sys, json
+import numpy as np, torch
+sys.path.insert(0, %r)
+from pylc_b200 import dist as pdist
+rank, world, _ = pdist.init_from_env(backend="gloo")
+mine = pdist.shard_indices(7)
+rng = np.random.default_rng(0)
+conf_all = rng.integers(0, 1000, (7, 9, 9))
+local = conf_all[mine].sum(axis=0)
+total = pdist.all_reduce_i64(local)
+part = torch.tensor([0.5 * (rank + 1), 2.0], dtype=torch.float64)
+pdist.all_reduce_(part)
+t = pdist.max_over_ranks(1.0 + rank)
+pdist.barrier()
+if rank == 0:
+    print(json.dumps({"world": world, "mine": mine, "ok": bool(np.array_equal(total, conf_all.sum(axis=0))),
+                      "part": part.tolist(), "t": t}))
+torch.distributed.destroy_process_group()
+"""
+
+
+def test_dist_gloo_two_ranks(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % ROOT)
+    port = 29000 + os.getpid() % 2000
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), str(script)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    res = json.loads(line)
+    assert res == {"world": 2, "mine": [0, 2, 4, 6], "ok": True, "part": [1.5, 4.0], "t": 2.0}
+
+
+def test_shard_indices_cover_everything_once():
+    from pylc_b200.dist import shard_indices
+    for world in (1, 2, 4, 8):
+        got = sorted(i for r in range(world) for i in shard_indices(64, r, world))
+        assert got == list(range(64))
+
+
+# ---- bench.py reference arm contract ----------------------------------------------------------
+
+def test_bench_cli_contract_flags():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True)
+    assert out.returncode == 0
+    for flag in ("--gpus", "--steps", "--warmup", "--impl"):
+        assert flag in out.stdout
