@@ -358,7 +358,10 @@ def main():
     ap.add_argument("--host-workers", type=int, default=6)
     ap.add_argument("--no-channels-last", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--images", type=int, default=64, help="images per GPU per step (profiling runs use fewer; "
+                    "the reported workload is only configs[1] at the default 64)")
     args = ap.parse_args()
+    globals()["N_IMAGES"] = args.images
     if args.impl == "reference":
         run_reference(args, int(os.environ.get("RANK", "0")))
         return

@@ -180,6 +180,8 @@ PYLC_API int pylc_confusion_u8(const uint8_t *y_true, const uint8_t *y_pred, int
  *                            (data-parallel ranks all-reduce `partials` here)
  *   pylc_multiloss_finalize  partials -> out[4] f32 = {loss, ce, dice, focal}
  *   pylc_multiloss_grad      logits + target + partials -> grad[B,C,HW] f32 = grad_scale * dL/dz
+ *                            (times *grad_scale_dev when that device pointer is non-NULL: the
+ *                            upstream autograd gradient, read on the device, no host sync)
  *
  *   logits  [B, C, HW] f32 ; target [B, HW], target_is_i64 ? int64 (the reference dtype) : u8
  *   class_w nullable [C] f32 device (CrossEntropyLoss weights; NULL = unweighted)
@@ -199,8 +201,8 @@ PYLC_API int pylc_multiloss_finalize(const double *partials, int C, int64_t n_px
                             const pylc_loss_cfg *cfg, float *out4, pylc_stream_t stream);
 PYLC_API int pylc_multiloss_grad(const float *logits, const void *target, int target_is_i64, int B, int C,
                         int64_t HW, const float *class_w, const pylc_loss_cfg *cfg,
-                        const double *partials, int64_t n_px_total, float grad_scale, float *grad,
-                        pylc_stream_t stream);
+                        const double *partials, int64_t n_px_total, float grad_scale,
+                        const float *grad_scale_dev, float *grad, pylc_stream_t stream);
 
 #ifdef __cplusplus
 }

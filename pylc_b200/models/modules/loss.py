@@ -47,9 +47,8 @@ class _MultiLossFn(torch.autograd.Function):
         pred, target, partials = ctx.saved_tensors
         # dL/dz from the kernel, scaled by the upstream gradient of out[0] (the weighted loss).
         # The component outputs out[1:4] are reporting values; gradients through them are dropped.
-        grad = ops.multiloss_grad(pred, target, ctx.cfg, partials, ctx.n_px, ctx.class_w)
-        g0 = grad_out[0]
-        grad.mul_(g0)
+        g0 = grad_out[0].to(torch.float32).contiguous()
+        grad = ops.multiloss_grad(pred, target, ctx.cfg, partials, ctx.n_px, ctx.class_w, grad_scale_dev=g0)
         return grad, None, None, None, None
 
 

@@ -317,10 +317,13 @@ def multiloss_finalize(partials, n_classes, n_px_total, cfg):
     return out
 
 
-def multiloss_grad(logits, target, cfg, partials, n_px_total, class_w=None, grad_scale=1.0, out=None):
+def multiloss_grad(logits, target, cfg, partials, n_px_total, class_w=None, grad_scale=1.0, out=None,
+                   grad_scale_dev=None):
+    """`grad_scale_dev`: optional CUDA f32 scalar tensor multiplied in on the device (autograd's upstream grad)."""
     logits, target, is_i64, B, C, HW = _loss_inputs(logits, target)
     grad = out if out is not None else torch.empty_like(logits)
     check(_lib.load().pylc_multiloss_grad(_p(logits), _p(target), is_i64, B, C, HW, _p(class_w), ctypes.byref(cfg),
-                                          _p(partials), n_px_total, float(grad_scale), _p(grad), _stream()),
+                                          _p(partials), n_px_total, float(grad_scale), _p(grad_scale_dev), _p(grad),
+                                          _stream()),
           "pylc_multiloss_grad")
     return grad

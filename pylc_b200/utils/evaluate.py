@@ -35,6 +35,7 @@ class Evaluator:
     def __init__(self, params=None, make_dirs=True):
         self.meta = Parameters(params) if params is not None else defaults
         self.metrics = Metrics()
+        self._schema = (self.meta.n_classes, self.meta.class_codes)
         self.fid = None
         self.logits = None
         self.mask_pred = None
@@ -62,6 +63,7 @@ class Evaluator:
         """Register a prediction (and its ground truth) for evaluation (reference evaluate.py:64-121).
         `mask_true` (extension) passes an already decoded RGB ground truth [H,W,3] u8."""
         self.meta = meta
+        self._schema = (meta.n_classes, meta.class_codes)    # survives reset(), which blanks self.meta
         self.fid = self.meta.extract['fid']
         self.mask_pred = mask_pred
         if mask_true_path or mask_true is not None:
@@ -140,8 +142,7 @@ class Evaluator:
     def validate(self):
         """Label list + aggregate bookkeeping (reference evaluate.py:150-176).  The coverage
         injection itself happens inside the confusion kernel (n_inject)."""
-        self.labels = defaults.class_codes if self.meta.n_classes == len(defaults.class_codes) \
-            else self.meta.class_codes
+        self.labels = defaults.class_codes if self._schema[0] == len(defaults.class_codes) else self._schema[1]
         if self.aggregate:
             self.fid = 'aggregate_metrics'
             assert self.n_aggregated > 0, "Aggregate evaluation failed. Data buffer is empty."

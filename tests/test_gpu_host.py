@@ -115,7 +115,7 @@ def test_tools_class_encode_and_colourize(ops, palettes):
         tools.class_encode(torch.zeros((1, 4, 8, 8), dtype=torch.uint8), pal)
 
 
-@pytest.mark.parametrize("w_full,h_full", [(2000, 1500), (1700, 1100)])
+@pytest.mark.parametrize("w_full,h_full", [(2000, 1500), (1700, 1300)])
 def test_tools_reconstruct_matches_port(ops, palettes, w_full, h_full):
     """tools.reconstruct(list of batches of 8, meta) == the reference's loops (tools.py:209-319)."""
     from pylc_b200.utils import tools

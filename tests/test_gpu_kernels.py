@@ -299,12 +299,13 @@ def test_resample_encode_confusion(ops, palettes, pk, h, w, h_full, w_full):
                                         lut_rgb=lut, n_inject=C, want_pred=True, want_rgb=True, want_gt=True)
     pred_full = orc.resample_labels(labels, w_full, h_full)
     gt_lab = orc.class_encode_hwc(gt, pal)
+    # label / RGB outputs are the plain resample and encode; only the counts see the coverage injection
+    assert np.array_equal(res["pred_full"].cpu().numpy(), pred_full)
+    assert np.array_equal(res["gt_full"].cpu().numpy(), gt_lab)
     yt, yp = orc.inject_coverage(gt_lab, pred_full, C)
-    assert np.array_equal(res["pred_full"].cpu().numpy().ravel(), yp)
-    assert np.array_equal(res["gt_full"].cpu().numpy().ravel(), yt)
     assert np.array_equal(res["conf"].cpu().numpy(), orc.confusion_counts(yt, yp, C))
     assert int(res["conf"].sum()) == h_full * w_full
-    assert np.array_equal(res["pred_rgb"].cpu().numpy().reshape(-1, 3), np.asarray(lut, dtype=np.uint8)[yp])
+    assert np.array_equal(res["pred_rgb"].cpu().numpy(), np.asarray(lut, dtype=np.uint8)[pred_full])
     # aggregate path: flat vectors
     conf2 = ops.confusion_u8(dev(gt_lab), dev(pred_full), C, n_inject=C)
     assert torch.equal(conf2, res["conf"])
@@ -328,8 +329,11 @@ def test_evaluate_golden(ops, golden, palettes):
     d_gt, gp = ops.upload_image(gt)
     res = ops.resample_encode_confusion(pred_lab, w, h, gt_rgb=d_gt, gt_pitch=gp, palette=pal, n_inject=C,
                                         want_pred=True, want_gt=True)
-    assert np.array_equal(res["gt_full"].cpu().numpy().ravel(), g["eval_y_true"])
-    assert np.array_equal(res["pred_full"].cpu().numpy().ravel(), g["eval_y_pred"])
+    # the golden vectors are the reference's y_true / y_pred AFTER validate()'s in-place injection
+    yt, yp = orc.inject_coverage(res["gt_full"].cpu().numpy(), res["pred_full"].cpu().numpy(), C)
+    assert np.array_equal(yt, g["eval_y_true"])
+    assert np.array_equal(yp, g["eval_y_pred"])
+    assert np.array_equal(res["conf"].cpu().numpy(), orc.confusion_counts(g["eval_y_true"], g["eval_y_pred"], C))
     M = res["conf"].cpu().numpy()
     m = orc.metrics_from_confusion(M)
     np.testing.assert_allclose([m["f1"], m["iou"], m["mcc"]], g["eval_scalars"], rtol=1e-12)

@@ -1,0 +1,20 @@
+#!/bin/bash
+# Round profiling pass (run under gpurun): ncu launch list of a short bench step + one `--set full`
+# capture per custom kernel at the BASELINE sizes (tools/kbench.py).  Reports land in gpurun_out/.
+set -u
+R=${1:-r1}
+mkdir -p gpurun_out
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_$R.csv \
+    python bench.py --steps 1 --warmup 1 --images 2 --no-cpu-baseline > gpurun_out/bench_under_ncu_$R.log 2>&1
+tail -3 gpurun_out/bench_under_ncu_$R.log
+wc -l gpurun_out/launches_$R.csv
+cap() {  # name, kernel regex, kbench --only filter, launches to keep (after 3 warm-up launches each)
+    ncu --set full --clock-control none --import-source on -k regex:"$2" -s 3 -c "$4" -o gpurun_out/prof_${R}_$1 \
+        python tools/kbench.py --iters 1 --only "$3" > gpurun_out/ncu_$1_$R.log 2>&1
+    tail -2 gpurun_out/ncu_$1_$R.log
+}
+cap stitch "stitch_kernel" "stitch_argmax_colour 273 tiles C9 labels" 1
+cap resample "resample_confusion" "resample" 1
+cap loss "loss_reduce|loss_grad" "multiloss_reduce B64 C9 i64,multiloss_grad" 2
+cap gather "gather_mask|gather_norm|gather_img" "mask_gather,gather_norm,tile_gather_u8 rgb" 3
+ls -la gpurun_out | head -30
