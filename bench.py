@@ -260,7 +260,7 @@ def run_ours(args, rank, world, local_rank):
 
     model = build_model(device)
     seg = TiledSegmenter(model, batch_tiles=args.batch_tiles, channels_last=not args.no_channels_last,
-                         autocast_dtype=dtype, host_workers=args.host_workers)
+                         autocast_dtype=dtype, host_workers=args.host_workers, fuse_network=not args.no_fuse)
     imgs, masks = make_inputs(rank, model.meta.palette_rgb)
     mpx_step = N_IMAGES * W_FULL * H_FULL / 1e6
     d2h = seg.C * seg.C * 8
@@ -326,6 +326,7 @@ def run_ours(args, rank, world, local_rank):
             "fp32 with cuDNN TF32 (PyTorch default, as the reference would run)" if dtype is None else args.backbone_dtype),
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "images_per_gpu": N_IMAGES, "tiles_per_image": 45, "batch_tiles": args.batch_tiles,
+                   "network_plan": "eager nn.Module" if args.no_fuse else "BatchNorm folded, cuDNN fused conv+bias(+add)+ReLU, channels_last",
                    "l2": "inputs larger than L2 (each step streams > 20 GB of logits per GPU)",
                    "parallelism": "dp%d, images sharded, one [9,9] i64 all-reduce per step" % world,
                    "value_region": "fitted u8 images + RGB ground truth resident in HBM -> all-reduced confusion matrix",
@@ -358,6 +359,7 @@ def main():
     ap.add_argument("--host-workers", type=int, default=6)
     ap.add_argument("--no-channels-last", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="run the eager nn.Module instead of the BN-folded cuDNN-fused plan")
     ap.add_argument("--images", type=int, default=64, help="images per GPU per step (profiling runs use fewer; "
                     "the reported workload is only configs[1] at the default 64)")
     args = ap.parse_args()

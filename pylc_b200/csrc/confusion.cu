@@ -117,7 +117,7 @@ __device__ __forceinline__ void count_runs(const uint32_t (&idxw)[4], uint32_t b
 // stream) and a 24-byte window of the L2-resident fitted label row; the column map costs nothing
 // per row.  PACKED: C <= 15, pair codes fit a byte (the shipped schemas have 9 and 11 classes).
 template <bool PACKED>
-__global__ void __launch_bounds__(kRsThreads)
+__global__ void __launch_bounds__(kRsThreads, 16)
     resample_confusion_kernel(ResampleArgs a, const __grid_constant__ PaletteHash ph, const __grid_constant__ ColourLut lut) {
     extern __shared__ unsigned s_dyn[];
     __shared__ uint32_t s_tab[256];

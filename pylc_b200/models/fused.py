@@ -1,0 +1,123 @@
+"""
+Inference-only execution plan for DeepLabv3+/ResNet-101 (pylc_b200.models.deeplab.DeepLab).
+
+The network stays on stock PyTorch / cuDNN tensor-core kernels (north_star).  What this module
+removes is the memory-bound glue around the convolutions that eval-mode inference does not need:
+
+  * every BatchNorm is folded into the preceding convolution's weight and bias
+    (w' = w * g / sqrt(var + eps), b' = beta - mean * g / sqrt(var + eps)) -- exact in real
+    arithmetic, ~1e-6 relative in fp32;
+  * conv + bias + ReLU and conv + bias + residual-add + ReLU run as single cuDNN fused calls
+    (torch.cudnn_convolution_relu / torch.cudnn_convolution_add_relu), so the [B,C,H,W]
+    activations are written once instead of being re-read and re-written by separate BN, add and
+    ReLU kernels (about a third of the unfused network's HBM traffic at 512 x 512 tiles);
+  * dropout layers (identity in eval mode) are dropped.
+
+`FusedDeepLab(net)` snapshots the weights of `net`; call `refresh()` after loading a new
+state_dict.  Outputs match `net.eval()(x)` to fp32 rounding of the folded weights, not bit for
+bit, so the pipeline uses it only when asked (`TiledSegmenter(fuse_network=True)`); parity tests of
+the custom kernels never depend on it.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def fold_conv_bn(conv, bn):
+    """(weight', bias') of conv followed by eval-mode batch-norm."""
+    w = conv.weight.detach().double()
+    b = conv.bias.detach().double() if conv.bias is not None else torch.zeros(w.shape[0], dtype=torch.float64, device=w.device)
+    if bn is None:
+        return w.float(), b.float()
+    scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+    w = w * scale[:, None, None, None]
+    b = (b - bn.running_mean.detach().double()) * scale + bn.bias.detach().double()
+    return w.float(), b.float()
+
+
+class _Conv(object):
+    """One folded convolution with an optional fused ReLU / residual add."""
+    __slots__ = ("w", "b", "stride", "padding", "dilation", "relu")
+
+    def __init__(self, conv, bn, relu, channels_last):
+        w, b = fold_conv_bn(conv, bn)
+        self.w = w.contiguous(memory_format=torch.channels_last) if channels_last else w.contiguous()
+        self.b = b.contiguous()
+        self.stride, self.padding, self.dilation, self.relu = conv.stride, conv.padding, conv.dilation, relu
+
+    def to(self, dtype):
+        self.w, self.b = self.w.to(dtype), self.b.to(dtype)
+        return self
+
+    def __call__(self, x, residual=None):
+        if x.is_cuda and self.relu:
+            if residual is not None:
+                return torch.cudnn_convolution_add_relu(x, self.w, residual, 1.0, self.b, self.stride, self.padding,
+                                                        self.dilation, 1)
+            return torch.cudnn_convolution_relu(x, self.w, self.b, self.stride, self.padding, self.dilation, 1)
+        y = F.conv2d(x, self.w, self.b, self.stride, self.padding, self.dilation)
+        if residual is not None:
+            y = y + residual
+        return F.relu(y) if self.relu else y
+
+
+class FusedDeepLab(object):
+    def __init__(self, net, channels_last=True, dtype=None):
+        self.net = net
+        self.channels_last = channels_last
+        self.dtype = dtype
+        self.refresh()
+
+    def refresh(self):
+        net, cl = self.net, self.channels_last
+        if any(not isinstance(m, nn.BatchNorm2d) for m in (net.backbone.bn1, net.aspp.bn1, net.decoder.bn1)):
+            raise ValueError("FusedDeepLab folds BatchNorm2d only")
+        mk = lambda conv, bn, relu: self._cast(_Conv(conv, bn, relu, cl))  # noqa: E731
+        bb = net.backbone
+        self.stem = mk(bb.conv1, bb.bn1, True)
+        self.blocks = []
+        for layer in (bb.layer1, bb.layer2, bb.layer3, bb.layer4):
+            stage = []
+            for blk in layer:
+                down = mk(blk.downsample[0], blk.downsample[1], False) if blk.downsample is not None else None
+                stage.append((mk(blk.conv1, blk.bn1, True), mk(blk.conv2, blk.bn2, True), mk(blk.conv3, blk.bn3, True), down))
+            self.blocks.append(stage)
+        a = net.aspp
+        self.aspp = [mk(m.atrous_conv, m.bn, True) for m in (a.aspp1, a.aspp2, a.aspp3, a.aspp4)]
+        self.aspp_pool = mk(a.global_avg_pool[1], a.global_avg_pool[2], True)
+        self.aspp_out = mk(a.conv1, a.bn1, True)
+        d = net.decoder
+        self.dec_low = mk(d.conv1, d.bn1, True)
+        self.dec1 = mk(d.last_conv[0], d.last_conv[1], True)
+        self.dec2 = mk(d.last_conv[4], d.last_conv[5], True)
+        self.dec_out = mk(d.last_conv[8], None, False)
+        return self
+
+    def _cast(self, conv):
+        return conv.to(self.dtype) if self.dtype is not None else conv
+
+    def features(self, x):
+        """Decoder output [B, n_classes, H/4, W/4] (before the final x4 bilinear up-sample)."""
+        if self.dtype is not None:
+            x = x.to(self.dtype)
+        if self.channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
+        x = F.max_pool2d(self.stem(x), 3, stride=2, padding=1)
+        low = None
+        for si, stage in enumerate(self.blocks):
+            for c1, c2, c3, down in stage:
+                skip = x if down is None else down(x)
+                x = c3(c2(c1(x)), residual=skip)
+            if si == 0:
+                low = x
+        pooled = self.aspp_pool(F.adaptive_avg_pool2d(x, 1))
+        pooled = F.interpolate(pooled, size=x.shape[2:], mode='bilinear', align_corners=True)
+        x = self.aspp_out(torch.cat([br(x) for br in self.aspp] + [pooled], dim=1))
+        low = self.dec_low(low)
+        x = F.interpolate(x, size=low.shape[2:], mode='bilinear', align_corners=True)
+        return self.dec_out(self.dec2(self.dec1(torch.cat((x, low), dim=1))))
+
+    @torch.no_grad()
+    def __call__(self, x):
+        y = self.features(x).float().contiguous()      # small [B,C,H/4,W/4]: make it NCHW here ...
+        return F.interpolate(y, size=x.shape[2:], mode='bilinear', align_corners=True)   # ... so the logits are NCHW

@@ -37,7 +37,7 @@ class FittedImage(object):
 
 class TiledSegmenter(object):
     def __init__(self, model, batch_tiles=32, channels_last=True, autocast_dtype=None, host_workers=4,
-                 n_inject=None, keep_masks=False):
+                 n_inject=None, keep_masks=False, fuse_network=False):
         self.model = model
         self.meta = model.meta
         self.net = model.net.eval()
@@ -51,6 +51,13 @@ class TiledSegmenter(object):
         self.channels_last = channels_last
         if channels_last:
             self.net = self.net.to(memory_format=torch.channels_last)
+        # inference plan: BatchNorm folded into the convolutions, cuDNN fused conv+bias(+add)+ReLU
+        # calls (models/fused.py).  Same network and precision; outputs equal the eager network to
+        # fp32 rounding of the folded weights, so it is opt-in.
+        self.fused = None
+        if fuse_network:
+            from .models.fused import FusedDeepLab
+            self.fused = FusedDeepLab(self.net, channels_last=channels_last)
         self.mean, self.std, self.post_div, self.out_ch = model.norm_params()
         self.palette = self.meta.palette_rgb
         self.lut = tools.colourize_lut(self.C, self.palette)
@@ -97,15 +104,20 @@ class TiledSegmenter(object):
         with torch.no_grad():
             for lo in range(0, tiles.shape[0], self.batch_tiles):
                 x = tiles[lo:lo + self.batch_tiles]
+                if self.fused is not None:
+                    outs.append(self.fused(x))
+                    continue
                 if self.channels_last:
                     x = x.contiguous(memory_format=torch.channels_last)
                 if self.autocast_dtype is not None:
                     with torch.autocast("cuda", dtype=self.autocast_dtype):
-                        y = self.net(x)
-                    y = y.float()
+                        y = self.net.features(x)
                 else:
-                    y = self.net(x)
-                outs.append(y.contiguous())
+                    y = self.net.features(x)
+                # the x4 bilinear up-sample of deeplab.py:38, applied to an NCHW copy of the small
+                # decoder output so the logits come out NCHW (what the stitch kernel reads)
+                y = y.float().contiguous()
+                outs.append(torch.nn.functional.interpolate(y, size=x.shape[2:], mode='bilinear', align_corners=True))
         return outs
 
     def segment_fitted(self, f, inject=None):

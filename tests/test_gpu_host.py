@@ -271,7 +271,8 @@ def test_model_train_step_runs_and_reports(ops):
 # Tiled pipeline (test.py's loop, GPU-resident)
 # ---------------------------------------------------------------------------------------------
 
-def test_pipeline_matches_reference_sequence(ops, palettes):
+@pytest.mark.parametrize("fuse", [False, True])
+def test_pipeline_matches_reference_sequence(ops, palettes, fuse):
     """TiledSegmenter on a 1600x1200 colour image == reference sequence evaluated by the oracle on
     the very logits the network produced (network is stock torch, so it is not under test)."""
     import cv2
@@ -281,14 +282,19 @@ def test_pipeline_matches_reference_sequence(ops, palettes):
     W, H = 1600, 1200
     img = orc.synth_image(9, W, H, 3)
     gt = orc.synth_mask(9, W, H, pal, skew=True)
-    seg = TiledSegmenter(model, batch_tiles=8, channels_last=False, keep_masks=True)
+    seg = TiledSegmenter(model, batch_tiles=8, channels_last=fuse, keep_masks=True, fuse_network=fuse)
     conf, results = seg.run_host([img], [gt])
     res = results[0]
     # oracle on the same network outputs
     w_fit, h_fit = orc.fit_dims(W, H, T)
     fitted = cv2.resize(img, (w_fit, h_fit), interpolation=cv2.INTER_AREA)
     tiles = torch.from_numpy(orc.split_tiles(fitted, T, 256))
-    outs = [model.test(tiles[i:i + 8])[0] for i in range(0, len(tiles), 8)]
+    if fuse:    # BN-folded cuDNN-fused plan: same batches through the same plan
+        outs = seg.forward_tiles(model._prepare(tiles))
+        eager = torch.cat([model.test(tiles[i:i + 8])[0] for i in range(0, len(tiles), 8)])
+        assert (torch.cat(outs) - eager).abs().max() <= 5e-3 * eager.abs().max()   # TF32 conv noise level
+    else:
+        outs = [model.test(tiles[i:i + 8])[0] for i in range(0, len(tiles), 8)]
     logits = torch.cat(outs).cpu().numpy()
     nr, nc = h_fit // 256 - 1, w_fit // 256 - 1
     ref_map = orc.stitch_map(logits, nr, nc, T, 256)

@@ -197,3 +197,26 @@ def test_bench_cli_contract_flags():
     assert out.returncode == 0
     for flag in ("--gpus", "--steps", "--warmup", "--impl"):
         assert flag in out.stdout
+
+
+# ---- inference plan (BN folding) ---------------------------------------------------------------
+
+def test_fused_deeplab_matches_eval_network_on_cpu():
+    from pylc_b200.models.deeplab import DeepLab
+    from pylc_b200.models.fused import FusedDeepLab
+    torch.manual_seed(0)
+    net = DeepLab(n_classes=9).eval()
+    g = torch.Generator().manual_seed(1)
+    for m in net.modules():                      # non-trivial running statistics and affine terms
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+    x = torch.randn(1, 3, 128, 128, generator=g)
+    with torch.no_grad():
+        want = net(x)
+    got = FusedDeepLab(net, channels_last=False)(x)
+    assert got.shape == want.shape and got.is_contiguous()
+    scale = want.abs().max().item()
+    assert (got - want).abs().max().item() <= 2e-4 * scale
