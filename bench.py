@@ -284,6 +284,7 @@ def run_ours(args, rank, world, local_rank):
         clocks.start()
         launches0 = _lib.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.profiler.start()     # no-op unless run under `ncu --profile-from-start off` (tools/gpu_profile.sh)
         ev0.record()
         for _ in range(args.steps):
             seg.reset()
@@ -291,6 +292,7 @@ def run_ours(args, rank, world, local_rank):
             conf_dev = pdist.all_reduce_(seg.conf.clone()) if world > 1 else seg.conf
         ev1.record()
         barrier_sync()
+        torch.cuda.profiler.stop()
         st.on = False
         launches = _lib.launch_count() - launches0
         ms = pdist.max_over_ranks(ev0.elapsed_time(ev1)) / args.steps

@@ -46,7 +46,8 @@ class _Conv(object):
         self.stride, self.padding, self.dilation, self.relu = conv.stride, conv.padding, conv.dilation, relu
 
     def to(self, dtype):
-        self.w, self.b = self.w.to(dtype), self.b.to(dtype)
+        self.w = self.w.to(dtype)
+        self.b = self.b.to(dtype) if self.b is not None else None
         return self
 
     def __call__(self, x, residual=None):
@@ -79,8 +80,15 @@ class FusedDeepLab(object):
         for layer in (bb.layer1, bb.layer2, bb.layer3, bb.layer4):
             stage = []
             for blk in layer:
-                down = mk(blk.downsample[0], blk.downsample[1], False) if blk.downsample is not None else None
-                stage.append((mk(blk.conv1, blk.bn1, True), mk(blk.conv2, blk.bn2, True), mk(blk.conv3, blk.bn3, True), down))
+                c3 = mk(blk.conv3, blk.bn3, True)
+                down = None
+                if blk.downsample is not None:
+                    # the projection's bias moves into conv3's (the two are summed before the ReLU), so
+                    # the projection runs as a bias-free convolution with no separate add kernel
+                    down = mk(blk.downsample[0], blk.downsample[1], False)
+                    c3.b = (c3.b + down.b).contiguous()
+                    down.b = None
+                stage.append((mk(blk.conv1, blk.bn1, True), mk(blk.conv2, blk.bn2, True), c3, down))
             self.blocks.append(stage)
         a = net.aspp
         self.aspp = [mk(m.atrous_conv, m.bn, True) for m in (a.aspp1, a.aspp2, a.aspp3, a.aspp4)]

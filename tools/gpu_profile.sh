@@ -4,8 +4,9 @@
 set -u
 R=${1:-r1}
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_$R.csv \
-    python bench.py --steps 1 --warmup 1 --images 2 --no-cpu-baseline > gpurun_out/bench_under_ncu_$R.log 2>&1
+# launch list of the TIMED region only (bench.py brackets it with cudaProfilerStart/Stop)
+ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 4000 --csv \
+    --log-file gpurun_out/launches_$R.csv python bench.py --steps 1 --warmup 2 --images 4 --no-cpu-baseline > gpurun_out/bench_under_ncu_$R.log 2>&1
 tail -3 gpurun_out/bench_under_ncu_$R.log
 wc -l gpurun_out/launches_$R.csv
 cap() {  # name, kernel regex, kbench --only filter, launches to keep (after 3 warm-up launches each)
