@@ -45,6 +45,16 @@ __device__ __forceinline__ uint32_t encode_key(uint32_t key, const uint32_t *tab
     return ((e ^ key) & 0x00FFFFFFu) ? 1u : (e >> 24);
 }
 
+// Table entry of a colour with the class byte replaced by `miss_e`'s when the colour is not in the
+// palette; four entries' class bytes pack into one word with three PRMTs.
+__device__ __forceinline__ uint32_t lookup_entry(uint32_t key, const uint32_t *tab, uint32_t mul, uint32_t miss_e) {
+    const uint32_t e = tab[__byte_perm(key * mul, 0, 0x4442)];
+    return ((e ^ key) & 0x00FFFFFFu) ? miss_e : e;
+}
+__device__ __forceinline__ uint32_t pack_top_bytes(uint32_t e0, uint32_t e1, uint32_t e2, uint32_t e3) {
+    return __byte_perm(__byte_perm(e0, e1, 0x0073), __byte_perm(e2, e3, 0x0073), 0x5410);
+}
+
 // Streaming 16-byte load (read once: bypass L1 allocation).
 __device__ __forceinline__ uint4 ld_stream16(const void *p) {
     uint4 r;

@@ -2,10 +2,13 @@
 // ground-truth palette encode, coverage injection and the confusion matrix in one pass
 // (utils/tools.py:316-317, utils/evaluate.py:87-119,150-176, utils/metrics.py:45-87).
 //
-// Confusion counting: each thread walks 16 consecutive pixels and run-length encodes the
-// (truth, prediction) pair, so spatially coherent masks issue roughly one shared-memory atomic per
-// run instead of one per pixel.  Every warp owns a private C x C table in shared memory; tables are
-// summed and flushed to the i64 global matrix once per CTA.
+// Confusion counting (C <= 15, the shipped schemas have 9 and 11 classes): every (truth, prediction)
+// pair is a byte code t*C + p, and every LANE owns a private column of 16-bit counters in shared
+// memory -- tab[warp][code][lane] -- so a pixel costs one conflict-free load / add / store and no
+// atomic at all (shared-memory atomics retire at ~2 cycles per lane on this part, which made the
+// earlier run-length + ATOMS scheme LSU-bound).  The cost is independent of how coherent the label
+// maps are.  Columns are summed and flushed to the i64 global matrix once per CTA.
+// C > 15 keeps per-warp u32 tables with run-length compressed shared atomics.
 #include "common.cuh"
 
 namespace pylc {
@@ -39,6 +42,7 @@ __device__ __forceinline__ void flush_tables(unsigned *s_conf, int CC, long long
 
 constexpr int kRsThreads = 64;  // resample CTA: 2 warps, one 1024-pixel column block of the full-res image
 constexpr int kRsWarps = kRsThreads / 32;
+constexpr int kRsMaxRows = 2048;  // rows per CTA: keeps every 16-bit lane counter below 2048 * 16
 
 struct ResampleArgs {
     const uint8_t *labels;
@@ -46,92 +50,58 @@ struct ResampleArgs {
     const uint8_t *gt_rgb;
     size_t gt_pitch;
     int h, w, h_full, w_full, C, n_inject;
-    int col_blocks, row_slots, rows_per_slot, replicas;
+    int col_blocks, rows_per_slot;
     long long *conf;
     uint8_t *pred_full, *pred_rgb, *gt_full;
     bool gt_aligned, out_aligned, rgb_aligned, labels_vec;
 };
 
-// 16 bytes starting at byte offset `start` of an 8-byte-aligned buffer of `total` bytes
-// (total % 8 == 0), as four little-endian words.  Three aligned 8-byte loads + funnel shifts.
-__device__ __forceinline__ void load_window16(const uint8_t *buf, size_t start, size_t total, uint32_t (&x)[4]) {
-    const size_t a8 = start & ~(size_t)7;
-    const unsigned r = (unsigned)(start & 7);
-    uint2 q[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-        q[k] = (a8 + 8 * k < total) ? __ldg(reinterpret_cast<const uint2 *>(buf + a8 + 8 * k)) : make_uint2(0u, 0u);
-    const uint32_t w[6] = {q[0].x, q[0].y, q[1].x, q[1].y, q[2].x, q[2].y};
-    const bool up = (r & 4) != 0;
-    const unsigned sh = (r & 3) * 8;
-    uint32_t v[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) v[i] = up ? w[i + 1] : w[i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) x[i] = __funnelshift_r(v[i], v[i + 1], sh);
-}
-
-// word i (0..3, dynamic) of a 4-word window; i + 1 == 4 yields 0 (never selected, see ColMap)
-__device__ __forceinline__ uint32_t pick_word(const uint32_t (&x)[4], uint32_t i) {
-    const uint32_t lo = (i & 1) ? x[1] : x[0];
-    const uint32_t hi = (i & 1) ? x[3] : x[2];
-    return (i & 4) ? 0u : ((i & 2) ? hi : lo);
-}
-
-// byte d (0..15, dynamic) of 16 bytes held in four words
-__device__ __forceinline__ uint32_t pick_byte(const uint32_t (&x)[4], uint32_t d) {
-    return __byte_perm(pick_word(x, d >> 2), 0, 0x4440u | (d & 3));
-}
-
-// Row-invariant nearest-neighbour column map of a thread's 16 destination pixels: source offsets
-// d_j = x_ofs[X+j] - x_ofs[X].  When they rise by 0 or 1 per pixel (any up-sampling map) the four
-// source bytes of destination word k lie inside the 8-byte pair starting at word d_4k / 4 of a
-// 16-byte window, so one PRMT with a precomputed selector gathers them.
+// Row-invariant nearest-neighbour column map of a thread's 16 destination pixels.  Destination
+// word k (4 pixels) reads source bytes x_ofs[X+4k .. X+4k+3]; when they all lie inside the two
+// aligned source words starting at lo[k] one PRMT with a precomputed selector gathers them -- true
+// for every up-sampling map and for down-sampling by less than 2.
 struct ColMap {
-    int base;
-    uint32_t sel[4];   // PRMT selector per destination word
-    uint32_t wsel;     // 4 x 2 bits: first window word per destination word
+    uint32_t lo[4], hi[4];  // byte offsets (multiples of 4) of the two source words inside a label row
+    uint32_t sel[4];        // PRMT selector per destination word
     bool fast;
 };
 
-// Counts (truth, prediction) pairs of one thread-row.  `idxw` holds the 16 pair codes t*C + p as
-// bytes.  Runs of equal codes are peeled with FFS from a boundary bitmap and added with one shared
-// atomic each; the trip count is the warp maximum of the run counts, so the loop is convergent.
-// Every lane adds into one of `replicas` copies of its warp's table (lane % replicas), which cuts
-// same-address serialisation on the dominant class pair.
-__device__ __forceinline__ void count_runs(const uint32_t (&idxw)[4], uint32_t bounds, int valid, unsigned *tab) {
-    const int n = __popc(bounds);
-    const int rounds = __reduce_max_sync(0xFFFFFFFFu, n);
-    for (int r = 0; r < rounds; ++r) {
-        if (bounds) {
-            const int start = __ffs(bounds) - 1;
-            bounds &= bounds - 1;
-            const int end = bounds ? __ffs(bounds) - 1 : valid;
-            atomicAdd(&tab[pick_byte(idxw, (uint32_t)start)], (unsigned)(end - start));
-        }
-    }
+// one lane-private 16-bit counter += 1 (32-bit shared-window address: one IMAD per pixel)
+__device__ __forceinline__ void bump_u16(uint32_t saddr) {
+    asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%0]; add.u16 t, t, 1; st.shared.u16 [%0], t; }" ::"r"(saddr) : "memory");
 }
-
 // Work decomposition: a CTA owns one column block (kRsThreads x 16 destination pixels) and a
-// contiguous range of rows.  Per row a thread needs three 16-byte ground-truth loads (the HBM
-// stream) and a 24-byte window of the L2-resident fitted label row; the column map costs nothing
-// per row.  PACKED: C <= 15, pair codes fit a byte (the shipped schemas have 9 and 11 classes).
-template <bool PACKED>
-__global__ void __launch_bounds__(kRsThreads, 16)
+// contiguous range of rows.  Per row a thread streams three 16-byte ground-truth loads (issued one
+// row ahead) and eight 4-byte loads of the L1/L2-resident fitted label row (skipped when the row
+// maps to the same source row as the previous one); the column map costs nothing per row.
+//   MODE 0: C <= 15, pair codes via a pre-multiplied palette table (entry byte = class * C)
+//   MODE 1: C <= 15, encoded ground truth also written out (entry byte = class)
+//   MODE 2: C  > 15, u32 codes, per-warp atomic tables
+template <int MODE>
+__global__ void __launch_bounds__(kRsThreads)
     resample_confusion_kernel(ResampleArgs a, const __grid_constant__ PaletteHash ph, const __grid_constant__ ColourLut lut) {
-    extern __shared__ unsigned s_dyn[];
+    constexpr bool PACKED = MODE != 2;
+    constexpr bool PREMUL = MODE == 0;
+    extern __shared__ __align__(16) unsigned s_dyn[];
     __shared__ uint32_t s_tab[256];
     __shared__ uint32_t s_lut[PYLC_MAX_CLASSES];
     const int CC = a.C * a.C;
-    const int n_tabs = kRsWarps * a.replicas;
-    for (int i = threadIdx.x; i < 256; i += kRsThreads) s_tab[i] = ph.tab[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t scale = PREMUL ? (uint32_t)a.C : 1u;
+    for (int i = threadIdx.x; i < 256; i += kRsThreads) {
+        const uint32_t e = ph.tab[i];
+        s_tab[i] = (e & 0x00FFFFFFu) | (((e >> 24) * scale) << 24);
+    }
+    const uint32_t miss_e = scale << 24;   // unmatched colours are class 1 (utils/tools.py:437)
     if (threadIdx.x < PYLC_MAX_CLASSES) s_lut[threadIdx.x] = lut.rgb[threadIdx.x];
-    for (int i = threadIdx.x; i < CC * n_tabs; i += kRsThreads) s_dyn[i] = 0;
+    const int tab_words = PACKED ? kRsWarps * CC * 16 : kRsWarps * CC;
+    for (int i = threadIdx.x; i < tab_words; i += kRsThreads) s_dyn[i] = 0;
     __syncthreads();
     const uint32_t mul = ph.mul;
-    unsigned *my_tab = s_dyn + ((threadIdx.x >> 5) * a.replicas + (threadIdx.x & 31) % a.replicas) * CC;
     const bool do_conf = a.conf != nullptr && a.gt_rgb != nullptr;
-    PairRun run;   // !PACKED path only
+    const uint32_t my_col = (uint32_t)__cvta_generic_to_shared(s_dyn) + (uint32_t)(warp * CC * 32 + lane) * 2u;   // PACKED
+    unsigned *my_tab = s_dyn + warp * CC;                                                                // !PACKED
+    PairRun run;
     run.reset();
 
     const int cb = blockIdx.x % a.col_blocks;
@@ -142,43 +112,72 @@ __global__ void __launch_bounds__(kRsThreads, 16)
     const bool full = valid == 16;
 
     ColMap cm;
-    cm.base = 0;
-    cm.wsel = 0;
     cm.fast = a.labels_vec && active;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) cm.sel[k] = 0;
+    for (int k = 0; k < 4; ++k) cm.lo[k] = cm.hi[k] = cm.sel[k] = 0;
     if (active) {
-        cm.base = __ldg(a.x_ofs + X);
-        int prev = 0;
+        int prev = __ldg(a.x_ofs + X);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            int first = 0;
+            int word0 = 0;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 const int j = 4 * k + jj;
-                const int d = j < valid ? __ldg(a.x_ofs + X + j) - cm.base : prev;
-                cm.fast = cm.fast && d >= prev && d <= prev + 1;
-                prev = d;
-                if (jj == 0) first = d >> 2;
-                cm.sel[k] |= (uint32_t)((d - 4 * first) & 7) << (4 * jj);
+                const int sx = j < valid ? __ldg(a.x_ofs + X + j) : prev;
+                prev = sx;
+                if (jj == 0) word0 = sx & ~3;
+                const int d = sx - word0;
+                cm.fast = cm.fast && d >= 0 && d <= 7;
+                cm.sel[k] |= (uint32_t)(d & 7) << (4 * jj);
             }
-            cm.wsel |= (uint32_t)(first & 3) << (2 * k);
+            cm.lo[k] = (uint32_t)word0;
+            cm.hi[k] = (uint32_t)min(word0 + 4, a.w - 4);   // never selected when clamped (source x < w)
         }
     }
-    const size_t label_bytes = (size_t)a.h * a.w;
     const int y_lo = slot * a.rows_per_slot, y_hi = min(a.h_full, y_lo + a.rows_per_slot);
+    const bool gt_vec = a.gt_rgb != nullptr && a.gt_aligned && active && (size_t)X * 3 + 48 <= a.gt_pitch;
+
+    uint4 q0 = make_uint4(0u, 0u, 0u, 0u), q1 = q0, q2 = q0;
+    if (gt_vec && y_lo < y_hi) {
+        const uint8_t *p = a.gt_rgb + (size_t)y_lo * a.gt_pitch + (size_t)X * 3;
+        q0 = ld_stream16(p);
+        q1 = ld_stream16(p + 16);
+        q2 = ld_stream16(p + 32);
+    }
+    uint32_t pw[4] = {0u, 0u, 0u, 0u};    // predicted labels, 4 per word (kept while the source row repeats)
+    int prev_sy = -1;
 
     for (int Y = y_lo; Y < y_hi; ++Y) {
-        uint32_t pw[4] = {0u, 0u, 0u, 0u};    // predicted labels, 4 per word
-        uint32_t gw[4] = {0u, 0u, 0u, 0u};    // encoded ground truth, 4 per word
+        uint32_t gw[4] = {0u, 0u, 0u, 0u};    // encoded ground truth (x C when PREMUL), 4 per word
+        uint4 n0 = q0, n1 = q1, n2 = q2;
+        if (gt_vec && Y + 1 < y_hi) {          // next row's ground truth: the HBM stream, one row ahead
+            const uint8_t *p = a.gt_rgb + (size_t)(Y + 1) * a.gt_pitch + (size_t)X * 3;
+            n0 = ld_stream16(p);
+            n1 = ld_stream16(p + 16);
+            n2 = ld_stream16(p + 32);
+        }
         if (active) {
-            // ground truth first: these are the HBM-streaming loads
-            uint32_t key[16];
+            // prediction: nearest-neighbour gather from the fitted label map
+            const int sy = __ldg(a.y_ofs + Y);
+            if (sy != prev_sy) {
+                prev_sy = sy;
+                const uint8_t *lrow = a.labels + (size_t)sy * a.w;
+                if (cm.fast) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        pw[k] = __byte_perm(__ldg(reinterpret_cast<const uint32_t *>(lrow + cm.lo[k])),
+                                            __ldg(reinterpret_cast<const uint32_t *>(lrow + cm.hi[k])), cm.sel[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) pw[k] = 0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < valid) pw[j >> 2] |= (uint32_t)__ldg(lrow + __ldg(a.x_ofs + X + j)) << (8 * (j & 3));
+                }
+            }
             if (a.gt_rgb) {
-                const uint8_t *p = a.gt_rgb + (size_t)Y * a.gt_pitch + (size_t)X * 3;
-                if (a.gt_aligned && (size_t)X * 3 + 48 <= a.gt_pitch) {
-                    const uint4 q0 = __ldg((const uint4 *)p), q1 = __ldg((const uint4 *)(p + 16)),
-                                q2 = __ldg((const uint4 *)(p + 32));
+                uint32_t key[16];
+                if (gt_vec) {
                     const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -188,46 +187,33 @@ __global__ void __launch_bounds__(kRsThreads, 16)
                         key[4 * k + 3] = w[3 * k + 2] >> 8;
                     }
                 } else {
+                    const uint8_t *p = a.gt_rgb + (size_t)Y * a.gt_pitch + (size_t)X * 3;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         key[j] = 0;
                         if (j < valid) key[j] = __ldg(p + 3 * j) | (__ldg(p + 3 * j + 1) << 8) | (__ldg(p + 3 * j + 2) << 16);
                     }
                 }
-            }
-            // prediction: nearest-neighbour gather from the fitted label map
-            const size_t row_off = (size_t)__ldg(a.y_ofs + Y) * a.w;
-            if (cm.fast) {
-                uint32_t x[4];
-                load_window16(a.labels, row_off + cm.base, label_bytes, x);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t i = (cm.wsel >> (2 * k)) & 3u;
-                    pw[k] = __byte_perm(pick_word(x, i), pick_word(x, i + 1), cm.sel[k]);
-                }
-            } else {
-                const uint8_t *lrow = a.labels + row_off;
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (j < valid) pw[j >> 2] |= (uint32_t)__ldg(lrow + __ldg(a.x_ofs + X + j)) << (8 * (j & 3));
-            }
-            if (a.gt_rgb) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    gw[k] = encode_key(key[4 * k], s_tab, mul) | (encode_key(key[4 * k + 1], s_tab, mul) << 8) |
-                            (encode_key(key[4 * k + 2], s_tab, mul) << 16) | (encode_key(key[4 * k + 3], s_tab, mul) << 24);
+                    gw[k] = pack_top_bytes(lookup_entry(key[4 * k], s_tab, mul, miss_e), lookup_entry(key[4 * k + 1], s_tab, mul, miss_e),
+                                           lookup_entry(key[4 * k + 2], s_tab, mul, miss_e), lookup_entry(key[4 * k + 3], s_tab, mul, miss_e));
             }
         }
 
-        if (do_conf) {
+        if (do_conf && active) {
             if (PACKED) {
-                // pair codes t*C + p for four pixels at a time (two 16-bit lanes per multiply)
+                // pair codes t*C + p, four per word (no carries: every code is < 256)
                 uint32_t idxw[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t even = (gw[k] & 0x00FF00FFu) * (uint32_t)a.C + (pw[k] & 0x00FF00FFu);
-                    const uint32_t odd = ((gw[k] >> 8) & 0x00FF00FFu) * (uint32_t)a.C + ((pw[k] >> 8) & 0x00FF00FFu);
-                    idxw[k] = even | (odd << 8);
+                    if (PREMUL) {
+                        idxw[k] = gw[k] + pw[k];
+                    } else {
+                        const uint32_t even = (gw[k] & 0x00FF00FFu) * (uint32_t)a.C + (pw[k] & 0x00FF00FFu);
+                        const uint32_t odd = ((gw[k] >> 8) & 0x00FF00FFu) * (uint32_t)a.C + ((pw[k] >> 8) & 0x00FF00FFu);
+                        idxw[k] = even | (odd << 8);
+                    }
                 }
                 // coverage injection (utils/evaluate.py:172-174): the first n_inject flat pixels count as
                 // (i, i).  Only the counts see it -- the label / RGB outputs stay the plain resample.
@@ -239,18 +225,15 @@ __global__ void __launch_bounds__(kRsThreads, 16)
                             idxw[j >> 2] = (idxw[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | (code << (8 * (j & 3)));
                         }
                 }
-                // run boundaries: byte j differs from byte j-1
-                uint32_t bounds = 0;
+                if (full) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t prevw = k == 0 ? (idxw[0] << 8) | (~idxw[0] & 0xFFu)   // byte 0 always opens a run
-                                                  : __funnelshift_l(idxw[k - 1], idxw[k], 8);
-                    const uint32_t ne = __vcmpne4(idxw[k], prevw);                       // 0xFF per differing byte
-                    bounds |= ((ne & 1u) | ((ne >> 7) & 2u) | ((ne >> 14) & 4u) | ((ne >> 21) & 8u)) << (4 * k);
+                    for (int j = 0; j < 16; ++j) bump_u16(my_col + __byte_perm(idxw[j >> 2], 0, 0x4440u | (j & 3)) * 64u);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < valid) bump_u16(my_col + __byte_perm(idxw[j >> 2], 0, 0x4440u | (j & 3)) * 64u);
                 }
-                bounds &= valid >= 16 ? 0xFFFFu : ((1u << valid) - 1u);
-                count_runs(idxw, bounds, valid, my_tab);
-            } else if (active) {
+            } else {
                 const long long flat0 = (long long)Y * a.w_full + X;
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
@@ -261,6 +244,9 @@ __global__ void __launch_bounds__(kRsThreads, 16)
                     }
             }
         }
+        q0 = n0;
+        q1 = n1;
+        q2 = n2;
 
         if (!active) continue;
         const size_t o = (size_t)Y * a.w_full + X;
@@ -273,7 +259,7 @@ __global__ void __launch_bounds__(kRsThreads, 16)
                     if (j < valid) a.pred_full[o + j] = (uint8_t)(pw[j >> 2] >> (8 * (j & 3)));
             }
         }
-        if (a.gt_full && a.gt_rgb) {
+        if (!PREMUL && a.gt_full && a.gt_rgb) {
             if (full && a.out_aligned) {
                 st_stream16(a.gt_full + o, make_uint4(gw[0], gw[1], gw[2], gw[3]));
             } else {
@@ -314,7 +300,20 @@ __global__ void __launch_bounds__(kRsThreads, 16)
         __syncthreads();
         for (int i = threadIdx.x; i < CC; i += kRsThreads) {
             unsigned long long t = 0;
-            for (int w = 0; w < n_tabs; ++w) t += s_dyn[w * CC + i];
+            if (PACKED) {
+#pragma unroll
+                for (int w = 0; w < kRsWarps; ++w) {
+                    const unsigned *col = s_dyn + (size_t)(w * CC + i) * 16;   // 32 u16 lane counters of code i
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const unsigned v = col[(k + i) & 15];                   // rotated: spreads the banks
+                        t += (v & 0xFFFFu) + (v >> 16);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int w = 0; w < kRsWarps; ++w) t += s_dyn[w * CC + i];
+            }
             if (t) atomicAdd((unsigned long long *)&a.conf[i], t);
         }
     }
@@ -403,25 +402,36 @@ extern "C" int pylc_resample_encode_confusion(const uint8_t *labels, int h, int 
     a.h = h; a.w = w; a.h_full = h_full; a.w_full = w_full; a.C = C; a.n_inject = n_inject;
     const int groups_per_row = (w_full + 15) / 16;
     a.col_blocks = (groups_per_row + kRsThreads - 1) / kRsThreads;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int slots = sms * 16 / a.col_blocks;                       // ~16 resident CTAs per SM
-    if (slots > (h_full + 1) / 2) slots = (h_full + 1) / 2;    // at least two rows per CTA amortise the column map
-    if (slots < 1) slots = 1;
-    a.rows_per_slot = (h_full + slots - 1) / slots;
-    a.row_slots = (h_full + a.rows_per_slot - 1) / a.rows_per_slot;
-    a.replicas = C <= 11 ? 8 : (C <= 15 ? 4 : 1);
     a.conf = reinterpret_cast<long long *>(conf);
     a.pred_full = pred_full; a.pred_rgb = pred_rgb; a.gt_full = gt_full;
     a.gt_aligned = gt_rgb && ((uintptr_t)gt_rgb % 16 == 0) && (gt_pitch % 16 == 0);
     a.out_aligned = (w_full % 16 == 0) && ((uintptr_t)pred_full % 16 == 0) && ((uintptr_t)gt_full % 16 == 0);
     a.rgb_aligned = (w_full % 16 == 0) && ((uintptr_t)pred_rgb % 16 == 0);
-    a.labels_vec = ((uintptr_t)labels % 8 == 0) && (((size_t)h * w) % 8 == 0);
-    const size_t smem = (size_t)C * C * kRsWarps * a.replicas * sizeof(unsigned);
-    const unsigned grid = (unsigned)(a.col_blocks * a.row_slots);
-    if (C <= 15) resample_confusion_kernel<true><<<grid, kRsThreads, smem, (cudaStream_t)stream>>>(a, ph, lut);
-    else resample_confusion_kernel<false><<<grid, kRsThreads, smem, (cudaStream_t)stream>>>(a, ph, lut);
+    a.labels_vec = ((uintptr_t)labels % 4 == 0) && (w % 4 == 0) && w >= 4;
+    const int mode = C > 15 ? 2 : (gt_full ? 1 : 0);
+    const size_t smem = mode == 2 ? (size_t)C * C * kRsWarps * sizeof(unsigned)
+                                  : (size_t)C * C * kRsWarps * 32 * sizeof(unsigned short);
+    // persistent-style grid: one wave of as many CTAs as fit (shared memory decides), each with a
+    // contiguous row range of its column block
+    int dev = 0, sms = 148, per_sm = 8;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t oe = cudaSuccess;
+    if (mode == 0) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resample_confusion_kernel<0>, kRsThreads, smem);
+    else if (mode == 1) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resample_confusion_kernel<1>, kRsThreads, smem);
+    else oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resample_confusion_kernel<2>, kRsThreads, smem);
+    if (oe != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 4; }
+    if (per_sm > 16) per_sm = 16;
+    int slots = sms * per_sm / a.col_blocks;
+    if (slots > (h_full + 1) / 2) slots = (h_full + 1) / 2;    // at least two rows per CTA amortise the column map
+    if (slots < 1) slots = 1;
+    a.rows_per_slot = (h_full + slots - 1) / slots;
+    if (a.rows_per_slot > kRsMaxRows) a.rows_per_slot = kRsMaxRows;   // 16-bit lane counters
+    const int row_slots = (h_full + a.rows_per_slot - 1) / a.rows_per_slot;
+    const unsigned grid = (unsigned)(a.col_blocks * row_slots);
+    if (mode == 0) resample_confusion_kernel<0><<<grid, kRsThreads, smem, (cudaStream_t)stream>>>(a, ph, lut);
+    else if (mode == 1) resample_confusion_kernel<1><<<grid, kRsThreads, smem, (cudaStream_t)stream>>>(a, ph, lut);
+    else resample_confusion_kernel<2><<<grid, kRsThreads, smem, (cudaStream_t)stream>>>(a, ph, lut);
     return finish_launch();
 }
 

@@ -94,6 +94,63 @@ __device__ __forceinline__ void load_unit(const GatherGeom &g, const Item &it, i
     }
 }
 
+// Per-thread cursor over the slabs of one S-block (T/S <= 2, i.e. at most four destination tiles):
+// the source unit pointer and the destination unit pointers are computed when the block changes and
+// advanced by constant strides from slab to slab, so the steady-state loop carries no multiplies.
+struct BlockCursor {
+    const uint8_t *src;
+    uint8_t *dst[4];
+    int n;
+};
+template <int CH>
+__device__ __forceinline__ const uint8_t *unit_src(const GatherGeom &g, const Item &it, int row, int grp) {
+    const int y = it.by * g.S + it.slab * g.rows_item + row;
+    const int x = it.bx * g.S + grp * 16;
+    return g.src + (size_t)y * g.pitch + (size_t)x * CH;
+}
+template <int CH>
+__device__ __forceinline__ void cursor_set(const GatherGeom &g, const Item &it, int row, int grp, uint8_t *dst, size_t tile_bytes,
+                                           BlockCursor &c) {
+    c.src = unit_src<CH>(g, it, row, grp);
+    const TileSpan ts = tile_span(g, it.by, it.bx);
+    const int ly = it.slab * g.rows_item + row, lx = grp * 16;
+    c.n = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c.dst[i] = dst;
+#pragma unroll
+    for (int dr = 0; dr < 2; ++dr)
+#pragma unroll
+        for (int dc = 0; dc < 2; ++dc) {
+            const int r = ts.r_lo + dr, cc = ts.c_lo + dc;
+            if (r <= ts.r_hi && cc <= ts.c_hi) {
+                uint8_t *d = dst + (size_t)(r * g.nW + cc) * tile_bytes + (size_t)((it.by - r) * g.S + ly) * g.T +
+                             (size_t)((it.bx - cc) * g.S + lx);
+                // compact into slots 0..n-1 without dynamic register indexing
+                if (c.n == 0) c.dst[0] = d;
+                else if (c.n == 1) c.dst[1] = d;
+                else if (c.n == 2) c.dst[2] = d;
+                else c.dst[3] = d;
+                ++c.n;
+            }
+        }
+}
+template <int CH>
+__device__ __forceinline__ void load_ptr(const uint8_t *p, bool aligned, SrcUnit<CH> &u) {
+    if (aligned) {
+        u.q[0] = ld_stream16(p);
+        if (CH == 3) {
+            u.q[CH == 3 ? 1 : 0] = ld_stream16(p + 16);
+            u.q[CH == 3 ? 2 : 0] = ld_stream16(p + 32);
+        }
+    } else {
+        u.q[0] = ld_bytes16(p);
+        if (CH == 3) {
+            u.q[CH == 3 ? 1 : 0] = ld_bytes16(p + 16);
+            u.q[CH == 3 ? 2 : 0] = ld_bytes16(p + 32);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // image gather: u8 -> u8 tiles (+ sum, sum of squares per destination tile and channel)
 // ------------------------------------------------------------------------------------------------
@@ -295,6 +352,107 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// T/S <= 2 version (the reference's two strides: S = T on extraction, S = T/2 on the test path):
+// BlockCursor addressing, warp-private histogram flushes (no CTA barrier anywhere in the loop, so
+// the eight warps of a CTA drift apart and hide each other's load latency).
+template <bool WIDE>
+__device__ __forceinline__ void flush_warp_hist(const GatherGeom &g, int blk, ClassCounter<WIDE> &cc, int C, long long *px_dist) {
+    const int lane = threadIdx.x & 31;
+    unsigned mine = 0;
+    for (int c = 0; c < C; ++c) {
+        const unsigned v = __reduce_add_sync(0xFFFFFFFFu, cc.count(c));
+        if (lane == c) mine = v;
+    }
+    cc.reset();
+    if (lane < C && mine) {
+        const int bx = blk % g.nbx, by = blk / g.nbx;
+        const TileSpan ts = tile_span(g, by, bx);
+        for (int r = ts.r_lo; r <= ts.r_hi; ++r)
+            for (int c = ts.c_lo; c <= ts.c_hi; ++c)
+                atomicAdd((unsigned long long *)&px_dist[(size_t)(r * g.nW + c) * C + lane], (unsigned long long)mine);
+    }
+}
+
+template <bool ALIGNED, bool WIDE, bool HIST>
+__global__ void __launch_bounds__(kThreads)
+    gather_mask_cursor_kernel(GatherGeom g, const __grid_constant__ PaletteHash ph, int C, uint8_t *__restrict__ dst,
+                              long long *__restrict__ px_dist) {
+    __shared__ uint32_t s_tab[256];
+    s_tab[threadIdx.x] = ph.tab[threadIdx.x];
+    __syncthreads();
+    const uint32_t mul = ph.mul;
+    const uint32_t miss_e = 1u << 24;   // unmatched colours are class 1 (utils/tools.py:437)
+    int first, last;
+    cta_item_range(g.items, first, last);
+    if (first >= last) return;
+    const int row = threadIdx.x / g.gpr, grp = threadIdx.x - row * g.gpr;
+    const bool on = row < g.rows_item;
+    const size_t TT = (size_t)g.T * g.T;
+    const size_t sstep = (size_t)g.rows_item * g.pitch;
+    const int dstep = g.rows_item * g.T;
+
+    ClassCounter<WIDE> cc;
+    cc.reset();
+    int since_flush = 0;
+    Item it = decode_item(g, first);
+    BlockCursor cur;
+    cursor_set<3>(g, it, row, grp, dst, TT, cur);
+    SrcUnit<3> q, nq;
+    if (on) load_ptr<3>(cur.src, ALIGNED, q);
+    for (int item = first; item < last; ++item) {
+        Item it_n = it;
+        const uint8_t *nsrc = cur.src;
+        bool chg = false;
+        if (item + 1 < last) {
+            it_n = next_item(g, it);
+            chg = it_n.blk != it.blk;
+            nsrc = chg ? unit_src<3>(g, it_n, row, grp) : cur.src + sstep;
+            if (on) load_ptr<3>(nsrc, ALIGNED, nq);
+        }
+        if (on) {
+            const uint32_t w[12] = {q.q[0].x, q.q[0].y, q.q[0].z, q.q[0].w, q.q[1].x, q.q[1].y,
+                                    q.q[1].z, q.q[1].w, q.q[2].x, q.q[2].y, q.q[2].z, q.q[2].w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t a = w[3 * k], b = w[3 * k + 1], c = w[3 * k + 2];
+                const uint32_t e0 = lookup_entry(a, s_tab, mul, miss_e);
+                const uint32_t e1 = lookup_entry(__funnelshift_r(a, b, 24), s_tab, mul, miss_e);
+                const uint32_t e2 = lookup_entry(__funnelshift_r(b, c, 16), s_tab, mul, miss_e);
+                const uint32_t e3 = lookup_entry(c >> 8, s_tab, mul, miss_e);
+                if (HIST) {
+                    cc.add(e0 >> 24);
+                    cc.add(e1 >> 24);
+                    cc.add(e2 >> 24);
+                    cc.add(e3 >> 24);
+                }
+                ow[k] = pack_top_bytes(e0, e1, e2, e3);
+            }
+            if (HIST) cc.end_unit();
+            const uint4 o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            st_stream16(cur.dst[0], o);
+            if (cur.n > 1) st_stream16(cur.dst[1], o);
+            if (cur.n > 2) st_stream16(cur.dst[2], o);
+            if (cur.n > 3) st_stream16(cur.dst[3], o);
+        }
+        // histograms are per destination tile: flush when the block changes, or before the packed
+        // per-thread fields could overflow (63 units of 5/10-bit fields, 15 units of 8-bit fields)
+        if (HIST && (chg || item + 1 == last || ++since_flush >= (WIDE ? 15 : 63))) {
+            flush_warp_hist<WIDE>(g, it.blk, cc, C, px_dist);
+            since_flush = 0;
+        }
+        if (chg) {
+            cursor_set<3>(g, it_n, row, grp, dst, TT, cur);
+        } else {
+            cur.src = nsrc;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cur.dst[i] += dstep;
+        }
+        it = it_n;
+        q = nq;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // normalising gather: u8 source -> network-ready f32 tiles (models/model.py:416-445, 376-377)
 // ------------------------------------------------------------------------------------------------
@@ -472,9 +630,19 @@ extern "C" int pylc_mask_gather_encode_hist(const uint8_t *src, int H, int W, si
 #define LAUNCH(AL, WD, HS)                                                                                         \
     gather_mask_kernel<AL, WD, HS><<<persistent_ctas(gather_mask_kernel<AL, WD, HS>, g.items), kThreads, 0, st>>>( \
         g, ph, C, dst, pd)
-    if (!px_dist) { if (al) LAUNCH(true, false, false); else LAUNCH(false, false, false); }
-    else if (C <= 12) { if (al) LAUNCH(true, false, true); else LAUNCH(false, false, true); }
-    else { if (al) LAUNCH(true, true, true); else LAUNCH(false, true, true); }
+#define LAUNCH_CUR(AL, WD, HS)                                                                          \
+    gather_mask_cursor_kernel<AL, WD, HS>                                                              \
+        <<<persistent_ctas(gather_mask_cursor_kernel<AL, WD, HS>, g.items), kThreads, 0, st>>>(g, ph, C, dst, pd)
+    if (g.m <= 2) {
+        if (!px_dist) { if (al) LAUNCH_CUR(true, false, false); else LAUNCH_CUR(false, false, false); }
+        else if (C <= 12) { if (al) LAUNCH_CUR(true, false, true); else LAUNCH_CUR(false, false, true); }
+        else { if (al) LAUNCH_CUR(true, true, true); else LAUNCH_CUR(false, true, true); }
+    } else {
+        if (!px_dist) { if (al) LAUNCH(true, false, false); else LAUNCH(false, false, false); }
+        else if (C <= 12) { if (al) LAUNCH(true, false, true); else LAUNCH(false, false, true); }
+        else { if (al) LAUNCH(true, true, true); else LAUNCH(false, true, true); }
+    }
+#undef LAUNCH_CUR
 #undef LAUNCH
     return finish_launch();
 }

@@ -315,6 +315,55 @@ def test_resample_encode_confusion(ops, palettes, pk, h, w, h_full, w_full):
     assert np.array_equal(ops.confusion_u8(dev(a), dev(b), C).cpu().numpy(), orc.confusion_counts(a, b, C))
 
 
+@pytest.mark.parametrize("C,h,w,h_full,w_full,pitched", [
+    (9, 1536, 2560, 2000, 3000, True),      # the bench geometry, counts only (pre-multiplied pair codes)
+    (11, 256, 512, 301, 777, False),        # ragged width, unpitched ground truth (byte-wise loads)
+    (15, 64, 160, 50, 100, True),           # down-sampling by < 2: still the PRMT gather
+    (9, 300, 400, 100, 130, True),          # down-sampling by ~3: per-pixel gather
+    (9, 97, 131, 120, 150, True),           # label row pitch not a multiple of 4: per-pixel gather
+    (20, 128, 192, 150, 250, True),         # C > 15: u32 pair codes, per-warp atomic tables
+    (32, 64, 64, 64, 64, False),            # identity maps, maximum class count
+])
+def test_resample_confusion_counts_only(ops, C, h, w, h_full, w_full, pitched):
+    rng = np.random.default_rng(C * 1000 + w)
+    pal = rng.permutation(256 ** 3)[:C]
+    pal = [[int(v) & 255, (int(v) >> 8) & 255, int(v) >> 16] for v in pal]
+    labels = orc.synth_labels(5, w, h, C, block=23)
+    gt = orc.synth_mask(6, w_full, h_full, pal, skew=False, off_palette=0.01)
+    if pitched:
+        d_gt, pitch = ops.upload_image(gt)
+    else:
+        d_gt, pitch = dev(gt), w_full * 3
+    conf = torch.zeros((C, C), dtype=torch.int64, device="cuda")
+    res = ops.resample_encode_confusion(dev(labels), w_full, h_full, gt_rgb=d_gt, gt_pitch=pitch, palette=pal,
+                                        n_inject=min(C, 9), conf=conf, want_pred=True)
+    pred_full = orc.resample_labels(labels, w_full, h_full)
+    gt_lab = orc.class_encode_hwc(gt, pal)
+    assert np.array_equal(res["pred_full"].cpu().numpy(), pred_full)
+    yt, yp = orc.inject_coverage(gt_lab, pred_full, min(C, 9))
+    assert np.array_equal(conf.cpu().numpy(), orc.confusion_counts(yt, yp, C))
+    # accumulates into the caller's matrix, and the optional ground-truth output does not change the counts
+    res2 = ops.resample_encode_confusion(dev(labels), w_full, h_full, gt_rgb=d_gt, gt_pitch=pitch, palette=pal,
+                                         n_inject=min(C, 9), conf=conf, want_gt=True)
+    assert np.array_equal(res2["gt_full"].cpu().numpy(), gt_lab)
+    assert np.array_equal(conf.cpu().numpy(), 2 * orc.confusion_counts(yt, yp, C))
+
+
+def test_resample_confusion_uniform_tall_image(ops, palettes):
+    """A single (truth, prediction) pair over a tall narrow image: every lane counter of one code
+    column carries the whole count, and ragged 48-px rows take the byte-wise ground-truth loads."""
+    pal = palettes["a"]
+    C = len(pal)
+    h_full, w_full = 9000, 48
+    labels = np.full((4500, 24), 3, dtype=np.uint8)
+    gt = np.empty((h_full, w_full, 3), dtype=np.uint8)
+    gt[:] = np.asarray(pal[5], dtype=np.uint8)
+    res = ops.resample_encode_confusion(dev(labels), w_full, h_full, gt_rgb=dev(gt), gt_pitch=w_full * 3, palette=pal, n_inject=0)
+    ref = np.zeros((C, C), dtype=np.int64)
+    ref[5, 3] = h_full * w_full
+    assert np.array_equal(res["conf"].cpu().numpy(), ref)
+
+
 def test_evaluate_golden(ops, golden, palettes):
     g = golden("evaluate")
     pal = palettes["a"]

@@ -107,6 +107,12 @@ def main():
            "0.75 B in + 12 B out per tile px")
     report("profile_tiles hist 273 tiles", m_out.numel() * 1.0,
            lambda: ops.profile_tiles(None, m_out, C), "1 B per px")
+    # an existing tile database is profiled in ONE launch (utils/profile.py sweeps the whole DB); the
+    # reference's DST.A historic set holds 3574 tiles (pylc_gpu.ipynb cell 9)
+    db_masks = m_out[torch.arange(3574, device="cuda") % m_out.shape[0]].contiguous()
+    report("profile_tiles hist 3574 tiles (DST.A-sized DB)", db_masks.numel() * 1.0,
+           lambda: ops.profile_tiles(None, db_masks, C), "1 B per px")
+    del db_masks
     report("profile_tiles moments 273x3 planes", g3_out.numel() * 1.0,
            lambda: ops.profile_tiles(g3_out, None, C), "1 B per px")
     del g3_out, n_out, g_out
