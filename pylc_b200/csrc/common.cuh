@@ -86,6 +86,22 @@ __device__ __forceinline__ void st_stream_f4(float *p, float4 v) {
                  : "memory");
 }
 
+// Asynchronous 16-byte global -> shared copy (LDGSTS, L2 only).  A thread that later reads only the
+// bytes it copied itself needs no barrier, just cp_async_wait<N>() on its own groups.
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t smem_addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_addr) : "memory");
+    return r;
+}
+
 // 16 bytes from an arbitrarily aligned address (slow path for unpitched sources).
 __device__ __forceinline__ uint4 ld_bytes16(const uint8_t *p) {
     uint32_t w[4];

@@ -42,6 +42,7 @@ __device__ __forceinline__ void flush_tables(unsigned *s_conf, int CC, long long
 
 constexpr int kRsThreads = 64;  // resample CTA: 2 warps, one 1024-pixel column block of the full-res image
 constexpr int kRsWarps = kRsThreads / 32;
+constexpr int kStageBytes = 544;  // staged label window per warp: 33 chunks of 16 B + pad
 constexpr int kRsMaxRows = 2048;  // rows per CTA: keeps every 16-bit lane counter below 2048 * 16
 
 struct ResampleArgs {
@@ -53,7 +54,7 @@ struct ResampleArgs {
     int col_blocks, rows_per_slot;
     long long *conf;
     uint8_t *pred_full, *pred_rgb, *gt_full;
-    bool gt_aligned, out_aligned, rgb_aligned, labels_vec;
+    bool gt_aligned, out_aligned, rgb_aligned, labels_vec, labels_stage;
 };
 
 // Row-invariant nearest-neighbour column map of a thread's 16 destination pixels.  Destination
@@ -67,8 +68,12 @@ struct ColMap {
 };
 
 // one lane-private 16-bit counter += 1 (32-bit shared-window address: one IMAD per pixel)
-__device__ __forceinline__ void bump_u16(uint32_t saddr) {
-    asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%0]; add.u16 t, t, 1; st.shared.u16 [%0], t; }" ::"r"(saddr) : "memory");
+template <bool CTR32>
+__device__ __forceinline__ void bump_counter(uint32_t saddr) {
+    if (CTR32)
+        asm volatile("{ .reg .u32 t; ld.shared.u32 t, [%0]; add.u32 t, t, 1; st.shared.u32 [%0], t; }" ::"r"(saddr) : "memory");
+    else
+        asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%0]; add.u16 t, t, 1; st.shared.u16 [%0], t; }" ::"r"(saddr) : "memory");
 }
 // Work decomposition: a CTA owns one column block (kRsThreads x 16 destination pixels) and a
 // contiguous range of rows.  Per row a thread streams three 16-byte ground-truth loads (issued one
@@ -77,8 +82,11 @@ __device__ __forceinline__ void bump_u16(uint32_t saddr) {
 //   MODE 0: C <= 15, pair codes via a pre-multiplied palette table (entry byte = class * C)
 //   MODE 1: C <= 15, encoded ground truth also written out (entry byte = class)
 //   MODE 2: C  > 15, u32 codes, per-warp atomic tables
-template <int MODE>
-__global__ void __launch_bounds__(kRsThreads)
+// CTR32: 32-bit lane counters (one bank word per lane: conflict-free; C <= 11 keeps the table at
+// <= 31 KB per CTA); otherwise 16-bit counters, two lanes per bank word (2-way conflicts, half the
+// shared memory).
+template <int MODE, bool CTR32>
+__global__ void __launch_bounds__(kRsThreads, 12)
     resample_confusion_kernel(ResampleArgs a, const __grid_constant__ PaletteHash ph, const __grid_constant__ ColourLut lut) {
     constexpr bool PACKED = MODE != 2;
     constexpr bool PREMUL = MODE == 0;
@@ -94,12 +102,14 @@ __global__ void __launch_bounds__(kRsThreads)
     }
     const uint32_t miss_e = scale << 24;   // unmatched colours are class 1 (utils/tools.py:437)
     if (threadIdx.x < PYLC_MAX_CLASSES) s_lut[threadIdx.x] = lut.rgb[threadIdx.x];
-    const int tab_words = PACKED ? kRsWarps * CC * 16 : kRsWarps * CC;
-    for (int i = threadIdx.x; i < tab_words; i += kRsThreads) s_dyn[i] = 0;
+    const int tab_words = PACKED ? kRsWarps * CC * (CTR32 ? 32 : 16) : kRsWarps * CC;
+    for (int i = threadIdx.x; i < tab_words / 4; i += kRsThreads) reinterpret_cast<uint4 *>(s_dyn)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = (tab_words & ~3) + threadIdx.x; i < tab_words; i += kRsThreads) s_dyn[i] = 0;
     __syncthreads();
     const uint32_t mul = ph.mul;
     const bool do_conf = a.conf != nullptr && a.gt_rgb != nullptr;
-    const uint32_t my_col = (uint32_t)__cvta_generic_to_shared(s_dyn) + (uint32_t)(warp * CC * 32 + lane) * 2u;   // PACKED
+    constexpr uint32_t kCtrBytes = CTR32 ? 4u : 2u, kCodeStride = 32u * kCtrBytes;
+    const uint32_t my_col = (uint32_t)__cvta_generic_to_shared(s_dyn) + (uint32_t)(warp * CC * 32 + lane) * kCtrBytes;   // PACKED
     unsigned *my_tab = s_dyn + warp * CC;                                                                // !PACKED
     PairRun run;
     run.reset();
@@ -115,18 +125,28 @@ __global__ void __launch_bounds__(kRsThreads)
     cm.fast = a.labels_vec && active;
 #pragma unroll
     for (int k = 0; k < 4; ++k) cm.lo[k] = cm.hi[k] = cm.sel[k] = 0;
+    int sx_first = 0, sx_last = 0;
     if (active) {
-        int prev = __ldg(a.x_ofs + X);
+        int sxs[16];
+        if (full && ((uintptr_t)a.x_ofs & 15) == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int4 v = __ldg(reinterpret_cast<const int4 *>(a.x_ofs + X) + k);
+                sxs[4 * k] = v.x, sxs[4 * k + 1] = v.y, sxs[4 * k + 2] = v.z, sxs[4 * k + 3] = v.w;
+            }
+        } else {
+            int prev = __ldg(a.x_ofs + X);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) prev = sxs[j] = j < valid ? __ldg(a.x_ofs + X + j) : prev;
+        }
+        sx_first = sxs[0];
+        sx_last = sxs[15];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            int word0 = 0;
+            const int word0 = sxs[4 * k] & ~3;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-                const int j = 4 * k + jj;
-                const int sx = j < valid ? __ldg(a.x_ofs + X + j) : prev;
-                prev = sx;
-                if (jj == 0) word0 = sx & ~3;
-                const int d = sx - word0;
+                const int d = sxs[4 * k + jj] - word0;
                 cm.fast = cm.fast && d >= 0 && d <= 7;
                 cm.sel[k] |= (uint32_t)(d & 7) << (4 * jj);
             }
@@ -134,8 +154,24 @@ __global__ void __launch_bounds__(kRsThreads)
             cm.hi[k] = (uint32_t)min(word0 + 4, a.w - 4);   // never selected when clamped (source x < w)
         }
     }
+    // Warp-staged label rows: when the 512 destination pixels of a warp read a source window of at
+    // most 33 16-byte chunks (any up-sampling map), each lane copies ONE chunk of the label row into
+    // the warp's shared-memory window and every lane gathers its 16 labels from there with
+    // thread-constant offsets -- instead of eight dependent global loads per row.
+    const int wbase = __shfl_sync(0xFFFFFFFFu, sx_first, 0) & ~15;
+    const bool lane_ok = !active || (cm.fast && sx_first >= wbase && sx_last - wbase < kStageBytes - 16);
+    const bool staged = a.labels_stage && __all_sync(0xFFFFFFFFu, lane_ok) && __any_sync(0xFFFFFFFFu, active);
+    if (staged && active) {     // inactive lanes keep offset 0: they still execute the (discarded) gather
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cm.lo[k] -= (uint32_t)wbase;
+    }
+    const size_t label_bytes = (size_t)a.h * a.w;
     const int y_lo = slot * a.rows_per_slot, y_hi = min(a.h_full, y_lo + a.rows_per_slot);
     const bool gt_vec = a.gt_rgb != nullptr && a.gt_aligned && active && (size_t)X * 3 + 48 <= a.gt_pitch;
+
+    __shared__ __align__(16) uint8_t s_stage[kRsWarps][2][kStageBytes];
+    const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(&s_stage[warp][0][0]);
+    int parity = 0;
 
     uint4 q0 = make_uint4(0u, 0u, 0u, 0u), q1 = q0, q2 = q0;
     if (gt_vec && y_lo < y_hi) {
@@ -146,6 +182,18 @@ __global__ void __launch_bounds__(kRsThreads)
     }
     uint32_t pw[4] = {0u, 0u, 0u, 0u};    // predicted labels, 4 per word (kept while the source row repeats)
     int prev_sy = -1;
+    // label-row chunk(s) of the next distinct source row (staged mode), fetched one row ahead
+    uint4 c0 = make_uint4(0u, 0u, 0u, 0u), c1 = c0;
+    auto fetch_chunks = [&](int sy) {
+        const size_t off = (size_t)sy * a.w + (size_t)wbase + 16u * lane;
+        c0 = off + 16 <= label_bytes ? __ldg(reinterpret_cast<const uint4 *>(a.labels + off)) : make_uint4(0u, 0u, 0u, 0u);
+        if (lane == 0) {
+            const size_t off1 = off + 512;
+            c1 = off1 + 16 <= label_bytes ? __ldg(reinterpret_cast<const uint4 *>(a.labels + off1)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+    int sy = y_lo < y_hi ? __ldg(a.y_ofs + y_lo) : 0;
+    if (staged && y_lo < y_hi) fetch_chunks(sy);
 
     for (int Y = y_lo; Y < y_hi; ++Y) {
         uint32_t gw[4] = {0u, 0u, 0u, 0u};    // encoded ground truth (x C when PREMUL), 4 per word
@@ -156,11 +204,29 @@ __global__ void __launch_bounds__(kRsThreads)
             n1 = ld_stream16(p + 16);
             n2 = ld_stream16(p + 32);
         }
+        const int sy_next = Y + 1 < y_hi ? __ldg(a.y_ofs + Y + 1) : sy;
+        const bool reload = sy != prev_sy;
+        prev_sy = sy;
+        if (staged) {
+            if (reload) {
+                const uint32_t buf = stage0 + (uint32_t)parity * kStageBytes;
+                parity ^= 1;
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(buf + 16u * lane), "r"(c0.x), "r"(c0.y), "r"(c0.z), "r"(c0.w) : "memory");
+                if (lane == 0)
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(buf + 512u), "r"(c1.x), "r"(c1.y), "r"(c1.z), "r"(c1.w) : "memory");
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t lo, hi;
+                    asm volatile("ld.shared.u32 %0, [%2]; ld.shared.u32 %1, [%2+4];" : "=r"(lo), "=r"(hi) : "r"(buf + cm.lo[k]) : "memory");
+                    pw[k] = __byte_perm(lo, hi, cm.sel[k]);
+                }
+            }
+            if (sy_next != sy) fetch_chunks(sy_next);      // after this row's chunks went to shared memory
+        }
         if (active) {
             // prediction: nearest-neighbour gather from the fitted label map
-            const int sy = __ldg(a.y_ofs + Y);
-            if (sy != prev_sy) {
-                prev_sy = sy;
+            if (reload && !staged) {
                 const uint8_t *lrow = a.labels + (size_t)sy * a.w;
                 if (cm.fast) {
 #pragma unroll
@@ -227,11 +293,11 @@ __global__ void __launch_bounds__(kRsThreads)
                 }
                 if (full) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) bump_u16(my_col + __byte_perm(idxw[j >> 2], 0, 0x4440u | (j & 3)) * 64u);
+                    for (int j = 0; j < 16; ++j) bump_counter<CTR32>(my_col + __byte_perm(idxw[j >> 2], 0, 0x4440u | (j & 3)) * kCodeStride);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (j < valid) bump_u16(my_col + __byte_perm(idxw[j >> 2], 0, 0x4440u | (j & 3)) * 64u);
+                        if (j < valid) bump_counter<CTR32>(my_col + __byte_perm(idxw[j >> 2], 0, 0x4440u | (j & 3)) * kCodeStride);
                 }
             } else {
                 const long long flat0 = (long long)Y * a.w_full + X;
@@ -244,9 +310,11 @@ __global__ void __launch_bounds__(kRsThreads)
                     }
             }
         }
+
         q0 = n0;
         q1 = n1;
         q2 = n2;
+        sy = sy_next;
 
         if (!active) continue;
         const size_t o = (size_t)Y * a.w_full + X;
@@ -303,11 +371,17 @@ __global__ void __launch_bounds__(kRsThreads)
             if (PACKED) {
 #pragma unroll
                 for (int w = 0; w < kRsWarps; ++w) {
-                    const unsigned *col = s_dyn + (size_t)(w * CC + i) * 16;   // 32 u16 lane counters of code i
+                    if (CTR32) {
+                        const unsigned *col = s_dyn + (size_t)(w * CC + i) * 32;   // 32 lane counters of code i
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        const unsigned v = col[(k + i) & 15];                   // rotated: spreads the banks
-                        t += (v & 0xFFFFu) + (v >> 16);
+                        for (int k = 0; k < 32; ++k) t += col[(k + i) & 31];       // rotated: spreads the banks
+                    } else {
+                        const unsigned *col = s_dyn + (size_t)(w * CC + i) * 16;   // 32 u16 lane counters of code i
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            const unsigned v = col[(k + i) & 15];
+                            t += (v & 0xFFFFu) + (v >> 16);
+                        }
                     }
                 }
             } else {
@@ -408,19 +482,24 @@ extern "C" int pylc_resample_encode_confusion(const uint8_t *labels, int h, int 
     a.out_aligned = (w_full % 16 == 0) && ((uintptr_t)pred_full % 16 == 0) && ((uintptr_t)gt_full % 16 == 0);
     a.rgb_aligned = (w_full % 16 == 0) && ((uintptr_t)pred_rgb % 16 == 0);
     a.labels_vec = ((uintptr_t)labels % 4 == 0) && (w % 4 == 0) && w >= 4;
+    a.labels_stage = a.labels_vec && ((uintptr_t)labels % 16 == 0) && (w % 16 == 0);
     const int mode = C > 15 ? 2 : (gt_full ? 1 : 0);
+    const bool ctr32 = false;   // measured: 16-bit counters (half the table set-up and flush) win at every C
     const size_t smem = mode == 2 ? (size_t)C * C * kRsWarps * sizeof(unsigned)
-                                  : (size_t)C * C * kRsWarps * 32 * sizeof(unsigned short);
-    // persistent-style grid: one wave of as many CTAs as fit (shared memory decides), each with a
-    // contiguous row range of its column block
+                                  : (size_t)C * C * kRsWarps * 32 * (ctr32 ? 4 : 2);
+    // persistent-style grid: one wave of as many CTAs as fit (registers / shared memory decide),
+    // each with a contiguous row range of its column block
+    using Kern = void (*)(ResampleArgs, const PaletteHash, const ColourLut);
+    const Kern kern = mode == 2 ? (Kern)resample_confusion_kernel<2, false>
+                    : mode == 1 ? (ctr32 ? (Kern)resample_confusion_kernel<1, true> : (Kern)resample_confusion_kernel<1, false>)
+                                : (ctr32 ? (Kern)resample_confusion_kernel<0, true> : (Kern)resample_confusion_kernel<0, false>);
     int dev = 0, sms = 148, per_sm = 8;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t oe = cudaSuccess;
-    if (mode == 0) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resample_confusion_kernel<0>, kRsThreads, smem);
-    else if (mode == 1) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resample_confusion_kernel<1>, kRsThreads, smem);
-    else oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resample_confusion_kernel<2>, kRsThreads, smem);
-    if (oe != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 4; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRsThreads, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 4;
+    }
     if (per_sm > 16) per_sm = 16;
     int slots = sms * per_sm / a.col_blocks;
     if (slots > (h_full + 1) / 2) slots = (h_full + 1) / 2;    // at least two rows per CTA amortise the column map
@@ -429,9 +508,7 @@ extern "C" int pylc_resample_encode_confusion(const uint8_t *labels, int h, int 
     if (a.rows_per_slot > kRsMaxRows) a.rows_per_slot = kRsMaxRows;   // 16-bit lane counters
     const int row_slots = (h_full + a.rows_per_slot - 1) / a.rows_per_slot;
     const unsigned grid = (unsigned)(a.col_blocks * row_slots);
-    if (mode == 0) resample_confusion_kernel<0><<<grid, kRsThreads, smem, (cudaStream_t)stream>>>(a, ph, lut);
-    else if (mode == 1) resample_confusion_kernel<1><<<grid, kRsThreads, smem, (cudaStream_t)stream>>>(a, ph, lut);
-    else resample_confusion_kernel<2><<<grid, kRsThreads, smem, (cudaStream_t)stream>>>(a, ph, lut);
+    kern<<<grid, kRsThreads, smem, (cudaStream_t)stream>>>(a, ph, lut);
     return finish_launch();
 }
 
