@@ -84,13 +84,15 @@ class ClockSampler(threading.Thread):
 
 
 def make_inputs(rank, palette):
-    """64 decoded image / RGB-mask pairs per rank in pinned host memory (global image index =
-    rank * 64 + i, so ranks hold different images)."""
+    """64 decoded image / RGB-mask pairs per rank as tightly packed [H,W,3] u8 tensors in PINNED host
+    memory -- what cv2.imread hands the reference, page-locked (global image index = rank * 64 + i,
+    so ranks hold different images)."""
     from pylc_b200 import synth
 
     def one(i):
         g = rank * N_IMAGES + i
-        return synth.image(g, W_FULL, H_FULL, CH), synth.mask(g, W_FULL, H_FULL, palette)
+        return (torch.from_numpy(synth.image(g, W_FULL, H_FULL, CH)).pin_memory(),
+                torch.from_numpy(synth.mask(g, W_FULL, H_FULL, palette)).pin_memory())
     with cf.ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 4)) as ex:
         pairs = list(ex.map(one, range(N_IMAGES)))
     imgs = [p[0] for p in pairs]
@@ -260,7 +262,8 @@ def run_ours(args, rank, world, local_rank):
 
     model = build_model(device)
     seg = TiledSegmenter(model, batch_tiles=args.batch_tiles, channels_last=not args.no_channels_last,
-                         autocast_dtype=dtype, host_workers=args.host_workers, fuse_network=not args.no_fuse)
+                         autocast_dtype=dtype, host_workers=args.host_workers, fuse_network=not args.no_fuse,
+                         device_fit=not args.host_fit)
     imgs, masks = make_inputs(rank, model.meta.palette_rgb)
     mpx_step = N_IMAGES * W_FULL * H_FULL / 1e6
     d2h = seg.C * seg.C * 8
@@ -271,9 +274,11 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- value: inputs resident in HBM -------------------------------------------------------
-    resident = [seg.stage(imgs[i], masks[i], index=rank * N_IMAGES + i) for i in range(N_IMAGES)]
+    stage = seg.stage_device if seg.can_fit_on_device(imgs[0]) else (lambda im, gt, index: seg.stage(im.numpy(), gt.numpy(), index=index))
+    resident = [stage(imgs[i], masks[i], index=rank * N_IMAGES + i) for i in range(N_IMAGES)]
     torch.cuda.synchronize()
-    h2d = sum(f.img.numel() + f.gt.numel() for f in resident)     # bytes run_host copies per step
+    h2d = sum(im.numel() + gt.numel() for im, gt in zip(imgs, masks)) if seg.can_fit_on_device(imgs[0]) \
+        else sum(f.img.numel() + f.gt.numel() for f in resident)      # bytes run_host copies per step
     clocks = ClockSampler(local_rank)
     with StitchTimer(ops) as st:
         for _ in range(args.warmup):
@@ -331,7 +336,8 @@ def run_ours(args, rank, world, local_rank):
                    "network_plan": "eager nn.Module" if args.no_fuse else "BatchNorm folded, cuDNN fused conv+bias(+add)+ReLU, channels_last",
                    "l2": "inputs larger than L2 (each step streams > 20 GB of logits per GPU)",
                    "parallelism": "dp%d, images sharded, one [9,9] i64 all-reduce per step" % world,
-                   "value_region": "fitted u8 images + RGB ground truth resident in HBM -> all-reduced confusion matrix",
+                   "fit_resize": "host cv2 threads" if args.host_fit else "device (pylc_fit_resize_area_u8, bit-exact INTER_AREA)",
+                   "value_region": ("fitted" if args.host_fit else "decoded") + " u8 images + RGB ground truth resident in HBM -> all-reduced confusion matrix",
                    "weighted_iou": scores["iou"], "confusion_sum": int(conf_host.sum()),
                    "resident_equals_e2e": bool(np.array_equal(conf_resident, conf_host))},
         "e2e": {"value": mpx_step * world / (e2e_ms * 1e-3), "unit": "Mpx/s", "ms_per_step": e2e_ms,
@@ -361,6 +367,8 @@ def main():
     ap.add_argument("--host-workers", type=int, default=6)
     ap.add_argument("--no-channels-last", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-fit", action="store_true", help="fit-resize on host threads with cv2 (the reference's call) "
+                    "instead of the bit-exact device kernel")
     ap.add_argument("--no-fuse", action="store_true", help="run the eager nn.Module instead of the BN-folded cuDNN-fused plan")
     ap.add_argument("--images", type=int, default=64, help="images per GPU per step (profiling runs use fewer; "
                     "the reported workload is only configs[1] at the default 64)")

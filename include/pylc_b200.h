@@ -115,6 +115,42 @@ PYLC_API int pylc_tile_gather_norm_f32(const uint8_t *src, int H, int W, int ch,
                               int S, const float *mean, const float *std, float post_div,
                               int out_ch, float *dst, pylc_stream_t stream);
 
+/* ---- test-time fit resize ----------------------------------------------------------------- */
+
+#define PYLC_AREA_TAPS 6 /* source cells per destination cell and axis: scale factors below 5 */
+
+/*
+ * cv2.resize(img, (w, h), interpolation=INTER_AREA) of tools.adjust_to_tile
+ * (utils/tools.py:189-206) on the device, bit-exact with OpenCV's general area filter for u8
+ * (imgproc/resize.cpp: computeResizeAreaTab + resizeArea_<uchar,float>; OpenCV is a third-party
+ * dependency of the reference, requirements.txt:8).
+ *
+ *   pylc_area_supported   HOST: 1 if OpenCV resizes (W,H)->(w,h) with that filter (a down-scale by
+ *                         non-integer factors below 5, or the identity); 0 otherwise -- the caller
+ *                         then keeps the host cv2 call
+ *   pylc_area_table       HOST: one axis of the area table.  For destination index d the source
+ *                         cells are start[d] .. start[d]+count[d]-1 with float weights
+ *                         weights[d*PYLC_AREA_TAPS + k]; all three arrays are HOST, length dsize
+ *                         (weights: dsize*PYLC_AREA_TAPS).  The caller uploads them once per geometry.
+ *   pylc_fit_resize_area_u8  src [H,W,ch] u8 (pitch bytes, any alignment) -> dst [h,w,ch] u8
+ *                         (dst_pitch bytes); x_* / y_* are DEVICE copies of the two tables.
+ */
+PYLC_API int pylc_area_supported(int W, int H, int w, int h);
+PYLC_API int pylc_area_table(int ssize, int dsize, int32_t *start, int32_t *count, float *weights);
+PYLC_API int pylc_fit_resize_area_u8(const uint8_t *src, int H, int W, int ch, size_t src_pitch, uint8_t *dst,
+                            int h, int w, size_t dst_pitch, const int32_t *x_start,
+                            const int32_t *x_count, const float *x_weights, const int32_t *y_start,
+                            const int32_t *y_count, const float *y_weights, pylc_stream_t stream);
+
+/*
+ * Pitched host -> device upload on the copy engine (cudaMemcpy2DAsync): a tightly packed decoded
+ * image (tools.get_image's array, utils/tools.py:127-131) lands in the 16-byte-pitched device
+ * layout the vectorised kernels want, without a host-side repack.  src_host: HOST, pinned for an
+ * asynchronous copy.
+ */
+PYLC_API int pylc_upload_pitched(void *dst, size_t dst_pitch, const void *src_host, size_t src_pitch,
+                        size_t width_bytes, size_t rows, pylc_stream_t stream);
+
 /* ---- stitching ---------------------------------------------------------------------------- */
 
 /*

@@ -138,6 +138,14 @@ def gen_fit(ref, out):
         _, w_fit, h_fit, off = ref.tools.adjust_to_tile(img, 512, 256, 1)
         rows.append([W, H, w_fit, h_fit, off])
     out["fit_dims"] = np.array(rows)
+    # the fitted pixels themselves: the reference's adjust_to_tile (cv2 INTER_AREA) on small seeded images
+    rng = np.random.default_rng(77)
+    for name, (W, H, T, ch) in {"g": (150, 110, 32, 1), "c": (100, 75, 32, 3), "n": (97, 161, 32, 3)}.items():
+        img = rng.integers(0, 256, size=(H, W) if ch == 1 else (H, W, ch), dtype=np.uint8)
+        fitted, w_fit, h_fit, off = ref.tools.adjust_to_tile(img, T, T // 2, ch)
+        assert fitted.shape[:2] == (h_fit, w_fit) and off == 0
+        out["fitimg_%s_in" % name] = img
+        out["fitimg_%s_out" % name] = fitted
     # OpenCV nearest-neighbour index maps (cv2.resize of a ramp), several size pairs
     pairs = [(1536, 2000), (1024, 1500), (2560, 3000), (5632, 6000), (3584, 4000), (64, 75), (48, 50),
              (3072, 3453), (4608, 4940), (512, 513)]

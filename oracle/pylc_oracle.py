@@ -58,6 +58,66 @@ def fit_dims(W, H, T):
     return w_fit, h_fit
 
 
+def area_table(ssize, dsize):
+    """One axis of OpenCV's computeResizeAreaTab (imgproc/resize.cpp; cv2 is a third-party dependency
+    of the reference -- requirements.txt:8 -- whose INTER_AREA call sits at utils/tools.py:194).
+    Returns a list of (dst index, src index, float32 weight) in OpenCV's order.  Pinned by
+    tests/test_oracle_golden.py against the installed cv2 itself."""
+    inv_scale = float(dsize) / float(ssize)
+    scale = 1.0 / inv_scale
+    tab = []
+    for dx in range(dsize):
+        fsx1 = dx * scale
+        fsx2 = fsx1 + scale
+        cell = min(scale, ssize - fsx1)
+        sx1, sx2 = math.ceil(fsx1), math.floor(fsx2)
+        sx2 = min(sx2, ssize - 1)
+        sx1 = min(sx1, sx2)
+        if sx1 - fsx1 > 1e-3:
+            tab.append((dx, sx1 - 1, np.float32((sx1 - fsx1) / cell)))
+        for sx in range(sx1, sx2):
+            tab.append((dx, sx, np.float32(1.0 / cell)))
+        if fsx2 - sx2 > 1e-3:
+            tab.append((dx, sx2, np.float32(min(min(fsx2 - sx2, 1.0), cell) / cell)))
+    return tab
+
+
+def resize_area(img, w, h):
+    """cv2.resize(img, (w, h), interpolation=cv2.INTER_AREA) for u8 images and non-integer down-scales,
+    restated from OpenCV's resizeArea_<uchar, float>: per source row a float buffer
+    buf[dx] = sum_k S[sx_k]*alpha_k (sequential, multiply and add rounded separately), rows combined
+    as sum = beta_0*buf, sum += beta_j*buf, output cvRound(sum) saturated.  Bit-exact with cv2 4.13."""
+    img = np.asarray(img)
+    sh, sw = img.shape[:2]
+    cn = 1 if img.ndim == 2 else img.shape[2]
+    src = img.reshape(sh, sw, cn)
+    xt, yt = area_table(sw, w), area_table(sh, h)
+    K = max(np.bincount([t[0] for t in xt]))
+    xi = np.zeros((w, K), np.int64)
+    xa = np.zeros((w, K), np.float32)
+    xn = np.zeros(w, np.int64)
+    for d, si, a in xt:
+        xi[d, xn[d]], xa[d, xn[d]] = si, a
+        xn[d] += 1
+    out = np.zeros((h, w, cn), np.uint8)
+    acc, prev_dy = None, -1
+    for dy, sy, beta in yt:
+        row = src[sy].astype(np.float32)
+        buf = np.zeros((w, cn), np.float32)
+        for k in range(K):
+            term = (row[xi[:, k]] * xa[:, k][:, None]).astype(np.float32)
+            buf = np.where((xn > k)[:, None], (buf + term).astype(np.float32), buf)
+        scaled = (np.float32(beta) * buf).astype(np.float32)
+        if dy != prev_dy:
+            if prev_dy >= 0:
+                out[prev_dy] = np.clip(np.rint(acc), 0, 255).astype(np.uint8)
+            acc, prev_dy = scaled, dy
+        else:
+            acc = (acc + scaled).astype(np.float32)
+    out[prev_dy] = np.clip(np.rint(acc), 0, 255).astype(np.uint8)
+    return out.reshape(h, w) if img.ndim == 2 else out
+
+
 # ----------------------------------------------------------------------------------------------
 # class_encode / colourize  (utils/tools.py:412-449, 322-358)
 # ----------------------------------------------------------------------------------------------

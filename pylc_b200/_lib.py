@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpylc_b200.so")
 
 MAX_CLASSES = 32
+AREA_TAPS = 6
 ABI_VERSION = 1
 
 
@@ -46,6 +47,11 @@ SIGNATURES = {
     "pylc_profile_tiles": (c_int, [_u8p, c_int, _u8p, c_int, c_int64, c_int, _ptr, _ptr, _ptr]),
     "pylc_tile_gather_norm_f32": (c_int, [_u8p, c_int, c_int, c_int, c_size_t, c_int, c_int,
                                           POINTER(c_float), POINTER(c_float), c_float, c_int, _ptr, _ptr]),
+    "pylc_area_supported": (c_int, [c_int, c_int, c_int, c_int]),
+    "pylc_area_table": (c_int, [c_int, c_int, _ptr, _ptr, _ptr]),
+    "pylc_fit_resize_area_u8": (c_int, [_u8p, c_int, c_int, c_int, c_size_t, _u8p, c_int, c_int, c_size_t,
+                                        _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "pylc_upload_pitched": (c_int, [_ptr, c_size_t, _ptr, c_size_t, c_size_t, c_size_t, _ptr]),
     "pylc_stitch_argmax_colour": (c_int, [_ptr, _ptr, c_int, c_int, c_int, c_int, c_int, c_int,
                                           POINTER(c_uint8), _u8p, _u8p, _ptr, _ptr]),
     "pylc_colourise_u8": (c_int, [_u8p, c_int64, POINTER(c_uint8), c_int, _u8p, _ptr]),

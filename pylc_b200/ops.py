@@ -57,6 +57,71 @@ def upload_image(img, device=None):
     return buf.to(device or torch.device("cuda"), non_blocking=True), pitch
 
 
+def upload_pitched(host, out=None, device=None):
+    """pylc_upload_pitched: H2D of a tightly packed (ideally pinned) [H,W] / [H,W,3] u8 host tensor
+    or array into a 16-byte-pitched device buffer on the copy engine -- no host-side repack.
+    Returns (tensor [H, pitch] u8, pitch)."""
+    t = host if torch.is_tensor(host) else torch.from_numpy(np.ascontiguousarray(host))
+    if t.is_cuda or t.dtype != torch.uint8 or not t.is_contiguous():
+        raise PylcError("upload_pitched takes a contiguous u8 host tensor")
+    H = t.shape[0]
+    row = t.numel() // H
+    pitch = pitch_for(row)
+    if out is None:
+        out = torch.empty((H, pitch), dtype=torch.uint8, device=device or torch.device("cuda"))
+    check(_lib.load().pylc_upload_pitched(_p(out), pitch, ctypes.c_void_p(t.data_ptr()), row, row, H, _stream()),
+          "pylc_upload_pitched")
+    return out, pitch
+
+
+# ---- test-time fit resize -------------------------------------------------------------------------
+
+_AREA_TABLES = {}
+
+
+def area_supported(W, H, w, h):
+    """True when cv2.resize((W,H)->(w,h), INTER_AREA) is the general area filter the device kernel
+    reproduces bit-exactly (pylc_area_supported)."""
+    return bool(_lib.load().pylc_area_supported(int(W), int(H), int(w), int(h)))
+
+
+def area_table_host(ssize, dsize):
+    """pylc_area_table: (start i32 [dsize], count i32 [dsize], weights f32 [dsize, AREA_TAPS]) on the host."""
+    start = np.empty(dsize, dtype=np.int32)
+    count = np.empty(dsize, dtype=np.int32)
+    weights = np.empty((dsize, _lib.AREA_TAPS), dtype=np.float32)
+    check(_lib.load().pylc_area_table(int(ssize), int(dsize), start.ctypes.data, count.ctypes.data, weights.ctypes.data),
+          "pylc_area_table")
+    return start, count, weights
+
+
+def area_tables(W, H, w, h, device):
+    """Device copies of the x and y area tables, cached per geometry."""
+    key = (W, H, w, h, str(device))
+    hit = _AREA_TABLES.get(key)
+    if hit is None:
+        if len(_AREA_TABLES) > 64:
+            _AREA_TABLES.clear()
+        hit = _AREA_TABLES[key] = tuple(torch.from_numpy(a).to(device) for a in area_table_host(W, w) + area_table_host(H, h))
+    return hit
+
+
+def fit_resize_area(src, H, W, ch, pitch, h, w, out=None):
+    """pylc_fit_resize_area_u8: cv2.resize(INTER_AREA) of a device-resident u8 image, bit-exact.
+    Returns (fitted [h, pitch_out] u8, pitch_out)."""
+    _need_cuda(src)
+    if not area_supported(W, H, w, h):
+        raise PylcError("fit_resize_area: (%d,%d)->(%d,%d) is not OpenCV's general area filter; use the host cv2 path"
+                        % (W, H, w, h))
+    tabs = area_tables(W, H, w, h, src.device)
+    pitch_out = pitch_for(w * ch)
+    if out is None:
+        out = torch.empty((h, pitch_out), dtype=torch.uint8, device=src.device)
+    check(_lib.load().pylc_fit_resize_area_u8(_p(src), H, W, ch, pitch, _p(out), h, w, pitch_out, *[_p(t) for t in tabs],
+                                              _stream()), "pylc_fit_resize_area_u8")
+    return out, pitch_out
+
+
 # ---- extraction ---------------------------------------------------------------------------------
 
 

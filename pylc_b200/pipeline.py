@@ -6,14 +6,17 @@ Per image, the reference does (host unless noted): fit-resize -> unfold tiles ->
 -> H2D per 8 tiles -> network (device) -> D2H of ALL logits -> band-merge loops -> argmax ->
 colourise -> NN resize -> class_encode(pred), class_encode(GT) -> five scikit-learn passes.
 
-Here, per image:
-    host   cv2 fit-resize (same OpenCV call => same bytes), staged in pinned memory
-    copy   one H2D of the fitted image and one of the RGB ground truth (copy stream, overlapped)
-    GPU    pylc_tile_gather_norm_f32     tiles, normalised, grayscale replicated   (1 launch)
+Here, per image (device_fit, the default whenever OpenCV's general area filter applies):
+    copy   one pitched H2D of the decoded image and one of the RGB ground truth, straight from the
+           caller's (pinned) arrays on the copy engine -- no host-side pass over the pixels
+    GPU    pylc_fit_resize_area_u8       cv2.resize(INTER_AREA) of adjust_to_tile, bit-exact (1 launch)
+           pylc_tile_gather_norm_f32     tiles, normalised, grayscale replicated   (1 launch)
            DeepLabv3+/ResNet-101         stock PyTorch / cuDNN, batches of `batch_tiles`
            pylc_stitch_argmax_colour     logits -> label map, reference band semantics (1 launch)
            pylc_resample_encode_confusion  NN resample + GT encode + [C,C] counts    (1 launch)
     D2H    nothing per image; the [C,C] i64 matrix (and optional masks) at the end
+With device_fit off (or for geometries OpenCV resizes with another filter) the fit-resize runs on
+host worker threads with cv2 itself and the fitted image is uploaded instead.
 Logits never leave the device.  Images are independent, so data-parallel ranks take images
 round-robin and all-reduce only the [C,C] matrix (pylc_b200.dist).
 """
@@ -32,12 +35,12 @@ from .utils.metrics import scores_from_confusion
 
 class FittedImage(object):
     """A fitted u8 image (and optional RGB ground truth) resident on the device."""
-    __slots__ = ("img", "pitch", "h", "w", "gt", "gt_pitch", "h_full", "w_full", "index", "ready")
+    __slots__ = ("img", "pitch", "h", "w", "gt", "gt_pitch", "h_full", "w_full", "index", "ready", "raw", "raw_pitch")
 
 
 class TiledSegmenter(object):
     def __init__(self, model, batch_tiles=32, channels_last=True, autocast_dtype=None, host_workers=4,
-                 n_inject=None, keep_masks=False, fuse_network=False):
+                 n_inject=None, keep_masks=False, fuse_network=False, device_fit=True):
         self.model = model
         self.meta = model.meta
         self.net = model.net.eval()
@@ -63,6 +66,7 @@ class TiledSegmenter(object):
         self.lut = tools.colourize_lut(self.C, self.palette)
         self.n_inject = min(len(defaults.class_codes), self.C) if n_inject is None else n_inject
         self.keep_masks = keep_masks
+        self.device_fit = device_fit
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.pool = cf.ThreadPoolExecutor(max_workers=host_workers)
         self.conf = torch.zeros((self.C, self.C), dtype=torch.int64, device=self.device)
@@ -78,19 +82,50 @@ class TiledSegmenter(object):
     def stage(self, img, gt=None, index=0):
         """Host fit + async H2D on the copy stream.  Returns a FittedImage; the compute stream must
         wait on `f.ready` before touching its tensors."""
+        if torch.is_tensor(img):
+            img = img.numpy()
         buf, pitch, h, w = self.fit_host(img)
         f = FittedImage()
         f.index = index
+        f.raw, f.raw_pitch = None, 0
         f.h, f.w, f.pitch = h, w, pitch
         f.h_full, f.w_full = img.shape[0], img.shape[1]
         with torch.cuda.stream(self.copy_stream):
             f.img = buf.to(self.device, non_blocking=True)
             if gt is not None:
-                if torch.is_tensor(gt):
+                if torch.is_tensor(gt) and gt.ndim == 2:      # already a pitched [H, pitch] buffer
                     gbuf, f.gt_pitch = gt, gt.shape[1]
                 else:
-                    gbuf, f.gt_pitch = ops.pinned_pitched(gt)
+                    gbuf, f.gt_pitch = ops.pinned_pitched(gt.numpy() if torch.is_tensor(gt) else gt)
                 f.gt = gbuf.to(self.device, non_blocking=True)
+            else:
+                f.gt, f.gt_pitch = None, 0
+            f.ready = torch.cuda.Event()
+            f.ready.record(self.copy_stream)
+        return f
+
+    def can_fit_on_device(self, img):
+        H, W = img.shape[:2]
+        w, h = tools.fit_dims(W, H, self.T)
+        return self.device_fit and h >= self.T and w >= self.T and ops.area_supported(W, H, w, h)
+
+    def stage_device(self, img, gt=None, index=0, after=None):
+        """Device fit: pitched H2D of the DECODED image (and ground truth) on the copy stream; the
+        INTER_AREA resize itself is launched by segment_fitted on the compute stream.  `after`: an event
+        the copy stream waits for first (bounds how far uploads run ahead of the compute stream)."""
+        t_img = img if torch.is_tensor(img) else torch.from_numpy(np.ascontiguousarray(img))
+        f = FittedImage()
+        f.index = index
+        f.h_full, f.w_full = t_img.shape[0], t_img.shape[1]
+        f.w, f.h = tools.fit_dims(f.w_full, f.h_full, self.T)
+        with torch.cuda.stream(self.copy_stream):
+            if after is not None:
+                self.copy_stream.wait_event(after)
+            f.raw, f.raw_pitch = ops.upload_pitched(t_img, device=self.device)
+            f.img, f.pitch = None, 0
+            if gt is not None:
+                t_gt = gt if torch.is_tensor(gt) else torch.from_numpy(np.ascontiguousarray(gt))
+                f.gt, f.gt_pitch = ops.upload_pitched(t_gt, device=self.device)
             else:
                 f.gt, f.gt_pitch = None, 0
             f.ready = torch.cuda.Event()
@@ -123,7 +158,10 @@ class TiledSegmenter(object):
     def segment_fitted(self, f, inject=None):
         """All device work for one fitted image; accumulates into self.conf when f.gt is set.
         Returns the fitted-resolution label map (and full-res masks when keep_masks)."""
-        tiles = ops.tile_gather_norm_f32(f.img, f.h, f.w, self.ch, f.pitch, self.T, self.S, self.mean, self.std,
+        img, pitch = f.img, f.pitch
+        if img is None:        # device fit: INTER_AREA resize of the uploaded decoded image
+            img, pitch = ops.fit_resize_area(f.raw, f.h_full, f.w_full, self.ch, f.raw_pitch, f.h, f.w)
+        tiles = ops.tile_gather_norm_f32(img, f.h, f.w, self.ch, pitch, self.T, self.S, self.mean, self.std,
                                          self.post_div, self.out_ch)
         nr, nc = f.h // self.S - 1, f.w // self.S - 1
         logits = self.forward_tiles(tiles)
@@ -154,6 +192,8 @@ class TiledSegmenter(object):
         idx = list(range(len(images))) if indices is None else list(indices)
         compute = torch.cuda.current_stream(self.device)
         prefetch = 3
+        if idx and all(self.can_fit_on_device(images[i]) for i in idx):
+            return self._run_host_device_fit(images, masks, idx, compute, prefetch, distributed)
 
         def submit(k):
             i = idx[k]
@@ -176,6 +216,40 @@ class TiledSegmenter(object):
         if distributed:
             conf = pdist.all_reduce_(conf.clone())
         return conf.cpu().numpy(), results           # the step's only D2H: C*C*8 bytes
+
+    def _run_host_device_fit(self, images, masks, idx, compute, prefetch, distributed):
+        """run_host without any host-side pixel work: uploads run `prefetch` images ahead on the copy
+        stream (throttled by compute-stream events, not by the host), everything else is device work."""
+        done = []                     # compute-stream event per finished image
+        staged = []
+        results = []
+
+        def submit(k):
+            i = idx[k]
+            after = done[k - prefetch] if k >= prefetch else None
+            staged.append(self.stage_device(images[i], None if masks is None else masks[i], i, after=after))
+
+        for k in range(min(prefetch, len(idx))):
+            submit(k)
+        for k in range(len(idx)):
+            f = staged[k]
+            staged[k] = None
+            compute.wait_event(f.ready)
+            res = self.segment_fitted(f, inject=self.n_inject if f.index == 0 else 0)
+            f.raw.record_stream(compute)
+            if f.gt is not None:
+                f.gt.record_stream(compute)
+            ev = torch.cuda.Event()
+            ev.record(compute)
+            done.append(ev)
+            if k + prefetch < len(idx):
+                submit(k + prefetch)
+            if self.keep_masks:
+                results.append(res)
+        conf = self.conf
+        if distributed:
+            conf = pdist.all_reduce_(conf.clone())
+        return conf.cpu().numpy(), results
 
     def scores(self, conf):
         labels = defaults.class_codes if self.C == len(defaults.class_codes) else self.meta.class_codes

@@ -281,6 +281,46 @@ def test_colourise(ops, golden, palettes):
 
 
 # ---------------------------------------------------------------------------------------------
+# test-time fit resize (cv2 INTER_AREA on the device)
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("W,H,T,ch", [(2000, 1500, 512, 1), (3000, 2000, 512, 3), (1300, 900, 256, 3), (1500, 1100, 512, 1),
+                                      (1025, 2300, 512, 3), (6000, 4000, 512, 1), (2560, 1536, 512, 3)])
+def test_fit_resize_area_bit_exact(ops, W, H, T, ch):
+    """Device INTER_AREA == the installed OpenCV (what tools.adjust_to_tile calls), every byte; the
+    source is uploaded unpitched and pitched."""
+    import cv2
+    w, h = orc.fit_dims(W, H, T)
+    assert ops.area_supported(W, H, w, h)
+    img = orc.synth_image(4, W, H, ch)
+    img = (img.astype(np.int32) + np.random.default_rng(W).integers(-40, 40, size=img.shape)).clip(0, 255).astype(np.uint8)
+    ref = cv2.resize(img, (w, h), interpolation=cv2.INTER_AREA).reshape(h, w * ch)
+    got, pitch = ops.fit_resize_area(dev(img), H, W, ch, W * ch, h, w)
+    assert np.array_equal(got.cpu().numpy()[:, :w * ch], ref)
+    d_img, sp = ops.upload_pitched(torch.from_numpy(img).pin_memory())
+    got2, _ = ops.fit_resize_area(d_img, H, W, ch, sp, h, w)
+    assert torch.equal(got, got2)
+
+
+def test_fit_resize_area_golden_and_refusals(ops, golden):
+    g = golden("fit")      # the reference's own adjust_to_tile outputs
+    for name in ("g", "c", "n"):
+        src, ref = g["fitimg_%s_in" % name], g["fitimg_%s_out" % name]
+        ch = 1 if src.ndim == 2 else 3
+        H, W = src.shape[:2]
+        h, w = ref.shape[:2]
+        got, _ = ops.fit_resize_area(dev(src), H, W, ch, W * ch, h, w)
+        assert np.array_equal(got.cpu().numpy()[:, :w * ch], ref.reshape(h, w * ch))
+    # integer factors are OpenCV's separate "fast area" code, up-scales its linear filter: refused, the
+    # caller keeps the host cv2 call
+    assert not ops.area_supported(1024, 1024, 512, 512)
+    assert not ops.area_supported(500, 500, 512, 512)
+    assert ops.area_supported(1024, 1000, 512, 512)
+    with pytest.raises(ops.PylcError):
+        ops.fit_resize_area(dev(np.zeros((1024, 1024), np.uint8)), 1024, 1024, 1, 1024, 512, 512)
+
+
+# ---------------------------------------------------------------------------------------------
 # resample + encode + confusion
 # ---------------------------------------------------------------------------------------------
 

@@ -220,3 +220,19 @@ def test_fused_deeplab_matches_eval_network_on_cpu():
     assert got.shape == want.shape and got.is_contiguous()
     scale = want.abs().max().item()
     assert (got - want).abs().max().item() <= 2e-4 * scale
+
+
+@pytest.mark.parametrize("ssize,dsize", [(3000, 2560), (2000, 1536), (4000, 3584), (1100, 512), (513, 512), (512, 512)])
+def test_area_table_host_equals_oracle(ssize, dsize):
+    """pylc_area_table (host code of the CUDA library, no GPU needed) == the oracle's restatement of
+    OpenCV's computeResizeAreaTab, weight for weight."""
+    from pylc_b200 import ops
+    start, count, weights = ops.area_table_host(ssize, dsize)
+    tab = orc.area_table(ssize, dsize)
+    k = 0
+    for d in range(dsize):
+        for j in range(count[d]):
+            dd, si, a = tab[k]
+            assert (dd, si) == (d, start[d] + j) and weights[d, j] == a
+            k += 1
+    assert k == len(tab)

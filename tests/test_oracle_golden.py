@@ -73,6 +73,30 @@ def test_fit_dims(golden):
         assert off == 0
 
 
+@pytest.mark.parametrize("W,H,T,ch", [(2000, 1500, 512, 1), (3000, 2000, 512, 3), (1300, 900, 256, 3), (1500, 1100, 512, 1),
+                                      (700, 650, 128, 3)])
+def test_resize_area_equals_cv2(W, H, T, ch):
+    """The INTER_AREA restatement (oracle for the device fit-resize) against the installed OpenCV,
+    the library the reference itself calls at utils/tools.py:194: every byte equal."""
+    import cv2
+    w, h = orc.fit_dims(W, H, T)
+    img = orc.synth_image(3, W, H, ch)
+    ref = cv2.resize(img, (w, h), interpolation=cv2.INTER_AREA)
+    assert np.array_equal(orc.resize_area(img, w, h), ref)
+    noise = np.random.default_rng(W).integers(0, 256, size=img.shape, dtype=np.uint8)
+    assert np.array_equal(orc.resize_area(noise, w, h), cv2.resize(noise, (w, h), interpolation=cv2.INTER_AREA))
+
+
+def test_resize_area_golden_fit(golden):
+    """... and against the reference's own adjust_to_tile output (tests/golden/fit.npz)."""
+    g = golden("fit")
+    keys = [k for k in g.files if k.startswith("fitimg_") and k.endswith("_in")]
+    assert len(keys) == 3
+    for k in keys:
+        src, ref = g[k], g[k.replace("_in", "_out")]
+        assert np.array_equal(orc.resize_area(src, ref.shape[1], ref.shape[0]), ref)
+
+
 def test_nn_index_map(golden):
     g = golden("fit")
     for src, dst in g["nn_pairs"]:
