@@ -240,6 +240,22 @@ PYLC_API int pylc_multiloss_grad(const float *logits, const void *target, int ta
                         const double *partials, int64_t n_px_total, float grad_scale,
                         const float *grad_scale_dev, float *grad, pylc_stream_t stream);
 
+/*
+ * Forward AND backward in one cooperative launch, for the single-GPU training step (no all-reduce
+ * between the passes): reduce pass -> grid-wide barrier -> out4 = {loss, ce, dice, focal} ->
+ * gradient pass, which walks the logits back to front so that it starts on what the reduce pass
+ * left in L2.  Same arguments as the two calls above; `partials` must be zeroed by the caller and
+ * holds the 2C+3 sums afterwards; out4 is nullable; n_px_total is B*HW.
+ *
+ * pylc_scale_unless_one_f32: data[i] *= *scale_dev unless *scale_dev == 1 -- applies autograd's
+ * upstream gradient to the stashed dL/dz without a host sync (a no-op for loss.backward()).
+ */
+PYLC_API int pylc_multiloss_fwd_bwd(const float *logits, const void *target, int target_is_i64, int B, int C,
+                           int64_t HW, const float *class_w, const pylc_loss_cfg *cfg,
+                           double *partials, float grad_scale, const float *grad_scale_dev,
+                           float *grad, float *out4, pylc_stream_t stream);
+PYLC_API int pylc_scale_unless_one_f32(float *data, int64_t n, const float *scale_dev, pylc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

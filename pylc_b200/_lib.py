@@ -64,6 +64,9 @@ SIGNATURES = {
     "pylc_multiloss_finalize": (c_int, [_ptr, c_int, c_int64, POINTER(LossCfg), _ptr, _ptr]),
     "pylc_multiloss_grad": (c_int, [_ptr, _ptr, c_int, c_int, c_int, c_int64, _ptr, POINTER(LossCfg),
                                     _ptr, c_int64, c_float, _ptr, _ptr, _ptr]),
+    "pylc_multiloss_fwd_bwd": (c_int, [_ptr, _ptr, c_int, c_int, c_int, c_int64, _ptr, POINTER(LossCfg),
+                                       _ptr, c_float, _ptr, _ptr, _ptr, _ptr]),
+    "pylc_scale_unless_one_f32": (c_int, [_ptr, c_int64, _ptr, _ptr]),
 }
 
 _lib = None

@@ -8,6 +8,8 @@
 //
 // Logits are [B, C, HW]; a thread handles PX consecutive pixels and reads one 16-byte vector per
 // class plane, so every warp-level load is a contiguous 512-byte segment.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace pylc {
@@ -101,7 +103,7 @@ __device__ __forceinline__ void softmax_px(const float (&z)[CMAX], int C, float 
 __device__ __forceinline__ float ln_fast(float x) { return lg2_approx(x) * kLn2; }
 
 template <int C_T, int CMAX, int PX>
-__global__ void __launch_bounds__(kThreads, (PX == 4 || CMAX > 9) ? 2 : 3) loss_reduce_kernel(LossArgs a, double *__restrict__ partials) {
+__device__ __forceinline__ void loss_reduce_pass(const LossArgs &a, double *partials) {
     const int C = C_T > 0 ? C_T : a.C;
     __shared__ float s_w[PYLC_MAX_CLASSES];
     __shared__ double s_part[2 * PYLC_MAX_CLASSES + 3];
@@ -196,9 +198,15 @@ __global__ void __launch_bounds__(kThreads, (PX == 4 || CMAX > 9) ? 2 : 3) loss_
 }
 
 template <int C_T, int CMAX, int PX>
-__global__ void __launch_bounds__(kThreads, (PX == 4 || CMAX > 9) ? 2 : 3)
-    loss_grad_kernel(LossArgs a, const double *__restrict__ partials, long long n_px_total, float grad_scale,
-                     const float *__restrict__ grad_scale_dev, float *__restrict__ grad) {
+__global__ void __launch_bounds__(kThreads, (PX == 4 || CMAX > 9) ? 2 : 3) loss_reduce_kernel(LossArgs a, double *__restrict__ partials) {
+    loss_reduce_pass<C_T, CMAX, PX>(a, partials);
+}
+
+// REVERSE walks the units back to front: in the fused kernel the reduce pass has just streamed the
+// logits front to back, so the tail it left in the 126 MB L2 is what this pass reads first.
+template <int C_T, int CMAX, int PX, bool REVERSE>
+__device__ __forceinline__ void loss_grad_pass(const LossArgs &a, const double *partials, long long n_px_total, float grad_scale,
+                                               const float *grad_scale_dev, float *grad) {
     const int C = C_T > 0 ? C_T : a.C;
     __shared__ float s_w[PYLC_MAX_CLASSES], s_a[PYLC_MAX_CLASSES], s_b[PYLC_MAX_CLASSES];
     __shared__ float s_inv_den;
@@ -207,14 +215,14 @@ __global__ void __launch_bounds__(kThreads, (PX == 4 || CMAX > 9) ? 2 : 3)
         s_w[c] = (a.class_w && c < C) ? a.class_w[c] : 1.f;
         float av = 0.f, bv = 0.f;
         if (c < C) {
-            const double I = partials[c], K = partials[C + c], sm = (double)a.cfg.dice_smooth;
+            const double I = __ldcg(partials + c), K = __ldcg(partials + C + c), sm = (double)a.cfg.dice_smooth;
             av = (float)(-2.0 / ((K + sm) * C));
             bv = (float)((2.0 * I + sm) / ((K + sm) * (K + sm) * C));
         }
         s_a[c] = av;
         s_b[c] = bv;
     }
-    if (threadIdx.x == 0) s_inv_den = (float)(1.0 / partials[2 * C + 1]);
+    if (threadIdx.x == 0) s_inv_den = (float)(1.0 / __ldcg(partials + 2 * C + 1));
     __syncthreads();
     if (grad_scale_dev) grad_scale *= __ldg(grad_scale_dev);   // upstream dL/d(loss) without a host sync
     const float eps = a.cfg.eps, gamma = a.cfg.fl_gamma;
@@ -224,8 +232,9 @@ __global__ void __launch_bounds__(kThreads, (PX == 4 || CMAX > 9) ? 2 : 3)
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) bb[c] = c < C ? s_b[c] : 0.f;
 
-    for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < a.total_units;
-         u += (long long)gridDim.x * kThreads) {
+    for (long long uf = (long long)blockIdx.x * kThreads + threadIdx.x; uf < a.total_units;
+         uf += (long long)gridDim.x * kThreads) {
+        const long long u = REVERSE ? a.total_units - 1 - uf : uf;
         const long long b = u / a.units_per_img;
         const long long off = (u - b * a.units_per_img) * PX;
         const size_t base = ((size_t)b * C) * a.HW + off;
@@ -272,19 +281,60 @@ __global__ void __launch_bounds__(kThreads, (PX == 4 || CMAX > 9) ? 2 : 3)
     }
 }
 
-__global__ void loss_finalize_kernel(const double *__restrict__ partials, int C, long long n_px_total, pylc_loss_cfg cfg,
-                                     float *__restrict__ out4) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const double ce = partials[2 * C] / partials[2 * C + 1];
+template <int C_T, int CMAX, int PX>
+__global__ void __launch_bounds__(kThreads, (PX == 4 || CMAX > 9) ? 2 : 3)
+    loss_grad_kernel(LossArgs a, const double *partials, long long n_px_total, float grad_scale,
+                     const float *__restrict__ grad_scale_dev, float *__restrict__ grad) {
+    loss_grad_pass<C_T, CMAX, PX, false>(a, partials, n_px_total, grad_scale, grad_scale_dev, grad);
+}
+
+__device__ __forceinline__ void loss_finalize(const double *partials, int C, long long n_px_total, const pylc_loss_cfg &cfg,
+                                              float *out4) {
+    const double ce = __ldcg(partials + 2 * C) / __ldcg(partials + 2 * C + 1);
     double dice = 0.0;
     for (int c = 0; c < C; ++c)
-        dice += 1.0 - (2.0 * partials[c] + cfg.dice_smooth) / (partials[C + c] + cfg.dice_smooth);
+        dice += 1.0 - (2.0 * __ldcg(partials + c) + cfg.dice_smooth) / (__ldcg(partials + C + c) + cfg.dice_smooth);
     dice /= C;
-    const double focal = partials[2 * C + 2] / (double)n_px_total;
+    const double focal = __ldcg(partials + 2 * C + 2) / (double)n_px_total;
     out4[0] = (float)(cfg.ce_weight * ce + cfg.dice_weight * dice + cfg.focal_weight * focal);
     out4[1] = (float)ce;
     out4[2] = (float)dice;
     out4[3] = (float)focal;
+}
+
+__global__ void loss_finalize_kernel(const double *partials, int C, long long n_px_total, pylc_loss_cfg cfg, float *__restrict__ out4) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    loss_finalize(partials, C, n_px_total, cfg, out4);
+}
+
+// Forward and backward in ONE cooperative launch (single-GPU training step): reduce pass, grid-wide
+// barrier, loss values written by one thread, gradient pass in reverse order.  Co-residency of the
+// whole grid is what cudaLaunchCooperativeKernel guarantees; the grid is the same one-wave
+// persistent grid the two-launch path uses.
+template <int C_T, int CMAX, int PX>
+__global__ void __launch_bounds__(kThreads, (PX == 4 || CMAX > 9) ? 2 : 3)
+    loss_fused_kernel(LossArgs a, double *partials, long long n_px_total, float grad_scale, const float *grad_scale_dev,
+                      float *grad, float *out4) {
+    loss_reduce_pass<C_T, CMAX, PX>(a, partials);
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    if (out4 && blockIdx.x == 0 && threadIdx.x == 0) loss_finalize(partials, C_T > 0 ? C_T : a.C, n_px_total, a.cfg, out4);
+    loss_grad_pass<C_T, CMAX, PX, true>(a, partials, n_px_total, grad_scale, grad_scale_dev, grad);
+}
+
+// grad *= *scale unless *scale == 1 (the usual loss.backward()): lets the fused kernel's gradient be
+// handed to autograd without a host sync and, in the usual case, without touching it again.
+__global__ void __launch_bounds__(kThreads) scale_unless_one_kernel(float *__restrict__ g, long long n4, long long n,
+                                                                    const float *__restrict__ scale) {
+    const float s = __ldg(scale);
+    if (s == 1.f) return;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (long long)gridDim.x * kThreads) {
+        float4 v = reinterpret_cast<float4 *>(g)[i];
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        reinterpret_cast<float4 *>(g)[i] = v;
+    }
+    if (blockIdx.x == 0)
+        for (long long i = n4 * 4 + threadIdx.x; i < n; i += kThreads) g[i] *= s;
 }
 
 static int fill_args(const float *logits, const void *target, int target_is_i64, int B, int C, int64_t HW,
@@ -378,5 +428,52 @@ extern "C" int pylc_multiloss_finalize(const double *partials, int C, int64_t n_
     if (!partials || !cfg || !out4 || n_px_total < 1) return PYLC_ERR_ARG;
     if (C < 1 || C > PYLC_MAX_CLASSES) return PYLC_ERR_CLASSES;
     loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partials, C, (long long)n_px_total, *cfg, out4);
+    return finish_launch();
+}
+
+extern "C" int pylc_multiloss_fwd_bwd(const float *logits, const void *target, int target_is_i64, int B, int C, int64_t HW,
+                                      const float *class_w, const pylc_loss_cfg *cfg, double *partials, float grad_scale,
+                                      const float *grad_scale_dev, float *grad, float *out4, pylc_stream_t stream) {
+    if (!partials || !grad) return PYLC_ERR_ARG;
+    if ((uintptr_t)grad % 16) return PYLC_ERR_ALIGN;
+    LossArgs a;
+    int px;
+    int rc = fill_args(logits, target, target_is_i64, B, C, HW, class_w, cfg, &a, &px);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long n_px_total = (long long)B * HW;
+    void *args[] = {&a, &partials, &n_px_total, &grad_scale, &grad_scale_dev, &grad, &out4};
+    cudaError_t e = cudaSuccess;
+#define LAUNCH_FUSED(K) e = cudaLaunchCooperativeKernel((void *)K, dim3(loss_grid(K, a.total_units)), dim3(kThreads), args, 0, st)
+    if (px == 4) {
+        if (C <= 4) LAUNCH_FUSED((loss_fused_kernel<0, 4, 4>));
+        else LAUNCH_FUSED((loss_fused_kernel<0, 6, 4>));
+    } else if (px == 2) {
+        if (C == 9) LAUNCH_FUSED((loss_fused_kernel<9, 9, 2>));
+        else if (C == 11) LAUNCH_FUSED((loss_fused_kernel<11, 11, 2>));
+        else if (C <= 8) LAUNCH_FUSED((loss_fused_kernel<0, 8, 2>));
+        else if (C <= 12) LAUNCH_FUSED((loss_fused_kernel<0, 12, 2>));
+        else LAUNCH_FUSED((loss_fused_kernel<0, 16, 2>));
+    } else {
+        if (C <= 12) LAUNCH_FUSED((loss_fused_kernel<0, 12, 1>));
+        else LAUNCH_FUSED((loss_fused_kernel<0, 32, 1>));
+    }
+#undef LAUNCH_FUSED
+    if (e != cudaSuccess) return (int)e;
+    return finish_launch();
+}
+
+extern "C" int pylc_scale_unless_one_f32(float *data, int64_t n, const float *scale_dev, pylc_stream_t stream) {
+    if (!data || !scale_dev || n < 0) return PYLC_ERR_ARG;
+    if ((uintptr_t)data % 16) return PYLC_ERR_ALIGN;
+    if (n == 0) return PYLC_OK;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long n4 = n / 4;
+    long long want = (n4 + kThreads - 1) / kThreads;
+    if (want > (long long)sms * 8) want = (long long)sms * 8;
+    if (want < 1) want = 1;
+    scale_unless_one_kernel<<<(unsigned)want, kThreads, 0, (cudaStream_t)stream>>>(data, n4, (long long)n, scale_dev);
     return finish_launch();
 }

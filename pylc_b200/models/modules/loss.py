@@ -5,11 +5,13 @@ MultiLoss -- host-side mirror of PyLC's models/modules/loss.py (reference loss.p
 
 The reference evaluates this with ~10 torch kernels forward (2 softmax, 2 one_hot to int64
 [B,H,W,C], CE, pow/log/sum ...) plus autograd backward.  Here the forward is ONE streaming pass
-over the logits (pylc_multiloss_reduce -> 2C+3 partial sums) and the backward ONE more
-(pylc_multiloss_grad, closed-form gradient of all three terms); Dice needs the
-batch-global sums before any gradient exists, so two passes is the minimum.  Under data
-parallelism the partials are all-reduced between the passes (`distributed=True`), which makes the
-loss and gradient those of the single large batch.
+over the logits (2C+3 partial sums) and the backward ONE more (closed-form gradient of all three
+terms); Dice needs the batch-global sums before any gradient exists, so two passes
+over the logits is the minimum.  On one GPU both passes run in a single cooperative launch
+(pylc_multiloss_fwd_bwd: grid-wide barrier between them, gradient pass back to front so it starts
+in L2) whenever the logits require a gradient; under data parallelism (`distributed=True`) they are
+two launches (pylc_multiloss_reduce / pylc_multiloss_grad) with the all-reduce of the partials in
+between, which makes the loss and gradient those of the single large batch.
 
 Interface kept: MultiLoss(loss_weights, schema); .forward(pred, target); .ce_loss / .dice_loss /
 .focal_loss callable on their own (models/model.py:360-362); .ce / .dsc / .fl hold the last
@@ -31,6 +33,14 @@ class _MultiLossFn(torch.autograd.Function):
         pred = pred.contiguous()
         target = target.contiguous()
         C = pred.shape[1]
+        ctx.fused_grad = None
+        if ctx.needs_input_grad[0] and not (distributed and pdist.world_size() > 1):
+            # single-GPU training step: forward and backward in ONE cooperative launch; the gradient is
+            # stashed for backward(), which only rescales it if the upstream gradient is not 1
+            out, grad, partials = ops.multiloss_fwd_bwd(pred, target, cfg, class_w)
+            ctx.fused_grad = grad
+            ctx.mark_non_differentiable(target)
+            return out
         partials = ops.multiloss_reduce(pred, target, cfg, class_w)
         n_px = target.numel()
         if distributed and pdist.world_size() > 1:
@@ -44,6 +54,10 @@ class _MultiLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.fused_grad is not None:
+            grad, ctx.fused_grad = ctx.fused_grad, None
+            ops.scale_unless_one_(grad, grad_out[0].to(torch.float32).contiguous())
+            return grad, None, None, None, None
         pred, target, partials = ctx.saved_tensors
         # dL/dz from the kernel, scaled by the upstream gradient of out[0] (the weighted loss).
         # The component outputs out[1:4] are reporting values; gradients through them are dropped.

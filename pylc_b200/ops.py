@@ -392,3 +392,23 @@ def multiloss_grad(logits, target, cfg, partials, n_px_total, class_w=None, grad
                                           _stream()),
           "pylc_multiloss_grad")
     return grad
+
+
+def multiloss_fwd_bwd(logits, target, cfg, class_w=None, grad_scale=1.0, out=None, partials=None):
+    """pylc_multiloss_fwd_bwd: one cooperative launch.  Returns (out4 = loss/ce/dice/focal, grad, partials)."""
+    logits, target, is_i64, B, C, HW = _loss_inputs(logits, target)
+    grad = out if out is not None else torch.empty_like(logits)
+    if partials is None:
+        partials = torch.zeros((2 * C + 3,), dtype=torch.float64, device=logits.device)
+    out4 = torch.empty((4,), dtype=torch.float32, device=logits.device)
+    check(_lib.load().pylc_multiloss_fwd_bwd(_p(logits), _p(target), is_i64, B, C, HW, _p(class_w), ctypes.byref(cfg),
+                                             _p(partials), float(grad_scale), None, _p(grad), _p(out4), _stream()),
+          "pylc_multiloss_fwd_bwd")
+    return out4, grad, partials
+
+
+def scale_unless_one_(data, scale_dev):
+    """In place data *= scale_dev (CUDA f32 scalar) unless it equals 1; no host sync."""
+    _need_cuda(data, scale_dev)
+    check(_lib.load().pylc_scale_unless_one_f32(_p(data), data.numel(), _p(scale_dev), _stream()), "pylc_scale_unless_one_f32")
+    return data

@@ -499,3 +499,35 @@ def test_multiloss_partials_are_additive_across_shards(ops):
     g_full = ops.multiloss_grad(dev(z), dev(t), cfg, full, t.size)
     g_half = ops.multiloss_grad(dev(z[2:]), dev(t[2:]), cfg, part, t.size)
     np.testing.assert_allclose(g_half.cpu().numpy(), g_full.cpu().numpy()[2:], rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("B,C,H,W,weighted,u8", [(4, 9, 128, 128, False, False), (2, 11, 64, 96, True, False),
+                                                 (3, 5, 17, 23, True, True), (2, 20, 32, 32, False, True),
+                                                 (8, 9, 512, 512, True, False)])
+def test_multiloss_fused_equals_two_pass(ops, B, C, H, W, weighted, u8):
+    """The single cooperative launch (reduce -> grid barrier -> gradient, back to front) against the
+    two-launch path and the oracle: same loss values (1e-4 relative, north_star) and gradient."""
+    rng = np.random.default_rng(B * C + H)
+    z = (rng.standard_normal((B, C, H, W)) * 3).astype(np.float32)
+    t = rng.integers(0, C, size=(B, H, W)).astype(np.uint8 if u8 else np.int64)
+    w = (rng.random(C) + 0.3).astype(np.float32)
+    cfg = ops.loss_cfg()
+    dz, dt = dev(z), dev(t)
+    cw = dev(w) if weighted else None
+    out4, grad, part = ops.multiloss_fwd_bwd(dz, dt, cfg, class_w=cw)
+    part2 = ops.multiloss_reduce(dz, dt, cfg, class_w=cw)
+    vals2 = ops.multiloss_finalize(part2, C, t.size, cfg)
+    grad2 = ops.multiloss_grad(dz, dt, cfg, part2, t.size, class_w=cw)
+    np.testing.assert_allclose(part.cpu().numpy(), part2.cpu().numpy(), rtol=1e-9)
+    np.testing.assert_allclose(out4.cpu().numpy(), vals2.cpu().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(grad.cpu().numpy(), grad2.cpu().numpy(), rtol=1e-5, atol=1e-12)
+    if B * H * W <= 1 << 17:
+        ref = orc.multiloss(z, t.astype(np.int64), C, weights=w if weighted else None, weighted=weighted)
+        np.testing.assert_allclose(out4.cpu().numpy(), ref[:4], rtol=LOSS_RTOL)
+        np.testing.assert_allclose(grad.cpu().numpy(), ref[4], rtol=2e-3, atol=1e-9)
+    # upstream-gradient rescale: untouched for 1, scaled otherwise
+    g1 = grad.clone()
+    ops.scale_unless_one_(g1, torch.ones((), device="cuda"))
+    assert torch.equal(g1, grad)
+    ops.scale_unless_one_(g1, torch.full((), 0.5, device="cuda"))
+    assert torch.equal(g1, grad * 0.5)

@@ -235,6 +235,12 @@ def main():
     report("multiloss fwd+bwd B64 C9 (algorithmic 8C+8)", npx * (8 * C + 8), fwd_bwd,
            "two passes physically move 12C + 16 B/px")
 
+    def fused():
+        p = torch.zeros((2 * C + 3,), dtype=torch.float64, device="cuda")
+        ops.multiloss_fwd_bwd(z, t64, cfg, out=grad, partials=p)
+    report("multiloss fwd+bwd B64 C9, one cooperative launch (algorithmic 8C+8)", npx * (8 * C + 8), fused,
+           "reduce + grid barrier + gradient back to front; physically moves <= 12C + 16 B/px")
+
     if args.out:
         os.makedirs(os.path.dirname(args.out), exist_ok=True)
         with open(args.out, "w") as f:
