@@ -115,6 +115,21 @@ PYLC_API int pylc_tile_gather_norm_f32(const uint8_t *src, int H, int W, int ch,
                               int S, const float *mean, const float *std, float post_div,
                               int out_ch, float *dst, pylc_stream_t stream);
 
+/*
+ * Augmentor.optimize grid search (utils/augment.py:92-187) over rate coefficients x thresholds: for
+ * grid point g = i*n_thresholds + j,
+ *     rates[n]        = clip(int((scores[n] > thresholds[j]) * rate_coefs[i] * scores[n]), rate_lo, rate_hi)
+ *     sum_rates[g]    = sum_n rates[n]
+ *     full_px_dist[g] = sum_n (1 + rates[n]) * px_dist[n, :]            (exact int64)
+ * scores [N] f64 (the host computes them with NumPy exactly as the reference, augment.py:108-116),
+ * px_dist [N, C] i64, rate_coefs / thresholds f64 -- all DEVICE.  The O(grid x C) tail (probabilities,
+ * M2, JSD, argmin) stays on the host in float64.
+ */
+PYLC_API int pylc_sample_rate_grid(const double *scores, const int64_t *px_dist, int N, int C,
+                          const double *rate_coefs, int n_coefs, const double *thresholds,
+                          int n_thresholds, int rate_lo, int rate_hi, int64_t *sum_rates,
+                          int64_t *full_px_dist, pylc_stream_t stream);
+
 /* ---- test-time fit resize ----------------------------------------------------------------- */
 
 #define PYLC_AREA_TAPS 6 /* source cells per destination cell and axis: scale factors below 5 */

@@ -258,6 +258,32 @@ def gen_loss(ref, out):
         out["loss_%s_grad" % name] = zt.grad.numpy()
 
 
+def gen_augment(ref, out):
+    """Augmentor.optimize (utils/augment.py:92-187) run by the reference itself on seeded profile metadata."""
+    import types
+    import utils.augment as ref_augment
+    rng = np.random.default_rng(41)
+    for name, (N, C, T) in {"a": (300, 9, 64), "b": (500, 11, 32)}.items():
+        # skewed per-tile class histograms that sum to T*T, like get_profile's px_dist
+        conc = np.concatenate([[8.0, 0.05, 3.0, 1.0], np.full(C - 4, 0.3)])
+        p = rng.dirichlet(conc, size=N)
+        px = np.floor(p * T * T).astype(np.int64)
+        px[:, 0] += T * T - px.sum(axis=1)
+        probs = px.sum(axis=0) / px.sum()
+        aug = ref_augment.Augmentor()
+        aug.input_meta = types.SimpleNamespace(px_dist=px, tile_px_count=T * T, probs=probs, n_classes=C)
+        aug.input_size = N
+        aug.optimize()
+        om = aug.optim_meta
+        out["aug_%s_px_dist" % name] = px
+        out["aug_%s_probs" % name] = probs
+        out["aug_%s_meta" % name] = np.array([N, C, T * T])
+        out["aug_%s_rates" % name] = np.asarray(om['rates'])
+        out["aug_%s_optim" % name] = np.array([om['threshold'], om['rate_coef'], om['jsd'], om['m2'], om['n_samples'],
+                                                  om['aug_n_samples']], dtype=np.float64)
+        out["aug_%s_optim_probs" % name] = np.asarray(om['probs'])
+
+
 def main():
     ref = ref_harness.load()
     # get_image() upscales anything whose short side is below defaults.tile_size
@@ -266,7 +292,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     for fname, fn in (("split", gen_split), ("encode", gen_encode), ("colourize", gen_colourize),
                       ("extract_profile", gen_extract_profile), ("fit", gen_fit),
-                      ("reconstruct", gen_reconstruct), ("evaluate", gen_evaluate), ("loss", gen_loss)):
+                      ("reconstruct", gen_reconstruct), ("evaluate", gen_evaluate), ("loss", gen_loss),
+                      ("augment", gen_augment)):
         out = {}
         fn(ref, out)
         path = os.path.join(OUT, fname + ".npz")

@@ -118,6 +118,39 @@ def resize_area(img, w, h):
     return out.reshape(h, w) if img.ndim == 2 else out
 
 
+def augment_optimize_port(px_dist, px_count, dset_probs, n_classes, input_size, rate_coef_range=(1, 21),
+                          threshold_range=(0, 3.), rate_range=(0, 4), n_samples_ratio=0.36):
+    """utils/augment.py:92-187 as written (grid search over rate coefficient x threshold, JSD argmin).
+    Returns (optim dict with 'rates', list of per-grid-point dicts)."""
+    eps = 1e-8
+    px_dist = np.array(px_dist, dtype='long')
+    dset_probs = np.array(dset_probs, dtype='float32') + eps
+    oversample_filter = np.clip(1 / n_classes - dset_probs, a_min=0, a_max=1.)
+    probs = px_dist / px_count
+    probs_weighted = np.multiply(np.multiply(probs, 1 / dset_probs), oversample_filter)
+    scores = np.sqrt(np.sum(probs_weighted, axis=1))
+    rate_coefs = np.arange(min(rate_coef_range), max(rate_coef_range), 1.)
+    thresholds = np.arange(min(threshold_range), max(threshold_range), 0.05)
+    balanced = np.empty(n_classes)
+    balanced.fill(1 / n_classes)
+    data, jsds = [], []
+    for rate_coef in rate_coefs:
+        for threshold in thresholds:
+            over_sample = scores > threshold
+            rates = np.multiply(over_sample, rate_coef * scores).astype(int)
+            rates = np.clip(rates, rate_range[0], rate_range[1])
+            if np.sum(rates) < int(n_samples_ratio * input_size):
+                full_px_dist = px_dist + np.multiply(np.expand_dims(rates, axis=1), px_dist)
+                full_px_probs = np.sum(full_px_dist, axis=0) / np.sum(full_px_dist)
+                m2_s, jsd_s = m2(full_px_probs, n_classes), jsd(full_px_probs, balanced)
+                jsds.append(jsd_s)
+                data.append({'probs': full_px_probs, 'threshold': threshold, 'rate_coef': rate_coef, 'rates': rates,
+                             'n_samples': int(np.sum(full_px_dist) / px_count), 'aug_n_samples': np.sum(rates),
+                             'jsd': jsd_s, 'm2': m2_s})
+    assert len(jsds) > 0, 'No augmentation optimization found.'
+    return data[int(np.argmin(np.asarray(jsds)))], data
+
+
 # ----------------------------------------------------------------------------------------------
 # class_encode / colourize  (utils/tools.py:412-449, 322-358)
 # ----------------------------------------------------------------------------------------------

@@ -350,3 +350,78 @@ extern "C" int pylc_colourise_u8(const uint8_t *labels, int64_t n_px, const uint
     colourise_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(labels, n_px, lut, rgb, aligned);
     return finish_launch();
 }
+
+// ------------------------------------------------------------------------------------------------
+// Augmentor.optimize grid search (utils/augment.py:92-187): for every (rate_coef, threshold) pair the
+// per-tile over-sampling rates and the class histogram of the over-sampled dataset.
+// ------------------------------------------------------------------------------------------------
+// One CTA per grid point; threads stride over the tiles and keep the C class sums in registers.
+// All arithmetic the reference does in float64 / int64 is done in the same types (one IEEE multiply,
+// truncation, clip, integer multiply-add), so every output integer equals NumPy's.  The inputs are
+// a few hundred KB and stay in L2: the kernel is latency-, not bandwidth-bound.
+namespace pylc {
+
+template <int CMAX>
+__global__ void __launch_bounds__(kThreads)
+    sample_rate_grid_kernel(const double *__restrict__ scores, const long long *__restrict__ px_dist, int N, int C,
+                            const double *__restrict__ rate_coefs, const double *__restrict__ thresholds, int n_thr,
+                            int rate_lo, int rate_hi, long long *__restrict__ sum_rates, long long *__restrict__ full_px_dist) {
+    const int g = blockIdx.x;
+    const double rc = __ldg(rate_coefs + g / n_thr), th = __ldg(thresholds + g % n_thr);
+    long long acc[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) acc[c] = 0;
+    long long rsum = 0;
+    for (int n = threadIdx.x; n < N; n += kThreads) {
+        const double s = __ldg(scores + n);
+        // np.multiply(scores > threshold, rate_coef * scores).astype(int), then np.clip (augment.py:142-152)
+        long long rate = s > th ? (long long)__dmul_rn(rc, s) : 0ll;
+        rate = rate < rate_lo ? rate_lo : (rate > rate_hi ? rate_hi : rate);
+        rsum += rate;
+        const long long mult = rate + 1;          // px_dist + rates * px_dist (augment.py:156-157)
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+            if (c < C) acc[c] += mult * __ldg(px_dist + (size_t)n * C + c);
+    }
+    __shared__ unsigned long long s_acc[PYLC_MAX_CLASSES + 1];
+    if (threadIdx.x <= PYLC_MAX_CLASSES) s_acc[threadIdx.x] = 0;
+    __syncthreads();
+    auto warp_sum = [](long long v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        return v;
+    };
+    const int lane = threadIdx.x & 31;
+    rsum = warp_sum(rsum);
+    if (lane == 0) atomicAdd(&s_acc[PYLC_MAX_CLASSES], (unsigned long long)rsum);
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+            const long long v = warp_sum(acc[c]);
+            if (lane == 0) atomicAdd(&s_acc[c], (unsigned long long)v);
+        }
+    __syncthreads();
+    if (threadIdx.x < C) full_px_dist[(size_t)g * C + threadIdx.x] = (long long)s_acc[threadIdx.x];
+    if (threadIdx.x == 0) sum_rates[g] = (long long)s_acc[PYLC_MAX_CLASSES];
+}
+
+}  // namespace pylc
+
+extern "C" int pylc_sample_rate_grid(const double *scores, const int64_t *px_dist, int N, int C, const double *rate_coefs,
+                                     int n_coefs, const double *thresholds, int n_thresholds, int rate_lo, int rate_hi,
+                                     int64_t *sum_rates, int64_t *full_px_dist, pylc_stream_t stream) {
+    if (!scores || !px_dist || !rate_coefs || !thresholds || !sum_rates || !full_px_dist) return PYLC_ERR_ARG;
+    if (N < 1 || n_coefs < 1 || n_thresholds < 1 || rate_lo > rate_hi) return PYLC_ERR_ARG;
+    if (C < 1 || C > PYLC_MAX_CLASSES) return PYLC_ERR_CLASSES;
+    const unsigned grid = (unsigned)(n_coefs * n_thresholds);
+    auto *pd = reinterpret_cast<const long long *>(px_dist);
+    auto *sr = reinterpret_cast<long long *>(sum_rates);
+    auto *fp = reinterpret_cast<long long *>(full_px_dist);
+    if (C <= 12)
+        pylc::sample_rate_grid_kernel<12><<<grid, pylc::kThreads, 0, (cudaStream_t)stream>>>(
+            scores, pd, N, C, rate_coefs, thresholds, n_thresholds, rate_lo, rate_hi, sr, fp);
+    else
+        pylc::sample_rate_grid_kernel<PYLC_MAX_CLASSES><<<grid, pylc::kThreads, 0, (cudaStream_t)stream>>>(
+            scores, pd, N, C, rate_coefs, thresholds, n_thresholds, rate_lo, rate_hi, sr, fp);
+    return pylc::finish_launch();
+}

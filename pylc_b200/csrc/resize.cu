@@ -14,63 +14,109 @@
 // every output byte equals OpenCV's.  Integer-factor down-scales (OpenCV's separate "fast area"
 // code) and any up-scale are refused with PYLC_ERR_GEOMETRY: the caller keeps the host cv2 path.
 //
-// One thread owns one destination column of a band of destination rows and walks down the source
-// rows it needs, holding `sum` in registers: no shared memory, no barrier.  Neighbouring threads
-// read neighbouring source bytes (L1-coalesced); every source row is read by exactly one band,
-// plus the single row two bands may share.
+// A CTA owns a band of destination rows x a strip of destination columns.  It first parks every
+// source byte the band needs in shared memory with 16-byte loads issued back to back (one memory
+// round trip per CTA instead of one per source row), then one thread per destination column walks
+// down the staged rows holding `sum` in registers.  Every source row is read by exactly one band,
+// plus the row two bands may share.
 #include <math.h>
 
 #include "common.cuh"
 
 namespace pylc {
 
-constexpr int kAreaRows = 16;  // destination rows per CTA band
+constexpr int kAreaThreads = 128;
+constexpr int kAreaRowBytes = 832;   // staged bytes per source row (52 chunks of 16 B)
+constexpr int kAreaMaxRows = 40;     // staged source rows per band
 
 struct AreaArgs {
     const uint8_t *src;
-    size_t src_pitch;
+    size_t src_pitch, src_bytes;     // src_bytes: one past the last valid source byte
     uint8_t *dst;
     size_t dst_pitch;
     int dw, dh;
+    int cols_cta, rows_cta;          // destination columns / rows per CTA (the host sizes them to the staging buffer)
+    int row_stride, stage_rows;      // staging buffer: bytes per staged source row (multiple of 16), rows
     const int32_t *xs, *xn, *ys, *yn;
     const float *xa, *ya;
 };
 
-template <int CN>
-__global__ void __launch_bounds__(128) area_resize_kernel(AreaArgs a) {
-    const int dx = blockIdx.x * 128 + threadIdx.x;
-    if (dx >= a.dw) return;
-    const int sx0 = __ldg(a.xs + dx) * CN, nx = __ldg(a.xn + dx);
-    float alpha[PYLC_AREA_TAPS];
+template <int CN, int NX>
+__global__ void __launch_bounds__(kAreaThreads) area_resize_kernel(AreaArgs a) {
+    extern __shared__ __align__(16) uint8_t s_src[];     // stage_rows x row_stride bytes (sized by the host to the patch)
+    const int dx0 = blockIdx.x * a.cols_cta, dx1 = min(a.dw, dx0 + a.cols_cta);
+    const int dy0 = blockIdx.y * a.rows_cta, dy1 = min(a.dh, dy0 + a.rows_cta);
+    const int x_lo = __ldg(a.xs + dx0), x_hi = __ldg(a.xs + dx1 - 1) + __ldg(a.xn + dx1 - 1);   // source columns [x_lo, x_hi)
+    const int s_lo = __ldg(a.ys + dy0), s_hi = __ldg(a.ys + dy1 - 1) + __ldg(a.yn + dy1 - 1);   // source rows    [s_lo, s_hi)
+    const int nrows = s_hi - s_lo, row_bytes = (x_hi - x_lo) * CN;
+
+    // ---- stage: row r of the band at s_src[r * kAreaRowBytes + (its global address & 15) ...] ----
+    const int cpr = (row_bytes + 15 + 15) / 16;           // chunks per row incl. the alignment slop
+    if (nrows > a.stage_rows || cpr * 16 > a.row_stride) __trap();   // the host sizes the patch; never taken
+    const uintptr_t src0 = (uintptr_t)a.src, src_end = src0 + a.src_bytes;
+    for (int id = threadIdx.x; id < nrows * cpr; id += kAreaThreads) {
+        const int r = id / cpr, ck = id - r * cpr;
+        const uintptr_t row_addr = src0 + (size_t)(s_lo + r) * a.src_pitch + (size_t)x_lo * CN;
+        const uintptr_t g = (row_addr & ~(uintptr_t)15) + 16u * ck;
+        uint8_t *d = s_src + r * a.row_stride + 16 * ck;
+        if (g >= src0 && g + 16 <= src_end) {
+            *reinterpret_cast<uint4 *>(d) = ld_stream16(reinterpret_cast<const void *>(g));
+        } else {
+            for (int i = 0; i < 16; ++i) d[i] = (g + i >= src0 && g + i < src_end) ? __ldg(reinterpret_cast<const uint8_t *>(g + i)) : 0;
+        }
+    }
+    __syncthreads();
+
+    // ---- filter ---------------------------------------------------------------------------------
+    // Running pointers and 32-bit shared-window addresses keep the per-row bookkeeping to a few
+    // instructions; NX is the compile-time tap bound (3 for scale factors below 2: the fit-resize case).
+    const int dx = dx0 + threadIdx.x;
+    if (threadIdx.x >= a.cols_cta || dx >= dx1) return;
+    const int nx = __ldg(a.xn + dx);
+    float alpha[NX];
 #pragma unroll
-    for (int k = 0; k < PYLC_AREA_TAPS; ++k) alpha[k] = __ldg(a.xa + (size_t)dx * PYLC_AREA_TAPS + k);
-    const int dy0 = blockIdx.y * kAreaRows, dy1 = min(a.dh, dy0 + kAreaRows);
-    for (int dy = dy0; dy < dy1; ++dy) {
-        const int sy0 = __ldg(a.ys + dy), ny = __ldg(a.yn + dy);
+    for (int k = 0; k < NX; ++k) alpha[k] = __ldg(a.xa + (size_t)dx * PYLC_AREA_TAPS + k);
+    const uint32_t sbase = (uint32_t)(__ldg(a.xs + dx) - x_lo) * CN;     // byte offset inside a staged row
+    const uint32_t lo0 = (uint32_t)((src0 + (size_t)s_lo * a.src_pitch + (size_t)x_lo * CN) & 15), plo = (uint32_t)(a.src_pitch & 15);
+    const int32_t *ys_p = a.ys + dy0, *yn_p = a.yn + dy0;
+    const float *ya_p = a.ya + (size_t)dy0 * PYLC_AREA_TAPS;
+    uint8_t *d = a.dst + (size_t)dy0 * a.dst_pitch + (size_t)dx * CN;
+    // `buf` of the last source row is kept: consecutive destination rows usually share one source row
+    // (OpenCV recomputes it, to the same value), which nearly halves the horizontal passes.
+    float buf[CN];
+    int r_buf = -1;
+    for (int dy = dy0; dy < dy1; ++dy, ++ys_p, ++yn_p, ya_p += PYLC_AREA_TAPS, d += a.dst_pitch) {
+        const int r0 = __ldg(ys_p) - s_lo, ny = __ldg(yn_p);
         float sum[CN];
 #pragma unroll
         for (int c = 0; c < CN; ++c) sum[c] = 0.f;
         for (int j = 0; j < ny; ++j) {
-            const uint8_t *srow = a.src + (size_t)(sy0 + j) * a.src_pitch + sx0;
-            const float beta = __ldg(a.ya + (size_t)dy * PYLC_AREA_TAPS + j);
-            float buf[CN];
+            const int r = r0 + j;
+            if (r != r_buf) {
+                r_buf = r;
+                const uint32_t addr = sbase + (uint32_t)r * (uint32_t)a.row_stride + ((lo0 + (uint32_t)r * plo) & 15u);
 #pragma unroll
-            for (int c = 0; c < CN; ++c) buf[c] = 0.f;
+                for (int c = 0; c < CN; ++c) buf[c] = 0.f;
 #pragma unroll
-            for (int k = 0; k < PYLC_AREA_TAPS; ++k) {
-                if (k < nx) {
+                for (int k = 0; k < NX; ++k) {
+                    if (k < nx) {
 #pragma unroll
-                    for (int c = 0; c < CN; ++c)
-                        buf[c] = __fadd_rn(buf[c], __fmul_rn((float)__ldg(srow + k * CN + c), alpha[k]));
+                        for (int c = 0; c < CN; ++c) {
+                            const uint32_t b = s_src[addr + k * CN + c];
+                            // (float)byte without the conversion pipe: 2^23 + b as a bit pattern, minus 2^23
+                            const float px = __uint_as_float(0x4B000000u | b) - 8388608.f;
+                            buf[c] = __fadd_rn(buf[c], __fmul_rn(px, alpha[k]));
+                        }
+                    }
                 }
             }
+            const float beta = __ldg(ya_p + j);
 #pragma unroll
             for (int c = 0; c < CN; ++c) {
                 const float t = __fmul_rn(beta, buf[c]);
                 sum[c] = j == 0 ? t : __fadd_rn(sum[c], t);
             }
         }
-        uint8_t *d = a.dst + (size_t)dy * a.dst_pitch + (size_t)dx * CN;
 #pragma unroll
         for (int c = 0; c < CN; ++c) d[c] = (uint8_t)min(255, max(0, __float2int_rn(sum[c])));
     }
@@ -135,11 +181,31 @@ extern "C" int pylc_fit_resize_area_u8(const uint8_t *src, int H, int W, int ch,
     if (src_pitch < (size_t)W * ch || dst_pitch < (size_t)w * ch) return PYLC_ERR_ARG;
     if (!pylc_area_supported(W, H, w, h)) return PYLC_ERR_GEOMETRY;
     AreaArgs a;
-    a.src = src; a.src_pitch = src_pitch; a.dst = dst; a.dst_pitch = dst_pitch; a.dw = w; a.dh = h;
+    a.src = src; a.src_pitch = src_pitch; a.src_bytes = (size_t)(H - 1) * src_pitch + (size_t)W * ch;
+    a.dst = dst; a.dst_pitch = dst_pitch; a.dw = w; a.dh = h;
     a.xs = x_start; a.xn = x_count; a.xa = x_weights; a.ys = y_start; a.yn = y_count; a.ya = y_weights;
-    const dim3 grid((unsigned)((w + 127) / 128), (unsigned)((h + kAreaRows - 1) / kAreaRows));
-    if (ch == 1) area_resize_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
-    else area_resize_kernel<3><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    // size the CTA's destination patch so that its source footprint fits the staging buffer:
+    // a run of n destination cells covers at most n*scale + 2 source cells
+    const double sx = (double)W / w, sy = (double)H / h;
+    int cols = (int)floor(((kAreaRowBytes - 30) / ch - 2) / sx);
+    int rows = (int)floor((kAreaMaxRows - 2) / sy);
+    a.cols_cta = cols > kAreaThreads ? kAreaThreads : (cols < 1 ? 1 : cols);
+    a.rows_cta = rows > 16 ? 16 : (rows < 1 ? 1 : rows);
+    // ... and the staging buffer to the patch, so small footprints leave room for many resident CTAs
+    a.row_stride = (((int)ceil(a.cols_cta * sx) + 2) * ch + 30 + 15) & ~15;
+    a.stage_rows = (int)ceil(a.rows_cta * sy) + 2;
+    if (a.row_stride > kAreaRowBytes) a.row_stride = kAreaRowBytes;
+    if (a.stage_rows > kAreaMaxRows) a.stage_rows = kAreaMaxRows;
+    const size_t smem = (size_t)a.row_stride * a.stage_rows;
+    const dim3 grid((unsigned)((w + a.cols_cta - 1) / a.cols_cta), (unsigned)((h + a.rows_cta - 1) / a.rows_cta));
+    const bool few = sx < 2.0;     // a destination cell overlaps at most floor(scale) + 2 source cells
+    if (ch == 1) {
+        if (few) area_resize_kernel<1, 3><<<grid, kAreaThreads, smem, (cudaStream_t)stream>>>(a);
+        else area_resize_kernel<1, PYLC_AREA_TAPS><<<grid, kAreaThreads, smem, (cudaStream_t)stream>>>(a);
+    } else {
+        if (few) area_resize_kernel<3, 3><<<grid, kAreaThreads, smem, (cudaStream_t)stream>>>(a);
+        else area_resize_kernel<3, PYLC_AREA_TAPS><<<grid, kAreaThreads, smem, (cudaStream_t)stream>>>(a);
+    }
     return finish_launch();
 }
 

@@ -412,3 +412,20 @@ def scale_unless_one_(data, scale_dev):
     _need_cuda(data, scale_dev)
     check(_lib.load().pylc_scale_unless_one_f32(_p(data), data.numel(), _p(scale_dev), _stream()), "pylc_scale_unless_one_f32")
     return data
+
+
+def sample_rate_grid(scores, px_dist, rate_coefs, thresholds, rate_lo, rate_hi):
+    """pylc_sample_rate_grid.  scores [N] f64, px_dist [N,C] i64, rate_coefs [R] f64, thresholds [T] f64
+    (CUDA) -> (sum_rates [R*T] i64, full_px_dist [R*T, C] i64)."""
+    _need_cuda(scores, px_dist, rate_coefs, thresholds)
+    if scores.dtype != torch.float64 or px_dist.dtype != torch.int64:
+        raise PylcError("sample_rate_grid: scores must be float64 and px_dist int64")
+    N, C = px_dist.shape
+    G = rate_coefs.numel() * thresholds.numel()
+    sum_rates = torch.empty((G,), dtype=torch.int64, device=scores.device)
+    full = torch.empty((G, C), dtype=torch.int64, device=scores.device)
+    check(_lib.load().pylc_sample_rate_grid(_p(scores.contiguous()), _p(px_dist.contiguous()), N, C,
+                                            _p(rate_coefs.contiguous()), rate_coefs.numel(), _p(thresholds.contiguous()),
+                                            thresholds.numel(), int(rate_lo), int(rate_hi), _p(sum_rates), _p(full),
+                                            _stream()), "pylc_sample_rate_grid")
+    return sum_rates, full

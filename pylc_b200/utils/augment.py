@@ -1,0 +1,107 @@
+"""
+Augmentor -- host-side mirror of PyLC's utils/augment.py for the sample-rate optimisation
+(reference augment.py:92-187), the consumer of the per-tile class histograms `px_dist` that the
+extraction / profiling kernels produce.
+
+`optimize()` is the reference's grid search over (rate coefficient, threshold): the per-tile scores
+are a handful of NumPy operations on [N, C] (kept verbatim, so thresholds decisions see the same
+float64 values), the grid itself -- |coefs| x |thresholds| passes over [N, C], each building the
+over-sampling rates and the class histogram of the over-sampled dataset -- is ONE kernel launch
+(pylc_sample_rate_grid, exact int64), and the O(grid x C) tail (probabilities, M2, JSD, argmin)
+is the reference's float64 NumPy again.
+
+Out of scope here: `oversample()` -- the perspective / brightness
+warps of tools.augment_transform are OpenCV calls on host arrays in the reference and are not part
+of the accelerated path.
+"""
+import numpy as np
+import torch
+
+from .. import ops
+from ..config import defaults
+from . import metrics
+
+
+class Augmentor(object):
+    def __init__(self):
+        self.input_path = None
+        self.input_dset = None
+        self.input_meta = None
+        self.input_size = 0
+        self.output_meta = None
+        self.optim_meta = None
+        self.profile_data = []
+        self.rates = []
+
+    def load(self, source):
+        """`source`: a database path, or an MLPDataset (reference augment.py:45-76 takes a path)."""
+        from ..db.dataset import MLPDataset
+        self.input_dset = source if isinstance(source, MLPDataset) else MLPDataset(source)
+        self.input_path = source if isinstance(source, str) else None
+        self.input_meta = self.input_dset.get_meta()
+        self.input_size = self.input_dset.size
+        return self
+
+    def load_profile(self, meta, n_tiles=None):
+        """Use profile metadata directly (px_dist [N,C], tile_px_count, probs [C], n_classes)."""
+        self.input_meta = meta
+        self.input_size = int(n_tiles if n_tiles is not None else len(meta.px_dist))
+        return self
+
+    def scores(self):
+        """Per-tile over-sampling scores, reference augment.py:104-116 verbatim."""
+        eps = 1e-8
+        px_dist = np.array(self.input_meta.px_dist, dtype='long')
+        px_count = self.input_meta.tile_px_count
+        dset_probs = np.array(self.input_meta.probs, dtype='float32') + eps
+        oversample_filter = np.clip(1 / self.input_meta.n_classes - dset_probs, a_min=0, a_max=1.)
+        probs = px_dist / px_count
+        probs_weighted = np.multiply(np.multiply(probs, 1 / dset_probs), oversample_filter)
+        return np.sqrt(np.sum(probs_weighted, axis=1)), px_dist, px_count
+
+    def optimize(self, device=None):
+        """Grid search for the sample rates that minimise the JSD to a balanced distribution
+        (reference augment.py:92-187).  Sets .optim_meta, .rates, .profile_data."""
+        device = device or torch.device("cuda")
+        n_classes = self.input_meta.n_classes
+        scores, px_dist, px_count = self.scores()
+        rate_coefs = np.arange(min(defaults.aug_rate_coef_range), max(defaults.aug_rate_coef_range), 1.)
+        thresholds = np.arange(min(defaults.aug_threshold_range), max(defaults.aug_threshold_range), 0.05)
+        assert (rate_coefs >= 1).all(), 'Rate coefficient must be >= 1.'
+        lo, hi = defaults.aug_oversample_rate_range
+        d_scores = torch.from_numpy(np.ascontiguousarray(scores, dtype=np.float64)).to(device)
+        d_dist = torch.from_numpy(np.ascontiguousarray(px_dist, dtype=np.int64)).to(device)
+        sum_rates, full = ops.sample_rate_grid(d_scores, d_dist, torch.from_numpy(rate_coefs).to(device),
+                                               torch.from_numpy(thresholds).to(device), lo, hi)
+        sum_rates, full = sum_rates.cpu().numpy(), full.cpu().numpy()       # [G], [G, C]: a few KB
+
+        balanced_px_prob = np.empty(n_classes)
+        balanced_px_prob.fill(1 / n_classes)
+        limit = int(defaults.aug_n_samples_ratio * self.input_size)
+        profile_data, jsd = [], []
+        for i, rate_coef in enumerate(rate_coefs):
+            for j, threshold in enumerate(thresholds):
+                g = i * len(thresholds) + j
+                if sum_rates[g] < limit:
+                    full_px_dist_sum = full[g]
+                    full_px_probs = full_px_dist_sum / np.sum(full_px_dist_sum)
+                    m2_sample = metrics.m2(full_px_probs, n_classes)
+                    jsd_sample = metrics.jsd(full_px_probs, balanced_px_prob)
+                    jsd += [jsd_sample]
+                    profile_data += [{
+                        'probs': full_px_probs, 'threshold': threshold, 'rate_coef': rate_coef,
+                        'n_samples': int(np.sum(full_px_dist_sum) / px_count), 'aug_n_samples': int(sum_rates[g]),
+                        'n_samples_max': defaults.aug_n_samples_ratio, 'jsd': jsd_sample, 'm2': m2_sample}]
+        assert len(jsd) > 0, 'No augmentation optimization found.'
+        self.profile_data = profile_data
+        self.optim_meta = profile_data[int(np.argmin(np.asarray(jsd)))]
+        # the per-tile rates of the winning grid point only (the reference keeps them for every point)
+        over = scores > self.optim_meta['threshold']
+        rates = np.multiply(over, self.optim_meta['rate_coef'] * scores).astype(int)
+        self.optim_meta['rates'] = np.clip(rates, lo, hi)
+        self.rates = self.optim_meta['rates']
+        return self
+
+    def oversample(self):
+        raise NotImplementedError("Augmentor.oversample (OpenCV warps on host arrays, reference augment.py:189-250) is "
+                                  "outside the accelerated path; use the optimised .rates with the reference's own augment step")

@@ -313,3 +313,45 @@ def test_pipeline_matches_reference_sequence(ops, palettes, fuse):
     assert np.array_equal(seg.conf.cpu().numpy(), conf)
     s = seg.scores(conf)
     assert s["iou"] == orc.metrics_port(yt, yp, model.meta.class_codes)["iou"]
+
+
+# ---------------------------------------------------------------------------------------------
+# Augmentor.optimize (sample-rate grid search on the device)
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_augmentor_optimize_golden(ops, golden, name):
+    """Augmentor.optimize: every grid point and the winner equal the reference's own run and the oracle,
+    to the last bit (int64 histograms on the device, float64 tail on the host)."""
+    import types
+    from pylc_b200.utils.augment import Augmentor
+    g = golden("augment")
+    N, C, px_count = (int(v) for v in g["aug_%s_meta" % name])
+    meta = types.SimpleNamespace(px_dist=g["aug_%s_px_dist" % name], tile_px_count=px_count,
+                                 probs=g["aug_%s_probs" % name], n_classes=C)
+    aug = Augmentor().load_profile(meta, n_tiles=N).optimize()
+    assert np.array_equal(aug.rates, g["aug_%s_rates" % name])
+    om, ref = aug.optim_meta, g["aug_%s_optim" % name]
+    assert [om["threshold"], om["rate_coef"], om["jsd"], om["m2"], om["n_samples"], om["aug_n_samples"]] == list(ref)
+    assert np.array_equal(om["probs"], g["aug_%s_optim_probs" % name])
+    best, data = orc.augment_optimize_port(meta.px_dist, px_count, meta.probs, C, N)
+    assert len(data) == len(aug.profile_data)
+    for a, b in zip(aug.profile_data, data):
+        assert a["jsd"] == b["jsd"] and a["m2"] == b["m2"] and a["aug_n_samples"] == b["aug_n_samples"]
+        assert np.array_equal(a["probs"], b["probs"])
+
+
+def test_sample_rate_grid_wide_classes(ops):
+    rng = np.random.default_rng(3)
+    N, C = 1234, 20
+    px = rng.integers(0, 5000, size=(N, C)).astype(np.int64)
+    scores = rng.random(N) * 4
+    coefs, thr = np.arange(1, 6, 1.), np.arange(0, 2, 0.25)
+    sr, full = ops.sample_rate_grid(torch.from_numpy(scores).cuda(), torch.from_numpy(px).cuda(),
+                                    torch.from_numpy(coefs).cuda(), torch.from_numpy(thr).cuda(), 0, 4)
+    for i, rc in enumerate(coefs):
+        for j, t in enumerate(thr):
+            rates = np.clip(np.multiply(scores > t, rc * scores).astype(int), 0, 4)
+            gi = i * len(thr) + j
+            assert int(sr[gi]) == rates.sum()
+            assert np.array_equal(full[gi].cpu().numpy(), (px + rates[:, None] * px).sum(axis=0))

@@ -168,3 +168,15 @@ def test_multiloss(golden, name, C, weighted):
     np.testing.assert_allclose([loss, ce, dice, focal], ref_vals, rtol=1e-5)
     np.testing.assert_allclose(grad, ref_grad, rtol=2e-4, atol=2e-9)
     assert partials.shape == (2 * C + 3,)
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_augment_optimize(golden, name):
+    """Augmentor.optimize restatement against the reference's own run (tests/golden/augment.npz)."""
+    g = golden("augment")
+    N, C, px_count = (int(v) for v in g["aug_%s_meta" % name])
+    best, data = orc.augment_optimize_port(g["aug_%s_px_dist" % name], px_count, g["aug_%s_probs" % name], C, N)
+    assert np.array_equal(best["rates"], g["aug_%s_rates" % name])
+    ref = g["aug_%s_optim" % name]
+    assert [best["threshold"], best["rate_coef"], best["jsd"], best["m2"], best["n_samples"], best["aug_n_samples"]] == list(ref)
+    assert np.array_equal(best["probs"], g["aug_%s_optim_probs" % name])

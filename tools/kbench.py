@@ -165,6 +165,18 @@ def main():
            lambda: ops.profile_tiles(g3_out, None, C), "1 B per px")
     del g3_out, n_out, g_out
 
+    # ---- test-time fit resize -----------------------------------------------------------------
+    for (Wr, Hr, chr_) in ((3000, 2000, 3), (6000, 4000, 1)):
+        wr, hr = orc.fit_dims(Wr, Hr, T)
+        raw = torch.from_numpy(orc.synth_image(2, Wr, Hr, chr_)).cuda()
+        fitted = torch.empty((hr, ops.pitch_for(wr * chr_)), dtype=torch.uint8, device="cuda")
+        ops.fit_resize_area(raw, Hr, Wr, chr_, Wr * chr_, hr, wr, out=fitted)      # builds + caches the tables
+        report("fit_resize_area %dx%d ch%d -> %dx%d" % (Wr, Hr, chr_, wr, hr), (Wr * Hr + wr * hr) * chr_,
+               lambda raw=raw, fitted=fitted, Wr=Wr, Hr=Hr, chr_=chr_, wr=wr, hr=hr:
+               ops.fit_resize_area(raw, Hr, Wr, chr_, Wr * chr_, hr, wr, out=fitted),
+               "source read once + fitted image written once")
+        del raw, fitted
+
     # ---- stitch ------------------------------------------------------------------------------
     nr, nc = Hf // 256 - 1, Wf // 256 - 1
     g = torch.Generator(device="cuda").manual_seed(0)
