@@ -166,6 +166,28 @@ PYLC_API int pylc_fit_resize_area_u8(const uint8_t *src, int H, int W, int ch, s
 PYLC_API int pylc_upload_pitched(void *dst, size_t dst_pitch, const void *src_host, size_t src_pitch,
                         size_t width_bytes, size_t rows, pylc_stream_t stream);
 
+/* ---- network glue (non-convolution steps of the DeepLabv3+ inference plan) ---------------- */
+
+/*
+ * The convolutions stay library tensor-core kernels; these are the HBM-bound data-movement steps
+ * between them, for channels-last (NHWC) f32 activations.  Bilinear = PyTorch's
+ * upsample_bilinear2d with align_corners=True (same index and weight arithmetic).
+ *
+ *   pylc_upsample_concat_nhwc_f32   F.interpolate(x, size=low.shape[2:]) + torch.cat((x, low), 1) of the
+ *                                   decoder (models/decoder.py:46-48):
+ *                                   x [B,h,w,Cx], low [B,H,W,Cl] -> out [B,H,W,Cx+Cl]   (Cx, Cl % 4 == 0)
+ *   pylc_maxpool3x3s2_nhwc_f32      nn.MaxPool2d(3, stride=2, padding=1) of the ResNet stem
+ *                                   (models/backbone/resnet.py): in [B,H,W,C] -> out [B,(H-1)/2+1,(W-1)/2+1,C]
+ *   pylc_upsample_nhwc_to_nchw_f32  the final F.interpolate(x, size=input.shape[2:]) (models/architectures/
+ *                                   deeplab.py:38), emitting planar logits for the stitch kernel:
+ *                                   in [B,h,w,C] NHWC -> out [B,C,H,W]                   (W % 4 == 0)
+ */
+PYLC_API int pylc_upsample_concat_nhwc_f32(const float *x, int B, int h, int w, int Cx, const float *low, int H,
+                                  int W, int Cl, float *out, pylc_stream_t stream);
+PYLC_API int pylc_maxpool3x3s2_nhwc_f32(const float *in, int B, int H, int W, int C, float *out, pylc_stream_t stream);
+PYLC_API int pylc_upsample_nhwc_to_nchw_f32(const float *in, int B, int h, int w, int C, float *out, int H, int W,
+                                   pylc_stream_t stream);
+
 /* ---- stitching ---------------------------------------------------------------------------- */
 
 /*

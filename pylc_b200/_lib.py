@@ -53,6 +53,9 @@ SIGNATURES = {
     "pylc_fit_resize_area_u8": (c_int, [_u8p, c_int, c_int, c_int, c_size_t, _u8p, c_int, c_int, c_size_t,
                                         _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "pylc_upload_pitched": (c_int, [_ptr, c_size_t, _ptr, c_size_t, c_size_t, c_size_t, _ptr]),
+    "pylc_upsample_concat_nhwc_f32": (c_int, [_ptr, c_int, c_int, c_int, c_int, _ptr, c_int, c_int, c_int, _ptr, _ptr]),
+    "pylc_maxpool3x3s2_nhwc_f32": (c_int, [_ptr, c_int, c_int, c_int, c_int, _ptr, _ptr]),
+    "pylc_upsample_nhwc_to_nchw_f32": (c_int, [_ptr, c_int, c_int, c_int, c_int, _ptr, c_int, c_int, _ptr]),
     "pylc_stitch_argmax_colour": (c_int, [_ptr, _ptr, c_int, c_int, c_int, c_int, c_int, c_int,
                                           POINTER(c_uint8), _u8p, _u8p, _ptr, _ptr]),
     "pylc_colourise_u8": (c_int, [_u8p, c_int64, POINTER(c_uint8), c_int, _u8p, _ptr]),

@@ -1,0 +1,234 @@
+// Non-convolution glue of the DeepLabv3+ inference plan (models/architectures/deeplab.py:38,
+// models/decoder.py:46-48, models/backbone/resnet.py max-pool of the stem): the three data-movement
+// steps between the library convolutions that the stock PyTorch kernels run at 10-30 % of HBM speed on
+// channels-last tensors.  All three are pure HBM streams (every output byte written once, every input
+// byte fetched from DRAM once) and keep PyTorch's arithmetic:
+//     bilinear, align_corners=True:  src = dst * (in-1)/(out-1);  i0 = (int)src;  l1 = src - i0;  l0 = 1 - l1
+//     out = h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11)              (upsample_bilinear2d, UpSample.cuh)
+// so results agree with the eager ops to float rounding (tests: 1e-6 relative; max-pool exact).
+#include "common.cuh"
+
+namespace pylc {
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float4 lerp4(float a0, const float4 &u, float a1, const float4 &v) {
+    return make_float4(a0 * u.x + a1 * v.x, a0 * u.y + a1 * v.y, a0 * u.z + a1 * v.z, a0 * u.w + a1 * v.w);
+}
+__device__ __forceinline__ float4 max4(const float4 &a, const float4 &b) {
+    return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoder: bilinear up-sample of the ASPP output to the low-level feature size + channel concat
+//   x [B, h, w, Cx] NHWC, low [B, H, W, Cl] NHWC  ->  out [B, H, W, Cx + Cl] NHWC   (decoder.py:46-48)
+// ------------------------------------------------------------------------------------------------
+// A warp owns one output row (b, Y) and walks X left to right; a lane owns VPL float4 channel groups
+// and keeps the horizontally adjacent source taps of both source rows in registers, re-loading a tap
+// only when the source column advances (every ~(W-1)/(w-1) output pixels).  Each step the warp
+// writes one contiguous Cx*4-byte run (the up-sampled channels) and lanes < Cl/4 copy the low-level
+// channels behind it, so an output pixel record is written in full, in order.
+template <int VPL>
+__global__ void __launch_bounds__(kThreads) upsample_concat_kernel(const float *__restrict__ x, const float *__restrict__ low,
+                                                                  float *__restrict__ out, int B, int h, int w, int Cx, int H,
+                                                                  int W, int Cl) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (row >= (long long)B * H) return;
+    const int b = (int)(row / H), Y = (int)(row - (long long)b * H);
+    const float rh = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rw = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    const float h1r = rh * Y;
+    const int y1 = (int)h1r, y1p = y1 < h - 1 ? 1 : 0;
+    const float hl1 = h1r - y1, hl0 = 1.f - hl1;
+    const int Co = Cx + Cl;
+    const float *r0 = x + ((size_t)b * h + y1) * w * Cx, *r1 = r0 + (size_t)y1p * w * Cx;
+    const float *lrow = low + ((size_t)b * H + Y) * W * Cl;
+    float *orow = out + ((size_t)b * H + Y) * W * Co;
+
+    float4 t00[VPL], t01[VPL], t10[VPL], t11[VPL];   // taps (row 0/1, column x1 / x1+1) of this lane's channels
+    int x1_cur = -1;
+    for (int X = 0; X < W; ++X) {
+        const float w1r = rw * X;
+        const int x1 = (int)w1r, x1p = x1 < w - 1 ? 1 : 0;
+        const float wl1 = w1r - x1, wl0 = 1.f - wl1;
+        if (x1 != x1_cur) {
+            const bool shift = x1 == x1_cur + 1 && x1_cur >= 0;   // the old right tap becomes the left tap
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int c = (v * 32 + lane) * 4;
+                if (c < Cx) {
+                    if (shift) {
+                        t00[v] = t01[v];
+                        t10[v] = t11[v];
+                    } else {
+                        t00[v] = ldg4(r0 + (size_t)x1 * Cx + c);
+                        t10[v] = ldg4(r1 + (size_t)x1 * Cx + c);
+                    }
+                    t01[v] = ldg4(r0 + (size_t)(x1 + x1p) * Cx + c);
+                    t11[v] = ldg4(r1 + (size_t)(x1 + x1p) * Cx + c);
+                }
+            }
+            x1_cur = x1;
+        }
+        float *o = orow + (size_t)X * Co;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const int c = (v * 32 + lane) * 4;
+            if (c < Cx) {
+                const float4 top = lerp4(wl0, t00[v], wl1, t01[v]), bot = lerp4(wl0, t10[v], wl1, t11[v]);
+                st_stream_f4(o + c, lerp4(hl0, top, hl1, bot));
+            }
+        }
+        for (int c = lane * 4; c < Cl; c += 128) st_stream_f4(o + Cx + c, ld_stream_f4(lrow + (size_t)X * Cl + c));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem: max_pool2d(kernel 3, stride 2, padding 1) on NHWC                      (backbone/resnet.py)
+//   in [B, H, W, C] -> out [B, Ho, Wo, C],  Ho = (H + 2 - 3)/2 + 1
+// ------------------------------------------------------------------------------------------------
+// One thread = one float4 channel group of TWO horizontally adjacent output pixels (they share an input
+// column): 15 loads for 2 outputs.  Consecutive threads walk the channel groups of a pixel pair, so a
+// warp reads and writes contiguous runs.  Rows shared by consecutive output rows come from L2.
+__global__ void __launch_bounds__(kThreads) maxpool3x3s2_kernel(const float *__restrict__ in, float *__restrict__ out, int B, int H,
+                                                               int W, int C, int Ho, int Wo) {
+    const int cg = C / 4, pairs = (Wo + 1) / 2;
+    const long long total = (long long)B * Ho * pairs * cg;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        const int g = (int)(i % cg);
+        long long r = i / cg;
+        const int px = (int)(r % pairs);
+        r /= pairs;
+        const int Y = (int)(r % Ho), b = (int)(r / Ho);
+        const int X0 = px * 2;
+        const float ninf = -INFINITY;
+        float4 m0 = make_float4(ninf, ninf, ninf, ninf), m1 = m0;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int y = 2 * Y - 1 + dy;
+            if (y < 0 || y >= H) continue;
+            const float *rowp = in + (((size_t)b * H + y) * W) * C + g * 4;
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) {
+                const int xx = 2 * X0 - 1 + dx;
+                if (xx < 0 || xx >= W) continue;
+                const float4 v = ldg4(rowp + (size_t)xx * C);
+                if (dx <= 2) m0 = max4(m0, v);
+                if (dx >= 2) m1 = max4(m1, v);
+            }
+        }
+        float *o = out + (((size_t)b * Ho + Y) * Wo + X0) * C + g * 4;
+        st_stream_f4(o, m0);
+        if (X0 + 1 < Wo) st_stream_f4(o + C, m1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// head: final bilinear up-sample of the decoder output to tile size, NHWC in -> NCHW logits out
+//   in [B, h, w, C] NHWC  ->  out [B, C, H, W] planar (what the stitch kernel reads)   (deeplab.py:38)
+// ------------------------------------------------------------------------------------------------
+// One thread = 4 consecutive output pixels of one row, all classes: one 16-byte store per class plane
+// (a warp writes 512 contiguous bytes per plane).  The <= 26 MB input stays in L1/L2.
+__global__ void __launch_bounds__(kThreads) upsample_to_nchw_kernel(const float *__restrict__ in, float *__restrict__ out, int B, int h,
+                                                                   int w, int C, int H, int W) {
+    const int gpr = W / 4;
+    const long long total = (long long)B * H * gpr;
+    const float rh = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rw = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    // up-sampling by more than 3x: the four pixels of a thread touch at most three source columns, so the
+    // taps are loaded once per class and selected per pixel
+    const bool few_cols = rw * 3.f < 1.f;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        const int gx = (int)(i % gpr);
+        const long long r = i / gpr;
+        const int Y = (int)(r % H), b = (int)(r / H);
+        const float h1r = rh * Y;
+        const int y1 = (int)h1r, y1p = y1 < h - 1 ? 1 : 0;
+        const float hl1 = h1r - y1, hl0 = 1.f - hl1;
+        const float *r0 = in + ((size_t)b * h + y1) * w * C, *r1 = r0 + (size_t)y1p * w * C;
+        int x1[4];
+        float wl0[4], wl1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float w1r = rw * (gx * 4 + j);
+            x1[j] = (int)w1r;
+            wl1[j] = w1r - x1[j];
+            wl0[j] = 1.f - wl1[j];
+        }
+        float *o = out + (((size_t)b * C) * H + Y) * W + gx * 4;
+        if (few_cols) {
+            const int xa = x1[0], xb = min(xa + 1, w - 1), xc = min(xa + 2, w - 1);
+            for (int c = 0; c < C; ++c) {
+                const float a0 = __ldg(r0 + (size_t)xa * C + c), a1 = __ldg(r0 + (size_t)xb * C + c), a2 = __ldg(r0 + (size_t)xc * C + c);
+                const float b0 = __ldg(r1 + (size_t)xa * C + c), b1 = __ldg(r1 + (size_t)xb * C + c), b2 = __ldg(r1 + (size_t)xc * C + c);
+                float res[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool first = x1[j] == xa;
+                    const float tl = first ? a0 : a1, tr = first ? a1 : a2, bl = first ? b0 : b1, br = first ? b1 : b2;
+                    res[j] = hl0 * (wl0[j] * tl + wl1[j] * tr) + hl1 * (wl0[j] * bl + wl1[j] * br);
+                }
+                st_stream_f4(o + (size_t)c * H * W, make_float4(res[0], res[1], res[2], res[3]));
+            }
+        } else {
+            for (int c = 0; c < C; ++c) {
+                float res[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int xr = min(x1[j] + 1, w - 1);
+                    res[j] = hl0 * (wl0[j] * __ldg(r0 + (size_t)x1[j] * C + c) + wl1[j] * __ldg(r0 + (size_t)xr * C + c)) +
+                             hl1 * (wl0[j] * __ldg(r1 + (size_t)x1[j] * C + c) + wl1[j] * __ldg(r1 + (size_t)xr * C + c));
+                }
+                st_stream_f4(o + (size_t)c * H * W, make_float4(res[0], res[1], res[2], res[3]));
+            }
+        }
+    }
+}
+
+static unsigned glue_grid(long long threads_wanted, int per_sm) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long want = (threads_wanted + kThreads - 1) / kThreads;
+    const long long cap = (long long)sms * per_sm;
+    if (want > cap) want = cap;
+    return (unsigned)(want < 1 ? 1 : want);
+}
+
+}  // namespace pylc
+
+using namespace pylc;
+
+extern "C" int pylc_upsample_concat_nhwc_f32(const float *x, int B, int h, int w, int Cx, const float *low, int H, int W, int Cl,
+                                             float *out, pylc_stream_t stream) {
+    if (!x || !low || !out || B < 1 || h < 1 || w < 1 || H < 1 || W < 1) return PYLC_ERR_ARG;
+    if (Cx < 4 || Cx % 4 || Cl < 0 || Cl % 4 || Cx > 512) return PYLC_ERR_GEOMETRY;
+    if (((uintptr_t)x | (uintptr_t)low | (uintptr_t)out) % 16) return PYLC_ERR_ALIGN;
+    const long long rows = (long long)B * H;
+    const unsigned grid = (unsigned)((rows + kWarps - 1) / kWarps);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cx <= 128) upsample_concat_kernel<1><<<grid, kThreads, 0, st>>>(x, low, out, B, h, w, Cx, H, W, Cl);
+    else if (Cx <= 256) upsample_concat_kernel<2><<<grid, kThreads, 0, st>>>(x, low, out, B, h, w, Cx, H, W, Cl);
+    else upsample_concat_kernel<4><<<grid, kThreads, 0, st>>>(x, low, out, B, h, w, Cx, H, W, Cl);
+    return finish_launch();
+}
+
+extern "C" int pylc_maxpool3x3s2_nhwc_f32(const float *in, int B, int H, int W, int C, float *out, pylc_stream_t stream) {
+    if (!in || !out || B < 1 || H < 1 || W < 1) return PYLC_ERR_ARG;
+    if (C < 4 || C % 4) return PYLC_ERR_GEOMETRY;
+    if (((uintptr_t)in | (uintptr_t)out) % 16) return PYLC_ERR_ALIGN;
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const long long total = (long long)B * Ho * ((Wo + 1) / 2) * (C / 4);
+    maxpool3x3s2_kernel<<<glue_grid(total, 16), kThreads, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, Ho, Wo);
+    return finish_launch();
+}
+
+extern "C" int pylc_upsample_nhwc_to_nchw_f32(const float *in, int B, int h, int w, int C, float *out, int H, int W,
+                                              pylc_stream_t stream) {
+    if (!in || !out || B < 1 || h < 1 || w < 1 || H < 1 || W < 1) return PYLC_ERR_ARG;
+    if (C < 1 || C > PYLC_MAX_CLASSES) return PYLC_ERR_CLASSES;
+    if (W % 4) return PYLC_ERR_GEOMETRY;
+    if ((uintptr_t)out % 16) return PYLC_ERR_ALIGN;
+    const long long total = (long long)B * H * (W / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    upsample_to_nchw_kernel<<<glue_grid(total, 8), kThreads, 0, st>>>(in, out, B, h, w, C, H, W);
+    return finish_launch();
+}

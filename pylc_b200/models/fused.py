@@ -11,7 +11,12 @@ removes is the memory-bound glue around the convolutions that eval-mode inferenc
     (torch.cudnn_convolution_relu / torch.cudnn_convolution_add_relu), so the [B,C,H,W]
     activations are written once instead of being re-read and re-written by separate BN, add and
     ReLU kernels (about a third of the unfused network's HBM traffic at 512 x 512 tiles);
-  * dropout layers (identity in eval mode) are dropped.
+  * dropout layers (identity in eval mode) are dropped;
+  * the three HBM-bound steps between the convolutions -- the stem's 3x3/2 max-pool, the decoder's
+    bilinear up-sample + channel concat, and the final x4 bilinear up-sample (emitted directly as
+    planar logits for the stitch kernel) -- run as pylc_b200 kernels (csrc/netglue.cu) on the
+    channels-last activations: the stock kernels reach 10-30 % of HBM speed on these layouts
+    (2.6 ms of a 21.8 ms image), ours are one streaming pass each.
 
 `FusedDeepLab(net)` snapshots the weights of `net`; call `refresh()` after loading a new
 state_dict.  Outputs match `net.eval()(x)` to fp32 rounding of the folded weights, not bit for
@@ -21,6 +26,8 @@ the custom kernels never depend on it.
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from .. import ops
 
 
 def fold_conv_bn(conv, bn):
@@ -63,10 +70,13 @@ class _Conv(object):
 
 
 class FusedDeepLab(object):
-    def __init__(self, net, channels_last=True, dtype=None):
+    def __init__(self, net, channels_last=True, dtype=None, glue=True):
         self.net = net
         self.channels_last = channels_last
         self.dtype = dtype
+        # the HBM-bound steps between the convolutions (stem max-pool, decoder up-sample + concat, final
+        # up-sample) run as pylc_b200 kernels on channels-last f32 activations; eager ops otherwise
+        self.glue = glue and channels_last and dtype is None
         self.refresh()
 
     def refresh(self):
@@ -110,7 +120,9 @@ class FusedDeepLab(object):
             x = x.to(self.dtype)
         if self.channels_last:
             x = x.contiguous(memory_format=torch.channels_last)
-        x = F.max_pool2d(self.stem(x), 3, stride=2, padding=1)
+        glue = self.glue and x.is_cuda and x.dtype == torch.float32
+        x = self.stem(x)
+        x = ops.maxpool3x3s2_nhwc(x) if glue else F.max_pool2d(x, 3, stride=2, padding=1)
         low = None
         for si, stage in enumerate(self.blocks):
             for c1, c2, c3, down in stage:
@@ -122,10 +134,16 @@ class FusedDeepLab(object):
         pooled = F.interpolate(pooled, size=x.shape[2:], mode='bilinear', align_corners=True)
         x = self.aspp_out(torch.cat([br(x) for br in self.aspp] + [pooled], dim=1))
         low = self.dec_low(low)
-        x = F.interpolate(x, size=low.shape[2:], mode='bilinear', align_corners=True)
-        return self.dec_out(self.dec2(self.dec1(torch.cat((x, low), dim=1))))
+        if glue:      # up-sample + concat in one pass (one write of the [B,304,H/4,W/4] tensor, nothing else)
+            x = ops.upsample_concat_nhwc(x, low)
+        else:
+            x = torch.cat((F.interpolate(x, size=low.shape[2:], mode='bilinear', align_corners=True), low), dim=1)
+        return self.dec_out(self.dec2(self.dec1(x)))
 
     @torch.no_grad()
     def __call__(self, x):
-        y = self.features(x).float().contiguous()      # small [B,C,H/4,W/4]: make it NCHW here ...
+        y = self.features(x).float()
+        if self.glue and y.is_cuda and y.is_contiguous(memory_format=torch.channels_last):
+            return ops.upsample_nhwc_to_nchw(y, x.shape[2:])      # planar logits straight from the NHWC decoder output
+        y = y.contiguous()                                   # small [B,C,H/4,W/4]: make it NCHW here ...
         return F.interpolate(y, size=x.shape[2:], mode='bilinear', align_corners=True)   # ... so the logits are NCHW

@@ -429,3 +429,46 @@ def sample_rate_grid(scores, px_dist, rate_coefs, thresholds, rate_lo, rate_hi):
                                             thresholds.numel(), int(rate_lo), int(rate_hi), _p(sum_rates), _p(full),
                                             _stream()), "pylc_sample_rate_grid")
     return sum_rates, full
+
+
+# ---- network glue (channels-last f32 activations) ---------------------------------------------------
+
+def _is_nhwc(t):
+    return t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def upsample_concat_nhwc(x, low):
+    """pylc_upsample_concat_nhwc_f32: bilinear(align_corners=True) up-sample of x to low's size + channel
+    concat, on channels-last tensors.  x [B,Cx,h,w], low [B,Cl,H,W] -> [B,Cx+Cl,H,W] (channels_last)."""
+    if not (_is_nhwc(x) and _is_nhwc(low)):
+        raise PylcError("upsample_concat_nhwc takes channels-last float32 CUDA tensors")
+    B, Cx, h, w = x.shape
+    _, Cl, H, W = low.shape
+    out = torch.empty((B, Cx + Cl, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    check(_lib.load().pylc_upsample_concat_nhwc_f32(_p(x), B, h, w, Cx, _p(low), H, W, Cl, _p(out), _stream()),
+          "pylc_upsample_concat_nhwc_f32")
+    return out
+
+
+def maxpool3x3s2_nhwc(x):
+    """pylc_maxpool3x3s2_nhwc_f32: max_pool2d(x, 3, stride=2, padding=1) on a channels-last tensor."""
+    if not _is_nhwc(x):
+        raise PylcError("maxpool3x3s2_nhwc takes a channels-last float32 CUDA tensor")
+    B, C, H, W = x.shape
+    out = torch.empty((B, C, (H - 1) // 2 + 1, (W - 1) // 2 + 1), dtype=torch.float32, device=x.device,
+                      memory_format=torch.channels_last)
+    check(_lib.load().pylc_maxpool3x3s2_nhwc_f32(_p(x), B, H, W, C, _p(out), _stream()), "pylc_maxpool3x3s2_nhwc_f32")
+    return out
+
+
+def upsample_nhwc_to_nchw(x, size):
+    """pylc_upsample_nhwc_to_nchw_f32: bilinear(align_corners=True) up-sample of a channels-last tensor to
+    `size`, returned as a plain contiguous NCHW tensor (the stitch kernel's layout)."""
+    if not _is_nhwc(x):
+        raise PylcError("upsample_nhwc_to_nchw takes a channels-last float32 CUDA tensor")
+    B, C, h, w = x.shape
+    H, W = size
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    check(_lib.load().pylc_upsample_nhwc_to_nchw_f32(_p(x), B, h, w, C, _p(out), H, W, _stream()),
+          "pylc_upsample_nhwc_to_nchw_f32")
+    return out

@@ -531,3 +531,37 @@ def test_multiloss_fused_equals_two_pass(ops, B, C, H, W, weighted, u8):
     assert torch.equal(g1, grad)
     ops.scale_unless_one_(g1, torch.full((), 0.5, device="cuda"))
     assert torch.equal(g1, grad * 0.5)
+
+
+# ---------------------------------------------------------------------------------------------
+# network glue kernels (channels-last activations) against the eager PyTorch ops they replace
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("B,Cx,h,w,Cl,H,W", [(3, 256, 32, 32, 48, 128, 128), (2, 64, 5, 7, 8, 19, 23), (1, 512, 4, 4, 4, 9, 9),
+                                              (2, 128, 8, 8, 48, 8, 8)])
+def test_upsample_concat_nhwc(ops, B, Cx, h, w, Cl, H, W):
+    g = torch.Generator(device="cuda").manual_seed(B * Cx)
+    x = torch.randn((B, Cx, h, w), device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    low = torch.randn((B, Cl, H, W), device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    ref = torch.cat((torch.nn.functional.interpolate(x, size=(H, W), mode="bilinear", align_corners=True), low), dim=1)
+    got = ops.upsample_concat_nhwc(x, low)
+    assert got.shape == ref.shape and got.is_contiguous(memory_format=torch.channels_last)
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-6)     # float rounding of the same bilinear formula
+    assert torch.equal(got[:, Cx:], low)                            # the concatenated channels are a copy
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 256, 256), (1, 8, 7, 9), (3, 16, 10, 5), (1, 4, 1, 1)])
+def test_maxpool3x3s2_nhwc(ops, B, C, H, W):
+    x = torch.randn((B, C, H, W), device="cuda").contiguous(memory_format=torch.channels_last)
+    ref = torch.nn.functional.max_pool2d(x, 3, stride=2, padding=1)
+    got = ops.maxpool3x3s2_nhwc(x)
+    assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("B,C,h,w,H,W", [(3, 9, 128, 128, 512, 512), (2, 11, 16, 16, 64, 64), (1, 20, 5, 6, 8, 12), (2, 9, 32, 32, 32, 32)])
+def test_upsample_nhwc_to_nchw(ops, B, C, h, w, H, W):
+    x = torch.randn((B, C, h, w), device="cuda").contiguous(memory_format=torch.channels_last)
+    ref = torch.nn.functional.interpolate(x.contiguous(), size=(H, W), mode="bilinear", align_corners=True)
+    got = ops.upsample_nhwc_to_nchw(x, (H, W))
+    assert got.is_contiguous()
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-6)

@@ -15,7 +15,10 @@ cap() {  # name, kernel regex, kbench --only filter, launches to keep (after 3 w
     tail -2 gpurun_out/ncu_$1_$R.log
 }
 cap stitch "stitch_kernel" "stitch_argmax_colour 273 tiles C9 labels" 1
+cap stitch45 "stitch_kernel" "stitch_argmax_colour 45 tiles" 1
 cap resample "resample_confusion" "resample" 1
 cap loss "loss_reduce|loss_grad" "multiloss_reduce B64 C9 i64,multiloss_grad" 2
+cap lossfused "loss_fused" "one cooperative launch" 1
+cap resize "area_resize" "fit_resize_area 3000" 1
 cap gather "gather_mask|gather_norm|gather_img" "mask_gather,gather_norm,tile_gather_u8 rgb" 3
 ls -la gpurun_out | head -30

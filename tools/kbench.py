@@ -188,6 +188,9 @@ def main():
     report("stitch_argmax_colour 273 tiles C9 labels+rgb", logits.numel() * 4 + hw * 4,
            lambda: ops.stitch_argmax_colour(logits, nr, nc, T, 256, lut_rgb=lut, want_rgb=True))
     labels, _, _ = ops.stitch_argmax_colour(logits, nr, nc, T, 256)
+    # the bench.py geometry: one fitted 2560x1536 image = 45 tiles (5 x 9)
+    report("stitch_argmax_colour 45 tiles C9 labels (bench.py image)", 45 * C * T * T * 4 + 2560 * 1536,
+           lambda: ops.stitch_argmax_colour(logits[:45], 5, 9, T, 256), "every logit once + 1 B label")
     del logits
 
     # ---- evaluation --------------------------------------------------------------------------
