@@ -188,6 +188,19 @@ PYLC_API int pylc_maxpool3x3s2_nhwc_f32(const float *in, int B, int H, int W, in
 PYLC_API int pylc_upsample_nhwc_to_nchw_f32(const float *in, int B, int h, int w, int C, float *out, int H, int W,
                                    pylc_stream_t stream);
 
+/*
+ * pylc_tile_gather_norm_f32 in the layout the space-to-depth form of the ResNet stem wants (the 7x7
+ * stride-2 convolution over 3 channels == a 4x4 stride-1 convolution over the 2x2 space-to-depth
+ * image with the kernel zero-extended to 8x8; models/fused.py rearranges the weights):
+ *   dst [nH*nW, T/2+3, T/2+3, 16] f32 channels-last,
+ *   dst[n, Y, X, (py*2+px)*3 + c] = ((x - mean[c]) / std[c]) / post_div of tile pixel (c, 2(Y-2)+py, 2(X-2)+px),
+ *   zero outside the tile (two border rows/columns before, one after) and in channels 12..15.
+ * ch = 1 replicates the grey value into the three channels (models/model.py:376-377).
+ */
+PYLC_API int pylc_tile_gather_norm_s2d_f32(const uint8_t *src, int H, int W, int ch, size_t src_pitch, int T,
+                                  int S, const float *mean, const float *std, float post_div,
+                                  float *dst, pylc_stream_t stream);
+
 /* ---- stitching ---------------------------------------------------------------------------- */
 
 /*

@@ -56,6 +56,8 @@ SIGNATURES = {
     "pylc_upsample_concat_nhwc_f32": (c_int, [_ptr, c_int, c_int, c_int, c_int, _ptr, c_int, c_int, c_int, _ptr, _ptr]),
     "pylc_maxpool3x3s2_nhwc_f32": (c_int, [_ptr, c_int, c_int, c_int, c_int, _ptr, _ptr]),
     "pylc_upsample_nhwc_to_nchw_f32": (c_int, [_ptr, c_int, c_int, c_int, c_int, _ptr, c_int, c_int, _ptr]),
+    "pylc_tile_gather_norm_s2d_f32": (c_int, [_u8p, c_int, c_int, c_int, c_size_t, c_int, c_int,
+                                              POINTER(c_float), POINTER(c_float), c_float, _ptr, _ptr]),
     "pylc_stitch_argmax_colour": (c_int, [_ptr, _ptr, c_int, c_int, c_int, c_int, c_int, c_int,
                                           POINTER(c_uint8), _u8p, _u8p, _ptr, _ptr]),
     "pylc_colourise_u8": (c_int, [_u8p, c_int64, POINTER(c_uint8), c_int, _u8p, _ptr]),

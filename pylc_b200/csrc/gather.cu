@@ -531,6 +531,54 @@ __global__ void __launch_bounds__(kThreads) gather_norm_kernel(GatherGeom g, Nor
 }
 
 // ------------------------------------------------------------------------------------------------
+// normalising gather, space-to-depth layout for the network stem
+// ------------------------------------------------------------------------------------------------
+// The ResNet stem is a 7x7 stride-2 convolution over 3 channels (models/backbone/resnet.py), the one
+// layer the library runs far from its roofline (K = 3 input channels).  It equals a 4x4 stride-1
+// convolution over the 2x2 space-to-depth image (12 channels, padded to 16) with the 7x7 kernel zero-
+// extended to 8x8 -- models/fused.py rearranges the weights -- so this kernel writes the tiles directly in
+// that layout, channels-last, border included:
+//     dst[n, Y, X, (py*2+px)*3 + c] = norm(tile_n[c, 2(Y-2)+py, 2(X-2)+px]),  Y, X in [0, T/2+3)
+// (two zero rows/columns before the image, one after; channels 12..15 zero), f32, same IEEE
+// normalisation tables as gather_norm_kernel.  One thread = one 64-byte output pixel record; a warp
+// writes 2 KB contiguous.
+template <int CH>
+__global__ void __launch_bounds__(kThreads) gather_norm_s2d_kernel(GatherGeom g, NormParams np, float *__restrict__ dst) {
+    __shared__ float s_lut[3][256];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        s_lut[k][threadIdx.x] = __fdiv_rn(__fdiv_rn(__fsub_rn((float)threadIdx.x, np.mean[k]), np.std[k]), np.post_div);
+    __syncthreads();
+    const int Hs = g.T / 2 + 3;
+    const long long total = (long long)g.nH * g.nW * Hs * Hs;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        const int X = (int)(i % Hs);
+        long long r = i / Hs;
+        const int Y = (int)(r % Hs), n = (int)(r / Hs);
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = 0.f;
+        const int ty = 2 * (Y - 2), tx = 2 * (X - 2);
+        if (ty >= 0 && ty < g.T && tx >= 0 && tx < g.T) {
+            const int tr = n / g.nW, tc = n - tr * g.nW;
+            const uint8_t *p = g.src + (size_t)(tr * g.S + ty) * g.pitch + (size_t)(tc * g.S + tx) * CH;
+#pragma unroll
+            for (int py = 0; py < 2; ++py)
+#pragma unroll
+                for (int px = 0; px < 2; ++px)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const uint32_t b = __ldg(p + (size_t)py * g.pitch + px * CH + (CH == 3 ? c : 0));
+                        v[(py * 2 + px) * 3 + c] = s_lut[CH == 3 ? c : 0][b];
+                    }
+        }
+        float *o = dst + (size_t)i * 16;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) st_stream_f4(o + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static int make_geom(const uint8_t *src, int H, int W, int ch, size_t pitch, int T, int S, GatherGeom *g) {
@@ -673,5 +721,35 @@ extern "C" int pylc_tile_gather_norm_f32(const uint8_t *src, int H, int W, int c
     if (ch == 1) { if (al) LAUNCH(1, true); else LAUNCH(1, false); }
     else         { if (al) LAUNCH(3, true); else LAUNCH(3, false); }
 #undef LAUNCH
+    return finish_launch();
+}
+
+extern "C" int pylc_tile_gather_norm_s2d_f32(const uint8_t *src, int H, int W, int ch, size_t src_pitch, int T, int S,
+                                             const float *mean, const float *std, float post_div, float *dst,
+                                             pylc_stream_t stream) {
+    if (!mean || !std || (ch != 1 && ch != 3)) return PYLC_ERR_ARG;
+    if (T % 2) return PYLC_ERR_GEOMETRY;
+    GatherGeom g;
+    int rc = make_geom(src, H, W, ch, src_pitch, T, S, &g);
+    if (rc) return rc;
+    if ((long long)g.nH * g.nW == 0) return PYLC_OK;
+    if (!dst) return PYLC_ERR_ARG;
+    if ((uintptr_t)dst % 16) return PYLC_ERR_ALIGN;
+    NormParams np;
+    for (int k = 0; k < 3; ++k) {
+        np.mean[k] = mean[ch == 1 ? 0 : k];
+        np.std[k] = std[ch == 1 ? 0 : k];
+    }
+    np.post_div = post_div;
+    np.out_ch = 16;
+    const long long Hs = T / 2 + 3, total = (long long)g.nH * g.nW * Hs * Hs;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long want = (total + kThreads - 1) / kThreads;
+    if (want > (long long)sms * 8) want = (long long)sms * 8;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ch == 1) gather_norm_s2d_kernel<1><<<(unsigned)want, kThreads, 0, st>>>(g, np, dst);
+    else gather_norm_s2d_kernel<3><<<(unsigned)want, kThreads, 0, st>>>(g, np, dst);
     return finish_launch();
 }

@@ -86,6 +86,7 @@ class FusedDeepLab(object):
         mk = lambda conv, bn, relu: self._cast(_Conv(conv, bn, relu, cl))  # noqa: E731
         bb = net.backbone
         self.stem = mk(bb.conv1, bb.bn1, True)
+        self.stem_s2d = self._make_s2d_stem(bb.conv1, self.stem) if self.glue else None
         self.blocks = []
         for layer in (bb.layer1, bb.layer2, bb.layer3, bb.layer4):
             stage = []
@@ -111,17 +112,40 @@ class FusedDeepLab(object):
         self.dec_out = mk(d.last_conv[8], None, False)
         return self
 
+    @staticmethod
+    def _make_s2d_stem(conv1, stem):
+        """The 7x7 stride-2 pad-3 stem over 3 channels as a 4x4 stride-1 convolution over the 2x2
+        space-to-depth image (ops.tile_gather_norm_s2d's layout): zero-extend the (BN-folded) kernel to
+        8x8 (one zero row/column in front), then w4[o, (py*2+px)*3+c, U, V] = w8[o, c, 2U+py, 2V+px];
+        input channels 12..15 carry zero weights.  Same products and sums as the 7x7 form."""
+        if tuple(conv1.kernel_size) != (7, 7) or tuple(conv1.stride) != (2, 2) or tuple(conv1.padding) != (3, 3) \
+                or conv1.in_channels != 3:
+            return None
+        w7 = stem.w.contiguous().float()                                    # [O, 3, 7, 7] folded weights
+        O = w7.shape[0]
+        w8 = torch.zeros((O, 3, 8, 8), dtype=w7.dtype, device=w7.device)
+        w8[:, :, 1:, 1:] = w7
+        w4 = torch.zeros((O, 16, 4, 4), dtype=w7.dtype, device=w7.device)
+        for py in range(2):
+            for px in range(2):
+                w4[:, (py * 2 + px) * 3:(py * 2 + px) * 3 + 3] = w8[:, :, py::2, px::2]
+        s = _Conv.__new__(_Conv)
+        s.w = w4.contiguous(memory_format=torch.channels_last)
+        s.b, s.stride, s.padding, s.dilation, s.relu = stem.b, (1, 1), (0, 0), (1, 1), True
+        return s
+
     def _cast(self, conv):
         return conv.to(self.dtype) if self.dtype is not None else conv
 
-    def features(self, x):
-        """Decoder output [B, n_classes, H/4, W/4] (before the final x4 bilinear up-sample)."""
+    def features(self, x, s2d=False):
+        """Decoder output [B, n_classes, H/4, W/4] (before the final x4 bilinear up-sample).
+        s2d: `x` is the space-to-depth stem input [B, 16, H/2+3, W/2+3] of ops.tile_gather_norm_s2d."""
         if self.dtype is not None:
             x = x.to(self.dtype)
         if self.channels_last:
             x = x.contiguous(memory_format=torch.channels_last)
         glue = self.glue and x.is_cuda and x.dtype == torch.float32
-        x = self.stem(x)
+        x = self.stem_s2d(x) if s2d else self.stem(x)
         x = ops.maxpool3x3s2_nhwc(x) if glue else F.max_pool2d(x, 3, stride=2, padding=1)
         low = None
         for si, stage in enumerate(self.blocks):
@@ -139,6 +163,15 @@ class FusedDeepLab(object):
         else:
             x = torch.cat((F.interpolate(x, size=low.shape[2:], mode='bilinear', align_corners=True), low), dim=1)
         return self.dec_out(self.dec2(self.dec1(x)))
+
+    @torch.no_grad()
+    def forward_s2d(self, xs):
+        """Logits [B, n_classes, T, T] from space-to-depth tiles (T = 2 * (xs.shape[2] - 3))."""
+        if self.stem_s2d is None:
+            raise ValueError("space-to-depth stem unavailable for this network / plan")
+        y = self.features(xs, s2d=True).float()
+        size = (2 * (xs.shape[2] - 3), 2 * (xs.shape[3] - 3))
+        return ops.upsample_nhwc_to_nchw(y, size)
 
     @torch.no_grad()
     def __call__(self, x):

@@ -162,6 +162,19 @@ def tile_gather_norm_f32(src, H, W, ch, pitch, T, S, mean, std, post_div=255.0, 
     return tiles
 
 
+def tile_gather_norm_s2d(src, H, W, ch, pitch, T, S, mean, std, post_div=255.0):
+    """pylc_tile_gather_norm_s2d_f32: network-ready tiles in the stem's space-to-depth layout, returned
+    as a channels-last tensor of logical shape [n, 16, T/2+3, T/2+3]."""
+    _need_cuda(src)
+    nH, nW = tile_grid(H, W, T, S)
+    n, Hs = nH * nW, T // 2 + 3
+    tiles = torch.empty((n, 16, Hs, Hs), dtype=torch.float32, device=src.device, memory_format=torch.channels_last)
+    check(_lib.load().pylc_tile_gather_norm_s2d_f32(_p(src), H, W, ch, pitch, T, S, _lib.float3(mean), _lib.float3(std),
+                                                    float(post_div), _p(tiles), _stream()),
+          "pylc_tile_gather_norm_s2d_f32")
+    return tiles
+
+
 def class_encode_nchw(rgb, palette, hist=False):
     """tools.class_encode on a CUDA [N,3,H,W] u8 tensor -> [N,H,W] u8 (+ [C] i64 histogram)."""
     _need_cuda(rgb)

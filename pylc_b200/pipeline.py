@@ -62,6 +62,8 @@ class TiledSegmenter(object):
             from .models.fused import FusedDeepLab
             self.fused = FusedDeepLab(self.net, channels_last=channels_last)
         self.mean, self.std, self.post_div, self.out_ch = model.norm_params()
+        # space-to-depth stem: the gather writes the tiles in the layout of the rearranged 4x4 stem convolution
+        self.s2d = self.fused is not None and self.fused.stem_s2d is not None and self.out_ch == 3 and self.T % 2 == 0
         self.palette = self.meta.palette_rgb
         self.lut = tools.colourize_lut(self.C, self.palette)
         self.n_inject = min(len(defaults.class_codes), self.C) if n_inject is None else n_inject
@@ -133,12 +135,16 @@ class TiledSegmenter(object):
         return f
 
     # ---- device stage -------------------------------------------------------------------------
-    def forward_tiles(self, tiles):
-        """Network forward over [n,3,T,T] f32 tiles in batches; returns the list of logit batches."""
+    def forward_tiles(self, tiles, s2d=False):
+        """Network forward over [n,3,T,T] f32 tiles (or their space-to-depth form) in batches; returns
+        the list of logit batches."""
         outs = []
         with torch.no_grad():
             for lo in range(0, tiles.shape[0], self.batch_tiles):
                 x = tiles[lo:lo + self.batch_tiles]
+                if s2d:
+                    outs.append(self.fused.forward_s2d(x))
+                    continue
                 if self.fused is not None:
                     outs.append(self.fused(x))
                     continue
@@ -161,10 +167,13 @@ class TiledSegmenter(object):
         img, pitch = f.img, f.pitch
         if img is None:        # device fit: INTER_AREA resize of the uploaded decoded image
             img, pitch = ops.fit_resize_area(f.raw, f.h_full, f.w_full, self.ch, f.raw_pitch, f.h, f.w)
-        tiles = ops.tile_gather_norm_f32(img, f.h, f.w, self.ch, pitch, self.T, self.S, self.mean, self.std,
-                                         self.post_div, self.out_ch)
+        if self.s2d:
+            tiles = ops.tile_gather_norm_s2d(img, f.h, f.w, self.ch, pitch, self.T, self.S, self.mean, self.std, self.post_div)
+        else:
+            tiles = ops.tile_gather_norm_f32(img, f.h, f.w, self.ch, pitch, self.T, self.S, self.mean, self.std,
+                                             self.post_div, self.out_ch)
         nr, nc = f.h // self.S - 1, f.w // self.S - 1
-        logits = self.forward_tiles(tiles)
+        logits = self.forward_tiles(tiles, s2d=self.s2d)
         labels, _, _ = ops.stitch_argmax_colour(logits if len(logits) > 1 else logits[0], nr, nc, self.T, self.S,
                                                 tiles_per_batch=self.batch_tiles)
         n_inject = self.n_inject if inject is None else inject

@@ -289,8 +289,11 @@ def test_pipeline_matches_reference_sequence(ops, palettes, fuse):
     w_fit, h_fit = orc.fit_dims(W, H, T)
     fitted = cv2.resize(img, (w_fit, h_fit), interpolation=cv2.INTER_AREA)
     tiles = torch.from_numpy(orc.split_tiles(fitted, T, 256))
-    if fuse:    # BN-folded cuDNN-fused plan: same batches through the same plan
-        outs = seg.forward_tiles(model._prepare(tiles))
+    if fuse:    # BN-folded cuDNN-fused plan: same batches through the same plan (space-to-depth stem layout)
+        assert seg.s2d
+        d_fit, fp = ops.upload_image(fitted)
+        xs = ops.tile_gather_norm_s2d(d_fit, h_fit, w_fit, 3, fp, T, 256, seg.mean, seg.std, seg.post_div)
+        outs = seg.forward_tiles(xs, s2d=True)
         eager = torch.cat([model.test(tiles[i:i + 8])[0] for i in range(0, len(tiles), 8)])
         assert (torch.cat(outs) - eager).abs().max() <= 5e-3 * eager.abs().max()   # TF32 conv noise level
     else:

@@ -565,3 +565,44 @@ def test_upsample_nhwc_to_nchw(ops, B, C, h, w, H, W):
     got = ops.upsample_nhwc_to_nchw(x, (H, W))
     assert got.is_contiguous()
     torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("ch,H,W,T,S", [(3, 1024, 1536, 512, 256), (1, 700, 650, 128, 64), (3, 96, 64, 32, 32)])
+def test_gather_norm_s2d_layout(ops, ch, H, W, T, S):
+    """The space-to-depth stem layout is the normalised tiles of pylc_tile_gather_norm_f32, re-indexed:
+    bit-equal values, zero border (2 before, 1 after) and zero channels 12..15."""
+    img = orc.synth_image(7, W, H, ch)
+    d, pitch = ops.upload_image(img)
+    mean, std = ([120.0], [40.0]) if ch == 1 else ([130.0, 140.0, 150.0], [25.0, 22.0, 19.0])
+    planar = ops.tile_gather_norm_f32(d, H, W, ch, pitch, T, S, mean, std, 255.0, 3)          # [n,3,T,T]
+    s2d = ops.tile_gather_norm_s2d(d, H, W, ch, pitch, T, S, mean, std, 255.0)                # [n,16,T/2+3,T/2+3]
+    n, Hs = planar.shape[0], T // 2 + 3
+    assert s2d.shape == (n, 16, Hs, Hs) and s2d.is_contiguous(memory_format=torch.channels_last)
+    ref = torch.zeros((n, 16, Hs, Hs), device="cuda")
+    for py in range(2):
+        for px in range(2):
+            ref[:, (py * 2 + px) * 3:(py * 2 + px) * 3 + 3, 2:2 + T // 2, 2:2 + T // 2] = planar[:, :, py::2, px::2]
+    assert torch.equal(s2d, ref)
+
+
+def test_s2d_stem_equals_7x7_stem(ops):
+    """FusedDeepLab's rearranged 4x4 stem on the space-to-depth tiles == its 7x7 stride-2 stem on the
+    planar tiles (same products; TF32 convolution noise only), and so are the final logits."""
+    from pylc_b200.models.deeplab import DeepLab
+    from pylc_b200.models.fused import FusedDeepLab
+    torch.manual_seed(0)
+    net = DeepLab(n_classes=9).cuda().eval().to(memory_format=torch.channels_last)
+    plan = FusedDeepLab(net, channels_last=True)
+    assert plan.stem_s2d is not None
+    img = orc.synth_image(5, 768, 512, 3)
+    d, pitch = ops.upload_image(img)
+    mean, std = [130.0, 140.0, 150.0], [25.0, 22.0, 19.0]
+    planar = ops.tile_gather_norm_f32(d, 512, 768, 3, pitch, 256, 128, mean, std, 255.0, 3)
+    s2d = ops.tile_gather_norm_s2d(d, 512, 768, 3, pitch, 256, 128, mean, std, 255.0)
+    a = plan.stem(planar.contiguous(memory_format=torch.channels_last))
+    b = plan.stem_s2d(s2d)
+    assert a.shape == b.shape
+    assert (a - b).abs().max() <= 2e-3 * a.abs().max()
+    ya, yb = plan(planar), plan.forward_s2d(s2d)
+    assert ya.shape == yb.shape == (planar.shape[0], 9, 256, 256)
+    assert (ya - yb).abs().max() <= 5e-3 * ya.abs().max()
