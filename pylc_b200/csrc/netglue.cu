@@ -22,63 +22,87 @@ __device__ __forceinline__ float4 max4(const float4 &a, const float4 &b) {
 // decoder: bilinear up-sample of the ASPP output to the low-level feature size + channel concat
 //   x [B, h, w, Cx] NHWC, low [B, H, W, Cl] NHWC  ->  out [B, H, W, Cx + Cl] NHWC   (decoder.py:46-48)
 // ------------------------------------------------------------------------------------------------
-// A warp owns one output row (b, Y) and walks X left to right; a lane owns VPL float4 channel groups
-// and keeps the horizontally adjacent source taps of both source rows in registers, re-loading a tap
-// only when the source column advances (every ~(W-1)/(w-1) output pixels).  Each step the warp
-// writes one contiguous Cx*4-byte run (the up-sampled channels) and lanes < Cl/4 copy the low-level
-// channels behind it, so an output pixel record is written in full, in order.
+// A warp takes 16-pixel segments of output rows (persistent grid, segments dealt round-robin so the
+// load balances to a fraction of a segment).  Per segment it first issues all loads of the low-level
+// channels it has to copy (independent, so they overlap), then walks X left to right: a lane owns VPL
+// float4 channel groups and keeps the horizontally adjacent source taps of both source rows in
+// registers, re-loading a tap only when the source column advances (every ~(W-1)/(w-1) output
+// pixels).  Each step the warp writes one contiguous Cx*4-byte run; the low-level channels follow.
+constexpr int kUpSeg = 16;      // output pixels per work item
+constexpr int kUpLowMax = 8;    // float4 per lane of low-level data per segment: Cl <= 64
+
 template <int VPL>
 __global__ void __launch_bounds__(kThreads) upsample_concat_kernel(const float *__restrict__ x, const float *__restrict__ low,
                                                                   float *__restrict__ out, int B, int h, int w, int Cx, int H,
                                                                   int W, int Cl) {
     const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
-    if (row >= (long long)B * H) return;
-    const int b = (int)(row / H), Y = (int)(row - (long long)b * H);
+    const int segs = (W + kUpSeg - 1) / kUpSeg;
+    const long long items = (long long)B * H * segs;
+    const long long nwarps = (long long)gridDim.x * kWarps;
     const float rh = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rw = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
-    const float h1r = rh * Y;
-    const int y1 = (int)h1r, y1p = y1 < h - 1 ? 1 : 0;
-    const float hl1 = h1r - y1, hl0 = 1.f - hl1;
-    const int Co = Cx + Cl;
-    const float *r0 = x + ((size_t)b * h + y1) * w * Cx, *r1 = r0 + (size_t)y1p * w * Cx;
-    const float *lrow = low + ((size_t)b * H + Y) * W * Cl;
-    float *orow = out + ((size_t)b * H + Y) * W * Co;
+    const int Co = Cx + Cl, lq = Cl / 4;                    // float4 per pixel of low-level channels
+    for (long long item = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5); item < items; item += nwarps) {
+        const int seg = (int)(item % segs);
+        const long long row = item / segs;
+        const int b = (int)(row / H), Y = (int)(row - (long long)b * H);
+        const int X0 = seg * kUpSeg, X1 = min(W, X0 + kUpSeg);
+        const float h1r = rh * Y;
+        const int y1 = (int)h1r, y1p = y1 < h - 1 ? 1 : 0;
+        const float hl1 = h1r - y1, hl0 = 1.f - hl1;
+        const float *r0 = x + ((size_t)b * h + y1) * w * Cx, *r1 = r0 + (size_t)y1p * w * Cx;
+        const float *lrow = low + (((size_t)b * H + Y) * W + X0) * Cl;
+        float *orow = out + ((size_t)b * H + Y) * W * Co;
 
-    float4 t00[VPL], t01[VPL], t10[VPL], t11[VPL];   // taps (row 0/1, column x1 / x1+1) of this lane's channels
-    int x1_cur = -1;
-    for (int X = 0; X < W; ++X) {
-        const float w1r = rw * X;
-        const int x1 = (int)w1r, x1p = x1 < w - 1 ? 1 : 0;
-        const float wl1 = w1r - x1, wl0 = 1.f - wl1;
-        if (x1 != x1_cur) {
-            const bool shift = x1 == x1_cur + 1 && x1_cur >= 0;   // the old right tap becomes the left tap
+        // low-level channels of the segment: (X1 - X0) * lq float4, lane-strided, all loads in flight at once
+        const int nlow = (X1 - X0) * lq;
+        float4 lv[kUpLowMax];
+#pragma unroll
+        for (int k = 0; k < kUpLowMax; ++k)
+            if (k * 32 + lane < nlow) lv[k] = ld_stream_f4(lrow + (size_t)(k * 32 + lane) * 4);
+
+        float4 t00[VPL], t01[VPL], t10[VPL], t11[VPL];   // taps (row 0/1, column x1 / x1+1) of this lane's channels
+        int x1_cur = -2;
+        for (int X = X0; X < X1; ++X) {
+            const float w1r = rw * X;
+            const int x1 = (int)w1r, x1p = x1 < w - 1 ? 1 : 0;
+            const float wl1 = w1r - x1, wl0 = 1.f - wl1;
+            if (x1 != x1_cur) {
+                const bool shift = x1 == x1_cur + 1;          // the old right tap becomes the left tap
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const int c = (v * 32 + lane) * 4;
+                    if (c < Cx) {
+                        if (shift) {
+                            t00[v] = t01[v];
+                            t10[v] = t11[v];
+                        } else {
+                            t00[v] = ldg4(r0 + (size_t)x1 * Cx + c);
+                            t10[v] = ldg4(r1 + (size_t)x1 * Cx + c);
+                        }
+                        t01[v] = ldg4(r0 + (size_t)(x1 + x1p) * Cx + c);
+                        t11[v] = ldg4(r1 + (size_t)(x1 + x1p) * Cx + c);
+                    }
+                }
+                x1_cur = x1;
+            }
+            float *o = orow + (size_t)X * Co;
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
                 const int c = (v * 32 + lane) * 4;
                 if (c < Cx) {
-                    if (shift) {
-                        t00[v] = t01[v];
-                        t10[v] = t11[v];
-                    } else {
-                        t00[v] = ldg4(r0 + (size_t)x1 * Cx + c);
-                        t10[v] = ldg4(r1 + (size_t)x1 * Cx + c);
-                    }
-                    t01[v] = ldg4(r0 + (size_t)(x1 + x1p) * Cx + c);
-                    t11[v] = ldg4(r1 + (size_t)(x1 + x1p) * Cx + c);
+                    const float4 top = lerp4(wl0, t00[v], wl1, t01[v]), bot = lerp4(wl0, t10[v], wl1, t11[v]);
+                    st_stream_f4(o + c, lerp4(hl0, top, hl1, bot));
                 }
             }
-            x1_cur = x1;
         }
-        float *o = orow + (size_t)X * Co;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            const int c = (v * 32 + lane) * 4;
-            if (c < Cx) {
-                const float4 top = lerp4(wl0, t00[v], wl1, t01[v]), bot = lerp4(wl0, t10[v], wl1, t11[v]);
-                st_stream_f4(o + c, lerp4(hl0, top, hl1, bot));
+        for (int k = 0; k < kUpLowMax; ++k) {
+            const int idx = k * 32 + lane;
+            if (idx < nlow) {
+                const int px = idx / lq, q = idx - px * lq;
+                st_stream_f4(orow + (size_t)(X0 + px) * Co + Cx + q * 4, lv[k]);
             }
         }
-        for (int c = lane * 4; c < Cl; c += 128) st_stream_f4(o + Cx + c, ld_stream_f4(lrow + (size_t)X * Cl + c));
     }
 }
 
@@ -200,10 +224,10 @@ using namespace pylc;
 extern "C" int pylc_upsample_concat_nhwc_f32(const float *x, int B, int h, int w, int Cx, const float *low, int H, int W, int Cl,
                                              float *out, pylc_stream_t stream) {
     if (!x || !low || !out || B < 1 || h < 1 || w < 1 || H < 1 || W < 1) return PYLC_ERR_ARG;
-    if (Cx < 4 || Cx % 4 || Cl < 0 || Cl % 4 || Cx > 512) return PYLC_ERR_GEOMETRY;
+    if (Cx < 4 || Cx % 4 || Cl < 0 || Cl % 4 || Cx > 512 || Cl * kUpSeg > kUpLowMax * 128) return PYLC_ERR_GEOMETRY;
     if (((uintptr_t)x | (uintptr_t)low | (uintptr_t)out) % 16) return PYLC_ERR_ALIGN;
-    const long long rows = (long long)B * H;
-    const unsigned grid = (unsigned)((rows + kWarps - 1) / kWarps);
+    const long long items = (long long)B * H * ((W + kUpSeg - 1) / kUpSeg);
+    const unsigned grid = glue_grid(items * 32, 3);            // persistent: 3 CTAs of 8 warps per SM
     cudaStream_t st = (cudaStream_t)stream;
     if (Cx <= 128) upsample_concat_kernel<1><<<grid, kThreads, 0, st>>>(x, low, out, B, h, w, Cx, H, W, Cl);
     else if (Cx <= 256) upsample_concat_kernel<2><<<grid, kThreads, 0, st>>>(x, low, out, B, h, w, Cx, H, W, Cl);

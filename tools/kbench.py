@@ -165,6 +165,26 @@ def main():
            lambda: ops.profile_tiles(g3_out, None, C), "1 B per px")
     del g3_out, n_out, g_out
 
+    # ---- network glue (bench.py batch: 45 tiles of 512 x 512) ------------------------------------------
+    if not only or any(o in "glue upsample_concat maxpool upsample_nhwc_to_nchw gather_norm_s2d" for o in only):
+        Bt, cl = 45, torch.channels_last
+        xa = torch.randn((Bt, 256, 32, 32), device="cuda").contiguous(memory_format=cl)
+        lo = torch.randn((Bt, 48, 128, 128), device="cuda").contiguous(memory_format=cl)
+        report("upsample_concat_nhwc 45x(256@32^2 -> 128^2 + 48)", (xa.numel() + lo.numel() + Bt * 304 * 128 * 128) * 4,
+               lambda: ops.upsample_concat_nhwc(xa, lo), "x + low read once, [B,304,128,128] written once")
+        st_ = torch.randn((Bt, 64, 256, 256), device="cuda").contiguous(memory_format=cl)
+        report("maxpool3x3s2_nhwc 45x64@256^2", (st_.numel() + st_.numel() // 4) * 4, lambda: ops.maxpool3x3s2_nhwc(st_),
+               "input read once, output written once")
+        de = torch.randn((Bt, 9, 128, 128), device="cuda").contiguous(memory_format=cl)
+        report("upsample_nhwc_to_nchw 45x9@128^2 -> 512^2", (de.numel() + Bt * 9 * 512 * 512) * 4,
+               lambda: ops.upsample_nhwc_to_nchw(de, (512, 512)), "decoder output read once, planar logits written once")
+        del xa, lo, st_, de
+        fit3 = torch.from_numpy(orc.synth_image(3, 2560, 1536, 3)).cuda()
+        report("tile_gather_norm_s2d rgb 2560x1536 S256 (45 tiles)", 2560 * 1536 * 3 + 45 * 259 * 259 * 64,
+               lambda: ops.tile_gather_norm_s2d(fit3, 1536, 2560, 3, 2560 * 3, T, 256, [128.0] * 3, [60.0] * 3),
+               "source read once + 64 B per space-to-depth pixel written")
+        del fit3
+
     # ---- test-time fit resize -----------------------------------------------------------------
     for (Wr, Hr, chr_) in ((3000, 2000, 3), (6000, 4000, 1)):
         wr, hr = orc.fit_dims(Wr, Hr, T)
