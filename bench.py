@@ -215,36 +215,76 @@ def cpu_baseline():
 # our arm
 # ---------------------------------------------------------------------------------------------
 
-class StitchTimer(object):
-    """Wraps ops.stitch_argmax_colour with CUDA events on the launching stream."""
+class KernelTimer(object):
+    """Wraps the ops.* calls of the pipeline with CUDA events on the launching stream and counts the
+    algorithmic bytes of every launch (compulsory HBM traffic of the call)."""
 
     def __init__(self, ops):
-        self.ops, self.orig, self.pairs, self.bytes, self.on = ops, ops.stitch_argmax_colour, [], 0, False
+        self.ops, self.on, self.rows, self.orig = ops, False, {}, {}
+        nb = lambda t: t.numel() * t.element_size()          # noqa: E731
+
+        def stitch_bytes(a, k, out):
+            lg = a[0]
+            n_logit = sum(t.numel() for t in lg) if isinstance(lg, (list, tuple)) else lg.numel()
+            return n_logit * 4 + out[0].numel()               # every logit once + 1 B label per output px
+        self.bytes_of = {
+            "fit_resize_area": lambda a, k, out: (a[1] * a[2] + a[5] * a[6]) * a[3],         # source once + fitted once
+            "tile_gather_norm_s2d": lambda a, k, out: a[1] * a[2] * a[3] + nb(out),          # fitted image once + tiles
+            "tile_gather_norm_f32": lambda a, k, out: a[1] * a[2] * a[3] + nb(out),
+            "maxpool3x3s2_nhwc": lambda a, k, out: nb(a[0]) + nb(out),
+            "upsample_concat_nhwc": lambda a, k, out: nb(a[0]) + nb(a[1]) + nb(out),
+            "upsample_nhwc_to_nchw": lambda a, k, out: nb(a[0]) + nb(out),
+            "stitch_argmax_colour": stitch_bytes,
+            "resample_encode_confusion": lambda a, k, out: a[1] * a[2] * 4,                  # 3 B ground truth + 1 B label per px
+        }
 
     def __enter__(self):
-        def timed(logits, nr, nc, T, S, **kw):
-            if not self.on:
-                return self.orig(logits, nr, nc, T, S, **kw)
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            out = self.orig(logits, nr, nc, T, S, **kw)
-            e.record()
-            self.pairs.append((s, e))
-            n_logit = sum(t.numel() for t in logits) if isinstance(logits, (list, tuple)) else logits.numel()
-            self.bytes += n_logit * 4 + out[0].numel()          # every logit once + 1 B label per output px
-            return out
-        self.ops.stitch_argmax_colour = timed
+        for name, fn_bytes in self.bytes_of.items():
+            orig = getattr(self.ops, name)
+            self.orig[name] = orig
+
+            def timed(*a, _orig=orig, _name=name, _fb=fn_bytes, **k):
+                if not self.on:
+                    return _orig(*a, **k)
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                out = _orig(*a, **k)
+                e.record()
+                row = self.rows.setdefault(_name, {"pairs": [], "bytes": 0})
+                row["pairs"].append((s, e))
+                row["bytes"] += _fb(a, k, out)
+                return out
+            setattr(self.ops, name, timed)
         return self
 
     def __exit__(self, *a):
-        self.ops.stitch_argmax_colour = self.orig
+        for name, orig in self.orig.items():
+            setattr(self.ops, name, orig)
 
-    def reset(self):
-        self.pairs, self.bytes = [], 0
+    def result(self, peak, step_ms, steps):
+        out = []
+        for name, row in self.rows.items():
+            ms = [s.elapsed_time(e) for s, e in row["pairs"]]
+            if not ms:
+                continue
+            avg_ms, avg_b = sum(ms) / len(ms), row["bytes"] / len(ms)
+            out.append({"op": name, "launches_per_step": len(ms) // steps, "avg_launch_ms": avg_ms,
+                        "algorithmic_bytes_per_launch": avg_b, "achieved_gbs": avg_b / (avg_ms * 1e-3) / 1e9,
+                        "frac": avg_b / (avg_ms * 1e-3) / 1e9 / peak, "share_of_step": sum(ms) / steps / step_ms})
+        return sorted(out, key=lambda r: -r["share_of_step"])
 
-    def result(self):
-        ms = [s.elapsed_time(e) for s, e in self.pairs]
-        return (sum(ms) / len(ms), self.bytes / len(ms)) if ms else (None, None)
+
+def ncu_traffic(tag, kernel_prefix):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu capture
+    (profiles/traffic_r1.json, written by tools/summarise_profiles.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as f:
+            for row in json.load(f).get(tag, []):
+                if row["kernel"].startswith(kernel_prefix):
+                    return row["dram_bytes"]
+    except Exception:
+        pass
+    return None
 
 
 def run_ours(args, rank, world, local_rank):
@@ -280,7 +320,7 @@ def run_ours(args, rank, world, local_rank):
     h2d = sum(im.numel() + gt.numel() for im, gt in zip(imgs, masks)) if seg.can_fit_on_device(imgs[0]) \
         else sum(f.img.numel() + f.gt.numel() for f in resident)      # bytes run_host copies per step
     clocks = ClockSampler(local_rank)
-    with StitchTimer(ops) as st:
+    with KernelTimer(ops) as st:
         for _ in range(args.warmup):
             seg.reset()
             seg.run_resident(resident)
@@ -301,7 +341,10 @@ def run_ours(args, rank, world, local_rank):
         st.on = False
         launches = _lib.launch_count() - launches0
         ms = pdist.max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
-        k_ms, k_bytes = st.result()
+        kernels = st.result(peak_gbs()[0], ms, args.steps)
+        stitch = next((r for r in kernels if r["op"] == "stitch_argmax_colour"), None)
+        k_ms = stitch["avg_launch_ms"] if stitch else None
+        k_bytes = stitch["algorithmic_bytes_per_launch"] if stitch else None
     conf_resident = conf_dev.cpu().numpy()
     del resident
 
@@ -333,7 +376,7 @@ def run_ours(args, rank, world, local_rank):
             "fp32 with cuDNN TF32 (PyTorch default, as the reference would run)" if dtype is None else args.backbone_dtype),
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "images_per_gpu": N_IMAGES, "tiles_per_image": 45, "batch_tiles": args.batch_tiles,
-                   "network_plan": "eager nn.Module" if args.no_fuse else "BatchNorm folded, cuDNN fused conv+bias(+add)+ReLU, channels_last",
+                   "network_plan": "eager nn.Module" if args.no_fuse else "BatchNorm folded, cuDNN fused conv+bias(+add)+ReLU, channels_last, space-to-depth stem, pylc max-pool / up-sample+concat / final up-sample kernels",
                    "l2": "inputs larger than L2 (each step streams > 20 GB of logits per GPU)",
                    "parallelism": "dp%d, images sharded, one [9,9] i64 all-reduce per step" % world,
                    "fit_resize": "host cv2 threads" if args.host_fit else "device (pylc_fit_resize_area_u8, bit-exact INTER_AREA)",
@@ -348,8 +391,12 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"kernel": "stitch_kernel (pylc_stitch_argmax_colour)", "bound": "hbm",
                      "achieved": (k_bytes / (k_ms * 1e-3) / 1e9) if k_ms else None, "peak": peak, "peak_kind": peak_kind,
                      "unit": "GB/s", "frac": (k_bytes / (k_ms * 1e-3) / 1e9 / peak) if k_ms else None,
-                     "avg_launch_ms": k_ms, "algorithmic_bytes_per_launch": k_bytes, "traffic": None,
-                     "share_of_step": (k_ms * N_IMAGES / ms) if k_ms else None},
+                     "avg_launch_ms": k_ms, "algorithmic_bytes_per_launch": k_bytes,
+                     "traffic": ncu_traffic("stitch45", "stitch_kernel"),
+                     "traffic_source": "profiles/traffic_r1.json: ncu --set full capture of this launch shape (45 tiles), dram read + write",
+                     "share_of_step": (k_ms * N_IMAGES / ms) if k_ms else None,
+                     "why_this_kernel": "largest algorithmic HBM stream of the SURVEY 8a hot path; every custom launch of the step is listed under `kernels`"},
+        "kernels": kernels,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()

@@ -72,6 +72,7 @@ def captures():
     reps = sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_%s_*.ncu-rep" % R)))
     if not reps:
         return
+    traffic = {}
     md = ["# ncu `--set full --clock-control none` captures, round %s" % R, "",
           "One launch per kernel at the BASELINE sizes of `tools/kbench.py` (6000x4000 image, 273 logit tiles,",
           "B=64 loss batch), after 3 warm-up launches.  ncu flushes caches and serialises, so durations are",
@@ -88,6 +89,13 @@ def captures():
             md.append("")
             md.append("| metric | value |")
             md.append("|---|---|")
+            try:     # dram bytes per launch, keyed by capture name (bench.py reads traffic_<round>.json)
+                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+                tag = os.path.basename(rep)[len("prof_%s_" % R):-len(".ncu-rep")]
+                traffic.setdefault(tag, []).append({"kernel": name, "dram_bytes": float(r[rd]) * mult[units[rd]] + float(r[wr]) * mult[units[wr]]})
+            except (ValueError, KeyError):
+                pass
             for key, label in KEYS:
                 if key in hdr:
                     i = hdr.index(key)
@@ -105,6 +113,9 @@ def captures():
             md.append("")
     with open(os.path.join(OUT, "ncu_%s_summary.md" % R), "w") as f:
         f.write("\n".join(md) + "\n")
+    import json
+    with open(os.path.join(OUT, "traffic_%s.json" % R), "w") as f:
+        json.dump(traffic, f, indent=1)
     print("captures:", len(reps))
 
 
