@@ -150,48 +150,103 @@ __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t s) {
 }
 
 // ---- per-thread class counters ----------------------------------------------------------------
-// Register-resident histogram of u8 class ids without shared-memory atomics in the pixel loop.
-//   C <= 12 : one u64 of 5-bit fields per 16-pixel unit, widened into two u64 of 10-bit fields
-//             (<= 63 units between flushes)
-//   C <= 32 : four u64 of 8-bit fields (<= 15 units between flushes)
-template <bool WIDE>
-struct ClassCounter;
-
-template <>
-struct ClassCounter<false> {
-    static constexpr unsigned long long kEven = 0x01F07C1F07C1Full | (0x1Full << 50);  // fields 0,2,..,10
-    unsigned long long unit, even, odd;
-    __device__ __forceinline__ void reset() { unit = even = odd = 0; }
-    // PTX shl.b64 clamps amounts >= 64 to zero, so out-of-range class ids (>= 13) vanish
-    // instead of being undefined; id 12 lands in bits 60..63, which count() never reads.
-    __device__ __forceinline__ void add(uint32_t cls) {
-        unsigned long long one;
-        asm("shl.b64 %0, 1, %1;" : "=l"(one) : "r"(cls * 5u));
-        unit += one;
+// Register-resident histograms of u8 class ids, fed SIXTEEN packed ids at a time (four words of four
+// class bytes, the form every encode kernel already holds them in); no shared-memory traffic in the
+// pixel loop.  Protocol: add16() per 16-pixel unit, widen() after at most kWidenUnits units, read
+// count() / reset() after at most kFlushUnits units.
+//
+// NibbleCounter<NG> (C <= 2*NG <= 14; ids >= 2*NG are ignored, ids must be < 16):
+//   PRMT is an 8-entry byte table look-up for four 4-bit indices at once.  Two words of class bytes
+//   fold into one word of eight nibbles (w0 + 16*w1), whose halves are the selectors.  The table of
+//   group g holds 0x01 for class 2g and 0x10 for class 2g+1 (zero elsewhere), so one PRMT turns four
+//   pixels into four byte lanes of two 4-bit one-hot fields, and the lanes add up with IADD3.  An
+//   index with bit 3 set makes PRMT replicate the sign bit of the table byte -- zero for these
+//   tables -- so classes 8..15 vanish from groups 0..3 and, with the selector XOR 0x8888, classes
+//   0..7 vanish from groups 4..7.  Cost: (4 PRMT + 2 IADD3) per group and 16 pixels, about 2.5
+//   instructions per pixel at C = 9 against ~6.5 for a shift-and-add of one-hot fields per pixel.
+//   A field grows by at most 4 per unit: widen() every 3 units moves the nibble fields into byte
+//   fields (<= 12 each time), which hold 21 widenings = 63 units.
+template <int NG>
+struct NibbleCounter {
+    static_assert(NG >= 1 && NG <= 7, "ids 14 and 15 must stay free: 15 is the 'no class' id");
+    static constexpr int kWidenUnits = 3, kFlushUnits = 63, kMaxClasses = 2 * NG;
+    static constexpr uint32_t kVoid = 0x0F0F0F0Fu;     // four ids that are never counted
+    uint32_t nib[NG], wide[NG][2];
+    // Arbitrary mask bytes (tiles read back from a database): ids >= 16 become 15.
+    static constexpr bool kNeedsSanitize = true;
+    static __device__ __forceinline__ uint32_t sanitize(uint32_t w) {
+        uint32_t t = w & 0xF0F0F0F0u;
+        t |= t >> 1;
+        t |= t >> 2;
+        const uint32_t bad = ((t >> 4) & 0x01010101u) * 0xFFu;   // 0xFF in every byte that was >= 16
+        return (w & ~bad) | (bad & 0x0F0F0F0Fu);
     }
-    // call after every <= 31 pixels
-    __device__ __forceinline__ void end_unit() {
-        even += unit & kEven;
-        odd += (unit >> 5) & kEven;
-        unit = 0;
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) nib[g] = wide[g][0] = wide[g][1] = 0u;
     }
-    __device__ __forceinline__ uint32_t count(int c) const {
-        unsigned long long src = (c & 1) ? odd : even;
-        return (uint32_t)(src >> ((c >> 1) * 10)) & 0x3FFu;
+    static __device__ __forceinline__ uint32_t look(int g, uint32_t sel) {
+        const uint32_t a = (g & 3) == 0 ? 0x00001001u : ((g & 3) == 1 ? 0x10010000u : 0u);
+        const uint32_t b = (g & 3) == 2 ? 0x00001001u : ((g & 3) == 3 ? 0x10010000u : 0u);
+        uint32_t d;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+        return d;
     }
+    __device__ __forceinline__ void add16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+        const uint32_t p0 = w0 + (w1 << 4), p1 = w2 + (w3 << 4);
+        const uint32_t q0 = p0 >> 16, q1 = p1 >> 16;
+#pragma unroll
+        for (int g = 0; g < (NG < 4 ? NG : 4); ++g) {
+            nib[g] += look(g, p0) + look(g, q0);
+            nib[g] += look(g, p1) + look(g, q1);
+        }
+        if (NG > 4) {
+            const uint32_t x0 = p0 ^ 0x88888888u, x1 = p1 ^ 0x88888888u;
+            const uint32_t y0 = x0 >> 16, y1 = x1 >> 16;
+#pragma unroll
+            for (int g = 4; g < NG; ++g) {
+                nib[g] += look(g, x0) + look(g, y0);
+                nib[g] += look(g, x1) + look(g, y1);
+            }
+        }
+    }
+    __device__ __forceinline__ void widen() {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            wide[g][0] += nib[g] & 0x0F0F0F0Fu;
+            wide[g][1] += (nib[g] >> 4) & 0x0F0F0F0Fu;
+            nib[g] = 0u;
+        }
+    }
+    // c must be a compile-time constant after unrolling (register arrays)
+    __device__ __forceinline__ uint32_t count(int c) const { return __dp4a(wide[c >> 1][c & 1], 0x01010101u, 0u); }
 };
 
-template <>
-struct ClassCounter<true> {
+// C <= 32: four u64 of 8-bit fields, one pixel at a time (<= 15 units between flushes)
+struct ByteCounter {
+    static constexpr int kWidenUnits = 1 << 30, kFlushUnits = 15, kMaxClasses = PYLC_MAX_CLASSES;
+    static constexpr uint32_t kVoid = 0xFFFFFFFFu;
     unsigned long long acc[4];
+    static constexpr bool kNeedsSanitize = false;
+    static __device__ __forceinline__ uint32_t sanitize(uint32_t w) { return w; }
     __device__ __forceinline__ void reset() { acc[0] = acc[1] = acc[2] = acc[3] = 0; }
-    __device__ __forceinline__ void add(uint32_t cls) {
+    __device__ __forceinline__ void add(uint32_t cls) {   // ids >= 32 are ignored
         unsigned long long one = 1ull << ((cls & 7u) * 8u);
         uint32_t w = cls >> 3;
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[i] += (w == (uint32_t)i) ? one : 0ull;
     }
-    __device__ __forceinline__ void end_unit() {}
+    __device__ __forceinline__ void add16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+        const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            add(w[k] & 0xFFu);
+            add((w[k] >> 8) & 0xFFu);
+            add((w[k] >> 16) & 0xFFu);
+            add(w[k] >> 24);
+        }
+    }
+    __device__ __forceinline__ void widen() {}
     __device__ __forceinline__ uint32_t count(int c) const {
         unsigned long long src = acc[0];
         if ((c >> 3) == 1) src = acc[1];
@@ -201,14 +256,36 @@ struct ClassCounter<true> {
     }
 };
 
-// Warp-aggregated flush of a ClassCounter into a shared-memory histogram (one atomic per class
-// per warp).  Must be called by all 32 lanes.
-template <bool WIDE>
-__device__ __forceinline__ void flush_counter(const ClassCounter<WIDE> &cc, int C, unsigned *s_hist) {
+// NG = 0 selects the byte counter (15 <= C <= 32), otherwise NibbleCounter<NG>
+template <int NG>
+struct CounterSel {
+    using type = NibbleCounter<NG>;
+};
+template <>
+struct CounterSel<0> {
+    using type = ByteCounter;
+};
+// host: counter variant for C classes
+inline int counter_groups(int C) { return C <= 10 ? 5 : (C <= 12 ? 6 : (C <= 14 ? 7 : 0)); }
+
+// Turns the bytes j >= valid of word k (of a 16-pixel unit) into the id that counter CC ignores.
+template <class CC>
+__device__ __forceinline__ uint32_t void_tail(uint32_t w, int k, int valid) {
+    const int n = valid - 4 * k;                        // valid bytes in this word
+    return n >= 4 ? w : (n <= 0 ? CC::kVoid : ((w & ~(0xFFFFFFFFu << (8 * n))) | (CC::kVoid << (8 * n))));
+}
+
+// Warp-aggregated flush of a counter into a shared-memory histogram (one atomic per class per
+// warp).  Must be called by all 32 lanes.
+template <class CC>
+__device__ __forceinline__ void flush_counter(const CC &cc, int C, unsigned *s_hist) {
     const int lane = threadIdx.x & 31;
-    for (int c = 0; c < C; ++c) {
-        unsigned v = __reduce_add_sync(0xFFFFFFFFu, cc.count(c));
-        if (lane == 0 && v) atomicAdd(&s_hist[c], v);
+#pragma unroll
+    for (int c = 0; c < CC::kMaxClasses; ++c) {
+        if (c < C) {
+            unsigned v = __reduce_add_sync(0xFFFFFFFFu, cc.count(c));
+            if (lane == 0 && v) atomicAdd(&s_hist[c], v);
+        }
     }
 }
 

@@ -61,16 +61,18 @@ struct EncodeArgs {
     bool src_aligned, out_aligned;
 };
 
-template <int LAYOUT, bool WIDE, bool HIST>
+template <int LAYOUT, int NG, bool HIST>
 __global__ void __launch_bounds__(kThreads) class_encode_kernel(EncodeArgs a, const __grid_constant__ PaletteHash ph) {
+    using CC = typename CounterSel<NG>::type;
     __shared__ uint32_t s_tab[256];
     __shared__ unsigned s_hist[PYLC_MAX_CLASSES];
     s_tab[threadIdx.x] = ph.tab[threadIdx.x];
     if (threadIdx.x < PYLC_MAX_CLASSES) s_hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t mul = ph.mul;
-    ClassCounter<WIDE> cc;
+    CC cc;
     cc.reset();
+    int since_widen = 0;
     const long long first = (long long)blockIdx.x * kThreads * kUnitsPerThread;
 #pragma unroll 1
     for (int it = 0; it < kUnitsPerThread; ++it) {
@@ -127,10 +129,17 @@ __global__ void __launch_bounds__(kThreads) class_encode_kernel(EncodeArgs a, co
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const uint32_t c = encode_key(key[j], s_tab, mul);
-            if (HIST && j < valid) cc.add(c);
             ow[j >> 2] |= c << ((j & 3) * 8);
         }
-        if (HIST) cc.end_unit();
+        if (HIST) {
+            if (valid == 16) cc.add16(ow[0], ow[1], ow[2], ow[3]);
+            else cc.add16(void_tail<CC>(ow[0], 0, valid), void_tail<CC>(ow[1], 1, valid), void_tail<CC>(ow[2], 2, valid),
+                          void_tail<CC>(ow[3], 3, valid));
+            if (++since_widen == CC::kWidenUnits) {
+                cc.widen();
+                since_widen = 0;
+            }
+        }
         uint8_t *o = a.out + (size_t)rowi * a.cols + x;
         if (a.out_aligned && valid == 16) {
             st_stream16(o, make_uint4(ow[0], ow[1], ow[2], ow[3]));
@@ -141,7 +150,8 @@ __global__ void __launch_bounds__(kThreads) class_encode_kernel(EncodeArgs a, co
         }
     }
     if (HIST) {
-        flush_counter<WIDE>(cc, a.C, s_hist);
+        cc.widen();
+        flush_counter(cc, a.C, s_hist);
         __syncthreads();
         if (threadIdx.x < a.C && s_hist[threadIdx.x])
             atomicAdd((unsigned long long *)&a.hist[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
@@ -151,7 +161,7 @@ __global__ void __launch_bounds__(kThreads) class_encode_kernel(EncodeArgs a, co
 // ------------------------------------------------------------------------------------------------
 // profiling over extracted tiles: per-tile class histogram of u8 masks
 // ------------------------------------------------------------------------------------------------
-template <bool WIDE>
+template <int NG>
 __global__ void __launch_bounds__(kThreads)
     tile_hist_kernel(const uint8_t *__restrict__ masks, long long tile_px, int chunks, int C,
                      long long *__restrict__ px_dist) {
@@ -162,7 +172,9 @@ __global__ void __launch_bounds__(kThreads)
     const int chunk = blockIdx.x % chunks;
     const uint8_t *base = masks + (size_t)tile * tile_px;
     const long long units = tile_px / 16;
-    ClassCounter<WIDE> cc;
+    using CC = typename CounterSel<NG>::type;
+    static_assert(kUnitsPerThread <= CC::kFlushUnits, "one flush per thread");
+    CC cc;
     cc.reset();
     uint4 v[kUnitsPerThread];
 #pragma unroll
@@ -172,17 +184,19 @@ __global__ void __launch_bounds__(kThreads)
     }
 #pragma unroll
     for (int it = 0; it < kUnitsPerThread; ++it) {
-        const uint32_t w[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            cc.add(w[j] & 0xFF);
-            cc.add((w[j] >> 8) & 0xFF);
-            cc.add((w[j] >> 16) & 0xFF);
-            cc.add(w[j] >> 24);
+        // masks come from a database: any byte value may occur; ids the counter cannot hold are dropped
+        uint32_t w0 = v[it].x, w1 = v[it].y, w2 = v[it].z, w3 = v[it].w;
+        if (CC::kNeedsSanitize && ((w0 | w1 | w2 | w3) & 0xF0F0F0F0u)) {   // rare: some id >= 16 in this unit
+            w0 = CC::sanitize(w0);
+            w1 = CC::sanitize(w1);
+            w2 = CC::sanitize(w2);
+            w3 = CC::sanitize(w3);
         }
-        cc.end_unit();
+        cc.add16(w0, w1, w2, w3);
+        if ((it + 1) % CC::kWidenUnits == 0) cc.widen();
     }
-    flush_counter<WIDE>(cc, C, s_hist);
+    cc.widen();
+    flush_counter(cc, C, s_hist);
     __syncthreads();
     if (threadIdx.x < C && s_hist[threadIdx.x])
         atomicAdd((unsigned long long *)&px_dist[tile * C + threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
@@ -300,12 +314,17 @@ extern "C" int pylc_class_encode(const uint8_t *rgb, int n_img, int rows, int co
     const long long per_cta = (long long)kThreads * kUnitsPerThread;
     const unsigned grid = (unsigned)((a.total_units + per_cta - 1) / per_cta);
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(L, WD, HS) class_encode_kernel<L, WD, HS><<<grid, kThreads, 0, st>>>(a, ph)
-    if (layout == 0) {
-        if (!hist) LAUNCH(0, false, false); else if (C <= 12) LAUNCH(0, false, true); else LAUNCH(0, true, true);
-    } else {
-        if (!hist) LAUNCH(1, false, false); else if (C <= 12) LAUNCH(1, false, true); else LAUNCH(1, true, true);
+#define LAUNCH(L, NG, HS) class_encode_kernel<L, NG, HS><<<grid, kThreads, 0, st>>>(a, ph)
+#define LAUNCH_L(L)                                                                    \
+    switch (hist ? counter_groups(C) : -1) {                                           \
+        case -1: LAUNCH(L, 5, false); break;                                           \
+        case 5: LAUNCH(L, 5, true); break;                                             \
+        case 6: LAUNCH(L, 6, true); break;                                             \
+        case 7: LAUNCH(L, 7, true); break;                                             \
+        default: LAUNCH(L, 0, true); break;                                            \
     }
+    if (layout == 0) { LAUNCH_L(0) } else { LAUNCH_L(1) }
+#undef LAUNCH_L
 #undef LAUNCH
     return finish_launch();
 }
@@ -323,8 +342,12 @@ extern "C" int pylc_profile_tiles(const uint8_t *imgs, int ch, const uint8_t *ma
     int rc = PYLC_OK;
     if (masks) {
         const unsigned grid = (unsigned)((long long)n * chunks);
-        if (C <= 12) tile_hist_kernel<false><<<grid, kThreads, 0, st>>>(masks, tile_px, chunks, C, (long long *)px_dist);
-        else tile_hist_kernel<true><<<grid, kThreads, 0, st>>>(masks, tile_px, chunks, C, (long long *)px_dist);
+        switch (counter_groups(C)) {
+            case 5: tile_hist_kernel<5><<<grid, kThreads, 0, st>>>(masks, tile_px, chunks, C, (long long *)px_dist); break;
+            case 6: tile_hist_kernel<6><<<grid, kThreads, 0, st>>>(masks, tile_px, chunks, C, (long long *)px_dist); break;
+            case 7: tile_hist_kernel<7><<<grid, kThreads, 0, st>>>(masks, tile_px, chunks, C, (long long *)px_dist); break;
+            default: tile_hist_kernel<0><<<grid, kThreads, 0, st>>>(masks, tile_px, chunks, C, (long long *)px_dist); break;
+        }
         rc = finish_launch();
         if (rc) return rc;
     }

@@ -261,10 +261,11 @@ __global__ void __launch_bounds__(kThreads) gather_img_kernel(GatherGeom g, uint
 // ------------------------------------------------------------------------------------------------
 // mask gather + palette encode + per-tile histogram
 // ------------------------------------------------------------------------------------------------
-template <bool WIDE>
-__device__ __forceinline__ void flush_block_hist(const GatherGeom &g, int blk, ClassCounter<WIDE> &cc, int C,
+template <class CC>
+__device__ __forceinline__ void flush_block_hist(const GatherGeom &g, int blk, CC &cc, int C,
                                                  unsigned *s_hist, long long *px_dist) {
-    flush_counter<WIDE>(cc, C, s_hist);
+    cc.widen();
+    flush_counter(cc, C, s_hist);
     cc.reset();
     __syncthreads();
     const int bx = blk % g.nbx, by = blk / g.nbx;
@@ -281,7 +282,7 @@ __device__ __forceinline__ void flush_block_hist(const GatherGeom &g, int blk, C
     __syncthreads();
 }
 
-template <bool ALIGNED, bool WIDE, bool HIST>
+template <bool ALIGNED, int NG, bool HIST>
 __global__ void __launch_bounds__(kThreads)
     gather_mask_kernel(GatherGeom g, const __grid_constant__ PaletteHash ph, int C, uint8_t *__restrict__ dst,
                        long long *__restrict__ px_dist) {
@@ -298,9 +299,10 @@ __global__ void __launch_bounds__(kThreads)
     const bool on = row < g.rows_item;
     const size_t TT = (size_t)g.T * g.T;
 
-    ClassCounter<WIDE> cc;
+    using CC = typename CounterSel<NG>::type;
+    CC cc;
     cc.reset();
-    int since_flush = 0;
+    int since_flush = 0, since_widen = 0;
     Item it = decode_item(g, first);
     SrcUnit<3> cur, nxt;
     if (on) load_unit<3, ALIGNED>(g, it, row, grp, cur);
@@ -321,15 +323,15 @@ __global__ void __launch_bounds__(kThreads)
                 const uint32_t c1 = encode_key(__funnelshift_r(a, b, 24), s_tab, mul);
                 const uint32_t c2 = encode_key(__funnelshift_r(b, c, 16), s_tab, mul);
                 const uint32_t c3 = encode_key(c >> 8, s_tab, mul);
-                if (HIST) {
-                    cc.add(c0);
-                    cc.add(c1);
-                    cc.add(c2);
-                    cc.add(c3);
-                }
                 ow[k] = c0 + (c1 << 8) + (c2 << 16) + (c3 << 24);
             }
-            if (HIST) cc.end_unit();
+            if (HIST) {
+                cc.add16(ow[0], ow[1], ow[2], ow[3]);
+                if (++since_widen == CC::kWidenUnits) {
+                    cc.widen();
+                    since_widen = 0;
+                }
+            }
             const uint4 o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             const TileSpan ts = tile_span(g, it.by, it.bx);
             const int ly = it.slab * g.rows_item + row, lx = grp * 16;
@@ -342,10 +344,10 @@ __global__ void __launch_bounds__(kThreads)
             }
         }
         // histograms are per destination tile: flush when the block changes, or before the packed
-        // per-thread fields could overflow (63 units of 5/10-bit fields, 15 units of 8-bit fields)
-        if (HIST && (it_n.blk != it.blk || item + 1 == last || ++since_flush >= (WIDE ? 15 : 63))) {
-            flush_block_hist<WIDE>(g, it.blk, cc, C, s_hist, px_dist);
-            since_flush = 0;
+        // per-thread fields could overflow (CC::kFlushUnits units)
+        if (HIST && (it_n.blk != it.blk || item + 1 == last || ++since_flush >= CC::kFlushUnits)) {
+            flush_block_hist(g, it.blk, cc, C, s_hist, px_dist);
+            since_flush = since_widen = 0;
         }
         it = it_n;
         cur = nxt;
@@ -355,13 +357,17 @@ __global__ void __launch_bounds__(kThreads)
 // T/S <= 2 version (the reference's two strides: S = T on extraction, S = T/2 on the test path):
 // BlockCursor addressing, warp-private histogram flushes (no CTA barrier anywhere in the loop, so
 // the eight warps of a CTA drift apart and hide each other's load latency).
-template <bool WIDE>
-__device__ __forceinline__ void flush_warp_hist(const GatherGeom &g, int blk, ClassCounter<WIDE> &cc, int C, long long *px_dist) {
+template <class CC>
+__device__ __forceinline__ void flush_warp_hist(const GatherGeom &g, int blk, CC &cc, int C, long long *px_dist) {
     const int lane = threadIdx.x & 31;
+    cc.widen();
     unsigned mine = 0;
-    for (int c = 0; c < C; ++c) {
-        const unsigned v = __reduce_add_sync(0xFFFFFFFFu, cc.count(c));
-        if (lane == c) mine = v;
+#pragma unroll
+    for (int c = 0; c < CC::kMaxClasses; ++c) {
+        if (c < C) {
+            const unsigned v = __reduce_add_sync(0xFFFFFFFFu, cc.count(c));
+            if (lane == c) mine = v;
+        }
     }
     cc.reset();
     if (lane < C && mine) {
@@ -373,8 +379,8 @@ __device__ __forceinline__ void flush_warp_hist(const GatherGeom &g, int blk, Cl
     }
 }
 
-template <bool ALIGNED, bool WIDE, bool HIST>
-__global__ void __launch_bounds__(kThreads)
+template <bool ALIGNED, int NG, bool HIST>
+__global__ void __launch_bounds__(kThreads, 4)
     gather_mask_cursor_kernel(GatherGeom g, const __grid_constant__ PaletteHash ph, int C, uint8_t *__restrict__ dst,
                               long long *__restrict__ px_dist) {
     __shared__ uint32_t s_tab[256];
@@ -391,9 +397,10 @@ __global__ void __launch_bounds__(kThreads)
     const size_t sstep = (size_t)g.rows_item * g.pitch;
     const int dstep = g.rows_item * g.T;
 
-    ClassCounter<WIDE> cc;
+    using CC = typename CounterSel<NG>::type;
+    CC cc;
     cc.reset();
-    int since_flush = 0;
+    int since_flush = 0, since_widen = 0;
     Item it = decode_item(g, first);
     BlockCursor cur;
     cursor_set<3>(g, it, row, grp, dst, TT, cur);
@@ -420,15 +427,15 @@ __global__ void __launch_bounds__(kThreads)
                 const uint32_t e1 = lookup_entry(__funnelshift_r(a, b, 24), s_tab, mul, miss_e);
                 const uint32_t e2 = lookup_entry(__funnelshift_r(b, c, 16), s_tab, mul, miss_e);
                 const uint32_t e3 = lookup_entry(c >> 8, s_tab, mul, miss_e);
-                if (HIST) {
-                    cc.add(e0 >> 24);
-                    cc.add(e1 >> 24);
-                    cc.add(e2 >> 24);
-                    cc.add(e3 >> 24);
-                }
                 ow[k] = pack_top_bytes(e0, e1, e2, e3);
             }
-            if (HIST) cc.end_unit();
+            if (HIST) {
+                cc.add16(ow[0], ow[1], ow[2], ow[3]);
+                if (++since_widen == CC::kWidenUnits) {
+                    cc.widen();
+                    since_widen = 0;
+                }
+            }
             const uint4 o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             st_stream16(cur.dst[0], o);
             if (cur.n > 1) st_stream16(cur.dst[1], o);
@@ -436,10 +443,10 @@ __global__ void __launch_bounds__(kThreads)
             if (cur.n > 3) st_stream16(cur.dst[3], o);
         }
         // histograms are per destination tile: flush when the block changes, or before the packed
-        // per-thread fields could overflow (63 units of 5/10-bit fields, 15 units of 8-bit fields)
-        if (HIST && (chg || item + 1 == last || ++since_flush >= (WIDE ? 15 : 63))) {
-            flush_warp_hist<WIDE>(g, it.blk, cc, C, px_dist);
-            since_flush = 0;
+        // per-thread fields could overflow (CC::kFlushUnits units)
+        if (HIST && (chg || item + 1 == last || ++since_flush >= CC::kFlushUnits)) {
+            flush_warp_hist(g, it.blk, cc, C, px_dist);
+            since_flush = since_widen = 0;
         }
         if (chg) {
             cursor_set<3>(g, it_n, row, grp, dst, TT, cur);
@@ -476,54 +483,63 @@ __global__ void __launch_bounds__(kThreads) gather_norm_kernel(GatherGeom g, Nor
         s_lut[k][threadIdx.x] = __fdiv_rn(__fdiv_rn(__fsub_rn((float)threadIdx.x, np.mean[k]), np.std[k]), np.post_div);
     __syncthreads();
     const size_t TT = (size_t)g.T * g.T;
+    // Items are `rows_item` consecutive rows of one S-block (sized by the host so that one item is about
+    // one unit per thread); CTA k takes a contiguous item range.  The item decode is CTA-uniform and the
+    // thread's (row, unit) position inside an item advances by constants, so the loop has no divisions.
     const int upr = g.S / 4;                                   // units per block row
-    const long long rows_total = (long long)g.nbx * g.nby * g.S;  // (block, row) pairs
-    const long long units_total = rows_total * upr;
-    const long long lo = units_total * blockIdx.x / gridDim.x, hi = units_total * (blockIdx.x + 1) / gridDim.x;
-    for (long long u = lo + threadIdx.x; u < hi; u += kThreads) {
-        const long long br = u / upr;
-        const int lx = (int)(u - br * upr) * 4;
-        const int ly = (int)(br % g.S);
-        const int blk = (int)(br / g.S);
+    const int per_item = g.rows_item * upr;
+    const int d_row = kThreads / upr, d_col = kThreads - d_row * upr;
+    int first, last;
+    cta_item_range(g.items, first, last);
+    for (int item = first; item < last; ++item) {
+        const int blk = item / g.slabs, slab = item - blk * g.slabs;
         const int bx = blk % g.nbx, by = blk / g.nbx;
-        const uint8_t *p = g.src + (size_t)(by * g.S + ly) * g.pitch + (size_t)(bx * g.S + lx) * CH;
-        uint32_t px[3];
-        if (CH == 1) {
-            px[0] = ALIGNED ? __ldg(reinterpret_cast<const uint32_t *>(p))
-                            : (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) |
-                                  ((uint32_t)__ldg(p + 3) << 24);
-        } else {
-            uint32_t w[3];
-            if (ALIGNED) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) w[k] = __ldg(reinterpret_cast<const uint32_t *>(p) + k);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    w[k] = (uint32_t)__ldg(p + 4 * k) | ((uint32_t)__ldg(p + 4 * k + 1) << 8) |
-                           ((uint32_t)__ldg(p + 4 * k + 2) << 16) | ((uint32_t)__ldg(p + 4 * k + 3) << 24);
-            }
-            deinterleave4(w[0], w[1], w[2], px[0], px[CH == 3 ? 1 : 0], px[CH == 3 ? 2 : 0]);
-        }
-        float4 f[CH];
-#pragma unroll
-        for (int k = 0; k < CH; ++k) {
-            f[k].x = s_lut[k][px[k] & 0xFF];
-            f[k].y = s_lut[k][(px[k] >> 8) & 0xFF];
-            f[k].z = s_lut[k][(px[k] >> 16) & 0xFF];
-            f[k].w = s_lut[k][px[k] >> 24];
-        }
         const TileSpan ts = tile_span(g, by, bx);
-        for (int r = ts.r_lo; r <= ts.r_hi; ++r) {
-            const int ty = (by - r) * g.S + ly;
-            for (int c = ts.c_lo; c <= ts.c_hi; ++c) {
-                const int tx = (bx - c) * g.S + lx;
-                float *d = dst + ((size_t)(r * g.nW + c) * np.out_ch) * TT + (size_t)ty * g.T + tx;
-                if (CH == 1) {
-                    for (int k = 0; k < np.out_ch; ++k) st_stream_f4(d + k * TT, f[0]);
+        int row = threadIdx.x / upr, col = threadIdx.x - row * upr;
+        for (int idx = threadIdx.x; idx < per_item; idx += kThreads, row += d_row, col += d_col) {
+            if (col >= upr) {
+                col -= upr;
+                ++row;
+            }
+            const int ly = slab * g.rows_item + row, lx = col * 4;
+            const uint8_t *p = g.src + (size_t)(by * g.S + ly) * g.pitch + (size_t)(bx * g.S + lx) * CH;
+            uint32_t px[3];
+            if (CH == 1) {
+                px[0] = ALIGNED ? __ldg(reinterpret_cast<const uint32_t *>(p))
+                                : (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) |
+                                      ((uint32_t)__ldg(p + 3) << 24);
+            } else {
+                uint32_t w[3];
+                if (ALIGNED) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) w[k] = __ldg(reinterpret_cast<const uint32_t *>(p) + k);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < CH; ++k) st_stream_f4(d + k * TT, f[k]);
+                    for (int k = 0; k < 3; ++k)
+                        w[k] = (uint32_t)__ldg(p + 4 * k) | ((uint32_t)__ldg(p + 4 * k + 1) << 8) |
+                               ((uint32_t)__ldg(p + 4 * k + 2) << 16) | ((uint32_t)__ldg(p + 4 * k + 3) << 24);
+                }
+                deinterleave4(w[0], w[1], w[2], px[0], px[CH == 3 ? 1 : 0], px[CH == 3 ? 2 : 0]);
+            }
+            float4 f[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                f[k].x = s_lut[k][px[k] & 0xFF];
+                f[k].y = s_lut[k][(px[k] >> 8) & 0xFF];
+                f[k].z = s_lut[k][(px[k] >> 16) & 0xFF];
+                f[k].w = s_lut[k][px[k] >> 24];
+            }
+            for (int r = ts.r_lo; r <= ts.r_hi; ++r) {
+                const int ty = (by - r) * g.S + ly;
+                for (int c = ts.c_lo; c <= ts.c_hi; ++c) {
+                    const int tx = (bx - c) * g.S + lx;
+                    float *d = dst + ((size_t)(r * g.nW + c) * np.out_ch) * TT + (size_t)ty * g.T + tx;
+                    if (CH == 1) {
+                        for (int k = 0; k < np.out_ch; ++k) st_stream_f4(d + k * TT, f[0]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < CH; ++k) st_stream_f4(d + k * TT, f[k]);
+                    }
                 }
             }
         }
@@ -540,9 +556,16 @@ __global__ void __launch_bounds__(kThreads) gather_norm_kernel(GatherGeom g, Nor
 // that layout, channels-last, border included:
 //     dst[n, Y, X, (py*2+px)*3 + c] = norm(tile_n[c, 2(Y-2)+py, 2(X-2)+px]),  Y, X in [0, T/2+3)
 // (two zero rows/columns before the image, one after; channels 12..15 zero), f32, same IEEE
-// normalisation tables as gather_norm_kernel.  One thread = one 64-byte output pixel record; a warp
-// writes 2 KB contiguous.
-template <int CH>
+// normalisation tables as gather_norm_kernel.
+//
+// Source-driven like the u8 gathers: a 2x2 source quad becomes ONE 64-byte record, built once and
+// stored into every tile that contains it (up to four at S = T/2), so the table look-ups are paid per
+// source pixel, not per tile pixel.  A lane owns one 16-byte quarter of a record (`part` = lane & 3,
+// constant per thread because the CTA strides by a multiple of four): quarters 0..2 take four source
+// bytes from two 16-bit loads, quarter 3 is the zero padding.  Consecutive lanes therefore write
+// consecutive 16-byte vectors -- a warp-level store is a contiguous 512-byte run of full sectors in
+// each destination tile.  A second, small loop zero-fills the border records (6*Hs - 9 per tile).
+template <int CH, bool AL2>
 __global__ void __launch_bounds__(kThreads) gather_norm_s2d_kernel(GatherGeom g, NormParams np, float *__restrict__ dst) {
     __shared__ float s_lut[3][256];
 #pragma unroll
@@ -550,31 +573,79 @@ __global__ void __launch_bounds__(kThreads) gather_norm_s2d_kernel(GatherGeom g,
         s_lut[k][threadIdx.x] = __fdiv_rn(__fdiv_rn(__fsub_rn((float)threadIdx.x, np.mean[k]), np.std[k]), np.post_div);
     __syncthreads();
     const int Hs = g.T / 2 + 3;
-    const long long total = (long long)g.nH * g.nW * Hs * Hs;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-        const int X = (int)(i % Hs);
-        long long r = i / Hs;
-        const int Y = (int)(r % Hs), n = (int)(r / Hs);
-        float v[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = 0.f;
-        const int ty = 2 * (Y - 2), tx = 2 * (X - 2);
-        if (ty >= 0 && ty < g.T && tx >= 0 && tx < g.T) {
-            const int tr = n / g.nW, tc = n - tr * g.nW;
-            const uint8_t *p = g.src + (size_t)(tr * g.S + ty) * g.pitch + (size_t)(tc * g.S + tx) * CH;
-#pragma unroll
-            for (int py = 0; py < 2; ++py)
-#pragma unroll
-                for (int px = 0; px < 2; ++px)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const uint32_t b = __ldg(p + (size_t)py * g.pitch + px * CH + (CH == 3 ? c : 0));
-                        v[(py * 2 + px) * 3 + c] = s_lut[CH == 3 ? c : 0][b];
-                    }
+    const int hq = g.S / 2;            // quads per block side
+    const int upr = hq * 4;            // 16-byte vectors per quad row of a block
+    const int part = threadIdx.x & 3;
+
+    // thread-constant byte sources inside the quad's two 2*CH-byte rows, and the table row per byte
+    size_t offA, offB;
+    uint32_t sel;
+    if (CH == 3) {   // record bytes 4*part .. 4*part+3 of [row0: 6 bytes][row1: 6 bytes]
+        offA = part == 0 ? 0 : (part == 1 ? 4 : g.pitch + 2);
+        offB = part == 0 ? 2 : (part == 1 ? g.pitch : g.pitch + 4);
+        sel = 0x3210u;
+    } else {         // gray replicated over c: channel k of the record is quad pixel k / 3
+        offA = part == 2 ? g.pitch : 0;
+        offB = g.pitch;
+        sel = part == 0 ? 0x1000u : (part == 1 ? 0x2211u : 0x1110u);
+    }
+    const float *lut0 = s_lut[(part * 4) % 3], *lut1 = s_lut[(part * 4 + 1) % 3], *lut2 = s_lut[(part * 4 + 2) % 3],
+                *lut3 = s_lut[(part * 4 + 3) % 3];
+    auto load16 = [](const uint8_t *p) -> uint32_t {
+        if (AL2) return (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(p));
+        return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8);
+    };
+
+    const int items = g.nbx * g.nby * hq;     // one quad row of one S-block
+    int first, last;
+    cta_item_range(items, first, last);
+    for (int item = first; item < last; ++item) {
+        const int blk = item / hq, qy = item - blk * hq;
+        const int bx = blk % g.nbx, by = blk / g.nbx;
+        const TileSpan ts = tile_span(g, by, bx);
+        const uint8_t *rowp = g.src + (size_t)(by * g.S + 2 * qy) * g.pitch + (size_t)bx * g.S * CH;
+        for (int f = threadIdx.x; f < upr; f += kThreads) {
+            const int qx = f >> 2;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (part != 3) {
+                const uint8_t *p = rowp + (size_t)qx * 2 * CH;
+                const uint32_t w = __byte_perm(load16(p + offA) | (load16(p + offB) << 16), 0u, sel);
+                v.x = lut0[w & 0xFF];
+                v.y = lut1[(w >> 8) & 0xFF];
+                v.z = lut2[(w >> 16) & 0xFF];
+                v.w = lut3[w >> 24];
+            }
+            for (int r = ts.r_lo; r <= ts.r_hi; ++r) {
+                const int Y = (by - r) * hq + qy + 2;
+                for (int c = ts.c_lo; c <= ts.c_hi; ++c) {
+                    const int X = (bx - c) * hq + qx + 2;
+                    st_stream_f4(dst + ((((size_t)(r * g.nW + c) * Hs + Y) * Hs + X) * 4 + part) * 4, v);
+                }
+            }
         }
-        float *o = dst + (size_t)i * 16;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) st_stream_f4(o + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+    }
+
+    // border records: rows 0, 1, Hs-1 whole; columns 0, 1, Hs-1 of the T/2 rows in between
+    const int nb = 6 * Hs - 9;
+    const long long total = (long long)g.nH * g.nW * nb * 4;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        const unsigned rec = (unsigned)(i >> 2);
+        const unsigned n = rec / (unsigned)nb;
+        int k = (int)(rec - n * (unsigned)nb), Y, X;
+        if (k < 2 * Hs) {
+            Y = k >= Hs;
+            X = k - Y * Hs;
+        } else if (k < 3 * Hs) {
+            Y = Hs - 1;
+            X = k - 2 * Hs;
+        } else {
+            k -= 3 * Hs;
+            Y = 2 + k / 3;
+            const int j = k - (Y - 2) * 3;
+            X = j < 2 ? j : Hs - 1;
+        }
+        st_stream_f4(dst + ((((size_t)n * Hs + Y) * Hs + X) * 4 + (i & 3)) * 4, zero);
     }
 }
 
@@ -675,21 +746,26 @@ extern "C" int pylc_mask_gather_encode_hist(const uint8_t *src, int H, int W, si
     cudaStream_t st = (cudaStream_t)stream;
     const bool al = aligned16(src, src_pitch);
     auto *pd = reinterpret_cast<long long *>(px_dist);
-#define LAUNCH(AL, WD, HS)                                                                                         \
-    gather_mask_kernel<AL, WD, HS><<<persistent_ctas(gather_mask_kernel<AL, WD, HS>, g.items), kThreads, 0, st>>>( \
+#define LAUNCH(AL, NG, HS)                                                                                         \
+    gather_mask_kernel<AL, NG, HS><<<persistent_ctas(gather_mask_kernel<AL, NG, HS>, g.items), kThreads, 0, st>>>( \
         g, ph, C, dst, pd)
-#define LAUNCH_CUR(AL, WD, HS)                                                                          \
-    gather_mask_cursor_kernel<AL, WD, HS>                                                              \
-        <<<persistent_ctas(gather_mask_cursor_kernel<AL, WD, HS>, g.items), kThreads, 0, st>>>(g, ph, C, dst, pd)
-    if (g.m <= 2) {
-        if (!px_dist) { if (al) LAUNCH_CUR(true, false, false); else LAUNCH_CUR(false, false, false); }
-        else if (C <= 12) { if (al) LAUNCH_CUR(true, false, true); else LAUNCH_CUR(false, false, true); }
-        else { if (al) LAUNCH_CUR(true, true, true); else LAUNCH_CUR(false, true, true); }
-    } else {
-        if (!px_dist) { if (al) LAUNCH(true, false, false); else LAUNCH(false, false, false); }
-        else if (C <= 12) { if (al) LAUNCH(true, false, true); else LAUNCH(false, false, true); }
-        else { if (al) LAUNCH(true, true, true); else LAUNCH(false, true, true); }
+#define LAUNCH_CUR(AL, NG, HS)                                                                          \
+    gather_mask_cursor_kernel<AL, NG, HS>                                                              \
+        <<<persistent_ctas(gather_mask_cursor_kernel<AL, NG, HS>, g.items), kThreads, 0, st>>>(g, ph, C, dst, pd)
+#define PICK(L, AL)                                                 \
+    switch (px_dist ? counter_groups(C) : -1) {                     \
+        case -1: L(AL, 5, false); break;                            \
+        case 5: L(AL, 5, true); break;                              \
+        case 6: L(AL, 6, true); break;                              \
+        case 7: L(AL, 7, true); break;                              \
+        default: L(AL, 0, true); break;                             \
     }
+    if (g.m <= 2) {
+        if (al) { PICK(LAUNCH_CUR, true) } else { PICK(LAUNCH_CUR, false) }
+    } else {
+        if (al) { PICK(LAUNCH, true) } else { PICK(LAUNCH, false) }
+    }
+#undef PICK
 #undef LAUNCH_CUR
 #undef LAUNCH
     return finish_launch();
@@ -715,9 +791,8 @@ extern "C" int pylc_tile_gather_norm_f32(const uint8_t *src, int H, int W, int c
     np.out_ch = out_ch;
     cudaStream_t st = (cudaStream_t)stream;
     const bool al = ((uintptr_t)src % 4 == 0) && (src_pitch % 4 == 0);   // 4-byte units on this path
-    const long long work = (long long)g.nbx * g.nby * g.S * (g.S / 4) / kThreads + 1;
 #define LAUNCH(CH, AL) \
-    gather_norm_kernel<CH, AL><<<persistent_ctas(gather_norm_kernel<CH, AL>, work), kThreads, 0, st>>>(g, np, dst)
+    gather_norm_kernel<CH, AL><<<persistent_ctas(gather_norm_kernel<CH, AL>, g.items), kThreads, 0, st>>>(g, np, dst)
     if (ch == 1) { if (al) LAUNCH(1, true); else LAUNCH(1, false); }
     else         { if (al) LAUNCH(3, true); else LAUNCH(3, false); }
 #undef LAUNCH
@@ -742,14 +817,15 @@ extern "C" int pylc_tile_gather_norm_s2d_f32(const uint8_t *src, int H, int W, i
     }
     np.post_div = post_div;
     np.out_ch = 16;
-    const long long Hs = T / 2 + 3, total = (long long)g.nH * g.nW * Hs * Hs;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long want = (total + kThreads - 1) / kThreads;
-    if (want > (long long)sms * 8) want = (long long)sms * 8;
+    if ((long long)g.nH * g.nW * (6 * (T / 2 + 3) - 9) > 0x3FFFFFFFll) return PYLC_ERR_GEOMETRY;
+    const long long items = (long long)g.nbx * g.nby * (S / 2);
+    if (items > 0x7FFFFFFF) return PYLC_ERR_GEOMETRY;
     cudaStream_t st = (cudaStream_t)stream;
-    if (ch == 1) gather_norm_s2d_kernel<1><<<(unsigned)want, kThreads, 0, st>>>(g, np, dst);
-    else gather_norm_s2d_kernel<3><<<(unsigned)want, kThreads, 0, st>>>(g, np, dst);
+    const bool al2 = ((uintptr_t)src % 2 == 0) && (src_pitch % 2 == 0);
+#define LAUNCH(CH, AL) \
+    gather_norm_s2d_kernel<CH, AL><<<persistent_ctas(gather_norm_s2d_kernel<CH, AL>, items), kThreads, 0, st>>>(g, np, dst)
+    if (ch == 1) { if (al2) LAUNCH(1, true); else LAUNCH(1, false); }
+    else         { if (al2) LAUNCH(3, true); else LAUNCH(3, false); }
+#undef LAUNCH
     return finish_launch();
 }

@@ -1,0 +1,257 @@
+"""Parity at BASELINE.json's FULL sizes (6000x4000 photos, 273 logit tiles, B = 64 loss batches), where the
+CPU oracle would take minutes: the CUDA path is checked through size-independent properties of the
+domain -- every tile equals its source window, histograms are checksums of the encoded tiles, a
+confusion matrix's marginals are the two label histograms -- and, for the floating-point kernels,
+against a plain PyTorch fp32 statement of the same formulas evaluated on the device.  The oracle
+still checks a sample of tiles / rows of each result.  Tolerances as in test_gpu_kernels.py."""
+import numpy as np
+import pytest
+import torch
+
+import pylc_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+STITCH_RTOL = 1e-5     # north_star: stitched probabilities within 1e-5 relative (fp32)
+LOSS_RTOL = 1e-4       # north_star: loss values within 1e-4 relative
+# Labels must agree wherever the fp32 reference's top-1 beats top-2 by more than this.  The small-size
+# tests use 1e-6; over 20 Mpx two fp32 softmax implementations differ by up to ~1e-6 on edge-block
+# probabilities close to 1, so the full-size bar is a few ulp wider.
+ARGMAX_MARGIN = 4e-6
+
+W_FULL, H_FULL = 6000, 4000          # BASELINE configs[4]
+W_FIT, H_FIT = 5632, 3584            # its adjust_to_tile geometry: 13 x 21 tiles at stride 256
+T = 512
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from pylc_b200 import ops as _ops
+    _ops._lib.load()
+    return _ops
+
+
+def windows(src_hw, S):
+    """[nH*nW, T, T(, ch)] view-copy of every T x T window at stride S (torch.unfold == the reference's
+    Extractor.__split, utils/extract.py:302-308)."""
+    u = src_hw.unfold(0, T, S).unfold(1, T, S)       # [nH, nW, (ch,) T, T]
+    return u.reshape((-1,) + tuple(u.shape[2:]))
+
+
+def test_extract_6000x4000_windows_histograms_moments(ops, palettes):
+    pal = palettes["a"]
+    C = len(pal)
+    img = orc.synth_image(11, W_FULL, H_FULL, 1)
+    mask = orc.synth_mask(11, W_FULL, H_FULL, pal)
+    d_img, ip = ops.upload_image(img)
+    d_mask, mp = ops.upload_image(mask)
+    tiles, stat = ops.tile_gather_u8(d_img, H_FULL, W_FULL, 1, ip, T, T, stats=True)
+    m_tiles, px_dist = ops.mask_gather_encode_hist(d_mask, H_FULL, W_FULL, mp, T, T, pal)
+    assert tiles.shape[0] == 7 * 11 and m_tiles.shape[0] == 77
+
+    # every tile is its source window, bit for bit
+    src = d_img.view(H_FULL, ip)[:, :W_FULL]
+    assert torch.equal(tiles[:, 0], windows(src, T))
+    # the moments are the checksums of the tiles
+    x = tiles.to(torch.int64).view(77, -1)
+    assert torch.equal(stat[:, 0, 0], x.sum(1)) and torch.equal(stat[:, 0, 1], (x * x).sum(1))
+
+    # encoded tiles = windows of the separately encoded full mask (class_encode kernel, other code path) ...
+    enc, hist = ops.class_encode_hwc(d_mask, H_FULL, W_FULL, mp, pal, hist=True)
+    assert torch.equal(m_tiles, windows(enc[0], T))
+    # ... whose histogram is a checksum of checksums: per tile, per used area, and against bincount
+    assert torch.equal(px_dist.sum(1), torch.full((77,), T * T, dtype=torch.int64, device="cuda"))
+    bins = torch.stack([torch.bincount(m_tiles[k].view(-1).long(), minlength=C) for k in range(77)])
+    assert torch.equal(px_dist, bins)
+    assert torch.equal(hist, torch.bincount(enc.view(-1).long(), minlength=C))
+    assert int(hist.sum()) == W_FULL * H_FULL
+    # the oracle on a sample of tiles (first, an interior one, last)
+    ref = orc.class_encode(orc.split_tiles(mask, T, T)[[0, 38, 76]], pal)
+    assert np.array_equal(m_tiles[[0, 38, 76]].cpu().numpy(), ref)
+    assert np.array_equal(px_dist[[0, 38, 76]].cpu().numpy(), orc.tile_histograms(ref, C))
+
+
+def test_test_tiling_5632x3584_gathers(ops):
+    """273 overlapping tiles (stride 256): u8 gather, normalising f32 gather and the stem's
+    space-to-depth gather all describe the same windows."""
+    S = 256
+    img = orc.synth_image(12, W_FIT, H_FIT, 3)
+    d_img, ip = ops.upload_image(img)
+    tiles = ops.tile_gather_u8(d_img, H_FIT, W_FIT, 3, ip, T, S)
+    assert tiles.shape[0] == 13 * 21
+    src = d_img.view(H_FIT, ip)[:, :W_FIT * 3].view(H_FIT, W_FIT, 3)
+    assert torch.equal(tiles, windows(src, S))            # unfold puts the channel axis first: [n, 3, T, T]
+
+    mean, std = [0.41, 0.45, 0.39], [0.21, 0.19, 0.23]
+    norm = ops.tile_gather_norm_f32(d_img, H_FIT, W_FIT, 3, ip, T, S, mean, std)
+    # ((x - mean) / std) / 255 evaluated by torch on the CPU for the 256 byte values (models/model.py:435)
+    lut = torch.stack([((torch.arange(256, dtype=torch.float32) - m) / s) / 255 for m, s in zip(mean, std)]).cuda()
+    for k in (0, 100, 272):
+        want = torch.stack([lut[c][tiles[k, c].long()] for c in range(3)])
+        assert torch.equal(norm[k], want)
+    # all tiles: a float checksum that is exact because both sides add the same f32 values in f64
+    idx = tiles.long()
+    want_sum = sum(lut[c].double()[idx[:, c]].sum() for c in range(3))
+    assert float(norm.double().sum()) == pytest.approx(float(want_sum), rel=1e-12)
+
+    s2d = ops.tile_gather_norm_s2d(d_img, H_FIT, W_FIT, 3, ip, T, S, mean, std)     # logical [n, 16, 259, 259]
+    Hs = T // 2 + 3
+    assert tuple(s2d.shape) == (273, 16, Hs, Hs)
+    inner = s2d[:, :12, 2:Hs - 1, 2:Hs - 1]                                         # [n, (py,px,c), 256, 256]
+    want = norm.view(273, 3, 256, 2, 256, 2).permute(0, 3, 5, 1, 2, 4).reshape(273, 12, 256, 256)
+    assert torch.equal(inner, want)
+    assert float(s2d[:, 12:].abs().sum()) == 0.0
+    border = s2d.clone()
+    border[:, :, 2:Hs - 1, 2:Hs - 1] = 0
+    assert float(border.abs().sum()) == 0.0
+
+
+def torch_stitch(tiles, nr, nc, S):
+    """tools.reconstruct's closed form in plain PyTorch fp32 on the device."""
+    C = tiles.shape[1]
+    out = torch.empty((C, (nr + 1) * S, (nc + 1) * S), dtype=torch.float32, device=tiles.device)
+    sm = lambda v: torch.softmax(v, dim=0)
+
+    def hrow(i, ys, kx):
+        if kx == 0:
+            return tiles[i * nc][:, ys, :S]
+        if kx == nc:
+            return tiles[i * nc + nc - 1][:, ys, S:]
+        return (sm(tiles[i * nc + kx - 1][:, ys, S:]) + sm(tiles[i * nc + kx][:, ys, :S])) / 2
+
+    top, bot = slice(0, S), slice(S, 2 * S)
+    for ky in range(nr + 1):
+        for kx in range(nc + 1):
+            if ky == 0:
+                m = hrow(0, top, kx)
+            elif ky == nr:
+                m = hrow(nr - 1, bot, kx)
+            else:
+                m = (sm(hrow(ky - 1, bot, kx)) + sm(hrow(ky, top, kx))) / 2
+            out[:, ky * S:(ky + 1) * S, kx * S:(kx + 1) * S] = m
+    return out
+
+
+def test_stitch_273_tiles_vs_torch_closed_form(ops, palettes):
+    nr, nc, S, C = 13, 21, 256, 9
+    g = torch.Generator(device="cuda").manual_seed(273)
+    logits = torch.randn((nr * nc, C, T, T), generator=g, device="cuda") * 3          # 2.58 GB, independent tiles
+    labels, rgb, stitched = ops.stitch_argmax_colour(logits, nr, nc, T, S, lut_rgb=palettes["a"], want_rgb=True,
+                                                     want_stitched=True)
+    assert tuple(labels.shape) == (H_FIT, W_FIT)
+    ref = torch_stitch(logits, nr, nc, S)
+    err = (stitched - ref).abs() - STITCH_RTOL * ref.abs()
+    assert float(err.max()) <= 1e-7
+    top2 = ref.topk(2, dim=0).values
+    decided = (top2[0] - top2[1]) > ARGMAX_MARGIN
+    assert torch.equal(labels[decided], ref.argmax(0).to(torch.uint8)[decided])
+    assert float(decided.float().mean()) > 0.999
+    # colourise is a table look-up of the labels
+    lut = torch.tensor(palettes["a"], dtype=torch.uint8, device="cuda")
+    assert torch.equal(rgb, lut[labels.long()])
+    # a band of the result against the oracle's stitch of the same tiles: the first two tile rows give
+    # output rows [0, 512) exactly as in the full image (rows [256, 512) only involve tile rows 0 and 1)
+    sub = logits[:2 * nc].cpu().numpy()
+    ref_band = orc.stitch_map(sub, 2, nc, T, S)[:, :2 * S]
+    got_band = stitched[:, :2 * S].cpu().numpy()
+    assert np.allclose(got_band, ref_band, rtol=STITCH_RTOL, atol=1e-7)
+
+
+def test_stitch_consistent_tiles_reproduce_the_field(ops):
+    """Tiles cut from ONE logit field agree wherever they overlap, so averaging softmaxes changes
+    nothing and every stage is monotone: the stitched labels are the field's argmax."""
+    nr, nc, S, C = 13, 21, 256, 9
+    g = torch.Generator(device="cuda").manual_seed(7)
+    field = torch.randn((C, H_FIT, W_FIT), generator=g, device="cuda") * 3
+    tiles = field.unfold(1, T, S).unfold(2, T, S).permute(1, 2, 0, 3, 4).reshape(nr * nc, C, T, T).contiguous()
+    labels, _, _ = ops.stitch_argmax_colour(tiles, nr, nc, T, S)
+    top2 = field.topk(2, dim=0).values
+    decided = (top2[0] - top2[1]) > 1e-3
+    assert torch.equal(labels[decided], field.argmax(0).to(torch.uint8)[decided])
+    assert float(decided.float().mean()) > 0.99
+
+
+def test_confusion_6000x4000_marginals_and_counts(ops, palettes):
+    pal = palettes["a"]
+    C = len(pal)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    labels = torch.randint(0, C, (H_FIT, W_FIT), generator=g, device="cuda", dtype=torch.uint8)
+    mask = orc.synth_mask(13, W_FULL, H_FULL, pal)
+    d_mask, mp = ops.upload_image(mask)
+    res = ops.resample_encode_confusion(labels, W_FULL, H_FULL, gt_rgb=d_mask, gt_pitch=mp, palette=pal, n_inject=C,
+                                        want_pred=True, want_gt=True)
+    conf, pred, gt = res["conf"], res["pred_full"], res["gt_full"]
+    # nearest-neighbour resample = OpenCV's index maps applied to the label map (utils/tools.py:316-317)
+    x_ofs, y_ofs = ops.device_index_maps(W_FIT, H_FIT, W_FULL, H_FULL, labels.device)
+    assert torch.equal(pred, labels[y_ofs.long()][:, x_ofs.long()])
+    # ground truth = the separately encoded mask
+    enc = ops.class_encode_hwc(d_mask, H_FULL, W_FULL, mp, pal)[0]
+    assert torch.equal(gt, enc)
+    # counts: bincount of the pair codes after the coverage injection (utils/evaluate.py:172-174)
+    yt, yp = gt.view(-1).long().clone(), pred.view(-1).long().clone()
+    yt[:C] = torch.arange(C, device="cuda")
+    yp[:C] = torch.arange(C, device="cuda")
+    want = torch.bincount(yt * C + yp, minlength=C * C).view(C, C)
+    assert torch.equal(conf, want)
+    assert int(conf.sum()) == W_FULL * H_FULL
+    assert torch.equal(conf.sum(1), torch.bincount(yt, minlength=C))      # row sums: ground-truth histogram
+    assert torch.equal(conf.sum(0), torch.bincount(yp, minlength=C))      # column sums: prediction histogram
+    # a label map against itself is diagonal (idempotence of the evaluation)
+    rgb = ops.colourise_u8(pred, pal)
+    self_res = ops.resample_encode_confusion(pred, W_FULL, H_FULL, gt_rgb=rgb.view(H_FULL, -1), gt_pitch=W_FULL * 3,
+                                             palette=pal, n_inject=0)
+    off = self_res["conf"] - torch.diag(torch.diag(self_res["conf"]))
+    assert int(off.abs().sum()) == 0 and int(self_res["conf"].sum()) == W_FULL * H_FULL
+    # the oracle on the first 64 rows
+    rows = 64
+    yt_o, yp_o = orc.inject_coverage(orc.class_encode_hwc(mask[:rows], pal), pred[:rows].cpu().numpy(), C)
+    part = ops.confusion_u8(gt[:rows].contiguous(), pred[:rows].contiguous(), C, n_inject=C)
+    assert np.array_equal(part.cpu().numpy(), orc.confusion_counts(yt_o, yp_o, C))
+
+
+def torch_multiloss(z, t, w, C, ce=0.5, dice=0.5, focal=0.5, smooth=1.0, gamma=2.0, alpha=0.25):
+    """models/modules/loss.py:66-69,137-146,174-189 in plain PyTorch fp32 (autograd for the gradient)."""
+    logp = torch.log_softmax(z, dim=1)
+    p = logp.exp()
+    l_ce = torch.nn.functional.nll_loss(logp, t, weight=w)
+    pt = p.gather(1, t.unsqueeze(1)).squeeze(1)
+    # the class sums run over 16.7 M pixels: accumulate them in f64 (fp32 atomics in index_add_ drift by
+    # ~1e-4 at this size); the reference's own reduction, torch.sum, is a tree and does not
+    inter = torch.zeros(C, dtype=torch.float64, device=z.device).index_add_(0, t.view(-1), pt.view(-1).double())
+    card = p.double().sum((0, 2, 3)) + torch.bincount(t.view(-1), minlength=C).double()
+    l_dice = (1 - (2 * inter + smooth) / (card + smooth)).mean().float()
+    q = pt + 1e-8
+    l_focal = (-alpha * (1 - q) ** gamma * q.log()).mean()
+    return ce * l_ce + dice * l_dice + focal * l_focal, l_ce, l_dice, l_focal
+
+
+@pytest.mark.parametrize("C,weighted", [(9, True), (11, False)])
+def test_multiloss_batch64_vs_torch(ops, C, weighted):
+    """BASELINE configs[2]: 64 tiles of 512 x 512 per GPU."""
+    B = 64
+    g = torch.Generator(device="cuda").manual_seed(C)
+    z = torch.randn((B, C, T, T), generator=g, device="cuda") * 3
+    t = torch.randint(0, C, (B, T, T), generator=g, device="cuda")
+    w = (torch.rand(C, generator=g, device="cuda") * 0.9 + 0.1) if weighted else None
+    cfg = ops.loss_cfg()
+    out4, grad, part = ops.multiloss_fwd_bwd(z, t, cfg, class_w=w)
+    # the two-pass (data-parallel) form gives the same numbers
+    part2 = ops.multiloss_reduce(z, t, cfg, class_w=w)
+    vals2 = ops.multiloss_finalize(part2, C, t.numel(), cfg)
+    assert torch.allclose(part, part2, rtol=1e-6, atol=0)   # threads pre-add ~300 pixels in f32, in launch-specific groups
+    assert torch.allclose(out4, vals2, rtol=1e-6)
+
+    zr = z.clone().requires_grad_(True)
+    ref = torch_multiloss(zr, t, w, C)
+    ref[0].backward()
+    want = torch.stack([r.detach() for r in ref])
+    assert torch.allclose(out4, want, rtol=LOSS_RTOL, atol=0)
+    gmax = float(zr.grad.abs().max())                   # ~1e-7: the mean over 16.7 Mpx is inside the gradient
+    err = (grad - zr.grad).abs() - 1e-3 * zr.grad.abs()
+    assert float(err.max()) <= 1e-4 * gmax
+    # softmax is shift-invariant, so each pixel's gradient sums to zero over the classes
+    assert float(grad.sum(1).abs().max()) < 1e-5 * gmax
+    # partials are additive over shards: two half batches, accumulated, equal the whole
+    acc = ops.multiloss_reduce(z[:32], t[:32], cfg, class_w=w)
+    acc = ops.multiloss_reduce(z[32:], t[32:], cfg, class_w=w, partials=acc)
+    assert torch.allclose(acc, part2, rtol=1e-6, atol=0)

@@ -137,6 +137,15 @@ def main():
                      [lambda d=d, q=q, o=o: ops.mask_gather_encode_hist(d, H, W, q, T, 512, pal, out=o) for d, q, o in sets],
                      "3 B in + 1 B out per tile px")
         del sets
+    enc_out = torch.empty((1, H, W), dtype=torch.uint8, device="cuda")
+    palc0, _ = ops._lib.palette_array(pal)
+    enc_hist = torch.zeros((C,), dtype=torch.int64, device="cuda")
+
+    def encode_full():
+        ops._lib.check(ops._lib.load().pylc_class_encode(ops._p(d_mask), 1, H, W, mp, 0, palc0, C, ops._p(enc_out),
+                                                         ops._p(enc_hist), ops._stream()), "pylc_class_encode")
+    report("class_encode + hist 6000x4000 interleaved C9", H * W * 4, encode_full, "3 B in + 1 B out per px")
+    del enc_out
     Wf, Hf = 5632, 3584
     img1 = orc.synth_image(0, Wf, Hf, 1)
     d_img1, ip1 = ops.upload_image(img1)
