@@ -227,31 +227,13 @@ __global__ void __launch_bounds__(kThreads, 2) stitch_kernel(StitchArgs a, const
     int bid = blockIdx.x;
     const int slab = bid % a.slabs;
     bid /= a.slabs;
-    int kx, ky;
-    if (!a.overlap) {
-        kx = bid % a.nbx;
-        ky = bid / a.nbx;
-    } else {
-        // Heaviest blocks first: interior blocks read four tile quadrants per pixel, edge blocks two,
-        // corners one.  The hardware hands CTAs out in blockIdx order, so the last, partially filled
-        // wave is made of the cheap CTAs.
-        const int ix = a.nbx - 2, iy = a.nby - 2;      // interior extent (>= 0)
-        const int n_int = ix * iy, n_eh = 2 * ix, n_ev = 2 * iy;
-        if (bid < n_int) {
-            ky = 1 + bid / ix;
-            kx = 1 + bid % ix;
-        } else if ((bid -= n_int) < n_eh) {            // top / bottom edge rows
-            ky = bid < ix ? 0 : a.nby - 1;
-            kx = 1 + bid % ix;
-        } else if ((bid -= n_eh) < n_ev) {             // left / right edge columns
-            kx = bid < iy ? 0 : a.nbx - 1;
-            ky = 1 + bid % iy;
-        } else {                                       // corners
-            bid -= n_ev;
-            ky = (bid >> 1) ? a.nby - 1 : 0;
-            kx = (bid & 1) ? a.nbx - 1 : 0;
-        }
-    }
+    // Blocks are walked from the LAST tile row to the first.  In the tiled pipeline the logits were
+    // written tile by tile just before this launch and are several times the L2: what is still cached
+    // are the most recently written tiles, so reading those first turns the tail of the producer's
+    // stores into L2 hits instead of evicting them unread.  (Ordering the blocks by weight -- interior
+    // blocks read four quadrants per pixel, corners one -- was measured and makes no difference.)
+    bid = a.nbx * a.nby - 1 - bid;
+    const int kx = bid % a.nbx, ky = bid / a.nbx;
     const bool two_h = a.overlap && kx > 0 && kx < a.nc;
     const bool two_v = a.overlap && ky > 0 && ky < a.nr;
     if (two_h) {

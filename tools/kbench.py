@@ -244,6 +244,14 @@ def main():
                                                                          conf=conf, maps=maps) for d, q, l in sets],
                      "3 B GT + 1 B label per full-res px")
         del sets
+    # the bench.py geometry: a 2560x1536 label map against a 3000x2000 ground truth
+    Wb, Hb, wb, hb = 3000, 2000, 2560, 1536
+    dmb, dpb = ops.upload_image(orc.synth_mask(30, Wb, Hb, pal, skew=True))
+    lab_b = torch.from_numpy(orc.synth_labels(31, wb, hb, C, skew=True, block=37)).cuda()
+    maps_b = (torch.from_numpy(ops.nn_index_map(wb, Wb)).cuda(), torch.from_numpy(ops.nn_index_map(hb, Hb)).cuda())
+    report("resample_encode_confusion 3000x2000 C9 (bench.py image)", Hb * Wb * 4,
+           lambda: ops.resample_encode_confusion(lab_b, Wb, Hb, gt_rgb=dmb, gt_pitch=dpb, palette=pal, n_inject=C,
+                                                 conf=conf, maps=maps_b), "3 B GT + 1 B label per full-res px")
     pred_full = torch.empty((H, W), dtype=torch.uint8, device="cuda")
     gt_full = torch.empty((H, W), dtype=torch.uint8, device="cuda")
 
