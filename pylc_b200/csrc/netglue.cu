@@ -22,6 +22,7 @@ __device__ __forceinline__ float4 max4(const float4 &a, const float4 &b) {
 // decoder: bilinear up-sample of the ASPP output to the low-level feature size + channel concat
 //   x [B, h, w, Cx] NHWC, low [B, H, W, Cl] NHWC  ->  out [B, H, W, Cx + Cl] NHWC   (decoder.py:46-48)
 // ------------------------------------------------------------------------------------------------
+// General form (any geometry; the pipeline's shapes take the staged kernel below).
 // A warp takes 16-pixel segments of output rows (persistent grid, segments dealt round-robin so the
 // load balances to a fraction of a segment).  Per segment it first issues all loads of the low-level
 // channels it has to copy (independent, so they overlap), then walks X left to right: a lane owns VPL
@@ -106,6 +107,65 @@ __global__ void __launch_bounds__(kThreads) upsample_concat_kernel(const float *
     }
 }
 
+// Staged form: one CTA per output row.  Every pixel of an output row interpolates between the same two
+// source rows, so the CTA blends those two rows ONCE into shared memory (w x Cx floats: 32 KB for the
+// decoder's 32 x 256) and an output pixel is one horizontal blend of two shared-memory columns: 2 LDS.128
+// + 8 FP instructions + 1 STG.128 per float4, against ~30 in the warp-per-segment kernel above, which is
+// issue-bound at 64 % of the roofline with 118 registers.  Many small CTAs (six resident per SM), lanes
+// walk the channel groups of a pixel, so loads, shared-memory accesses and stores are all contiguous.
+// (Rows are blended before columns: results differ from h0*(w0*a + w1*b) + h1*(...) by an ulp or two.)
+__global__ void __launch_bounds__(kThreads) upsample_concat_staged_kernel(const float *__restrict__ x, const float *__restrict__ low,
+                                                                         float *__restrict__ out, int B, int h, int w, int Cx, int H,
+                                                                         int W, int Cl) {
+    extern __shared__ __align__(16) float4 s_v[];            // [w][Cx/4] row-blended source, then x1[W], wl1[W]
+    const int cq = Cx / 4, lq = Cl / 4, Co4 = (Cx + Cl) / 4;
+    int *s_x1 = reinterpret_cast<int *>(s_v + (size_t)w * cq);
+    float *s_w1 = reinterpret_cast<float *>(s_x1 + W);
+    const int b = blockIdx.x / H, Y = blockIdx.x - b * H;
+    const float rh = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rw = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    const float h1r = rh * Y;
+    const int y1 = (int)h1r, y1p = y1 < h - 1 ? 1 : 0;
+    const float hl1 = h1r - y1, hl0 = 1.f - hl1;
+    const float4 *r0 = reinterpret_cast<const float4 *>(x + ((size_t)b * h + y1) * w * Cx);
+    const float4 *r1 = r0 + (size_t)y1p * w * cq;
+    for (int i = threadIdx.x; i < w * cq; i += kThreads) s_v[i] = lerp4(hl0, __ldg(r0 + i), hl1, __ldg(r1 + i));
+    for (int X = threadIdx.x; X < W; X += kThreads) {
+        const float w1r = rw * X;
+        const int x1 = (int)w1r;
+        s_x1[X] = x1 * cq + ((x1 < w - 1 ? cq : 0) << 16);   // left column offset | right-column step << 16 (w * cq < 65536)
+        s_w1[X] = w1r - x1;
+    }
+    __syncthreads();
+
+    float4 *orow = reinterpret_cast<float4 *>(out) + ((size_t)b * H + Y) * W * Co4;
+    {   // up-sampled channels: thread walks (X, g) with constant steps, no divisions in the loop
+        int X = threadIdx.x / cq, g = threadIdx.x - X * cq;
+        const int dX = kThreads / cq, dg = kThreads - dX * cq;
+        for (; X < W; X += dX, g += dg) {
+            if (g >= cq) {
+                g -= cq;
+                if (++X >= W) break;
+            }
+            const int pk = s_x1[X];
+            const float wl1 = s_w1[X], wl0 = 1.f - wl1;
+            const float4 *c0 = s_v + (pk & 0xFFFF) + g;
+            st_stream_f4(reinterpret_cast<float *>(orow + (size_t)X * Co4 + g), lerp4(wl0, c0[0], wl1, c0[pk >> 16]));
+        }
+    }
+    if (lq > 0) {   // low-level channels: a contiguous row of W * lq float4 copied behind each pixel's up-sampled channels
+        const float *lrow = low + ((size_t)b * H + Y) * W * Cl;
+        int X = threadIdx.x / lq, q = threadIdx.x - X * lq;
+        const int dX = kThreads / lq, dq = kThreads - dX * lq;
+        for (int idx = threadIdx.x; idx < W * lq; idx += kThreads, X += dX, q += dq) {
+            if (q >= lq) {
+                q -= lq;
+                ++X;
+            }
+            st_stream_f4(reinterpret_cast<float *>(orow + (size_t)X * Co4 + cq + q), ld_stream_f4(lrow + (size_t)idx * 4));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // stem: max_pool2d(kernel 3, stride 2, padding 1) on NHWC                      (backbone/resnet.py)
 //   in [B, H, W, C] -> out [B, Ho, Wo, C],  Ho = (H + 2 - 3)/2 + 1
@@ -150,6 +210,7 @@ __global__ void __launch_bounds__(kThreads) maxpool3x3s2_kernel(const float *__r
 // head: final bilinear up-sample of the decoder output to tile size, NHWC in -> NCHW logits out
 //   in [B, h, w, C] NHWC  ->  out [B, C, H, W] planar (what the stitch kernel reads)   (deeplab.py:38)
 // ------------------------------------------------------------------------------------------------
+// General form (any geometry; up-sampling shapes take the staged kernel below).
 // One thread = 4 consecutive output pixels of one row, all classes: one 16-byte store per class plane
 // (a warp writes 512 contiguous bytes per plane).  The <= 26 MB input stays in L1/L2.
 __global__ void __launch_bounds__(kThreads) upsample_to_nchw_kernel(const float *__restrict__ in, float *__restrict__ out, int B, int h,
@@ -207,6 +268,98 @@ __global__ void __launch_bounds__(kThreads) upsample_to_nchw_kernel(const float 
     }
 }
 
+// Staged form (the pipeline's case: x4 up-sampling of [128,128,C] decoder outputs).  The kernel above
+// reads its taps with scalar loads whose lanes are C floats apart: 54 load instructions per thread, each
+// touching nine 128-byte lines, which makes it L1-tag bound at 69 % of the write roofline.  Here a CTA
+// owns kUpRows consecutive output rows of one image: the two or three source rows they interpolate are
+// one contiguous run of the NHWC input, copied to shared memory with coalesced 16-byte cp.async, and the
+// taps come from there (lane stride C words: conflict-free for odd C).  Same arithmetic, same order.
+constexpr int kUpRows = 4;
+constexpr int kUpStageBytes = 40 * 1024;
+
+__global__ void __launch_bounds__(kThreads, 4) upsample_to_nchw_staged_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                                          int B, int h, int w, int C, int H, int W, int cap_f) {
+    extern __shared__ __align__(16) float s_src[];
+    const int groups = (H + kUpRows - 1) / kUpRows;
+    const int b = blockIdx.x / groups, Y0 = (blockIdx.x - b * groups) * kUpRows;
+    const int Y1 = min(H, Y0 + kUpRows);
+    const float rh = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rw = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    const int y_first = (int)(rh * Y0), y_last = min(h - 1, (int)(rh * (Y1 - 1)) + 1);
+    const int row_f = w * C;                                   // floats per source row
+    const int n_f = (y_last - y_first + 1) * row_f;
+    const float *src = in + ((size_t)b * h + y_first) * row_f;
+    if (n_f > cap_f) __trap();                                 // the host sizes the buffer with a row to spare; never taken
+    if ((((uintptr_t)src) & 15) == 0 && (n_f & 3) == 0) {
+        const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(s_src);
+        for (int i = threadIdx.x; i < n_f / 4; i += kThreads) cp_async16(s0 + 16u * i, src + 4 * i);
+        cp_async_commit();
+        cp_async_wait<0>();
+    } else {
+        for (int i = threadIdx.x; i < n_f; i += kThreads) s_src[i] = __ldg(src + i);
+    }
+    __syncthreads();
+
+    const int gpr = W / 4;
+    const bool few_cols = rw * 3.f < 1.f;
+    for (int u = threadIdx.x; u < (Y1 - Y0) * gpr; u += kThreads) {
+        const int row = u / gpr, gx = u - row * gpr;
+        const int Y = Y0 + row;
+        const float h1r = rh * Y;
+        const int y1 = (int)h1r, y1p = y1 < h - 1 ? 1 : 0;
+        const float hl1 = h1r - y1, hl0 = 1.f - hl1;
+        const float *r0 = s_src + (y1 - y_first) * row_f, *r1 = r0 + y1p * row_f;
+        int x1[4], xr[4];
+        float wl0[4], wl1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float w1r = rw * (gx * 4 + j);
+            x1[j] = (int)w1r;
+            xr[j] = min(x1[j] + 1, w - 1) * C;
+            wl1[j] = w1r - x1[j];
+            wl0[j] = 1.f - wl1[j];
+            x1[j] *= C;
+        }
+        float *o = out + (((size_t)b * C) * H + Y) * W + gx * 4;
+        if (few_cols) {
+            // The four pixels touch at most three source columns.  Each pixel's bilinear weights are spread
+            // over the three columns once per thread (zero where a column is not used), so a class costs six
+            // taps from shared memory and no per-class selects; the kernel is issue-bound, not store-bound.
+            // (The rows are blended before the columns: results differ from h0*(w0*a + w1*b) + h1*(...)
+            // by an ulp or two.)
+            const int xa = x1[0], xb = min(xa + C, (w - 1) * C), xc = min(xa + 2 * C, (w - 1) * C);
+            float cw[4][3];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool first = x1[j] == xa;
+                const float l = wl0[j], r = wl1[j];
+                const bool right_same = xr[j] == x1[j];     // clamped at the last column: both taps coincide
+                float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+                if (first) { c0 = l; if (right_same) c0 += r; else c1 = r; }
+                else { c1 = l; if (right_same) c1 += r; else c2 = r; }
+                cw[j][0] = c0; cw[j][1] = c1; cw[j][2] = c2;
+            }
+            for (int c = 0; c < C; ++c) {
+                // vertical blend of the three columns, then each pixel's horizontal blend: 6 + 12 FP ops per class
+                const float v0 = fmaf(hl0, r0[xa + c], hl1 * r1[xa + c]);
+                const float v1 = fmaf(hl0, r0[xb + c], hl1 * r1[xb + c]);
+                const float v2 = fmaf(hl0, r0[xc + c], hl1 * r1[xc + c]);
+                float res[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) res[j] = fmaf(cw[j][0], v0, fmaf(cw[j][1], v1, cw[j][2] * v2));
+                st_stream_f4(o + (size_t)c * H * W, make_float4(res[0], res[1], res[2], res[3]));
+            }
+        } else {
+            for (int c = 0; c < C; ++c) {
+                float res[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    res[j] = hl0 * (wl0[j] * r0[x1[j] + c] + wl1[j] * r0[xr[j] + c]) + hl1 * (wl0[j] * r1[x1[j] + c] + wl1[j] * r1[xr[j] + c]);
+                st_stream_f4(o + (size_t)c * H * W, make_float4(res[0], res[1], res[2], res[3]));
+            }
+        }
+    }
+}
+
 static unsigned glue_grid(long long threads_wanted, int per_sm) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -226,9 +379,15 @@ extern "C" int pylc_upsample_concat_nhwc_f32(const float *x, int B, int h, int w
     if (!x || !low || !out || B < 1 || h < 1 || w < 1 || H < 1 || W < 1) return PYLC_ERR_ARG;
     if (Cx < 4 || Cx % 4 || Cl < 0 || Cl % 4 || Cx > 512 || Cl * kUpSeg > kUpLowMax * 128) return PYLC_ERR_GEOMETRY;
     if (((uintptr_t)x | (uintptr_t)low | (uintptr_t)out) % 16) return PYLC_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    // staged form when one blended source row fits the default shared-memory window
+    const size_t smem = (size_t)w * Cx * 4 + (size_t)W * 8;
+    if (smem <= 48 * 1024 && (long long)w * (Cx / 4) < 65536 && (long long)B * H < 0x7FFFFFFF) {
+        upsample_concat_staged_kernel<<<(unsigned)(B * H), kThreads, smem, st>>>(x, low, out, B, h, w, Cx, H, W, Cl);
+        return finish_launch();
+    }
     const long long items = (long long)B * H * ((W + kUpSeg - 1) / kUpSeg);
     const unsigned grid = glue_grid(items * 32, 3);            // persistent: 3 CTAs of 8 warps per SM
-    cudaStream_t st = (cudaStream_t)stream;
     if (Cx <= 128) upsample_concat_kernel<1><<<grid, kThreads, 0, st>>>(x, low, out, B, h, w, Cx, H, W, Cl);
     else if (Cx <= 256) upsample_concat_kernel<2><<<grid, kThreads, 0, st>>>(x, low, out, B, h, w, Cx, H, W, Cl);
     else upsample_concat_kernel<4><<<grid, kThreads, 0, st>>>(x, low, out, B, h, w, Cx, H, W, Cl);
@@ -253,6 +412,16 @@ extern "C" int pylc_upsample_nhwc_to_nchw_f32(const float *in, int B, int h, int
     if ((uintptr_t)out % 16) return PYLC_ERR_ALIGN;
     const long long total = (long long)B * H * (W / 4);
     cudaStream_t st = (cudaStream_t)stream;
+    // staged form when the source rows of kUpRows output rows fit the staging buffer (any up-sampling)
+    const double rh = H > 1 ? (double)(h - 1) / (H - 1) : 0.0;
+    long long stage_rows = (long long)(rh * (kUpRows - 1)) + 4;   // floor bound + one row for float rounding
+    if (stage_rows > h) stage_rows = h;
+    const long long groups = (long long)B * ((H + kUpRows - 1) / kUpRows);
+    if (stage_rows * w * C * 4 <= kUpStageBytes && groups < 0x7FFFFFFF) {
+        const size_t smem = (size_t)stage_rows * w * C * 4;
+        upsample_to_nchw_staged_kernel<<<(unsigned)groups, kThreads, smem, st>>>(in, out, B, h, w, C, H, W, (int)(smem / 4));
+        return finish_launch();
+    }
     upsample_to_nchw_kernel<<<glue_grid(total, 8), kThreads, 0, st>>>(in, out, B, h, w, C, H, W);
     return finish_launch();
 }
