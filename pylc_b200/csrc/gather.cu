@@ -649,6 +649,129 @@ __global__ void __launch_bounds__(kThreads) gather_norm_s2d_kernel(GatherGeom g,
     }
 }
 
+// Staged form for 16-byte aligned sources (the pipeline's case): one small CTA per kS2dRows quad rows
+// of an S-block.  The 2 * kS2dRows source rows of the strip go to shared memory with coalesced 16-byte
+// cp.async while the normalisation tables are built, so the per-record work below starts from shared
+// memory (no global-load latency inside a thread's chain, no 64-bit source addressing), and the
+// destination tile bases are computed once per CTA.  Same records, same stores as the kernel above.
+constexpr int kS2dRows = 8;
+
+template <int CH>
+__global__ void __launch_bounds__(kThreads) gather_norm_s2d_staged_kernel(GatherGeom g, NormParams np, float *__restrict__ dst, int gpb) {
+    __shared__ float s_lut[3][256];
+    extern __shared__ __align__(16) uint8_t s_src[];          // 2 * kS2dRows rows of S * CH bytes
+    const int Hs = g.T / 2 + 3;
+    const int hq = g.S / 2;            // quads per block side
+    const int upr = hq * 4;            // 16-byte vectors per quad row of a block
+    const int blk = blockIdx.x / gpb, qy0 = (blockIdx.x - blk * gpb) * kS2dRows;
+    const int nq = min(kS2dRows, hq - qy0);
+    const int bx = blk % g.nbx, by = blk / g.nbx;
+    const int row_bytes = g.S * CH, cpr = row_bytes / 16;
+    {
+        const uint8_t *src0 = g.src + (size_t)(by * g.S + 2 * qy0) * g.pitch + (size_t)bx * row_bytes;
+        const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(s_src);
+        int r = threadIdx.x / cpr, ck = threadIdx.x - r * cpr;
+        const int dr = kThreads / cpr, dck = kThreads - dr * cpr;
+        for (; r < 2 * nq; r += dr, ck += dck) {
+            if (ck >= cpr) {
+                ck -= cpr;
+                if (++r >= 2 * nq) break;
+            }
+            cp_async16(s0 + (uint32_t)(r * row_bytes + ck * 16), src0 + (size_t)r * g.pitch + ck * 16);
+        }
+        cp_async_commit();
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        s_lut[k][threadIdx.x] = __fdiv_rn(__fdiv_rn(__fsub_rn((float)threadIdx.x, np.mean[k]), np.std[k]), np.post_div);
+
+    // destination: record (Y, X) = (qy + 2, qx + 2) of every tile that contains the block
+    float4 *tb[4];
+    int nt = 0;
+    {
+        const TileSpan ts = tile_span(g, by, bx);
+        float4 *d4 = reinterpret_cast<float4 *>(dst);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tb[i] = d4;
+        for (int r = ts.r_lo; r <= ts.r_hi; ++r)
+            for (int c = ts.c_lo; c <= ts.c_hi; ++c) {
+                float4 *b = d4 + (((size_t)(r * g.nW + c) * Hs + (by - r) * hq + qy0 + 2) * Hs + (bx - c) * hq + 2) * 4;
+                if (nt == 0) tb[0] = b;
+                else if (nt == 1) tb[1] = b;
+                else if (nt == 2) tb[2] = b;
+                else if (nt == 3) tb[3] = b;
+                ++nt;
+            }
+    }
+    const int part = threadIdx.x & 3;
+    // thread-constant byte sources inside the quad's two 2*CH-byte rows (see the kernel above)
+    int offA, offB;
+    uint32_t sel;
+    if (CH == 3) {
+        offA = part == 0 ? 0 : (part == 1 ? 4 : row_bytes + 2);
+        offB = part == 0 ? 2 : (part == 1 ? row_bytes : row_bytes + 4);
+        sel = 0x3210u;
+    } else {
+        offA = part == 2 ? row_bytes : 0;
+        offB = row_bytes;
+        sel = part == 0 ? 0x1000u : (part == 1 ? 0x2211u : 0x1110u);
+    }
+    const float *lut0 = s_lut[(part * 4) % 3], *lut1 = s_lut[(part * 4 + 1) % 3], *lut2 = s_lut[(part * 4 + 2) % 3],
+                *lut3 = s_lut[(part * 4 + 3) % 3];
+    cp_async_wait<0>();
+    __syncthreads();
+
+    if (nt <= 4) {       // T/S <= 2; larger overlaps take the general kernel (the host checks)
+        int ql = threadIdx.x / upr, f = threadIdx.x - ql * upr;
+        const int dq = kThreads / upr, df = kThreads - dq * upr;       // df is a multiple of 4: `part` stays put
+        for (; ql < nq; ql += dq, f += df) {
+            if (f >= upr) {
+                f -= upr;
+                if (++ql >= nq) break;
+            }
+            const int qx = f >> 2;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (part != 3) {
+                const uint8_t *p = s_src + (2 * ql) * row_bytes + qx * 2 * CH;
+                const uint32_t a = *reinterpret_cast<const uint16_t *>(p + offA), b = *reinterpret_cast<const uint16_t *>(p + offB);
+                const uint32_t w = __byte_perm(a | (b << 16), 0u, sel);
+                v.x = lut0[w & 0xFF];
+                v.y = lut1[(w >> 8) & 0xFF];
+                v.z = lut2[(w >> 16) & 0xFF];
+                v.w = lut3[w >> 24];
+            }
+            const int off = (ql * Hs + qx) * 4 + part;
+            st_stream_f4(reinterpret_cast<float *>(tb[0] + off), v);
+            if (nt > 1) st_stream_f4(reinterpret_cast<float *>(tb[1] + off), v);
+            if (nt > 2) st_stream_f4(reinterpret_cast<float *>(tb[2] + off), v);
+            if (nt > 3) st_stream_f4(reinterpret_cast<float *>(tb[3] + off), v);
+        }
+    }
+
+    // border records: rows 0, 1, Hs-1 whole; columns 0, 1, Hs-1 of the T/2 rows in between
+    const int nb = 6 * Hs - 9;
+    const long long total = (long long)g.nH * g.nW * nb * 4;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        const unsigned rec = (unsigned)(i >> 2);
+        const unsigned n = rec / (unsigned)nb;
+        int k = (int)(rec - n * (unsigned)nb), Y, X;
+        if (k < 2 * Hs) {
+            Y = k >= Hs;
+            X = k - Y * Hs;
+        } else if (k < 3 * Hs) {
+            Y = Hs - 1;
+            X = k - 2 * Hs;
+        } else {
+            k -= 3 * Hs;
+            Y = 2 + k / 3;
+            const int j = k - (Y - 2) * 3;
+            X = j < 2 ? j : Hs - 1;
+        }
+        st_stream_f4(dst + ((((size_t)n * Hs + Y) * Hs + X) * 4 + (i & 3)) * 4, zero);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -821,6 +944,15 @@ extern "C" int pylc_tile_gather_norm_s2d_f32(const uint8_t *src, int H, int W, i
     const long long items = (long long)g.nbx * g.nby * (S / 2);
     if (items > 0x7FFFFFFF) return PYLC_ERR_GEOMETRY;
     cudaStream_t st = (cudaStream_t)stream;
+    // staged form: 16-byte aligned rows, T/S <= 2, and a strip of source rows that fits shared memory
+    const size_t strip = (size_t)2 * kS2dRows * S * ch;
+    const int gpb = (S / 2 + kS2dRows - 1) / kS2dRows;
+    if (aligned16(src, src_pitch) && g.m <= 2 && strip <= 40 * 1024 && (long long)g.nbx * g.nby * gpb < 0x7FFFFFFF) {
+        const unsigned grid = (unsigned)(g.nbx * g.nby * gpb);
+        if (ch == 1) gather_norm_s2d_staged_kernel<1><<<grid, kThreads, strip, st>>>(g, np, dst, gpb);
+        else gather_norm_s2d_staged_kernel<3><<<grid, kThreads, strip, st>>>(g, np, dst, gpb);
+        return finish_launch();
+    }
     const bool al2 = ((uintptr_t)src % 2 == 0) && (src_pitch % 2 == 0);
 #define LAUNCH(CH, AL) \
     gather_norm_s2d_kernel<CH, AL><<<persistent_ctas(gather_norm_s2d_kernel<CH, AL>, items), kThreads, 0, st>>>(g, np, dst)
