@@ -546,6 +546,94 @@ __global__ void __launch_bounds__(kThreads) gather_norm_kernel(GatherGeom g, Nor
     }
 }
 
+// Staged form for 16-byte aligned sources: one small CTA per kNormRows rows of an S-block.  The strip's
+// source rows reach shared memory through coalesced 16-byte cp.async while the tables are built; a
+// thread then takes four pixels (12 bytes at a 12-byte lane stride: conflict-free) from there, and the
+// destination tile bases are computed once per CTA -- the per-unit work is table look-ups and stores.
+constexpr int kNormRows = 16;
+
+template <int CH>
+__global__ void __launch_bounds__(kThreads) gather_norm_staged_kernel(GatherGeom g, NormParams np, float *__restrict__ dst, int gpb) {
+    __shared__ float s_lut[CH][256];
+    extern __shared__ __align__(16) uint8_t s_src[];          // kNormRows rows of S * CH bytes
+    const int blk = blockIdx.x / gpb, y0 = (blockIdx.x - blk * gpb) * kNormRows;
+    const int nrow = min(kNormRows, g.S - y0);
+    const int bx = blk % g.nbx, by = blk / g.nbx;
+    const int row_bytes = g.S * CH, cpr = row_bytes / 16;
+    {
+        const uint8_t *src0 = g.src + (size_t)(by * g.S + y0) * g.pitch + (size_t)bx * row_bytes;
+        const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(s_src);
+        int r = threadIdx.x / cpr, ck = threadIdx.x - r * cpr;
+        const int dr = kThreads / cpr, dck = kThreads - dr * cpr;
+        for (; r < nrow; r += dr, ck += dck) {
+            if (ck >= cpr) {
+                ck -= cpr;
+                if (++r >= nrow) break;
+            }
+            cp_async16(s0 + (uint32_t)(r * row_bytes + ck * 16), src0 + (size_t)r * g.pitch + ck * 16);
+        }
+        cp_async_commit();
+    }
+#pragma unroll
+    for (int k = 0; k < CH; ++k)
+        s_lut[k][threadIdx.x] = __fdiv_rn(__fdiv_rn(__fsub_rn((float)threadIdx.x, np.mean[k]), np.std[k]), np.post_div);
+
+    const size_t TT = (size_t)g.T * g.T;
+    float *tb[4];
+    int nt = 0;
+    {
+        const TileSpan ts = tile_span(g, by, bx);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tb[i] = dst;
+        for (int r = ts.r_lo; r <= ts.r_hi; ++r)
+            for (int c = ts.c_lo; c <= ts.c_hi; ++c) {
+                float *b = dst + ((size_t)(r * g.nW + c) * np.out_ch) * TT + (size_t)((by - r) * g.S + y0) * g.T + (bx - c) * g.S;
+                if (nt == 0) tb[0] = b;
+                else if (nt == 1) tb[1] = b;
+                else if (nt == 2) tb[2] = b;
+                else if (nt == 3) tb[3] = b;
+                ++nt;
+            }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const int upr = g.S / 4;                                   // 4-pixel units per row
+    int row = threadIdx.x / upr, col = threadIdx.x - row * upr;
+    const int d_row = kThreads / upr, d_col = kThreads - d_row * upr;
+    for (; row < nrow; row += d_row, col += d_col) {
+        if (col >= upr) {
+            col -= upr;
+            if (++row >= nrow) break;
+        }
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(s_src + row * row_bytes + col * 4 * CH);
+        uint32_t px[3];
+        if (CH == 1) px[0] = p[0];
+        else deinterleave4(p[0], p[CH == 3 ? 1 : 0], p[CH == 3 ? 2 : 0], px[0], px[CH == 3 ? 1 : 0], px[CH == 3 ? 2 : 0]);
+        float4 f[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            f[k].x = s_lut[k][px[k] & 0xFF];
+            f[k].y = s_lut[k][(px[k] >> 8) & 0xFF];
+            f[k].z = s_lut[k][(px[k] >> 16) & 0xFF];
+            f[k].w = s_lut[k][px[k] >> 24];
+        }
+        const int off = row * g.T + col * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i < nt) {
+                float *d = tb[i] + off;
+                if (CH == 1) {
+                    for (int k = 0; k < np.out_ch; ++k) st_stream_f4(d + k * TT, f[0]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) st_stream_f4(d + k * TT, f[k]);
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // normalising gather, space-to-depth layout for the network stem
 // ------------------------------------------------------------------------------------------------
@@ -913,6 +1001,15 @@ extern "C" int pylc_tile_gather_norm_f32(const uint8_t *src, int H, int W, int c
     np.post_div = post_div;
     np.out_ch = out_ch;
     cudaStream_t st = (cudaStream_t)stream;
+    // staged form: 16-byte aligned rows, T/S <= 2, and a strip of source rows that fits shared memory
+    const size_t strip = (size_t)kNormRows * S * ch;
+    const int gpb = (S + kNormRows - 1) / kNormRows;
+    if (aligned16(src, src_pitch) && g.m <= 2 && strip <= 40 * 1024 && (long long)g.nbx * g.nby * gpb < 0x7FFFFFFF) {
+        const unsigned grid = (unsigned)(g.nbx * g.nby * gpb);
+        if (ch == 1) gather_norm_staged_kernel<1><<<grid, kThreads, strip, st>>>(g, np, dst, gpb);
+        else gather_norm_staged_kernel<3><<<grid, kThreads, strip, st>>>(g, np, dst, gpb);
+        return finish_launch();
+    }
     const bool al = ((uintptr_t)src % 4 == 0) && (src_pitch % 4 == 0);   // 4-byte units on this path
 #define LAUNCH(CH, AL) \
     gather_norm_kernel<CH, AL><<<persistent_ctas(gather_norm_kernel<CH, AL>, g.items), kThreads, 0, st>>>(g, np, dst)
