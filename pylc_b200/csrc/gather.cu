@@ -258,6 +258,116 @@ __global__ void __launch_bounds__(kThreads) gather_img_kernel(GatherGeom g, uint
     }
 }
 
+// Staged form for 16-byte aligned sources and T/S <= 2: one small CTA per strip of rows of an S-block.
+// The strip's source bytes reach shared memory through coalesced 16-byte cp.async (every load of the
+// CTA in flight at once), a thread takes its 16-pixel units from there with conflict-free 16-byte reads,
+// the destination tile bases are computed once per CTA, and the moments -- the strip lies in one block --
+// are reduced and added to the block's tiles once per CTA.
+template <int CH, bool STATS>
+__global__ void __launch_bounds__(kThreads) gather_img_staged_kernel(GatherGeom g, uint8_t *__restrict__ dst,
+                                                                    unsigned long long *__restrict__ stat, int strip_rows, int spb) {
+    __shared__ unsigned long long s_sum[CH * 2];
+    extern __shared__ __align__(16) uint8_t s_src[];          // strip_rows rows of S * CH bytes
+    if (STATS && threadIdx.x < CH * 2) s_sum[threadIdx.x] = 0;
+    const int blk = blockIdx.x / spb, y0 = (blockIdx.x - blk * spb) * strip_rows;
+    const int nrow = min(strip_rows, g.S - y0);
+    const int bx = blk % g.nbx, by = blk / g.nbx;
+    const int row_bytes = g.S * CH, cpr = row_bytes / 16;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_src);
+    {
+        const uint8_t *src0 = g.src + (size_t)(by * g.S + y0) * g.pitch + (size_t)bx * row_bytes;
+        int r = threadIdx.x / cpr, ck = threadIdx.x - r * cpr;
+        const int dr = kThreads / cpr, dck = kThreads - dr * cpr;
+        for (; r < nrow; r += dr, ck += dck) {
+            if (ck >= cpr) {
+                ck -= cpr;
+                if (++r >= nrow) break;
+            }
+            cp_async16(sbase + (uint32_t)(r * row_bytes + ck * 16), src0 + (size_t)r * g.pitch + ck * 16);
+        }
+        cp_async_commit();
+    }
+    const size_t TT = (size_t)g.T * g.T;
+    const TileSpan ts = tile_span(g, by, bx);
+    uint8_t *tb[4];
+    int nt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tb[i] = dst;
+    for (int r = ts.r_lo; r <= ts.r_hi; ++r)
+        for (int c = ts.c_lo; c <= ts.c_hi; ++c) {
+            uint8_t *b = dst + ((size_t)(r * g.nW + c) * CH) * TT + (size_t)((by - r) * g.S + y0) * g.T + (bx - c) * g.S;
+            if (nt == 0) tb[0] = b;
+            else if (nt == 1) tb[1] = b;
+            else if (nt == 2) tb[2] = b;
+            else if (nt == 3) tb[3] = b;
+            ++nt;
+        }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    uint32_t s1[CH], s2[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) s1[k] = s2[k] = 0;
+    int row = threadIdx.x / g.gpr, grp = threadIdx.x - row * g.gpr;
+    const int d_row = kThreads / g.gpr, d_grp = kThreads - d_row * g.gpr;
+    for (; row < nrow; row += d_row, grp += d_grp) {
+        if (grp >= g.gpr) {
+            grp -= g.gpr;
+            if (++row >= nrow) break;
+        }
+        const uint32_t sa = sbase + (uint32_t)(row * row_bytes + grp * 16 * CH);
+        uint4 o[CH];
+        if (CH == 1) {
+            o[0] = lds128(sa);
+        } else {
+            const uint4 q0 = lds128(sa), q1 = lds128(sa + 16), q2 = lds128(sa + 32);
+            const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+            uint32_t r[4], gg[4], b[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) deinterleave4(w[3 * k], w[3 * k + 1], w[3 * k + 2], r[k], gg[k], b[k]);
+            o[0] = make_uint4(r[0], r[1], r[2], r[3]);
+            o[CH > 1 ? 1 : 0] = make_uint4(gg[0], gg[1], gg[2], gg[3]);
+            o[CH > 2 ? 2 : 0] = make_uint4(b[0], b[1], b[2], b[3]);
+        }
+        if (STATS) {
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const uint32_t ww[4] = {o[k].x, o[k].y, o[k].z, o[k].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s1[k] = __dp4a(ww[j], 0x01010101u, s1[k]);
+                    s2[k] = __dp4a(ww[j], ww[j], s2[k]);
+                }
+            }
+        }
+        const int off = row * g.T + grp * 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < nt) {
+#pragma unroll
+                for (int k = 0; k < CH; ++k) st_stream16(tb[i] + k * TT + off, o[k]);
+            }
+    }
+    if (STATS) {     // u32 partials hold 4096 units per thread; a strip is at most a few per thread
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            const uint32_t a = __reduce_add_sync(0xFFFFFFFFu, s1[k] & 0xFFFFu), ah = __reduce_add_sync(0xFFFFFFFFu, s1[k] >> 16);
+            const uint32_t b = __reduce_add_sync(0xFFFFFFFFu, s2[k] & 0xFFFFu), bh = __reduce_add_sync(0xFFFFFFFFu, s2[k] >> 16);
+            if ((threadIdx.x & 31) == 0) {
+                atomicAdd(&s_sum[k * 2], (unsigned long long)a + ((unsigned long long)ah << 16));
+                atomicAdd(&s_sum[k * 2 + 1], (unsigned long long)b + ((unsigned long long)bh << 16));
+            }
+        }
+        __syncthreads();
+        const int nt_c = ts.c_hi - ts.c_lo + 1;
+        for (int i = threadIdx.x; i < nt * CH * 2; i += kThreads) {
+            const int t = i / (CH * 2), k = i - t * (CH * 2);
+            const int r = ts.r_lo + t / nt_c, c = ts.c_lo + t % nt_c;
+            atomicAdd(&stat[(size_t)(r * g.nW + c) * CH * 2 + k], s_sum[k]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // mask gather + palette encode + per-tile histogram
 // ------------------------------------------------------------------------------------------------
@@ -927,6 +1037,22 @@ extern "C" int pylc_tile_gather_u8(const uint8_t *src, int H, int W, int ch, siz
     cudaStream_t st = (cudaStream_t)stream;
     const bool al = aligned16(src, src_pitch);
     auto *sp = reinterpret_cast<unsigned long long *>(stat);
+    // staged form: strips of up to 32 KB (64 rows) of source rows per CTA
+    int strip_rows = 1;
+    while (strip_rows * 2 <= S && (size_t)strip_rows * 2 * S * ch <= 32 * 1024 && strip_rows < 64) strip_rows *= 2;
+    const size_t strip = (size_t)strip_rows * S * ch;
+    const int spb = (S + strip_rows - 1) / strip_rows;
+    if (al && g.m <= 2 && strip <= 32 * 1024 && (long long)g.nbx * g.nby * spb < 0x7FFFFFFF) {
+        const unsigned grid = (unsigned)(g.nbx * g.nby * spb);
+        if (ch == 1) {
+            if (stat) gather_img_staged_kernel<1, true><<<grid, kThreads, strip, st>>>(g, dst, sp, strip_rows, spb);
+            else gather_img_staged_kernel<1, false><<<grid, kThreads, strip, st>>>(g, dst, sp, strip_rows, spb);
+        } else {
+            if (stat) gather_img_staged_kernel<3, true><<<grid, kThreads, strip, st>>>(g, dst, sp, strip_rows, spb);
+            else gather_img_staged_kernel<3, false><<<grid, kThreads, strip, st>>>(g, dst, sp, strip_rows, spb);
+        }
+        return finish_launch();
+    }
 #define LAUNCH(CH, AL, ST) \
     gather_img_kernel<CH, AL, ST><<<persistent_ctas(gather_img_kernel<CH, AL, ST>, g.items), kThreads, 0, st>>>(g, dst, sp)
     if (ch == 1) {
