@@ -31,4 +31,3 @@ print("stem 7x7/2 4->64 @512      : %.0f us" % conv(4, 64, 7, 512, 2, 3))
 print("stem 7x7/2 8->64 @512      : %.0f us" % conv(8, 64, 7, 512, 2, 3))
 print("dec1 3x3 320->256 @128     : %.0f us" % conv(320, 256, 3, 128, 1, 1))
 print("dec1 3x3 384->256 @128     : %.0f us" % conv(384, 256, 3, 128, 1, 1))
-print("aspp 3x3 d6 2048->256 @32  : n/a")
