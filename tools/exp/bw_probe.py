@@ -1,4 +1,5 @@
-"""Pure-write / pure-read / copy bandwidth probes (context for the write-dominated kernels' roofline)."""
+"""Pure-write / pure-read / copy bandwidth probes (context for the write-dominated kernels' roofline).
+Measured on B200: fill 7247 GB/s, copy 6348 GB/s (read + write), torch.sum 5784 GB/s, cudaMemset 3857 GB/s."""
 import torch, json
 def timeit(fn, n=10):
     for _ in range(3): fn()
@@ -17,7 +18,7 @@ out["memset_zero_GBs"] = N / timeit(lambda: a.zero_()) / 1e6
 out["fill_f32_GBs"] = N / timeit(lambda: af.fill_(1.5)) / 1e6
 out["copy_GBs_rw"] = 2 * N / timeit(lambda: b.copy_(a)) / 1e6
 out["read_sum_GBs"] = N / timeit(lambda: af.sum()) / 1e6
-# 1:3 read:write like the x4 up-sample (read 1 byte, write 4)
+# 1 read : 4 written, like the x4 up-sample (stock strided copy: far from the roofline)
 q = a[: N // 4].view(torch.float32)
-out["repeat_interleave_1r4w_GBs"] = (N // 4 + N) / timeit(lambda: torch.repeat_interleave(q, 4, out=af) if False else af.view(-1, 4).copy_(q.unsqueeze(1).expand(-1, 4))) / 1e6
+out["expand_1r4w_GBs"] = (N // 4 + N) / timeit(lambda: af.view(-1, 4).copy_(q.unsqueeze(1).expand(-1, 4))) / 1e6
 print(json.dumps(out))
