@@ -173,36 +173,46 @@ __global__ void __launch_bounds__(kThreads) upsample_concat_staged_kernel(const 
 // One thread = one float4 channel group of TWO horizontally adjacent output pixels (they share an input
 // column): 15 loads for 2 outputs.  Consecutive threads walk the channel groups of a pixel pair, so a
 // warp reads and writes contiguous runs.  Rows shared by consecutive output rows come from L2.
+// One CTA per output row; a thread's (pixel pair, channel group) position advances by constants, so the
+// loop carries no divisions (the earlier grid-stride form spent most of its instructions on 64-bit index
+// arithmetic).  Column maxima over the three input rows are formed first, then combined per output.
 __global__ void __launch_bounds__(kThreads) maxpool3x3s2_kernel(const float *__restrict__ in, float *__restrict__ out, int B, int H,
                                                                int W, int C, int Ho, int Wo) {
     const int cg = C / 4, pairs = (Wo + 1) / 2;
-    const long long total = (long long)B * Ho * pairs * cg;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-        const int g = (int)(i % cg);
-        long long r = i / cg;
-        const int px = (int)(r % pairs);
-        r /= pairs;
-        const int Y = (int)(r % Ho), b = (int)(r / Ho);
+    const int b = blockIdx.x / Ho, Y = blockIdx.x - b * Ho;
+    const float ninf = -INFINITY;
+    const float4 lowest = make_float4(ninf, ninf, ninf, ninf);
+    const float *rows[3];
+    bool have[3];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+        const int y = 2 * Y - 1 + dy;
+        have[dy] = y >= 0 && y < H;
+        rows[dy] = in + (((size_t)b * H + (have[dy] ? y : 0)) * W) * C;
+    }
+    float *orow = out + (((size_t)b * Ho + Y) * Wo) * C;
+    int px = threadIdx.x / cg, g = threadIdx.x - px * cg;
+    const int dpx = kThreads / cg, dg = kThreads - dpx * cg;
+    for (; px < pairs; px += dpx, g += dg) {
+        if (g >= cg) {
+            g -= cg;
+            if (++px >= pairs) break;
+        }
         const int X0 = px * 2;
-        const float ninf = -INFINITY;
-        float4 m0 = make_float4(ninf, ninf, ninf, ninf), m1 = m0;
+        float4 col[5];
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-            const int y = 2 * Y - 1 + dy;
-            if (y < 0 || y >= H) continue;
-            const float *rowp = in + (((size_t)b * H + y) * W) * C + g * 4;
+        for (int dx = 0; dx < 5; ++dx) {
+            const int xx = 2 * X0 - 1 + dx;
+            col[dx] = lowest;
+            if (xx >= 0 && xx < W) {
 #pragma unroll
-            for (int dx = 0; dx < 5; ++dx) {
-                const int xx = 2 * X0 - 1 + dx;
-                if (xx < 0 || xx >= W) continue;
-                const float4 v = ldg4(rowp + (size_t)xx * C);
-                if (dx <= 2) m0 = max4(m0, v);
-                if (dx >= 2) m1 = max4(m1, v);
+                for (int dy = 0; dy < 3; ++dy)
+                    if (have[dy]) col[dx] = max4(col[dx], ldg4(rows[dy] + (size_t)xx * C + g * 4));
             }
         }
-        float *o = out + (((size_t)b * Ho + Y) * Wo + X0) * C + g * 4;
-        st_stream_f4(o, m0);
-        if (X0 + 1 < Wo) st_stream_f4(o + C, m1);
+        float *o = orow + (size_t)X0 * C + g * 4;
+        st_stream_f4(o, max4(max4(col[0], col[1]), col[2]));
+        if (X0 + 1 < Wo) st_stream_f4(o + C, max4(max4(col[2], col[3]), col[4]));
     }
 }
 
@@ -399,8 +409,8 @@ extern "C" int pylc_maxpool3x3s2_nhwc_f32(const float *in, int B, int H, int W, 
     if (C < 4 || C % 4) return PYLC_ERR_GEOMETRY;
     if (((uintptr_t)in | (uintptr_t)out) % 16) return PYLC_ERR_ALIGN;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-    const long long total = (long long)B * Ho * ((Wo + 1) / 2) * (C / 4);
-    maxpool3x3s2_kernel<<<glue_grid(total, 16), kThreads, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, Ho, Wo);
+    if ((long long)B * Ho > 0x7FFFFFFF) return PYLC_ERR_GEOMETRY;
+    maxpool3x3s2_kernel<<<(unsigned)(B * Ho), kThreads, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, Ho, Wo);
     return finish_launch();
 }
 
