@@ -102,6 +102,42 @@ __device__ __forceinline__ void softmax_px(const float (&z)[CMAX], int C, float 
 
 __device__ __forceinline__ float ln_fast(float x) { return lg2_approx(x) * kLn2; }
 
+// (image, unit-in-image) position of a thread's grid-stride walk over the units, forwards or backwards:
+// one 64-bit division when the walk starts, constant steps with a carry afterwards.
+template <bool REVERSE>
+struct UnitWalk {
+    int b, r, left;                  // image, unit inside the image, units this thread still has to do
+    int step_b, step_r, upi;         // (the host rejects images of 2^31 units or more)
+    __device__ __forceinline__ UnitWalk(const LossArgs &a) {
+        const long long stride = (long long)gridDim.x * kThreads, first = (long long)blockIdx.x * kThreads + threadIdx.x;
+        upi = (int)a.units_per_img;
+        left = first < a.total_units ? (int)((a.total_units - first + stride - 1) / stride) : 0;
+        const long long u = REVERSE ? a.total_units - 1 - first : first;
+        b = left ? (int)(u / upi) : 0;
+        r = left ? (int)(u - (long long)b * upi) : 0;
+        step_b = (int)(stride / upi);
+        step_r = (int)(stride - (long long)step_b * upi);
+    }
+    __device__ __forceinline__ void next() {
+        --left;
+        if (REVERSE) {
+            b -= step_b;
+            r -= step_r;
+            if (r < 0) {
+                r += upi;
+                --b;
+            }
+        } else {
+            b += step_b;
+            r += step_r;
+            if (r >= upi) {
+                r -= upi;
+                ++b;
+            }
+        }
+    }
+};
+
 template <int C_T, int CMAX, int PX>
 __device__ __forceinline__ void loss_reduce_pass(const LossArgs &a, double *partials) {
     const int C = C_T > 0 ? C_T : a.C;
@@ -122,10 +158,8 @@ __device__ __forceinline__ void loss_reduce_pass(const LossArgs &a, double *part
     float ce_num = 0.f, ce_den = 0.f, focal = 0.f;
     const float eps = a.cfg.eps, gamma = a.cfg.fl_gamma, alpha = a.cfg.fl_alpha;
 
-    for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < a.total_units;
-         u += (long long)gridDim.x * kThreads) {
-        const long long b = u / a.units_per_img;
-        const long long off = (u - b * a.units_per_img) * PX;
+    for (UnitWalk<false> w(a); w.left > 0; w.next()) {
+        const long long b = w.b, off = (long long)w.r * PX;
         const float *p = a.logits + ((size_t)b * C) * a.HW + off;
         float z[CMAX][PX];
 #pragma unroll
@@ -232,11 +266,8 @@ __device__ __forceinline__ void loss_grad_pass(const LossArgs &a, const double *
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) bb[c] = c < C ? s_b[c] : 0.f;
 
-    for (long long uf = (long long)blockIdx.x * kThreads + threadIdx.x; uf < a.total_units;
-         uf += (long long)gridDim.x * kThreads) {
-        const long long u = REVERSE ? a.total_units - 1 - uf : uf;
-        const long long b = u / a.units_per_img;
-        const long long off = (u - b * a.units_per_img) * PX;
+    for (UnitWalk<REVERSE> w(a); w.left > 0; w.next()) {
+        const long long b = w.b, off = (long long)w.r * PX;
         const size_t base = ((size_t)b * C) * a.HW + off;
         float z[CMAX][PX];
 #pragma unroll
@@ -341,6 +372,7 @@ static int fill_args(const float *logits, const void *target, int target_is_i64,
                      const float *class_w, const pylc_loss_cfg *cfg, LossArgs *a, int *px) {
     if (!logits || !target || !cfg || B < 1 || HW < 1) return PYLC_ERR_ARG;
     if (C < 1 || C > PYLC_MAX_CLASSES) return PYLC_ERR_CLASSES;
+    if (HW > 0x7FFFFFFFll) return PYLC_ERR_GEOMETRY;   // 32-bit position inside an image (UnitWalk)
     // pixels per lane: 4 (one 128-bit load per class plane) while the per-thread state fits the
     // register file (C <= 6), else 2 (64-bit loads, 3 CTAs per SM) -- the warp-level access stays one
     // contiguous run per plane either way, and nothing is demoted to local memory
