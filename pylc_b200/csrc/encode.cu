@@ -73,13 +73,20 @@ __global__ void __launch_bounds__(kThreads) class_encode_kernel(EncodeArgs a, co
     CC cc;
     cc.reset();
     int since_widen = 0;
-    const long long first = (long long)blockIdx.x * kThreads * kUnitsPerThread;
+    // a thread's units are kThreads apart: (row, group) advance by constants with a carry -- one 64-bit
+    // division per thread instead of one per unit
+    const long long first = (long long)blockIdx.x * kThreads * kUnitsPerThread + threadIdx.x;
+    long long rowi = first / a.groups_per_row;        // global row index (img * rows + row)
+    long long grp = first - rowi * a.groups_per_row;
+    const long long d_row = kThreads / a.groups_per_row, d_grp = kThreads - d_row * a.groups_per_row;
 #pragma unroll 1
-    for (int it = 0; it < kUnitsPerThread; ++it) {
-        const long long u = first + (long long)it * kThreads + threadIdx.x;
-        if (u >= a.total_units) continue;
-        const long long rowi = u / a.groups_per_row;  // global row index (img * rows + row)
-        const long long x = (u - rowi * a.groups_per_row) * 16;
+    for (int it = 0; it < kUnitsPerThread; ++it, rowi += d_row, grp += d_grp) {
+        if (grp >= a.groups_per_row) {
+            grp -= a.groups_per_row;
+            ++rowi;
+        }
+        if (first + (long long)it * kThreads >= a.total_units) break;
+        const long long x = grp * 16;
         const int valid = (int)min(16ll, a.cols - x);
         uint32_t key[16];
         if (LAYOUT == 0) {
