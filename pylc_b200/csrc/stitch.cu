@@ -180,11 +180,16 @@ __device__ __forceinline__ void stitch_units(const StitchArgs &a, const uint32_t
 #pragma unroll
         for (int q = 0; q < NH; ++q) base[s][q] = tile_base(a, ti[s], tj[q]) + (size_t)ty0[s] * T + tx0[q];
 
-    const int units = nrows * a.upr;
-    for (int u = threadIdx.x; u < units; u += kThreads) {
-        const int row = u / a.upr;
+    // a thread's units are kThreads apart: (row, column) advance by constants with a carry
+    int row = threadIdx.x / a.upr, col = threadIdx.x - row * a.upr;
+    const int d_row = kThreads / a.upr, d_col = kThreads - d_row * a.upr;
+    for (; row < nrows; row += d_row, col += d_col) {
+        if (col >= a.upr) {
+            col -= a.upr;
+            if (++row >= nrows) break;
+        }
         const int yl = row0 + row;
-        const int xl = (u - row * a.upr) * PX;
+        const int xl = col * PX;
         const size_t off = (size_t)yl * T + xl;
 
         float v[NV][NH][CMAX][PX];
