@@ -37,10 +37,20 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_IMAGES, W_FULL, H_FULL, CH = 64, 3000, 2000, 3
+N_IMAGES, W_FULL, H_FULL, CH, TILES_PER_IMAGE = 64, 3000, 2000, 3, 45
 WORKLOAD = "configs[1]: 64 synthetic 3000x2000 colour image/mask pairs per GPU, schema_a, DeepLabv3+ " \
            "ResNet-101 random-init, 512px tiles stride 256, stitch+argmax+resample+confusion/mIoU"
 METRIC = "megapixels/sec end-to-end tiled inference"
+# BASELINE.json configs this file can run (--config): image set, geometry, channels.  configs[1] is the
+# one the metric is quoted on (and what the driver runs); configs[4] is the sharded 6000x4000 gray set.
+CONFIGS = {
+    1: dict(n=64, w=3000, h=2000, ch=3, tiles=45,
+            name="configs[1]: 64 synthetic 3000x2000 colour image/mask pairs {per}, schema_a, DeepLabv3+ "
+                 "ResNet-101 random-init, 512px tiles stride 256, stitch+argmax+resample+confusion/mIoU"),
+    4: dict(n=16, w=6000, h=4000, ch=1, tiles=273,
+            name="configs[4]: 16 synthetic 6000x4000 grayscale image/mask pairs {per}, schema_a, DeepLabv3+ "
+                 "ResNet-101 random-init, 512px tiles stride 256 (273 tiles/image), stitch+argmax+resample+confusion"),
+}
 
 
 def peak_gbs():
@@ -83,18 +93,17 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
-def make_inputs(rank, palette):
-    """64 decoded image / RGB-mask pairs per rank as tightly packed [H,W,3] u8 tensors in PINNED host
-    memory -- what cv2.imread hands the reference, page-locked (global image index = rank * 64 + i,
-    so ranks hold different images)."""
+def make_inputs(global_indices, palette):
+    """The rank's decoded image / RGB-mask pairs as tightly packed [H,W(,3)] u8 tensors in PINNED host
+    memory -- what cv2.imread hands the reference, page-locked.  Image g is a function of its GLOBAL
+    index only, so every partition of the same set over any number of ranks sees the same pixels."""
     from pylc_b200 import synth
 
-    def one(i):
-        g = rank * N_IMAGES + i
+    def one(g):
         return (torch.from_numpy(synth.image(g, W_FULL, H_FULL, CH)).pin_memory(),
                 torch.from_numpy(synth.mask(g, W_FULL, H_FULL, palette)).pin_memory())
     with cf.ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 4)) as ex:
-        pairs = list(ex.map(one, range(N_IMAGES)))
+        pairs = list(ex.map(one, global_indices))
     imgs = [p[0] for p in pairs]
     masks = [p[1] for p in pairs]
     return imgs, masks
@@ -107,8 +116,10 @@ def build_model(device, seed=0):
     model = Model()
     model.track = False
     model.device = device
+    px_mean = list(defaults.px_rgb_mean) if CH == 3 else [defaults.px_grayscale_mean]
+    px_std = list(defaults.px_rgb_std) if CH == 3 else [defaults.px_grayscale_std]
     model.update_meta({"ch": CH, "arch": "deeplab", "backbone": "resnet", "pretrained": False,
-                       "px_mean": list(defaults.px_rgb_mean), "px_std": list(defaults.px_rgb_std),
+                       "px_mean": px_mean, "px_std": px_std,
                        "weights": [1.0] * defaults.n_classes, "normalize_default": False})
     model.build()
     model.net.eval()
@@ -120,13 +131,15 @@ def build_model(device, seed=0):
 # ---------------------------------------------------------------------------------------------
 
 def reference_sample():
-    """Bounded sample of the workload: the top-left 2000x1500 crop of image 0 and its mask
-    (fitted 1536x1024 -> 15 of the image's 45 tiles); every phase of the path scales with pixels."""
+    """Bounded sample of the workload at image granularity: ONE whole image of the configuration and its
+    mask (configs[1]: 3000x2000 -> fitted 2560x1536 -> all 45 tiles), i.e. 1/64 of a step; every phase
+    of the path is per image."""
     from pylc_b200 import synth
     from pylc_b200.config import defaults
-    img = synth.image(0, W_FULL, H_FULL, CH)[:1500, :2000].copy()
-    gt = synth.mask(0, W_FULL, H_FULL, defaults.palette_rgb)[:1500, :2000].copy()
-    return img, gt, "top-left 2000x1500 crop of image 0 (+mask): 15 of its 45 tiles, all phases incl. CPU network"
+    img = synth.image(0, W_FULL, H_FULL, CH)
+    gt = synth.mask(0, W_FULL, H_FULL, defaults.palette_rgb)
+    return img, gt, "image 0 of the set, whole (%dx%d, %s + RGB mask): all its tiles, every phase incl. the CPU network" % (
+        W_FULL, H_FULL, "colour" if CH == 3 else "gray")
 
 
 class ReferenceCPU(object):
@@ -142,8 +155,12 @@ class ReferenceCPU(object):
         torch.set_num_threads(self.cores)
         torch.manual_seed(0)
         self.net = DeepLab(n_classes=defaults.n_classes).eval()
-        self.mean = torch.tensor(defaults.px_rgb_mean)[None, :, None, None]
-        self.std = torch.tensor(defaults.px_rgb_std)[None, :, None, None]
+        if CH == 3:
+            self.mean = torch.tensor(defaults.px_rgb_mean)[None, :, None, None]
+            self.std = torch.tensor(defaults.px_rgb_std)[None, :, None, None]
+        else:                                            # model.py:433-435: one gray mean / std
+            self.mean = torch.tensor([defaults.px_grayscale_mean])[None, :, None, None]
+            self.std = torch.tensor([defaults.px_grayscale_std])[None, :, None, None]
 
     def step(self, img, gt):
         import cv2
@@ -160,6 +177,8 @@ class ReferenceCPU(object):
             for lo in range(0, len(tiles), 8):                                       # test.py:68-83, batch 8
                 x = torch.tensor(tiles[lo:lo + 8]).float()
                 x = ((x - self.mean) / self.std) / 255                               # model.py:443-445
+                if x.shape[1] == 1:
+                    x = torch.cat((x, x, x), 1)                                      # model.py:376-377
                 outs.append(self.net(x).numpy())
         ph["network_cpu"] = time.perf_counter() - t0
         t0 = time.perf_counter()
@@ -304,18 +323,18 @@ def run_ours(args, rank, world, local_rank):
     seg = TiledSegmenter(model, batch_tiles=args.batch_tiles, channels_last=not args.no_channels_last,
                          autocast_dtype=dtype, host_workers=args.host_workers, fuse_network=not args.no_fuse,
                          device_fit=not args.host_fit)
-    imgs, masks = make_inputs(rank, model.meta.palette_rgb)
-    mpx_step = N_IMAGES * W_FULL * H_FULL / 1e6
+    # weak: every rank owns N_IMAGES images (global index rank * N_IMAGES + i); strong: ONE set of
+    # N_IMAGES images dealt round-robin over the ranks (dist.shard_indices)
+    strong = args.scaling == "strong"
+    gidx = pdist.shard_indices(N_IMAGES, rank, world) if strong else [rank * N_IMAGES + i for i in range(N_IMAGES)]
+    imgs, masks = make_inputs(gidx, model.meta.palette_rgb)
+    n_mine = len(gidx)
+    mpx_job = (N_IMAGES if strong else N_IMAGES * world) * W_FULL * H_FULL / 1e6      # whole job, all ranks
     d2h = seg.C * seg.C * 8
-
-    def barrier_sync():
-        torch.cuda.synchronize()
-        pdist.barrier()
-        torch.cuda.synchronize()
 
     # ---- value: inputs resident in HBM -------------------------------------------------------
     stage = seg.stage_device if seg.can_fit_on_device(imgs[0]) else (lambda im, gt, index: seg.stage(im.numpy(), gt.numpy(), index=index))
-    resident = [stage(imgs[i], masks[i], index=rank * N_IMAGES + i) for i in range(N_IMAGES)]
+    resident = [stage(imgs[i], masks[i], index=gidx[i]) for i in range(n_mine)]
     torch.cuda.synchronize()
     h2d = sum(im.numel() + gt.numel() for im, gt in zip(imgs, masks)) if seg.can_fit_on_device(imgs[0]) \
         else sum(f.img.numel() + f.gt.numel() for f in resident)      # bytes run_host copies per step
@@ -351,13 +370,13 @@ def run_ours(args, rank, world, local_rank):
     # ---- e2e: host buffers, copies inside the timed region -------------------------------------
     for _ in range(max(1, min(args.warmup, 2))):
         seg.reset()
-        seg.run_host(imgs, masks, distributed=world > 1)
+        seg.run_host(imgs, masks, distributed=world > 1, global_indices=gidx)
     barrier_sync()
     t0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
         seg.reset()
-        conf_host, _ = seg.run_host(imgs, masks, distributed=world > 1)
+        conf_host, _ = seg.run_host(imgs, masks, distributed=world > 1, global_indices=gidx)
     ev1.record()
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -370,20 +389,22 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_kind = peak_gbs()
     scores = seg.scores(conf_host)
     line = {
-        "metric": METRIC, "value": mpx_step * world / (ms * 1e-3), "unit": "Mpx/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": mpx_job / (ms * 1e-3), "unit": "Mpx/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32 hot-path kernels (u8/i64 integer paths); network %s" % (
             "fp32 with cuDNN TF32 (PyTorch default, as the reference would run)" if dtype is None else args.backbone_dtype),
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "images_per_gpu": N_IMAGES, "tiles_per_image": 45, "batch_tiles": args.batch_tiles,
+        "config": {"workload": WORKLOAD, "images_per_gpu": n_mine, "images_total": N_IMAGES if strong else N_IMAGES * world,
+                   "tiles_per_image": TILES_PER_IMAGE, "batch_tiles": args.batch_tiles,
                    "network_plan": "eager nn.Module" if args.no_fuse else "BatchNorm folded, cuDNN fused conv+bias(+add)+ReLU, channels_last, space-to-depth stem, pylc max-pool / up-sample+concat / final up-sample kernels",
                    "l2": "inputs larger than L2 (each step streams > 20 GB of logits per GPU)",
-                   "parallelism": "dp%d, images sharded, one [9,9] i64 all-reduce per step" % world,
+                   "parallelism": "dp%d, images sharded (%s), one [9,9] i64 all-reduce per step" % (
+                       world, "one fixed set dealt round-robin" if strong else "a fixed set per rank"),
                    "fit_resize": "host cv2 threads" if args.host_fit else "device (pylc_fit_resize_area_u8, bit-exact INTER_AREA)",
                    "value_region": ("fitted" if args.host_fit else "decoded") + " u8 images + RGB ground truth resident in HBM -> all-reduced confusion matrix",
                    "weighted_iou": scores["iou"], "confusion_sum": int(conf_host.sum()),
                    "resident_equals_e2e": bool(np.array_equal(conf_resident, conf_host))},
-        "e2e": {"value": mpx_step * world / (e2e_ms * 1e-3), "unit": "Mpx/s", "ms_per_step": e2e_ms,
+        "e2e": {"value": mpx_job / (e2e_ms * 1e-3), "unit": "Mpx/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "api": "pylc_b200.pipeline.TiledSegmenter.run_host"},
         "gpu_launches": int(launches),
@@ -392,15 +413,19 @@ def run_ours(args, rank, world, local_rank):
                      "achieved": (k_bytes / (k_ms * 1e-3) / 1e9) if k_ms else None, "peak": peak, "peak_kind": peak_kind,
                      "unit": "GB/s", "frac": (k_bytes / (k_ms * 1e-3) / 1e9 / peak) if k_ms else None,
                      "avg_launch_ms": k_ms, "algorithmic_bytes_per_launch": k_bytes,
-                     "traffic": ncu_traffic("stitch45", "stitch_kernel"),
-                     "traffic_source": "profiles/traffic_r1.json: ncu --set full capture of this launch shape (45 tiles), dram read + write",
-                     "share_of_step": (k_ms * N_IMAGES / ms) if k_ms else None,
+                     "traffic": ncu_traffic("stitch45" if TILES_PER_IMAGE == 45 else "stitch", "stitch_kernel"),
+                     "traffic_source": "profiles/traffic_r*.json: ncu --set full capture of this launch shape (%d tiles), dram read + write" % TILES_PER_IMAGE,
+                     "share_of_step": (k_ms * n_mine / ms) if k_ms else None,
                      "why_this_kernel": "largest algorithmic HBM stream of the SURVEY 8a hot path; every custom launch of the step is listed under `kernels`"},
         "kernels": kernels,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line), flush=True)
+    if not line["config"]["resident_equals_e2e"]:
+        # both paths process the same images with ONE coverage injection (global image 0): the integer
+        # matrices must be identical at every GPU count -- anything else is a parity failure
+        raise SystemExit("bench.py: confusion matrix of the resident pass differs from the end-to-end pass")
 
 
 def main():
@@ -417,10 +442,18 @@ def main():
     ap.add_argument("--host-fit", action="store_true", help="fit-resize on host threads with cv2 (the reference's call) "
                     "instead of the bit-exact device kernel")
     ap.add_argument("--no-fuse", action="store_true", help="run the eager nn.Module instead of the BN-folded cuDNN-fused plan")
-    ap.add_argument("--images", type=int, default=64, help="images per GPU per step (profiling runs use fewer; "
-                    "the reported workload is only configs[1] at the default 64)")
+    ap.add_argument("--images", type=int, default=None, help="images per GPU per step (weak) or in total (strong); "
+                    "default: the configuration's own count (profiling runs use fewer)")
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS), help="BASELINE.json configs index: 1 = the "
+                    "colour 3000x2000 set the metric is quoted on (default, what the driver runs); 4 = gray 6000x4000")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --images per GPU (default); "
+                    "strong: ONE set of --images dealt round-robin over the ranks")
     args = ap.parse_args()
-    globals()["N_IMAGES"] = args.images
+    cfg = CONFIGS[args.config]
+    n_img = cfg["n"] if args.images is None else args.images
+    globals().update(N_IMAGES=n_img, W_FULL=cfg["w"], H_FULL=cfg["h"], CH=cfg["ch"], TILES_PER_IMAGE=cfg["tiles"],
+                     WORKLOAD=cfg["name"].format(per="per GPU" if args.scaling == "weak" else "in total (strong scaling)")
+                     .replace("%d synthetic" % cfg["n"], "%d synthetic" % n_img))
     if args.impl == "reference":
         run_reference(args, int(os.environ.get("RANK", "0")))
         return

@@ -26,6 +26,13 @@ from .deeplab import DeepLab
 from .modules.loss import MultiLoss
 
 
+def strip_module_prefix(state_dict):
+    """State dict saved from a DistributedDataParallel / DataParallel wrapper -> bare network keys."""
+    if state_dict and all(k.startswith('module.') for k in state_dict):
+        return type(state_dict)((k[len('module.'):], v) for k, v in state_dict.items())
+    return state_dict
+
+
 class Checkpoint:
     """Training checkpoint + best-model files under <save_dir>/<id>/ (reference checkpoint.py:17-66)."""
 
@@ -46,7 +53,10 @@ class Checkpoint:
             os.remove(self.checkpoint_file)
 
     def save(self, model, is_best=False):
-        state = {"model": model.net.state_dict(), "optim": model.optim.state_dict(), "meta": model.meta}
+        # a DistributedDataParallel wrapper prefixes every key with "module."; the model file holds the
+        # bare network's keys (what Model.load, resume and the reference read back)
+        net = getattr(model.net, 'module', model.net)
+        state = {"model": net.state_dict(), "optim": model.optim.state_dict(), "meta": model.meta}
         torch.save(dict(state, epoch=model.epoch, iter=model.iter), self.checkpoint_file)
         if is_best:
             torch.save(state, self.model_file)
@@ -111,7 +121,10 @@ class RunningLoss(object):
 class Model:
     def __init__(self):
         self.meta = defaults
-        self.device = torch.device(self.meta.device)
+        # one process per GPU: the process's current CUDA device (dist.init_from_env selects LOCAL_RANK's),
+        # not the import-time default "cuda:0" of config.py
+        self.device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
+            else torch.device(self.meta.device)
         self.net = None
         self.model_path = None
         self.iter = 0
@@ -124,6 +137,7 @@ class Model:
         self.checkpoint = None
         self.resume_checkpoint = False
         self.distributed = False
+        self.is_writer = True       # data parallel: only rank 0 writes checkpoint / loss-log files
         self.track = True           # False: no checkpoint / loss-log files (benchmarks, tests)
         self.normalizers = {'batch': nn.BatchNorm2d, 'instance': nn.InstanceNorm2d,
                             'layer': nn.LayerNorm, 'syncbatch': nn.SyncBatchNorm}
@@ -149,7 +163,7 @@ class Model:
         self.meta.update(model_data["meta"] if isinstance(model_data["meta"], dict) else vars(model_data["meta"]))
         self.meta.pretrained = False
         self.build()
-        self.net.load_state_dict(model_data["model"])
+        self.net.load_state_dict(strip_module_prefix(model_data["model"]))
         return self
 
     def build(self):
@@ -172,9 +186,10 @@ class Model:
                           'dice': self.meta.dice_weight, 'focal': self.meta.focal_weight},
             schema={'n_classes': self.meta.n_classes, 'class_codes': self.meta.class_codes,
                     'class_labels': self.meta.class_labels},
-            distributed=self.distributed)
+            distributed=self.distributed, ddp_average=self.distributed)
         if self.track:
-            self.checkpoint = Checkpoint(self.meta.id, self.meta.save_dir)
+            self.checkpoint = Checkpoint(self.meta.id, self.meta.save_dir)      # every rank may resume from it
+        if self.track and self.is_writer:
             self.loss = RunningLoss(self.meta.id, save_dir=self.meta.save_dir, resume=self.meta.resume_checkpoint)
         else:
             self.loss = _NullLoss()
@@ -187,9 +202,9 @@ class Model:
             data = self.checkpoint.load()
             if data is not None:
                 self.epoch, self.iter, self.meta = data['epoch'], data['iter'], data["meta"]
-                self.net.load_state_dict(data["model"])
+                self.net.load_state_dict(strip_module_prefix(data["model"]))
                 self.optim.load_state_dict(data["optim"])
-        elif self.checkpoint is not None:
+        elif self.checkpoint is not None and self.is_writer:
             self.checkpoint.reset()
 
     def init_optim(self):
@@ -288,7 +303,7 @@ class Model:
         self.loss.save()
 
     def save(self):
-        if self.checkpoint is not None:
+        if self.checkpoint is not None and self.is_writer:
             self.checkpoint.save(self, is_best=self.loss.is_best)
         self.loss.save()
 

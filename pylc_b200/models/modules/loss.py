@@ -29,16 +29,22 @@ class _MultiLossFn(torch.autograd.Function):
     """pred [B,C,H,W] f32, target [B,H,W] i64/u8 -> out[4] = (loss, ce, dice, focal)."""
 
     @staticmethod
-    def forward(ctx, pred, target, class_w, cfg, distributed):
+    def forward(ctx, pred, target, class_w, cfg, distributed, grad_mult):
         pred = pred.contiguous()
         target = target.contiguous()
         C = pred.shape[1]
         ctx.fused_grad = None
+        ctx.grad_mult = float(grad_mult)
+        ctx.class_w, ctx.cfg = class_w, cfg
         if ctx.needs_input_grad[0] and not (distributed and pdist.world_size() > 1):
             # single-GPU training step: forward and backward in ONE cooperative launch; the gradient is
-            # stashed for backward(), which only rescales it if the upstream gradient is not 1
+            # stashed for the first backward(), which only rescales it if the upstream gradient is not 1.
+            # A second backward over the same graph (retain_graph=True, checkpointing) recomputes the
+            # gradient from the saved tensors with pylc_multiloss_grad.
             out, grad, partials = ops.multiloss_fwd_bwd(pred, target, cfg, class_w)
             ctx.fused_grad = grad
+            ctx.n_px = target.numel()
+            ctx.save_for_backward(pred, target, partials)
             ctx.mark_non_differentiable(target)
             return out
         partials = ops.multiloss_reduce(pred, target, cfg, class_w)
@@ -48,27 +54,36 @@ class _MultiLossFn(torch.autograd.Function):
             n_px *= pdist.world_size()
         out = ops.multiloss_finalize(partials, C, n_px, cfg)
         ctx.save_for_backward(pred, target, partials)
-        ctx.class_w, ctx.cfg, ctx.n_px = class_w, cfg, n_px
+        ctx.n_px = n_px
         ctx.mark_non_differentiable(target)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        if ctx.fused_grad is not None:
-            grad, ctx.fused_grad = ctx.fused_grad, None
-            ops.scale_unless_one_(grad, grad_out[0].to(torch.float32).contiguous())
-            return grad, None, None, None, None
-        pred, target, partials = ctx.saved_tensors
         # dL/dz from the kernel, scaled by the upstream gradient of out[0] (the weighted loss).
         # The component outputs out[1:4] are reporting values; gradients through them are dropped.
         g0 = grad_out[0].to(torch.float32).contiguous()
+        if ctx.grad_mult != 1.0:
+            g0 = g0 * ctx.grad_mult
+        if ctx.fused_grad is not None:
+            grad, ctx.fused_grad = ctx.fused_grad, None
+            ops.scale_unless_one_(grad, g0)
+            return grad, None, None, None, None, None
+        pred, target, partials = ctx.saved_tensors
         grad = ops.multiloss_grad(pred, target, ctx.cfg, partials, ctx.n_px, ctx.class_w, grad_scale_dev=g0)
-        return grad, None, None, None, None
+        return grad, None, None, None, None, None
 
 
 class MultiLoss(torch.nn.Module):
-    def __init__(self, loss_weights, schema, distributed=False):
+    def __init__(self, loss_weights, schema, distributed=False, ddp_average=False):
+        """distributed: all-reduce the 2C+3 partial sums between the two passes, so the loss is that of
+        the single large batch and each rank's gradient is d(global loss)/d(local logits).
+        ddp_average: the parameter gradients will be AVERAGED over ranks afterwards (stock
+        DistributedDataParallel); the logit gradient is then multiplied by the world size so that the
+        averaged parameter gradient equals the single-large-batch gradient (it matters: Model.train clips
+        the gradient norm at 0.5 before the optimiser step, reference model.py:325)."""
         super(MultiLoss, self).__init__()
+        self.ddp_average = ddp_average
         self.n_classes = schema['n_classes']
         self.codes = schema['class_codes']
         self.categories = schema['class_labels']
@@ -81,7 +96,8 @@ class MultiLoss(torch.nn.Module):
         self.dsc = 0.
         self.fl = 0.
         self.distributed = distributed
-        self.device = torch.device(defaults.device)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
+            else torch.device(defaults.device)
         w = loss_weights.get('weights')
         if w is not None:
             self.weights = torch.tensor(np.array(w)).float().to(self.device)
@@ -112,8 +128,9 @@ class MultiLoss(torch.nn.Module):
 
     def _run(self, pred, target, ce, dice, focal):
         self._check(pred, target)
+        mult = pdist.world_size() if (self.distributed and self.ddp_average) else 1
         return _MultiLossFn.apply(pred.float(), target, self._class_w(pred), self._cfg(ce, dice, focal),
-                                  self.distributed)
+                                  self.distributed, mult)
 
     # -- reference API -----------------------------------------------------------------------
     def forward(self, pred, target):

@@ -195,10 +195,24 @@ class TiledSegmenter(object):
             out = self.segment_fitted(f, inject=self.n_inject if f.index == 0 else 0)
         return out
 
-    def run_host(self, images, masks=None, indices=None, distributed=False):
+    def run_host(self, images, masks=None, indices=None, distributed=False, global_offset=None, global_indices=None):
         """End-to-end pass from decoded host arrays (bench.py `e2e`, test.py's loop): host fit and
-        H2D of image k+1 overlap the device work of image k.  Returns (conf ndarray, results)."""
+        H2D of image k+1 overlap the device work of image k.  Returns (conf ndarray, results).
+
+        The coverage injection of Evaluator.validate (reference evaluate.py:172-174) is applied to the
+        image whose GLOBAL index is 0 and to no other, so the all-reduced matrix is the same for every
+        GPU count.  `images[i]` has global index `global_offset + i`; with `distributed=True` and no
+        explicit offset the caller is taken to hold a contiguous shard of equal size per rank
+        (offset = rank * len(images)); pass `global_offset`, or `global_indices` (one global index per
+        entry of `images`, e.g. dist.shard_indices(n) for a round-robin shard) for any other partition."""
         idx = list(range(len(images))) if indices is None else list(indices)
+        if global_indices is not None:
+            assert len(global_indices) == len(images)
+            self._gidx = [int(g) for g in global_indices]
+        else:
+            if global_offset is None:
+                global_offset = pdist.rank() * len(images) if distributed else 0
+            self._gidx = [int(global_offset) + i for i in range(len(images))]
         compute = torch.cuda.current_stream(self.device)
         prefetch = 3
         if idx and all(self.can_fit_on_device(images[i]) for i in idx):
@@ -206,7 +220,7 @@ class TiledSegmenter(object):
 
         def submit(k):
             i = idx[k]
-            return self.pool.submit(self.stage, images[i], None if masks is None else masks[i], i)
+            return self.pool.submit(self.stage, images[i], None if masks is None else masks[i], self._gidx[i])
 
         pending = [submit(k) for k in range(min(prefetch, len(idx)))]
         results = []
@@ -236,7 +250,7 @@ class TiledSegmenter(object):
         def submit(k):
             i = idx[k]
             after = done[k - prefetch] if k >= prefetch else None
-            staged.append(self.stage_device(images[i], None if masks is None else masks[i], i, after=after))
+            staged.append(self.stage_device(images[i], None if masks is None else masks[i], self._gidx[i], after=after))
 
         for k in range(min(prefetch, len(idx))):
             submit(k)

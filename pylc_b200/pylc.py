@@ -88,32 +88,46 @@ def train(args):
     model.meta.pretrained = getattr(args, 'pretrained', None) or False
     model.resume_checkpoint = bool(getattr(args, 'resume', False))
     model.distributed = world > 1
+    model.is_writer = rank == 0                      # one rank writes checkpoints / loss logs
     model.build()
     model.resume()
     if world > 1:                                    # stock DDP for the network gradients
-        model.net = torch.nn.parallel.DistributedDataParallel(model.net, device_ids=[local])
+        model.net = torch.nn.parallel.DistributedDataParallel(model.net, device_ids=[local] if torch.cuda.is_available() else None)
     model.net.train()
     if rank == 0:
         model.print_settings()
     for epoch in range(model.epoch, params.n_epochs - model.epoch):
         model.loss.lr += [(model.iter, model.get_lr())]
-        print('\nEpoch {} / {}   lr {}'.format(epoch + 1, params.n_epochs, model.get_lr()))
+        if rank == 0:
+            print('\nEpoch {} / {}   lr {}'.format(epoch + 1, params.n_epochs, model.get_lr()))
         if epoch == 0:
-            _validate(model, va_loader, rank, world)
+            _validate(model, va_loader, va_batches, rank, world)
         model.net.train()
         for i, (x, y) in enumerate(tr_loader):
+            if i >= rank_steps(tr_batches, world) * world:
+                break
             if i % world == rank:                    # batches round-robin across ranks
                 model.train(x, y)
-        _validate(model, va_loader, rank, world)
+        _validate(model, va_loader, va_batches, rank, world)
         if model.sched is not None:
             model.sched.step()
         model.epoch += 1
     return model
 
 
-def _validate(model, loader, rank, world):
+def rank_steps(n_batches, world):
+    """Steps every rank takes over `n_batches` batches dealt round-robin.  Each step issues collectives
+    (DDP's gradient all-reduce, the loss-partials all-reduce of MultiLoss(distributed=True)), so all
+    ranks must take the SAME number: the trailing n_batches mod world batches are dropped (the loaders
+    already drop the trailing partial batch, drop_last=True)."""
+    return n_batches // world
+
+
+def _validate(model, loader, n_batches, rank, world):
     model.net.eval()
     for i, (x, y) in enumerate(loader):
+        if i >= rank_steps(n_batches, world) * world:
+            break
         if i % world == rank:
             model.eval(x, y)
     model.log()

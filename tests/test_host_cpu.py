@@ -183,6 +183,38 @@ def test_dist_gloo_two_ranks(tmp_path):
     assert res == {"world": 2, "mine": [0, 2, 4, 6], "ok": True, "part": [1.5, 4.0], "t": 2.0}
 
 
+def test_rank_steps_equal_on_every_rank():
+    """Data-parallel training: every step issues collectives, so every rank must take the same number of
+    steps whatever the batch count (pylc.py train / _validate)."""
+    from pylc_b200.pylc import rank_steps
+    for world in (1, 2, 3, 4, 8):
+        for n_batches in range(0, 40):
+            steps = rank_steps(n_batches, world)
+            taken = [sum(1 for i in range(n_batches) if i < steps * world and i % world == r) for r in range(world)]
+            assert taken == [steps] * world
+            assert n_batches - steps * world < world          # at most world-1 trailing batches dropped
+
+
+def test_checkpoint_of_ddp_wrapped_net_has_bare_keys(tmp_path):
+    """Model files written from a DistributedDataParallel-wrapped network carry the bare network's keys
+    (reference checkpoint.py:53-66 format), and a 'module.'-prefixed dict still loads."""
+    import types
+    from pylc_b200.models.model import Checkpoint, strip_module_prefix
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 1), torch.nn.BatchNorm2d(4))
+    wrapper = torch.nn.Module()
+    wrapper.module = net                                   # what DDP / DataParallel look like from outside
+    optim = torch.optim.SGD(net.parameters(), lr=0.1)
+    model = types.SimpleNamespace(net=wrapper, optim=optim, meta={"id": "x"}, epoch=1, iter=2)
+    ck = Checkpoint("ddp_case", save_dir=str(tmp_path))
+    ck.save(model, is_best=True)
+    for f in (ck.checkpoint_file, ck.model_file):
+        keys = list(torch.load(f, weights_only=False)["model"].keys())
+        assert keys == list(net.state_dict().keys())
+    prefixed = {"module." + k: v for k, v in net.state_dict().items()}
+    assert list(strip_module_prefix(prefixed).keys()) == list(net.state_dict().keys())
+    assert strip_module_prefix(net.state_dict()) is not None and list(strip_module_prefix(net.state_dict())) == list(net.state_dict())
+
+
 def test_shard_indices_cover_everything_once():
     from pylc_b200.dist import shard_indices
     for world in (1, 2, 4, 8):
