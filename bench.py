@@ -332,6 +332,11 @@ def run_ours(args, rank, world, local_rank):
     mpx_job = (N_IMAGES if strong else N_IMAGES * world) * W_FULL * H_FULL / 1e6      # whole job, all ranks
     d2h = seg.C * seg.C * 8
 
+    def barrier_sync():
+        torch.cuda.synchronize()
+        pdist.barrier()
+        torch.cuda.synchronize()
+
     # ---- value: inputs resident in HBM -------------------------------------------------------
     stage = seg.stage_device if seg.can_fit_on_device(imgs[0]) else (lambda im, gt, index: seg.stage(im.numpy(), gt.numpy(), index=index))
     resident = [stage(imgs[i], masks[i], index=gidx[i]) for i in range(n_mine)]

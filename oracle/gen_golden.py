@@ -284,6 +284,35 @@ def gen_augment(ref, out):
         out["aug_%s_optim_probs" % name] = np.asarray(om['probs'])
 
 
+def gen_model(ref, out):
+    """Model-file boundary: the reference's DeepLabv3+/ResNet-101 state-dict keys and shapes, its output
+    on a seeded input with deterministic weights (oracle.fill_state_dict), and a model file whose `meta` is
+    the reference's own pickled config.Parameters (models/modules/checkpoint.py:53-66) with an empty
+    state dict -- what Model.load has to unpickle (models/model.py:78-121)."""
+    import pylc_oracle as orc
+    mm = ref_harness.load_model_modules()
+    with ref_harness.in_workdir(), ref_harness.quiet():
+        model = mm.model.Model()
+        model.meta.update(types.SimpleNamespace(ch=3, arch='deeplab', backbone='resnet', pretrained=False))
+        model.meta.px_mean, model.meta.px_std = [130.0, 140.0, 150.0], [25.0, 22.0, 19.0]
+        model.meta.weights = [1.0] * model.meta.n_classes
+        model.build()
+        net = model.net.cpu().eval()
+        sd = net.state_dict()
+        out["keys"] = np.array(list(sd.keys()))
+        out["shapes"] = np.array(json.dumps([list(v.shape) for v in sd.values()]))
+        out["dtypes"] = np.array([str(v.dtype) for v in sd.values()])
+        net.load_state_dict(orc.fill_state_dict(sd))
+        x = torch.randn(2, 3, 96, 80, generator=torch.Generator().manual_seed(123))
+        with torch.no_grad():
+            y = net(x)
+        out["x"] = x.numpy()
+        out["y"] = y.numpy()
+        torch.save({"model": {}, "optim": None, "meta": model.meta}, os.path.join(OUT, "ref_meta_model.pth"))
+        out["meta_id"] = np.array(str(model.meta.id))
+        out["meta_n_classes"] = np.array(model.meta.n_classes)
+
+
 def main():
     ref = ref_harness.load()
     # get_image() upscales anything whose short side is below defaults.tile_size
@@ -293,7 +322,7 @@ def main():
     for fname, fn in (("split", gen_split), ("encode", gen_encode), ("colourize", gen_colourize),
                       ("extract_profile", gen_extract_profile), ("fit", gen_fit),
                       ("reconstruct", gen_reconstruct), ("evaluate", gen_evaluate), ("loss", gen_loss),
-                      ("augment", gen_augment)):
+                      ("augment", gen_augment), ("model", gen_model)):
         out = {}
         fn(ref, out)
         path = os.path.join(OUT, fname + ".npz")

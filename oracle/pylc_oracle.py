@@ -643,3 +643,28 @@ def synth_mask(index, W, H, palette, skew=False, off_palette=0.001):
         xs = rng.integers(0, W, n_off)
         rgb[ys, xs] = rng.integers(0, 256, size=(n_off, 3), dtype=np.uint8)
     return rgb
+
+
+# ---------------------------------------------------------------------------------------------
+# model-file boundary (models/modules/checkpoint.py:53-66, models/model.py:78-121)
+# ---------------------------------------------------------------------------------------------
+
+def fill_state_dict(state_dict):
+    """Deterministic, name-independent fill of a network state dict (tensor i of the ordered dict is drawn
+    from generator seed i), used to give the reference DeepLab and ours THE SAME weights without shipping a
+    240 MB file: gen_golden.py runs the reference network with these weights and stores the output."""
+    out = type(state_dict)()
+    for i, (k, v) in enumerate(state_dict.items()):
+        g = torch.Generator().manual_seed(i)
+        if v.dtype in (torch.int64, torch.int32):
+            out[k] = torch.zeros_like(v)
+        elif k.endswith("running_var"):
+            out[k] = torch.rand(v.shape, generator=g) * 0.5 + 0.75
+        elif k.endswith("running_mean"):
+            out[k] = torch.randn(v.shape, generator=g) * 0.05
+        elif v.dim() <= 1:                       # BatchNorm affine terms, biases
+            out[k] = 1.0 + torch.randn(v.shape, generator=g) * 0.05 if k.endswith("weight") else torch.randn(v.shape, generator=g) * 0.05
+        else:                                    # convolution kernels: keep activations O(1) through 100 layers
+            fan_in = v[0].numel()
+            out[k] = torch.randn(v.shape, generator=g) * (1.6 / fan_in) ** 0.5
+    return out

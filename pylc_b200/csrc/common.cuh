@@ -37,6 +37,12 @@ struct ColourLut {
 };
 void build_colour_lut(const uint8_t *lut_rgb, int C, ColourLut *out);
 
+// TMA forms (gather_tma.cu).  Return PYLC_OK / a CUDA error after launching, or -1 when the form does not
+// apply to the arguments (alignment, geometry, driver without tensor maps): the caller then launches the
+// per-thread kernel.
+int launch_mask_gather_tma(const uint8_t *src, int H, int W, size_t pitch, int T, int S, int nH, int nW, const PaletteHash &ph, int C,
+                           uint8_t *dst, long long *px_dist, cudaStream_t st);
+
 #ifdef __CUDACC__
 
 __device__ __forceinline__ uint32_t encode_key(uint32_t key, const uint32_t *tab, uint32_t mul) {

@@ -137,14 +137,16 @@ def tile_gather_u8(src, H, W, ch, pitch, T, S, stats=False, out=None):
     return (tiles, stat) if stats else tiles
 
 
-def mask_gather_encode_hist(src, H, W, pitch, T, S, palette, hist=True, out=None):
-    """pylc_mask_gather_encode_hist: returns (tiles [n,T,T] u8, px_dist [n,C] i64 or None)."""
+def mask_gather_encode_hist(src, H, W, pitch, T, S, palette, hist=True, out=None, px_dist=None):
+    """pylc_mask_gather_encode_hist: returns (tiles [n,T,T] u8, px_dist [n,C] i64 or None).
+    `px_dist`: an existing [n,C] i64 tensor to ADD the histograms into (the C ABI accumulates)."""
     _need_cuda(src)
     pal, C = _lib.palette_array(palette)
     nH, nW = tile_grid(H, W, T, S)
     n = nH * nW
     tiles = out if out is not None else torch.empty((n, T, T), dtype=torch.uint8, device=src.device)
-    px_dist = torch.zeros((n, C), dtype=torch.int64, device=src.device) if hist else None
+    if px_dist is None:
+        px_dist = torch.zeros((n, C), dtype=torch.int64, device=src.device) if hist else None
     check(_lib.load().pylc_mask_gather_encode_hist(_p(src), H, W, pitch, T, S, pal, C, _p(tiles), _p(px_dist),
                                                    _stream()), "pylc_mask_gather_encode_hist")
     return tiles, px_dist

@@ -116,6 +116,45 @@ def test_mask_gather_encode_hist(ops, palettes, pk, H, W, T, S, skew):
     assert (ref == 1).sum() > 0
 
 
+@pytest.mark.parametrize("pattern", ["noise", "uniform", "stripes3", "stripes4", "sparse", "pairs"])
+@pytest.mark.parametrize("S,C", [(512, 9), (256, 9), (512, 20)])
+def test_mask_gather_run_patterns(ops, palettes, pattern, S, C):
+    """The TMA form encodes one pixel per 4-pixel group and re-encodes the groups whose 12 bytes are not
+    one repeated pixel (palette_warp.cuh): masks built to hit every branch -- pure noise (dense
+    fall-back), one colour (no fix-up), runs of 3 / 4 pixels (every / no group mixed), a few isolated
+    off-palette pixels (queue path), pixels that differ from the group's anchor in ONE channel only."""
+    rng = np.random.default_rng(11)
+    pal = palettes["a"] if C == 9 else rng.integers(0, 256, size=(C, 3)).tolist()
+    H, W, T = 1100, 1600, 512
+    pal_a = np.asarray(pal, dtype=np.uint8)
+    if pattern == "noise":
+        lab = rng.integers(0, C, size=(H, W))
+        mask = pal_a[lab]
+        mask[rng.random((H, W)) < 0.3] = rng.integers(0, 256, size=3, dtype=np.uint8)
+    elif pattern == "uniform":
+        mask = np.broadcast_to(pal_a[C - 1], (H, W, 3)).copy()
+    elif pattern in ("stripes3", "stripes4"):
+        k = int(pattern[-1])
+        mask = pal_a[(np.arange(W) // k + np.arange(H)[:, None]) % C]
+    elif pattern == "sparse":
+        mask = pal_a[orc.synth_labels(4, W, H, C, skew=False, block=200)]
+        ys, xs = rng.integers(0, H, 300), rng.integers(0, W, 300)
+        mask[ys, xs] = rng.integers(0, 256, size=(300, 3), dtype=np.uint8)
+    else:   # pairs: neighbours equal in two channels, off by one in the third -> class 1 next to a palette colour
+        mask = pal_a[orc.synth_labels(5, W, H, C, skew=False, block=64)]
+        ch = rng.integers(0, 3, size=(H, W))
+        hit = rng.random((H, W)) < 0.05
+        for k in range(3):
+            sel = hit & (ch == k)
+            mask[..., k][sel] ^= 1
+    mask = np.ascontiguousarray(mask)
+    d, pitch = ops.upload_image(mask)
+    tiles, px_dist = ops.mask_gather_encode_hist(d, H, W, pitch, T, S, pal)
+    ref = orc.class_encode(orc.split_tiles(mask, T, S), pal)
+    assert np.array_equal(tiles.cpu().numpy(), ref)
+    assert np.array_equal(px_dist.cpu().numpy(), orc.tile_histograms(ref, C))
+
+
 def test_mask_gather_wide_palette_duplicates_unaligned(ops):
     rng = np.random.default_rng(8)
     pal = rng.integers(0, 256, size=(20, 3)).tolist()

@@ -1,11 +1,14 @@
 """The CPU oracle (oracle/pylc_oracle.py) against vectors produced by the unmodified reference
 (oracle/gen_golden.py).  This is what pins the oracle: the reference ships no tests of its own."""
 import json
+import os
 
 import numpy as np
 import pytest
 
 import pylc_oracle as orc
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 @pytest.mark.parametrize("name", ["gray_s32", "gray_s16", "rgb_s32", "rgb_s16"])
@@ -180,3 +183,55 @@ def test_augment_optimize(golden, name):
     ref = g["aug_%s_optim" % name]
     assert [best["threshold"], best["rate_coef"], best["jsd"], best["m2"], best["n_samples"], best["aug_n_samples"]] == list(ref)
     assert np.array_equal(best["probs"], g["aug_%s_optim_probs" % name])
+
+
+# ---------------------------------------------------------------------------------------------
+# model-file boundary (models/modules/checkpoint.py:53-66, models/model.py:78-121)
+# ---------------------------------------------------------------------------------------------
+
+def test_deeplab_state_dict_manifest_equals_reference(golden):
+    """pylc_b200's DeepLabv3+/ResNet-101 has the reference network's state-dict keys, order, shapes and
+    dtypes (so a reference model file loads with strict keys, and ours loads in the reference)."""
+    import json
+    import torch
+    from pylc_b200.models.deeplab import DeepLab
+    g = golden("model")
+    sd = DeepLab(n_classes=int(g["meta_n_classes"])).state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]
+    assert [list(v.shape) for v in sd.values()] == json.loads(str(g["shapes"]))
+    assert [str(v.dtype) for v in sd.values()] == [str(d) for d in g["dtypes"]]
+
+
+def test_deeplab_forward_equals_reference_network(golden):
+    """Same weights (oracle.fill_state_dict, a deterministic fill), same input -> the reference network's
+    own output, recorded by gen_golden.py from the unmodified reference: the two networks are the same
+    function, not just the same parameter names."""
+    import torch
+    from pylc_b200.models.deeplab import DeepLab
+    g = golden("model")
+    net = DeepLab(n_classes=int(g["meta_n_classes"])).eval()
+    net.load_state_dict(orc.fill_state_dict(net.state_dict()))
+    with torch.no_grad():
+        y = net(torch.from_numpy(g["x"])).numpy()
+    want = g["y"]
+    assert y.shape == want.shape
+    assert np.abs(want).max() > 1e-3                         # a live output, not zeros
+    assert np.abs(y - want).max() <= 1e-5 * np.abs(want).max()
+
+
+def test_model_load_reads_reference_pickled_meta(tmp_path, monkeypatch):
+    """A model file written by the reference pickles `meta` as config.Parameters of ITS module tree
+    (checkpoint.py:53-66); Model.load resolves it to pylc_b200.config.Parameters and builds from it."""
+    import torch
+    from pylc_b200.config import Parameters
+    from pylc_b200.models.model import _load_model_file
+    path = os.path.join(GOLDEN, "ref_meta_model.pth")
+    data = _load_model_file(path, torch.device("cpu"))
+    assert set(data) >= {"model", "meta"}
+    meta = data["meta"]
+    assert isinstance(meta, Parameters)
+    assert meta.arch == "deeplab" and meta.backbone == "resnet" and meta.ch == 3 and meta.n_classes == 9
+    assert meta.px_mean == [130.0, 140.0, 150.0] and len(meta.palette_rgb) == 9
+    fresh = Parameters()
+    fresh.update(vars(meta))                                  # Model.load: self.meta.update(model_data["meta"])
+    assert fresh.class_codes == meta.class_codes

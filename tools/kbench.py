@@ -126,15 +126,31 @@ def main():
     nH, nW = ops.tile_grid(H, W, T, 512)
     m_out = torch.empty((nH * nW, T, T), dtype=torch.uint8, device="cuda")
     tile_px = nH * nW * T * T
+    m_hist = torch.zeros((nH * nW, C), dtype=torch.int64, device="cuda")
     report("mask_gather_encode_hist 6000x4000 S512 C9", tile_px * 4,
-           lambda: ops.mask_gather_encode_hist(d_mask, H, W, mp, T, 512, pal, out=m_out), "3 B in + 1 B out per tile px")
+           lambda: ops.mask_gather_encode_hist(d_mask, H, W, mp, T, 512, pal, out=m_out, px_dist=m_hist),
+           "3 B in + 1 B out per tile px; 50-px label blocks, 0.1 % off-palette pixels")
+    if not only or any("mask_gather" in o for o in only):
+        rng = np.random.default_rng(3)
+        noise = np.asarray(pal, dtype=np.uint8)[rng.integers(0, C, size=(H, W))]
+        d_noise, np_ = ops.upload_image(np.ascontiguousarray(noise))
+        report("mask_gather_encode_hist 6000x4000 S512 C9, worst case: per-pixel noise labels", tile_px * 4,
+               lambda: ops.mask_gather_encode_hist(d_noise, H, W, np_, T, 512, pal, out=m_out, px_dist=m_hist),
+               "run length 1: every 4-pixel group is re-encoded pixel by pixel")
+        del d_noise, noise
+        W2, H2 = 2000, 1500
+        d_small, sp = ops.upload_image(orc.synth_mask(1, W2, H2, pal, skew=True))
+        nH3, nW3 = ops.tile_grid(H2, W2, T, 512)
+        report("mask_gather_encode_hist 2000x1500 S512 C9 (6 tiles)", nH3 * nW3 * T * T * 4,
+               lambda: ops.mask_gather_encode_hist(d_small, H2, W2, sp, T, 512, pal, out=m_out[:nH3 * nW3], px_dist=m_hist[:nH3 * nW3]),
+               "configs[0] size; launch-bound")
     if not only or any("sweep" in o or "mask_gather" in o for o in only):
         sets = []
         for i in range(4):
             dm, dp = ops.upload_image(orc.synth_mask(i, W, H, pal, skew=True))
             sets.append((dm, dp, torch.empty_like(m_out)))
         report_sweep("mask_gather_encode_hist 6000x4000 S512 C9, sweep", tile_px * 4,
-                     [lambda d=d, q=q, o=o: ops.mask_gather_encode_hist(d, H, W, q, T, 512, pal, out=o) for d, q, o in sets],
+                     [lambda d=d, q=q, o=o: ops.mask_gather_encode_hist(d, H, W, q, T, 512, pal, out=o, px_dist=m_hist) for d, q, o in sets],
                      "3 B in + 1 B out per tile px")
         del sets
     enc_out = torch.empty((1, H, W), dtype=torch.uint8, device="cuda")
