@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PYLC_ABI_VERSION 1
+#define PYLC_ABI_VERSION 2
 #define PYLC_MAX_CLASSES 32
 
 #define PYLC_OK 0
@@ -272,6 +272,12 @@ PYLC_API int pylc_confusion_u8(const uint8_t *y_true, const uint8_t *y_pred, int
  *   logits  [B, C, HW] f32 ; target [B, HW], target_is_i64 ? int64 (the reference dtype) : u8
  *   class_w nullable [C] f32 device (CrossEntropyLoss weights; NULL = unweighted)
  *   n_px_total: pixels over ALL ranks (= B*HW on one GPU)
+ *   target_u8_out (reduce) / target_u8_ws (fwd_bwd): nullable [B*HW] u8 device workspace.  With int64
+ *     targets the reduce pass leaves a one-byte copy of them there, which the gradient pass reads
+ *     instead (1 B/px instead of 8): pass it to pylc_multiloss_grad as `target` with target_is_i64 = 0;
+ *     the single-launch form does so itself.  Ignored for u8 targets.
+ *   A target outside [0, C) makes every loss value and gradient of the batch NaN (the reference's
+ *     CrossEntropyLoss / one_hot raise, models/modules/loss.py:66-69,137); the host mirror raises.
  */
 typedef struct pylc_loss_cfg {
     float ce_weight, dice_weight, focal_weight; /* config.py:201-203, defaults 0.5 each */
@@ -282,7 +288,7 @@ typedef struct pylc_loss_cfg {
 
 PYLC_API int pylc_multiloss_reduce(const float *logits, const void *target, int target_is_i64, int B, int C,
                           int64_t HW, const float *class_w, const pylc_loss_cfg *cfg,
-                          double *partials, pylc_stream_t stream);
+                          double *partials, uint8_t *target_u8_out, pylc_stream_t stream);
 PYLC_API int pylc_multiloss_finalize(const double *partials, int C, int64_t n_px_total,
                             const pylc_loss_cfg *cfg, float *out4, pylc_stream_t stream);
 PYLC_API int pylc_multiloss_grad(const float *logits, const void *target, int target_is_i64, int B, int C,
@@ -303,7 +309,7 @@ PYLC_API int pylc_multiloss_grad(const float *logits, const void *target, int ta
 PYLC_API int pylc_multiloss_fwd_bwd(const float *logits, const void *target, int target_is_i64, int B, int C,
                            int64_t HW, const float *class_w, const pylc_loss_cfg *cfg,
                            double *partials, float grad_scale, const float *grad_scale_dev,
-                           float *grad, float *out4, pylc_stream_t stream);
+                           float *grad, float *out4, uint8_t *target_u8_ws, pylc_stream_t stream);
 PYLC_API int pylc_scale_unless_one_f32(float *data, int64_t n, const float *scale_dev, pylc_stream_t stream);
 
 #ifdef __cplusplus

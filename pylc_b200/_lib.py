@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpylc_b200.so")
 
 MAX_CLASSES = 32
 AREA_TAPS = 6
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class PylcError(RuntimeError):
@@ -66,12 +66,12 @@ SIGNATURES = {
                                                _u8p, _u8p, _u8p, _ptr]),
     "pylc_confusion_u8": (c_int, [_u8p, _u8p, c_int64, c_int, c_int, _ptr, _ptr]),
     "pylc_multiloss_reduce": (c_int, [_ptr, _ptr, c_int, c_int, c_int, c_int64, _ptr, POINTER(LossCfg),
-                                      _ptr, _ptr]),
+                                      _ptr, _u8p, _ptr]),
     "pylc_multiloss_finalize": (c_int, [_ptr, c_int, c_int64, POINTER(LossCfg), _ptr, _ptr]),
     "pylc_multiloss_grad": (c_int, [_ptr, _ptr, c_int, c_int, c_int, c_int64, _ptr, POINTER(LossCfg),
                                     _ptr, c_int64, c_float, _ptr, _ptr, _ptr]),
     "pylc_multiloss_fwd_bwd": (c_int, [_ptr, _ptr, c_int, c_int, c_int, c_int64, _ptr, POINTER(LossCfg),
-                                       _ptr, c_float, _ptr, _ptr, _ptr, _ptr]),
+                                       _ptr, c_float, _ptr, _ptr, _ptr, _u8p, _ptr]),
     "pylc_scale_unless_one_f32": (c_int, [_ptr, c_int64, _ptr, _ptr]),
 }
 

@@ -321,6 +321,10 @@ extern "C" int pylc_class_encode(const uint8_t *rgb, int n_img, int rows, int co
     const long long per_cta = (long long)kThreads * kUnitsPerThread;
     const unsigned grid = (unsigned)((a.total_units + per_cta - 1) / per_cta);
     cudaStream_t st = (cudaStream_t)stream;
+    if (layout == 0) {   // TMA form: 16-byte aligned rows, whole 16-pixel units per output row
+        rc = launch_class_encode_tma(rgb, a.rows, a.cols, pitch, ph, C, out, a.hist, st);
+        if (rc != -1) return rc;
+    }
 #define LAUNCH(L, NG, HS) class_encode_kernel<L, NG, HS><<<grid, kThreads, 0, st>>>(a, ph)
 #define LAUNCH_L(L)                                                                    \
     switch (hist ? counter_groups(C) : -1) {                                           \

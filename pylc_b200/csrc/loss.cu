@@ -22,7 +22,25 @@ struct LossArgs {
     int B, C;
     long long HW, units_per_img, total_units;
     pylc_loss_cfg cfg;
+    uint8_t *t8_out;       // nullable: the reduce pass leaves a u8 copy of the targets here (1 B/px instead of 8 in the second pass)
+    int t8_coherent;       // u8 targets were written earlier in THIS launch by other CTAs: read them through L2 (ld.global.cg)
 };
+
+__device__ __forceinline__ uint32_t ld_cg_u32(const void *p) {
+    uint32_t r;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_cg_u16(const void *p) {
+    unsigned short r;
+    asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_cg_u8(const void *p) {
+    uint32_t r;
+    asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
 
 template <int PX>
 struct PxVec;
@@ -35,15 +53,19 @@ struct PxVec<4> {
     static __device__ __forceinline__ void store(float *p, const float (&v)[4]) {
         st_stream_f4(p, make_float4(v[0], v[1], v[2], v[3]));
     }
-    static __device__ __forceinline__ void load_target(const void *t, int is_i64, long long idx, int (&o)[4]) {
+    static __device__ __forceinline__ void load_target(const void *t, int is_i64, int cg, long long idx, int (&o)[4]) {
         if (is_i64) {
             const longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(static_cast<const long long *>(t) + idx));
             const longlong2 b = __ldg(reinterpret_cast<const longlong2 *>(static_cast<const long long *>(t) + idx + 2));
             o[0] = (int)a.x; o[1] = (int)a.y; o[2] = (int)b.x; o[3] = (int)b.y;
         } else {
-            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(t) + idx));
+            const uint8_t *p = static_cast<const uint8_t *>(t) + idx;
+            const uint32_t w = cg ? ld_cg_u32(p) : __ldg(reinterpret_cast<const uint32_t *>(p));
             o[0] = w & 0xFF; o[1] = (w >> 8) & 0xFF; o[2] = (w >> 16) & 0xFF; o[3] = w >> 24;
         }
+    }
+    static __device__ __forceinline__ void store_t8(uint8_t *p, const int (&t)[4]) {
+        *reinterpret_cast<uint32_t *>(p) = (uint32_t)(t[0] & 0xFF) | ((uint32_t)(t[1] & 0xFF) << 8) | ((uint32_t)(t[2] & 0xFF) << 16) | ((uint32_t)t[3] << 24);
     }
 };
 template <>
@@ -55,24 +77,29 @@ struct PxVec<2> {
     static __device__ __forceinline__ void store(float *p, const float (&v)[2]) {
         asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
     }
-    static __device__ __forceinline__ void load_target(const void *t, int is_i64, long long idx, int (&o)[2]) {
+    static __device__ __forceinline__ void load_target(const void *t, int is_i64, int cg, long long idx, int (&o)[2]) {
         if (is_i64) {
             const longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(static_cast<const long long *>(t) + idx));
             o[0] = (int)a.x; o[1] = (int)a.y;
         } else {
-            const unsigned short w = __ldg(reinterpret_cast<const unsigned short *>(static_cast<const uint8_t *>(t) + idx));
+            const uint8_t *p = static_cast<const uint8_t *>(t) + idx;
+            const uint32_t w = cg ? ld_cg_u16(p) : (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(p));
             o[0] = w & 0xFF; o[1] = w >> 8;
         }
+    }
+    static __device__ __forceinline__ void store_t8(uint8_t *p, const int (&t)[2]) {
+        *reinterpret_cast<unsigned short *>(p) = (unsigned short)((t[0] & 0xFF) | ((t[1] & 0xFF) << 8));
     }
 };
 template <>
 struct PxVec<1> {
     static __device__ __forceinline__ void load(const float *p, float (&o)[1]) { o[0] = __ldg(p); }
     static __device__ __forceinline__ void store(float *p, const float (&v)[1]) { *p = v[0]; }
-    static __device__ __forceinline__ void load_target(const void *t, int is_i64, long long idx, int (&o)[1]) {
+    static __device__ __forceinline__ void load_target(const void *t, int is_i64, int cg, long long idx, int (&o)[1]) {
         o[0] = is_i64 ? (int)__ldg(static_cast<const long long *>(t) + idx)
-                      : (int)__ldg(static_cast<const uint8_t *>(t) + idx);
+                      : (cg ? (int)ld_cg_u8(static_cast<const uint8_t *>(t) + idx) : (int)__ldg(static_cast<const uint8_t *>(t) + idx));
     }
+    static __device__ __forceinline__ void store_t8(uint8_t *p, const int (&t)[1]) { *p = (uint8_t)t[0]; }
 };
 
 __device__ __forceinline__ float pow_gamma(float base, float gamma) {
@@ -156,6 +183,7 @@ __device__ __forceinline__ void loss_reduce_pass(const LossArgs &a, double *part
         accN[c] = 0;
     }
     float ce_num = 0.f, ce_den = 0.f, focal = 0.f;
+    bool bad = false;      // a target outside [0, C): the reference's CrossEntropyLoss / one_hot raise (loss.py:66-69,137)
     const float eps = a.cfg.eps, gamma = a.cfg.fl_gamma, alpha = a.cfg.fl_alpha;
 
     for (UnitWalk<false> w(a); w.left > 0; w.next()) {
@@ -166,9 +194,11 @@ __device__ __forceinline__ void loss_reduce_pass(const LossArgs &a, double *part
         for (int c = 0; c < CMAX; ++c)
             if (c < C) PxVec<PX>::load(p + (size_t)c * a.HW, z[c]);
         int t[PX];
-        PxVec<PX>::load_target(a.target, a.target_is_i64, b * a.HW + off, t);
+        PxVec<PX>::load_target(a.target, a.target_is_i64, 0, b * a.HW + off, t);
+        if (a.t8_out) PxVec<PX>::store_t8(a.t8_out + b * a.HW + off, t);
 #pragma unroll
         for (int j = 0; j < PX; ++j) {
+            bad |= (unsigned)t[j] >= (unsigned)C;
             float zc[CMAX], e[CMAX], m, s;
 #pragma unroll
             for (int c = 0; c < CMAX; ++c) zc[c] = z[c][j];
@@ -198,6 +228,9 @@ __device__ __forceinline__ void loss_reduce_pass(const LossArgs &a, double *part
         }
     }
 
+    // an out-of-range target poisons the CE numerator: every loss value and every gradient of this batch
+    // becomes NaN instead of silently using another class's weight (the host mirror turns it into an error)
+    if (bad) ce_num = __int_as_float(0x7FC00000);
     // block reduction: warp shuffles in f32, cross-warp in f64 shared atomics
     const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -274,7 +307,7 @@ __device__ __forceinline__ void loss_grad_pass(const LossArgs &a, const double *
         for (int c = 0; c < CMAX; ++c)
             if (c < C) PxVec<PX>::load(a.logits + base + (size_t)c * a.HW, z[c]);
         int t[PX];
-        PxVec<PX>::load_target(a.target, a.target_is_i64, b * a.HW + off, t);
+        PxVec<PX>::load_target(a.target, a.target_is_i64, a.t8_coherent, b * a.HW + off, t);
 #pragma unroll
         for (int j = 0; j < PX; ++j) {
             float zc[CMAX], e[CMAX], m, s;
@@ -350,6 +383,12 @@ __global__ void __launch_bounds__(kThreads, (PX == 4 || CMAX > 9) ? 2 : 3)
     __threadfence();
     cooperative_groups::this_grid().sync();
     if (out4 && blockIdx.x == 0 && threadIdx.x == 0) loss_finalize(partials, C_T > 0 ? C_T : a.C, n_px_total, a.cfg, out4);
+    if (a.t8_out) {            // the gradient pass reads the 1-byte targets the reduce pass left behind
+        a.target = a.t8_out;
+        a.target_is_i64 = 0;
+        a.t8_coherent = 1;
+        a.t8_out = nullptr;
+    }
     loss_grad_pass<C_T, CMAX, PX, true>(a, partials, n_px_total, grad_scale, grad_scale_dev, grad);
 }
 
@@ -369,7 +408,7 @@ __global__ void __launch_bounds__(kThreads) scale_unless_one_kernel(float *__res
 }
 
 static int fill_args(const float *logits, const void *target, int target_is_i64, int B, int C, int64_t HW,
-                     const float *class_w, const pylc_loss_cfg *cfg, LossArgs *a, int *px) {
+                     const float *class_w, const pylc_loss_cfg *cfg, LossArgs *a, int *px, uint8_t *t8_out = nullptr) {
     if (!logits || !target || !cfg || B < 1 || HW < 1) return PYLC_ERR_ARG;
     if (C < 1 || C > PYLC_MAX_CLASSES) return PYLC_ERR_CLASSES;
     if (HW > 0x7FFFFFFFll) return PYLC_ERR_GEOMETRY;   // 32-bit position inside an image (UnitWalk)
@@ -378,8 +417,11 @@ static int fill_args(const float *logits, const void *target, int target_is_i64,
     // contiguous run per plane either way, and nothing is demoted to local memory
     const int want = C <= 6 ? 4 : 2;
     const uintptr_t talign = (uintptr_t)(target_is_i64 ? 8 : 1) * want;
-    const bool vec = (HW % want == 0) && ((uintptr_t)logits % (4 * want) == 0) && ((uintptr_t)target % talign == 0) && C <= 16;
+    const bool vec = (HW % want == 0) && ((uintptr_t)logits % (4 * want) == 0) && ((uintptr_t)target % talign == 0) && C <= 16 &&
+                     ((uintptr_t)t8_out % want == 0);
     *px = vec ? want : 1;
+    a->t8_out = target_is_i64 ? t8_out : nullptr;      // u8 targets need no copy
+    a->t8_coherent = 0;
     a->logits = logits;
     a->target = target;
     a->class_w = class_w;
@@ -429,11 +471,11 @@ using namespace pylc;
 
 extern "C" int pylc_multiloss_reduce(const float *logits, const void *target, int target_is_i64, int B, int C,
                                      int64_t HW, const float *class_w, const pylc_loss_cfg *cfg, double *partials,
-                                     pylc_stream_t stream) {
+                                     uint8_t *target_u8_out, pylc_stream_t stream) {
     if (!partials) return PYLC_ERR_ARG;
     LossArgs a;
     int px;
-    int rc = fill_args(logits, target, target_is_i64, B, C, HW, class_w, cfg, &a, &px);
+    int rc = fill_args(logits, target, target_is_i64, B, C, HW, class_w, cfg, &a, &px, target_u8_out);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     DISPATCH_LOSS(loss_reduce_kernel, a, partials);
@@ -465,12 +507,13 @@ extern "C" int pylc_multiloss_finalize(const double *partials, int C, int64_t n_
 
 extern "C" int pylc_multiloss_fwd_bwd(const float *logits, const void *target, int target_is_i64, int B, int C, int64_t HW,
                                       const float *class_w, const pylc_loss_cfg *cfg, double *partials, float grad_scale,
-                                      const float *grad_scale_dev, float *grad, float *out4, pylc_stream_t stream) {
+                                      const float *grad_scale_dev, float *grad, float *out4, uint8_t *target_u8_ws,
+                                      pylc_stream_t stream) {
     if (!partials || !grad) return PYLC_ERR_ARG;
     if ((uintptr_t)grad % 16) return PYLC_ERR_ALIGN;
     LossArgs a;
     int px;
-    int rc = fill_args(logits, target, target_is_i64, B, C, HW, class_w, cfg, &a, &px);
+    int rc = fill_args(logits, target, target_is_i64, B, C, HW, class_w, cfg, &a, &px, target_u8_ws);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     long long n_px_total = (long long)B * HW;

@@ -110,11 +110,15 @@ constexpr uint32_t kVoidId = 0x0Fu;
 // `tab` holds key | byte << 24 per slot; the byte is what gets emitted (a class id, or class * C for the
 // confusion kernel).  COUNT: feed `gc` (GroupCounter) -- anchors with weight 4, re-encoded pixels with 1;
 // requires the emitted bytes to be class ids < 15.
+// `unit_ok`: bit j set = unit j of this lane lies inside the image (edge boxes of a TMA load are zero- or
+// padding-filled outside it): the bytes of an outside unit are still written (a clipped store drops them)
+// but never counted and never sent to the fix-up.
 // Must be called by all 32 lanes.  On return the output box holds the exact encode of all 32 NU units
 // once the warp's shared-memory writes are made visible (__syncwarp / __syncthreads by the caller).
 template <int NU, bool COUNT, class GC>
 __device__ __forceinline__ void warp_encode_units(uint32_t in_warp, uint32_t in_stride, uint32_t out_warp, uint32_t out_stride,
-                                                  uint32_t q_warp, uint32_t tab, uint32_t mul, uint32_t miss_e, GC &gc) {
+                                                  uint32_t q_warp, uint32_t tab, uint32_t mul, uint32_t miss_e, GC &gc,
+                                                  uint32_t unit_ok = 3u) {
     static_assert(NU == 1 || NU == 2, "group ids are one byte");
     constexpr int kDenseGroups = NU * 48;            // of NU * 128 groups per warp
     const uint32_t lane = threadIdx.x & 31;
@@ -130,9 +134,10 @@ __device__ __forceinline__ void warp_encode_units(uint32_t in_warp, uint32_t in_
             const uint32_t a = w[3 * k], b = w[3 * k + 1], c = w[3 * k + 2];
             e[k] = lookup_entry_s(a, tab, mul, miss_e);
             ow[k] = __byte_perm(e[k], 0, 0x3333);
-            const bool mixed = group_spread(a, b, c) != 0;
+            const bool ok = (unit_ok >> j) & 1u;
+            const bool mixed = ok && group_spread(a, b, c) != 0;
             flags |= mixed ? (1u << (4 * j + k)) : 0u;
-            if (COUNT) e[k] = mixed ? (kVoidId << 24) : e[k];
+            if (COUNT) e[k] = (mixed || !ok) ? (kVoidId << 24) : e[k];
         }
         sts128(out_warp + (uint32_t)j * out_stride + lane * 16u, make_uint4(ow[0], ow[1], ow[2], ow[3]));
         if (COUNT) aw[j] = pack_top_bytes(e[0], e[1], e[2], e[3]);

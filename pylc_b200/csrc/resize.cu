@@ -122,6 +122,137 @@ __global__ void __launch_bounds__(kAreaThreads) area_resize_kernel(AreaArgs a) {
     }
 }
 
+
+// ---- two-pass form for scale factors below 2 (the fit-resize case: 1.0 <= scale < 2) -------------------
+// With at most 3 source cells per destination cell and axis the filter is a fixed 3 x 3 tap structure:
+// missing taps have weight 0 in the tables, and adding `0 * x` is an exact no-op in OpenCV's float
+// sequence (all terms are >= 0), so the kernel has no tap-count predicates at all.
+//   stage  the CTA's source patch -> shared memory (16-byte loads, as above)
+//   H      buf[r][e] = ((S*a0) + S*a1) + S*a2 for every staged source row r and every element e = (dx, c)
+//          of the CTA's 384 destination bytes per row -- each horizontal sum is computed ONCE (OpenCV
+//          recomputes it for every destination row that uses the source row, to the same value).
+//          `S * a` is one FFMA on the bit pattern 2^23 + S with addend -(2^23 * a): the exact product
+//          rounded once, i.e. what __fmul_rn((float)S, a) gives, without the int -> float conversion.
+//   V      a thread walks its three elements down the destination rows with a rolling window of three
+//          horizontal sums in registers (consecutive destination rows start 1 or 2 source rows apart), so a
+//          destination byte costs ~1.2 shared-memory loads, 3 FMUL + 2 FADD, one saturating convert, one store.
+constexpr int kArea2Elems = 384;     // destination bytes per row and CTA: 128 RGB columns or 384 gray columns
+constexpr int kArea2NE = kArea2Elems / kAreaThreads;
+
+template <int CN>
+__global__ void __launch_bounds__(kAreaThreads) area_resize_lt2_kernel(AreaArgs a) {
+    extern __shared__ __align__(16) uint8_t s_dyn2[];
+    // layout: [stage_rows + 1][kArea2Elems] float sums | [rows_cta] uint4 {r0, beta0, beta1, beta2} | staged bytes
+    float *s_buf = reinterpret_cast<float *>(s_dyn2);
+    uint4 *s_row = reinterpret_cast<uint4 *>(s_dyn2 + (size_t)(a.stage_rows + 1) * kArea2Elems * 4);
+    uint8_t *s_src = reinterpret_cast<uint8_t *>(s_row + a.rows_cta);
+    const int dx0 = blockIdx.x * a.cols_cta, dx1 = min(a.dw, dx0 + a.cols_cta);
+    const int dy0 = blockIdx.y * a.rows_cta, dy1 = min(a.dh, dy0 + a.rows_cta);
+    const int x_lo = __ldg(a.xs + dx0), x_hi = __ldg(a.xs + dx1 - 1) + __ldg(a.xn + dx1 - 1);
+    const int s_lo = __ldg(a.ys + dy0), s_hi = __ldg(a.ys + dy1 - 1) + __ldg(a.yn + dy1 - 1);
+    const int nrows = s_hi - s_lo, row_bytes = (x_hi - x_lo) * CN;
+    const int cpr = (row_bytes + 15 + 15) / 16;
+    if (nrows > a.stage_rows || cpr * 16 > a.row_stride) __trap();   // the host sizes the patch; never taken
+    const uintptr_t src0 = (uintptr_t)a.src, src_end = src0 + a.src_bytes;
+    {
+        int r = threadIdx.x / cpr, ck = threadIdx.x - r * cpr;
+        const int dr = kAreaThreads / cpr, dck = kAreaThreads - dr * cpr;
+        for (; r < nrows; r += dr, ck += dck) {
+            if (ck >= cpr) {
+                ck -= cpr;
+                if (++r >= nrows) break;
+            }
+            const uintptr_t row_addr = src0 + (size_t)(s_lo + r) * a.src_pitch + (size_t)x_lo * CN;
+            const uintptr_t g = (row_addr & ~(uintptr_t)15) + 16u * ck;
+            uint8_t *d = s_src + r * a.row_stride + 16 * ck;
+            if (g >= src0 && g + 16 <= src_end) {
+                *reinterpret_cast<uint4 *>(d) = ld_stream16(reinterpret_cast<const void *>(g));
+            } else {
+                for (int i = 0; i < 16; ++i) d[i] = (g + i >= src0 && g + i < src_end) ? __ldg(reinterpret_cast<const uint8_t *>(g + i)) : 0;
+            }
+        }
+    }
+    for (int i = threadIdx.x; i < dy1 - dy0; i += kAreaThreads) {
+        const float *w = a.ya + (size_t)(dy0 + i) * PYLC_AREA_TAPS;
+        s_row[i] = make_uint4((uint32_t)(__ldg(a.ys + dy0 + i) - s_lo), __float_as_uint(__ldg(w)), __float_as_uint(__ldg(w + 1)),
+                              __float_as_uint(__ldg(w + 2)));
+    }
+    // per-element column tables (registers): start byte inside a staged row, three weights and their addends
+    uint32_t sb[kArea2NE];
+    float al[kArea2NE][3], ad[kArea2NE][3];
+    bool on[kArea2NE];
+#pragma unroll
+    for (int i = 0; i < kArea2NE; ++i) {
+        const int e = threadIdx.x + i * kAreaThreads;
+        const int dxl = e / CN, c = e - dxl * CN, dx = dx0 + dxl;
+        on[i] = dxl < a.cols_cta && dx < dx1;
+        const int dxs = on[i] ? dx : dx0;
+        sb[i] = (uint32_t)(__ldg(a.xs + dxs) - x_lo) * CN + c;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            al[i][k] = __ldg(a.xa + (size_t)dxs * PYLC_AREA_TAPS + k);
+            ad[i][k] = -8388608.f * al[i][k];          // exact: a power-of-two multiple
+        }
+    }
+    __syncthreads();
+
+    // ---- H: one horizontal sum per (staged row, element); row `nrows` is a finite don't-care for 0-weight taps
+    const uint32_t lo0 = (uint32_t)((src0 + (size_t)s_lo * a.src_pitch + (size_t)x_lo * CN) & 15), plo = (uint32_t)(a.src_pitch & 15);
+    const uint32_t src_s = (uint32_t)__cvta_generic_to_shared(s_src), buf_s = (uint32_t)__cvta_generic_to_shared(s_buf);
+#pragma unroll 2
+    for (int r = 0; r <= nrows; ++r) {
+        const uint32_t row = src_s + (uint32_t)r * (uint32_t)a.row_stride + ((lo0 + (uint32_t)r * plo) & 15u);
+#pragma unroll
+        for (int i = 0; i < kArea2NE; ++i) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                uint32_t b;
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(row + sb[i] + (uint32_t)(k * CN)));
+                const float prod = __fmaf_rn(__uint_as_float(0x4B000000u | b), al[i][k], ad[i][k]);   // == __fmul_rn((float)b, alpha)
+                acc = k == 0 ? prod : __fadd_rn(acc, prod);
+            }
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(buf_s + (uint32_t)(r * kArea2Elems + threadIdx.x + i * kAreaThreads) * 4u), "f"(acc) : "memory");
+        }
+    }
+    __syncthreads();
+
+    // ---- V: rolling three-row window per element ---------------------------------------------------------
+    float w0[kArea2NE], w1[kArea2NE], w2[kArea2NE];
+    int r_prev = -4;
+    uint8_t *d = a.dst + (size_t)dy0 * a.dst_pitch + (size_t)dx0 * CN + threadIdx.x;
+    const uint32_t row_s = (uint32_t)__cvta_generic_to_shared(s_row);
+    for (int i = 0; i < dy1 - dy0; ++i, d += a.dst_pitch) {
+        uint4 rw;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rw.x), "=r"(rw.y), "=r"(rw.z), "=r"(rw.w) : "r"(row_s + 16u * i));
+        const int r0 = (int)rw.x, adv = r0 - r_prev;
+        r_prev = r0;
+        const float b0 = __uint_as_float(rw.y), b1 = __uint_as_float(rw.z), b2 = __uint_as_float(rw.w);
+        const uint32_t base = buf_s + (uint32_t)(r0 * kArea2Elems + threadIdx.x) * 4u;
+#pragma unroll
+        for (int e = 0; e < kArea2NE; ++e) {
+            const uint32_t p = base + (uint32_t)(e * kAreaThreads) * 4u;
+            if (adv == 1) {
+                w0[e] = w1[e];
+                w1[e] = w2[e];
+            } else if (adv == 2) {
+                w0[e] = w2[e];
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w1[e]) : "r"(p + kArea2Elems * 4u));
+            } else {
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w0[e]) : "r"(p));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w1[e]) : "r"(p + kArea2Elems * 4u));
+            }
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w2[e]) : "r"(p + 2u * kArea2Elems * 4u));
+            float sum = __fmul_rn(b0, w0[e]);
+            sum = __fadd_rn(sum, __fmul_rn(b1, w1[e]));
+            sum = __fadd_rn(sum, __fmul_rn(b2, w2[e]));
+            uint32_t o;
+            asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(o) : "f"(sum));      // saturate_cast<uchar>(cvRound(sum))
+            if (on[e]) d[e * kAreaThreads] = (uint8_t)o;
+        }
+    }
+}
+
 }  // namespace pylc
 
 using namespace pylc;
@@ -184,9 +315,24 @@ extern "C" int pylc_fit_resize_area_u8(const uint8_t *src, int H, int W, int ch,
     a.src = src; a.src_pitch = src_pitch; a.src_bytes = (size_t)(H - 1) * src_pitch + (size_t)W * ch;
     a.dst = dst; a.dst_pitch = dst_pitch; a.dw = w; a.dh = h;
     a.xs = x_start; a.xn = x_count; a.xa = x_weights; a.ys = y_start; a.yn = y_count; a.ya = y_weights;
+    const double sx = (double)W / w, sy = (double)H / h;
+    if (sx < 2.0 && sy < 2.0) {
+        // two-pass form: 384 destination bytes per row and CTA, up to 16 destination rows
+        a.cols_cta = kArea2Elems / ch;
+        a.rows_cta = 16;
+        a.row_stride = (((int)ceil(a.cols_cta * sx) + 2) * ch + 30 + 15) & ~15;
+        a.stage_rows = (int)ceil(a.rows_cta * sy) + 2;
+        const size_t smem = (size_t)(a.stage_rows + 1) * kArea2Elems * 4 + (size_t)a.rows_cta * 16 + (size_t)(a.stage_rows + 1) * a.row_stride + 64;   // + slack: 0-weight taps read a few bytes past the last row
+        const dim3 grid((unsigned)((w + a.cols_cta - 1) / a.cols_cta), (unsigned)((h + a.rows_cta - 1) / a.rows_cta));
+        cudaError_t e = ch == 1 ? cudaFuncSetAttribute(area_resize_lt2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                : cudaFuncSetAttribute(area_resize_lt2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        if (ch == 1) area_resize_lt2_kernel<1><<<grid, kAreaThreads, smem, (cudaStream_t)stream>>>(a);
+        else area_resize_lt2_kernel<3><<<grid, kAreaThreads, smem, (cudaStream_t)stream>>>(a);
+        return finish_launch();
+    }
     // size the CTA's destination patch so that its source footprint fits the staging buffer:
     // a run of n destination cells covers at most n*scale + 2 source cells
-    const double sx = (double)W / w, sy = (double)H / h;
     int cols = (int)floor(((kAreaRowBytes - 30) / ch - 2) / sx);
     int rows = (int)floor((kAreaMaxRows - 2) / sy);
     a.cols_cta = cols > kAreaThreads ? kAreaThreads : (cols < 1 ? 1 : cols);

@@ -23,6 +23,8 @@ state_dict.  Outputs match `net.eval()(x)` to fp32 rounding of the folded weight
 bit, so the pipeline uses it only when asked (`TiledSegmenter(fuse_network=True)`); parity tests of
 the custom kernels never depend on it.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -42,31 +44,73 @@ def fold_conv_bn(conv, bn):
     return w.float(), b.float()
 
 
+# Per layer and input shape, the plan times its two library routes once and keeps the faster:
+#   0  torch.cudnn_convolution_relu / _add_relu: one fused cuDNN call, engine chosen by cuDNN's heuristic
+#   1  F.conv2d (engine chosen by torch.backends.cudnn.benchmark when that is on) + in-place add / ReLU
+# Measured on B200 (round 1 launch list): the heuristic of route 0 puts one ASPP dilated 3x3 branch on an
+# sm80 implicit-GEMM kernel with two layout conversions (1.94 ms against 0.53 ms for its sibling branches);
+# route 1 finds the sm100 kernel.  Both are stock library convolutions on the same folded weights.
+AUTOTUNE = os.environ.get("PYLC_CONV_AUTOTUNE", "1") != "0"
+
+
 class _Conv(object):
     """One folded convolution with an optional fused ReLU / residual add."""
-    __slots__ = ("w", "b", "stride", "padding", "dilation", "relu")
+    __slots__ = ("w", "b", "stride", "padding", "dilation", "relu", "choice")
 
     def __init__(self, conv, bn, relu, channels_last):
         w, b = fold_conv_bn(conv, bn)
         self.w = w.contiguous(memory_format=torch.channels_last) if channels_last else w.contiguous()
         self.b = b.contiguous()
         self.stride, self.padding, self.dilation, self.relu = conv.stride, conv.padding, conv.dilation, relu
+        self.choice = {}
 
     def to(self, dtype):
         self.w = self.w.to(dtype)
         self.b = self.b.to(dtype) if self.b is not None else None
         return self
 
-    def __call__(self, x, residual=None):
-        if x.is_cuda and self.relu:
-            if residual is not None:
-                return torch.cudnn_convolution_add_relu(x, self.w, residual, 1.0, self.b, self.stride, self.padding,
-                                                        self.dilation, 1)
-            return torch.cudnn_convolution_relu(x, self.w, self.b, self.stride, self.padding, self.dilation, 1)
+    def _fused(self, x, residual):
+        if residual is not None:
+            return torch.cudnn_convolution_add_relu(x, self.w, residual, 1.0, self.b, self.stride, self.padding,
+                                                    self.dilation, 1)
+        return torch.cudnn_convolution_relu(x, self.w, self.b, self.stride, self.padding, self.dilation, 1)
+
+    def _plain(self, x, residual):
         y = F.conv2d(x, self.w, self.b, self.stride, self.padding, self.dilation)
         if residual is not None:
-            y = y + residual
-        return F.relu(y) if self.relu else y
+            y.add_(residual)
+        return y.relu_() if self.relu else y
+
+    def _pick(self, x, residual):
+        """Time both routes on this very input (CUDA events, after a warm-up each)."""
+        best, best_ms = 0, None
+        for route, fn in enumerate((self._fused, self._plain)):
+            try:
+                for _ in range(2):
+                    fn(x, residual)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    fn(x, residual)
+                e1.record()
+                e1.synchronize()
+                ms = e0.elapsed_time(e1)
+            except RuntimeError:
+                continue
+            if best_ms is None or ms < 0.97 * best_ms:      # the fused call keeps ties
+                best, best_ms = route, ms
+        return best
+
+    def __call__(self, x, residual=None):
+        if x.is_cuda and self.relu:
+            if not AUTOTUNE:
+                return self._fused(x, residual)
+            key = (tuple(x.shape), x.dtype, residual is not None)
+            route = self.choice.get(key)
+            if route is None:
+                route = self.choice[key] = self._pick(x, residual)
+            return self._fused(x, residual) if route == 0 else self._plain(x, residual)
+        return self._plain(x, residual)
 
 
 class FusedDeepLab(object):
@@ -131,7 +175,7 @@ class FusedDeepLab(object):
                 w4[:, (py * 2 + px) * 3:(py * 2 + px) * 3 + 3] = w8[:, :, py::2, px::2]
         s = _Conv.__new__(_Conv)
         s.w = w4.contiguous(memory_format=torch.channels_last)
-        s.b, s.stride, s.padding, s.dilation, s.relu = stem.b, (1, 1), (0, 0), (1, 1), True
+        s.b, s.stride, s.padding, s.dilation, s.relu, s.choice = stem.b, (1, 1), (0, 0), (1, 1), True, {}
         return s
 
     def _cast(self, conv):

@@ -187,6 +187,9 @@ class Model:
             schema={'n_classes': self.meta.n_classes, 'class_codes': self.meta.class_codes,
                     'class_labels': self.meta.class_labels},
             distributed=self.distributed, ddp_average=self.distributed)
+        # no host sync per training step: a target outside [0, n_classes) turns the step's loss values into
+        # NaN on the device, and log() -- the first place they are read -- raises
+        self.crit.validate_targets = False
         if self.track:
             self.checkpoint = Checkpoint(self.meta.id, self.meta.save_dir)      # every rank may resume from it
         if self.track and self.is_writer:
@@ -300,6 +303,9 @@ class Model:
     # ---- bookkeeping --------------------------------------------------------------------------
     def log(self):
         self.loss.log(self.iter, self.net.training)
+        if self.loss.avg_ce != self.loss.avg_ce:
+            raise FloatingPointError("loss is NaN: a target outside [0, n_classes) (the reference's CrossEntropyLoss "
+                                     "raises on it) or non-finite logits")
         self.loss.save()
 
     def save(self):
@@ -348,6 +354,7 @@ class Model:
 class _NullLoss(object):
     """Loss log that keeps nothing on disk (track=False)."""
     is_best = False
+    avg_ce = 0.
 
     def __init__(self):
         self.intv, self.lr = [], []

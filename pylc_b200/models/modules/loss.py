@@ -47,13 +47,18 @@ class _MultiLossFn(torch.autograd.Function):
             ctx.save_for_backward(pred, target, partials)
             ctx.mark_non_differentiable(target)
             return out
-        partials = ops.multiloss_reduce(pred, target, cfg, class_w)
+        # int64 targets (the reference dtype) are copied to one byte per pixel by the reduce pass; the
+        # gradient pass, and autograd's saved tensors, keep the 8x smaller copy
+        t8 = None
+        if ctx.needs_input_grad[0] and target.dtype == torch.int64:
+            t8 = torch.empty((target.numel(),), dtype=torch.uint8, device=target.device)
+        partials = ops.multiloss_reduce(pred, target, cfg, class_w, target_u8_out=t8)
         n_px = target.numel()
         if distributed and pdist.world_size() > 1:
             pdist.all_reduce_(partials)
             n_px *= pdist.world_size()
         out = ops.multiloss_finalize(partials, C, n_px, cfg)
-        ctx.save_for_backward(pred, target, partials)
+        ctx.save_for_backward(pred, target if t8 is None else t8.view(target.shape), partials)
         ctx.n_px = n_px
         ctx.mark_non_differentiable(target)
         return out
@@ -84,6 +89,9 @@ class MultiLoss(torch.nn.Module):
         the gradient norm at 0.5 before the optimiser step, reference model.py:325)."""
         super(MultiLoss, self).__init__()
         self.ddp_average = ddp_average
+        # True: every call reads the loss back (one 4-byte D2H) and raises on an out-of-range target like the
+        # reference; False: no host sync -- the values are NaN instead (Model.log raises when it reads them)
+        self.validate_targets = True
         self.n_classes = schema['n_classes']
         self.codes = schema['class_codes']
         self.categories = schema['class_labels']
@@ -129,8 +137,16 @@ class MultiLoss(torch.nn.Module):
     def _run(self, pred, target, ce, dice, focal):
         self._check(pred, target)
         mult = pdist.world_size() if (self.distributed and self.ddp_average) else 1
-        return _MultiLossFn.apply(pred.float(), target, self._class_w(pred), self._cfg(ce, dice, focal),
-                                  self.distributed, mult)
+        out = _MultiLossFn.apply(pred.float(), target, self._class_w(pred), self._cfg(ce, dice, focal),
+                                 self.distributed, mult)
+        if self.validate_targets and bool(torch.isnan(out[0])):
+            # the kernels poison the batch with NaN when a target lies outside [0, n_classes) -- where the
+            # reference's CrossEntropyLoss / one_hot raise (loss.py:66-69,137)
+            if int(target.min()) < 0 or int(target.max()) >= self.n_classes:
+                raise IndexError("Target {} is out of bounds.".format(
+                    int(target.max()) if int(target.max()) >= self.n_classes else int(target.min())))
+            raise FloatingPointError("MultiLoss is NaN: non-finite logits")
+        return out
 
     # -- reference API -----------------------------------------------------------------------
     def forward(self, pred, target):

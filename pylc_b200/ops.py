@@ -381,12 +381,16 @@ def _loss_inputs(logits, target):
     return logits, target, is_i64, B, C, HW
 
 
-def multiloss_reduce(logits, target, cfg, class_w=None, partials=None):
+def multiloss_reduce(logits, target, cfg, class_w=None, partials=None, target_u8_out=None):
+    """pylc_multiloss_reduce.  `target_u8_out`: optional [B*HW] u8 CUDA tensor that receives a one-byte copy of
+    int64 targets -- hand THAT to multiloss_grad as the target (it then reads 1 B/px instead of 8)."""
     logits, target, is_i64, B, C, HW = _loss_inputs(logits, target)
     if partials is None:
         partials = torch.zeros((2 * C + 3,), dtype=torch.float64, device=logits.device)
+    if target_u8_out is not None and (target_u8_out.dtype != torch.uint8 or target_u8_out.numel() != B * HW):
+        raise PylcError("target_u8_out must be a uint8 tensor of B*HW elements")
     check(_lib.load().pylc_multiloss_reduce(_p(logits), _p(target), is_i64, B, C, HW, _p(class_w), ctypes.byref(cfg),
-                                            _p(partials), _stream()), "pylc_multiloss_reduce")
+                                            _p(partials), _p(target_u8_out), _stream()), "pylc_multiloss_reduce")
     return partials
 
 
@@ -409,15 +413,23 @@ def multiloss_grad(logits, target, cfg, partials, n_px_total, class_w=None, grad
     return grad
 
 
-def multiloss_fwd_bwd(logits, target, cfg, class_w=None, grad_scale=1.0, out=None, partials=None):
-    """pylc_multiloss_fwd_bwd: one cooperative launch.  Returns (out4 = loss/ce/dice/focal, grad, partials)."""
+def multiloss_fwd_bwd(logits, target, cfg, class_w=None, grad_scale=1.0, out=None, partials=None, target_u8_ws=None,
+                      use_u8_ws=True):
+    """pylc_multiloss_fwd_bwd: one cooperative launch.  Returns (out4 = loss/ce/dice/focal, grad, partials).
+    With int64 targets a [B*HW] u8 workspace (`target_u8_ws`, allocated here unless given or `use_u8_ws` is
+    off) carries the targets from the reduce pass to the gradient pass: 1 B/px instead of 8 on the second read."""
     logits, target, is_i64, B, C, HW = _loss_inputs(logits, target)
     grad = out if out is not None else torch.empty_like(logits)
     if partials is None:
         partials = torch.zeros((2 * C + 3,), dtype=torch.float64, device=logits.device)
+    if is_i64 and use_u8_ws and target_u8_ws is None:
+        target_u8_ws = torch.empty((B * HW,), dtype=torch.uint8, device=logits.device)
+    if not (is_i64 and use_u8_ws):
+        target_u8_ws = None
     out4 = torch.empty((4,), dtype=torch.float32, device=logits.device)
     check(_lib.load().pylc_multiloss_fwd_bwd(_p(logits), _p(target), is_i64, B, C, HW, _p(class_w), ctypes.byref(cfg),
-                                             _p(partials), float(grad_scale), None, _p(grad), _p(out4), _stream()),
+                                             _p(partials), float(grad_scale), None, _p(grad), _p(out4), _p(target_u8_ws),
+                                             _stream()),
           "pylc_multiloss_fwd_bwd")
     return out4, grad, partials
 

@@ -14,10 +14,12 @@ pytestmark = pytest.mark.gpu
 
 STITCH_RTOL = 1e-5     # north_star: stitched probabilities within 1e-5 relative (fp32)
 LOSS_RTOL = 1e-4       # north_star: loss values within 1e-4 relative
-# Labels must agree wherever the fp32 reference's top-1 beats top-2 by more than this.  The small-size
-# tests use 1e-6; over 20 Mpx two fp32 softmax implementations differ by up to ~1e-6 on edge-block
-# probabilities close to 1, so the full-size bar is a few ulp wider.
-ARGMAX_MARGIN = 4e-6
+# Labels must agree wherever the fp32 reference's top-1 beats top-2 by more than ARGMAX_MARGIN (the bar of
+# the small-size tests).  Over 20 Mpx two fp32 softmax implementations differ by up to ~1e-6 on edge-block
+# probabilities close to 1 (8 ulp at 1.0), so a handful of pixels whose margin lies in
+# (ARGMAX_MARGIN, ARGMAX_MARGIN_HARD] may flip; the test counts them (<= 1 per Mpx) and allows none above.
+ARGMAX_MARGIN = 1e-6
+ARGMAX_MARGIN_HARD = 4e-6
 
 W_FULL, H_FULL = 6000, 4000          # BASELINE configs[4]
 W_FIT, H_FIT = 5632, 3584            # its adjust_to_tile geometry: 13 x 21 tiles at stride 256
@@ -143,9 +145,11 @@ def test_stitch_273_tiles_vs_torch_closed_form(ops, palettes):
     err = (stitched - ref).abs() - STITCH_RTOL * ref.abs()
     assert float(err.max()) <= 1e-7
     top2 = ref.topk(2, dim=0).values
-    decided = (top2[0] - top2[1]) > ARGMAX_MARGIN
-    assert torch.equal(labels[decided], ref.argmax(0).to(torch.uint8)[decided])
-    assert float(decided.float().mean()) > 0.999
+    margin = top2[0] - top2[1]
+    differs = labels != ref.argmax(0).to(torch.uint8)
+    assert not bool((differs & (margin > ARGMAX_MARGIN_HARD)).any())
+    assert int((differs & (margin > ARGMAX_MARGIN)).sum()) <= labels.numel() // 1_000_000
+    assert float((margin > ARGMAX_MARGIN).float().mean()) > 0.999
     # colourise is a table look-up of the labels
     lut = torch.tensor(palettes["a"], dtype=torch.uint8, device="cuda")
     assert torch.equal(rgb, lut[labels.long()])
@@ -207,6 +211,66 @@ def test_confusion_6000x4000_marginals_and_counts(ops, palettes):
     yt_o, yp_o = orc.inject_coverage(orc.class_encode_hwc(mask[:rows], pal), pred[:rows].cpu().numpy(), C)
     part = ops.confusion_u8(gt[:rows].contiguous(), pred[:rows].contiguous(), C, n_inject=C)
     assert np.array_equal(part.cpu().numpy(), orc.confusion_counts(yt_o, yp_o, C))
+
+
+def test_pipeline_one_6000x4000_gray_image(ops, palettes):
+    """BASELINE configs[4] geometry through the whole pipeline (TiledSegmenter.run_host, fused plan): one
+    6000x4000 grayscale photograph -> fitted 5632x3584 -> 273 tiles -> labels -> full-resolution confusion
+    matrix.  Checked by composition: the label map is the closed-form stitch of the very logits the plan
+    produced, the full-size prediction is OpenCV's nearest-neighbour map of the labels, and the matrix is the
+    bincount of (encoded ground truth, prediction) with one coverage injection."""
+    from pylc_b200.config import defaults
+    from pylc_b200.models.model import Model
+    from pylc_b200.pipeline import TiledSegmenter
+    pal = palettes["a"]
+    C = len(pal)
+    torch.manual_seed(0)
+    model = Model()
+    model.track = False
+    model.update_meta({"ch": 1, "arch": "deeplab", "backbone": "resnet", "pretrained": False, "px_mean": [120.0],
+                       "px_std": [40.0], "weights": [1.0] * C, "normalize_default": False, "weighted": False,
+                       "schema": defaults.schema})
+    model.build()
+    img = orc.synth_image(17, W_FULL, H_FULL, 1)
+    gt = orc.synth_mask(17, W_FULL, H_FULL, pal)
+    seg = TiledSegmenter(model, batch_tiles=39, keep_masks=True, fuse_network=True)
+    assert seg.can_fit_on_device(img)
+    conf, results = seg.run_host([img], [gt])
+    res = results[0]
+    labels, pred = res["labels"], res["pred_full"]
+    assert tuple(labels.shape) == (H_FIT, W_FIT) and tuple(pred.shape) == (H_FULL, W_FULL)
+    # the same plan on the same fitted image -> the logits the label map was stitched from
+    d_img, ip = ops.upload_image(img)
+    fitted, fp = ops.fit_resize_area(d_img, H_FULL, W_FULL, 1, ip, H_FIT, W_FIT)
+    if seg.s2d:
+        xs = ops.tile_gather_norm_s2d(fitted, H_FIT, W_FIT, 1, fp, T, 256, seg.mean, seg.std, seg.post_div)
+    else:
+        xs = ops.tile_gather_norm_f32(fitted, H_FIT, W_FIT, 1, fp, T, 256, seg.mean, seg.std, seg.post_div, seg.out_ch)
+    logits = torch.cat(seg.forward_tiles(xs, s2d=seg.s2d))
+    assert tuple(logits.shape) == (273, C, T, T)
+    ref = torch_stitch(logits, 13, 21, 256)
+    del logits, xs
+    top2 = ref.topk(2, dim=0).values
+    margin = top2[0] - top2[1]
+    differs = labels != ref.argmax(0).to(torch.uint8)
+    # the plan is re-run here: cuDNN picks the same algorithms for the same shapes, so the logits repeat
+    # exactly; the margin only has to absorb the two softmax implementations (see ARGMAX_MARGIN above)
+    assert not bool((differs & (margin > ARGMAX_MARGIN_HARD)).any())
+    assert int((differs & (margin > ARGMAX_MARGIN)).sum()) <= labels.numel() // 1_000_000
+    del ref, top2, margin
+    x_ofs, y_ofs = ops.device_index_maps(W_FIT, H_FIT, W_FULL, H_FULL, labels.device)
+    assert torch.equal(pred, labels[y_ofs.long()][:, x_ofs.long()])
+    d_gt, gp = ops.upload_image(gt)
+    enc = ops.class_encode_hwc(d_gt, H_FULL, W_FULL, gp, pal)[0]
+    yt, yp = enc.view(-1).long(), pred.view(-1).long().clone()
+    yt = yt.clone()
+    yt[:C] = torch.arange(C, device="cuda")
+    yp[:C] = torch.arange(C, device="cuda")
+    want = torch.bincount(yt * C + yp, minlength=C * C).view(C, C)
+    assert np.array_equal(conf, want.cpu().numpy())
+    assert int(conf.sum()) == W_FULL * H_FULL
+    # the encoded ground truth against the oracle on a band of rows
+    assert np.array_equal(enc[1000:1064].cpu().numpy(), orc.class_encode_hwc(gt[1000:1064], pal))
 
 
 def torch_multiloss(z, t, w, C, ce=0.5, dice=0.5, focal=0.5, smooth=1.0, gamma=2.0, alpha=0.25):

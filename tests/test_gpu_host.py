@@ -318,6 +318,50 @@ def test_pipeline_matches_reference_sequence(ops, palettes, fuse):
     assert s["iou"] == orc.metrics_port(yt, yp, model.meta.class_codes)["iou"]
 
 
+@pytest.mark.parametrize("fuse", [False, True])
+def test_pipeline_grayscale_image(ops, palettes, fuse):
+    """ch = 1 (historic photographs, BASELINE configs[0] / configs[4]): the gather replicates the gray
+    plane x3 and normalises with the single profiled mean / std (reference model.py:372-377,433-435);
+    everything downstream equals the reference sequence evaluated by the oracle on the same logits."""
+    import cv2
+    from pylc_b200.pipeline import TiledSegmenter
+    model = _tiny_model(1)
+    pal = palettes["a"]
+    W, H = 2000, 1500                                          # configs[0] geometry: fitted 1536 x 1024, 15 tiles
+    img = orc.synth_image(21, W, H, 1)
+    gt = orc.synth_mask(21, W, H, pal, skew=True)
+    seg = TiledSegmenter(model, batch_tiles=8, channels_last=fuse, keep_masks=True, fuse_network=fuse)
+    conf, results = seg.run_host([img], [gt])
+    res = results[0]
+    w_fit, h_fit = orc.fit_dims(W, H, T)
+    assert (w_fit, h_fit) == (1536, 1024)
+    fitted = cv2.resize(img, (w_fit, h_fit), interpolation=cv2.INTER_AREA)
+    tiles = torch.from_numpy(orc.split_tiles(fitted, T, 256))
+    assert tiles.shape == (15, 1, T, T)
+    if fuse:
+        d_fit, fp = ops.upload_image(fitted)
+        if seg.s2d:
+            xs = ops.tile_gather_norm_s2d(d_fit, h_fit, w_fit, 1, fp, T, 256, seg.mean, seg.std, seg.post_div)
+        else:
+            xs = ops.tile_gather_norm_f32(d_fit, h_fit, w_fit, 1, fp, T, 256, seg.mean, seg.std, seg.post_div, seg.out_ch)
+        outs = seg.forward_tiles(xs, s2d=seg.s2d)
+        eager = torch.cat([model.test(tiles[i:i + 8])[0] for i in range(0, len(tiles), 8)])
+        assert (torch.cat(outs) - eager).abs().max() <= 5e-3 * eager.abs().max()   # TF32 conv noise level
+    else:
+        outs = [model.test(tiles[i:i + 8])[0] for i in range(0, len(tiles), 8)]
+    logits = torch.cat(outs).cpu().numpy()
+    nr, nc = h_fit // 256 - 1, w_fit // 256 - 1
+    ref_map = orc.stitch_map(logits, nr, nc, T, 256)
+    near_tie = orc.top2_margin(ref_map) <= 1e-6
+    got_lab = res["labels"].cpu().numpy()
+    assert not ((got_lab != orc.stitch_labels(ref_map)) & ~near_tie).any()
+    pred_full = orc.resample_labels(got_lab, W, H)
+    assert np.array_equal(res["pred_full"].cpu().numpy(), pred_full)
+    yt, yp = orc.inject_coverage(orc.class_encode_hwc(gt, pal), pred_full, 9)
+    assert np.array_equal(conf, orc.confusion_counts(yt, yp, 9))
+    assert int(conf.sum()) == W * H
+
+
 # ---------------------------------------------------------------------------------------------
 # Augmentor.optimize (sample-rate grid search on the device)
 # ---------------------------------------------------------------------------------------------

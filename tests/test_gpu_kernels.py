@@ -195,6 +195,25 @@ def test_class_encode_golden_and_layouts(ops, golden, palettes):
         assert np.array_equal(out.cpu().numpy()[0], want)
 
 
+@pytest.mark.parametrize("rows,cols,n_img", [(45, 272, 1), (100, 1008, 1), (33, 16, 1), (70, 528, 3), (1500, 2000, 1), (64, 250, 1)])
+@pytest.mark.parametrize("C", [9, 20])
+def test_class_encode_hwc_box_edges(ops, palettes, rows, cols, n_img, C):
+    """Interleaved class_encode through the TMA form (cols % 16 == 0: partial boxes on the right and bottom
+    edges are zero-filled on load, clipped on store, and must not reach the histogram) and through the
+    per-thread form (cols = 250); several images stacked as one tall image."""
+    rng = np.random.default_rng(rows * 7 + cols)
+    pal = palettes["a"] if C == 9 else rng.integers(0, 256, size=(C, 3)).tolist()
+    imgs = [orc.synth_mask(40 + i, cols, rows, pal, skew=False, off_palette=0.01) for i in range(n_img)]
+    stack = np.ascontiguousarray(np.concatenate(imgs, axis=0))
+    d, pitch = ops.upload_image(stack)
+    out, hist = ops.class_encode_hwc(d, rows, cols, pitch, pal, n_img=n_img, hist=True)
+    ref = np.stack([orc.class_encode_hwc(im, pal) for im in imgs])
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert np.array_equal(hist.cpu().numpy(), np.bincount(ref.ravel(), minlength=C))
+    out2 = ops.class_encode_hwc(d, rows, cols, pitch, pal, n_img=n_img)
+    assert torch.equal(out, out2)
+
+
 def test_class_encode_rejects_non_rgb(ops):
     with pytest.raises(ops.PylcError):   # utils/tools.py:433
         ops.class_encode_nchw(torch.zeros((1, 4, 8, 8), dtype=torch.uint8, device="cuda"), [[0, 0, 0]])
@@ -570,6 +589,72 @@ def test_multiloss_fused_equals_two_pass(ops, B, C, H, W, weighted, u8):
     assert torch.equal(g1, grad)
     ops.scale_unless_one_(g1, torch.full((), 0.5, device="cuda"))
     assert torch.equal(g1, grad * 0.5)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(4, 9, 128, 128), (3, 11, 31, 37), (2, 5, 64, 64)])
+def test_multiloss_u8_target_workspace(ops, B, C, H, W):
+    """int64 targets (the reference dtype): the reduce pass leaves a one-byte copy of the targets, the
+    gradient pass reads that instead -- identical partials, loss values and gradient with and without it,
+    in the two-launch and the single-launch form."""
+    rng = np.random.default_rng(B + C + H)
+    dz = dev((rng.standard_normal((B, C, H, W)) * 3).astype(np.float32))
+    t = rng.integers(0, C, size=(B, H, W)).astype(np.int64)
+    dt = dev(t)
+    cfg = ops.loss_cfg()
+    t8 = torch.full((t.size,), 255, dtype=torch.uint8, device="cuda")
+    part = ops.multiloss_reduce(dz, dt, cfg, target_u8_out=t8)
+    assert torch.equal(t8.view(B, H, W), dt.to(torch.uint8))
+    part0 = ops.multiloss_reduce(dz, dt, cfg)
+    assert torch.equal(part, part0)
+    g8 = ops.multiloss_grad(dz, t8.view(B, H, W), cfg, part, t.size)
+    g64 = ops.multiloss_grad(dz, dt, cfg, part, t.size)
+    assert torch.equal(g8, g64)
+    o_ws, g_ws, p_ws = ops.multiloss_fwd_bwd(dz, dt, cfg)                     # workspace on (default)
+    o_no, g_no, p_no = ops.multiloss_fwd_bwd(dz, dt, cfg, use_u8_ws=False)
+    assert torch.equal(o_ws, o_no) and torch.equal(g_ws, g_no)
+    np.testing.assert_allclose(p_ws.cpu().numpy(), p_no.cpu().numpy(), rtol=1e-12)
+
+
+def test_multiloss_out_of_range_target_is_loud(ops):
+    """A target outside [0, C) (a mask encoded with another schema, a 255 'ignore' label): the reference's
+    CrossEntropyLoss / one_hot raise (loss.py:66-69,137).  The kernels turn every value and gradient of the
+    batch into NaN instead of silently using another class's weight; the host mirror raises."""
+    from pylc_b200.models.modules.loss import MultiLoss
+    C = 9
+    g = torch.Generator().manual_seed(5)
+    z = (torch.randn(2, C, 32, 32, generator=g) * 3).cuda()
+    t = torch.randint(0, C, (2, 32, 32), generator=g).cuda()
+    t[1, 7, 9] = C + 2
+    cfg = ops.loss_cfg()
+    part = ops.multiloss_reduce(z, t, cfg)
+    vals = ops.multiloss_finalize(part, C, t.numel(), cfg)
+    assert bool(torch.isnan(vals[0])) and bool(torch.isnan(vals[1]))
+    out4, grad, _ = ops.multiloss_fwd_bwd(z, t, cfg)
+    assert bool(torch.isnan(out4[0])) and bool(torch.isnan(grad).any())
+    crit = MultiLoss({"weighted": False, "weights": None, "ce": 0.5, "dice": 0.5, "focal": 0.5},
+                     {"n_classes": C, "class_codes": list("abcdefghi"), "class_labels": list("abcdefghi")})
+    with pytest.raises(IndexError):
+        crit(z, t)
+    t[1, 7, 9] = 0
+    assert bool(torch.isfinite(crit(z, t)))
+
+
+def test_multiloss_second_backward_over_retained_graph(ops):
+    """retain_graph=True / gradient checkpointing: the single-launch path hands its stashed gradient to the
+    first backward and recomputes it from the saved tensors for any later one -- same values."""
+    from pylc_b200.models.modules.loss import MultiLoss
+    C = 9
+    g = torch.Generator().manual_seed(6)
+    z = (torch.randn(2, C, 48, 48, generator=g) * 3).cuda().requires_grad_(True)
+    t = torch.randint(0, C, (2, 48, 48), generator=g).cuda()
+    crit = MultiLoss({"weighted": True, "weights": list(np.linspace(0.2, 1.0, C)), "ce": 0.5, "dice": 0.5, "focal": 0.5},
+                     {"n_classes": C, "class_codes": list("abcdefghi"), "class_labels": list("abcdefghi")})
+    loss = crit(z, t)
+    loss.backward(retain_graph=True)
+    g1 = z.grad.clone()
+    z.grad = None
+    (2.0 * loss).backward()
+    np.testing.assert_allclose(z.grad.cpu().numpy(), 2.0 * g1.cpu().numpy(), rtol=1e-5, atol=1e-12)
 
 
 # ---------------------------------------------------------------------------------------------
