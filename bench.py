@@ -254,6 +254,7 @@ class KernelTimer(object):
             "upsample_concat_nhwc": lambda a, k, out: nb(a[0]) + nb(a[1]) + nb(out),
             "upsample_nhwc_to_nchw": lambda a, k, out: nb(a[0]) + nb(out),
             "stitch_argmax_colour": stitch_bytes,
+            "stitch_upsample_argmax_colour": stitch_bytes,     # decoder output once + 1 B label per output px
             "resample_encode_confusion": lambda a, k, out: a[1] * a[2] * 4,                  # 3 B ground truth + 1 B label per px
         }
 
@@ -294,16 +295,47 @@ class KernelTimer(object):
 
 
 def ncu_traffic(tag, kernel_prefix):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu capture
-    (profiles/traffic_r1.json, written by tools/summarise_profiles.py)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as f:
-            for row in json.load(f).get(tag, []):
-                if row["kernel"].startswith(kernel_prefix):
-                    return row["dram_bytes"]
-    except Exception:
-        pass
-    return None
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu captures
+    (profiles/traffic_r2.json, else traffic_r1.json; written by tools/summarise_profiles.py)."""
+    for name in ("traffic_r2.json", "traffic_r1.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                for row in json.load(f).get(tag, []):
+                    if row["kernel"].startswith(kernel_prefix):
+                        return row["dram_bytes"], "profiles/" + name
+        except Exception:
+            pass
+    return None, None
+
+
+# op of the pipeline -> (kernel it launches, tag of its ncu capture in profiles/traffic_r*.json, bound)
+KERNEL_OF = {
+    "stitch_argmax_colour": ("stitch_kernel", "stitch45", "hbm"),
+    "stitch_upsample_argmax_colour": ("stitch_up_kernel", "stitchup45", "issue (exp + FMA per class; reads 16x fewer bytes than the logits)"),
+    "upsample_concat_nhwc": ("upsample_concat_staged_kernel", "upcat", "hbm"),
+    "maxpool3x3s2_nhwc": ("maxpool3x3s2_kernel", "maxpool", "hbm"),
+    "upsample_nhwc_to_nchw": ("upsample_to_nchw_staged_kernel", "upnchw", "hbm"),
+    "tile_gather_norm_s2d": ("gather_norm_s2d_staged_kernel", "gather_s2d", "hbm"),
+    "tile_gather_norm_f32": ("gather_norm_staged_kernel", "gather_norm", "hbm"),
+    "fit_resize_area": ("area_resize_lt2_kernel", "resize", "issue (OpenCV's float sequence replayed exactly)"),
+    "resample_encode_confusion": ("resample_confusion_kernel", "resample", "issue (exact palette look-up + counters)"),
+}
+
+
+def roofline_of(kernels, peak, peak_kind, images_per_step, step_ms):
+    """The `roofline` object of the JSON line: the custom kernel with the largest share of the timed step
+    (timed live with CUDA events on its stream; every custom launch is listed under `kernels`)."""
+    if not kernels:
+        return None
+    top = max(kernels, key=lambda r: r["share_of_step"])
+    kern, tag, bound = KERNEL_OF.get(top["op"], (top["op"], None, "hbm"))
+    traffic, src = ncu_traffic(tag, kern) if tag else (None, None)
+    return {"kernel": "%s (pylc op %s)" % (kern, top["op"]), "bound": "hbm", "limited_by": bound,
+            "achieved": top["achieved_gbs"], "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": top["frac"],
+            "avg_launch_ms": top["avg_launch_ms"], "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"],
+            "traffic": traffic, "traffic_source": (src + ": ncu --set full capture of this launch shape, dram read + write") if src else None,
+            "share_of_step": top["share_of_step"],
+            "why_this_kernel": "the custom kernel with the largest share of the timed step; every custom launch of the step is listed under `kernels` with its own fraction"}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -322,7 +354,7 @@ def run_ours(args, rank, world, local_rank):
     model = build_model(device)
     seg = TiledSegmenter(model, batch_tiles=args.batch_tiles, channels_last=not args.no_channels_last,
                          autocast_dtype=dtype, host_workers=args.host_workers, fuse_network=not args.no_fuse,
-                         device_fit=not args.host_fit)
+                         device_fit=not args.host_fit, fuse_upsample=not args.no_fuse_upsample)
     # weak: every rank owns N_IMAGES images (global index rank * N_IMAGES + i); strong: ONE set of
     # N_IMAGES images dealt round-robin over the ranks (dist.shard_indices)
     strong = args.scaling == "strong"
@@ -366,9 +398,6 @@ def run_ours(args, rank, world, local_rank):
         launches = _lib.launch_count() - launches0
         ms = pdist.max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
         kernels = st.result(peak_gbs()[0], ms, args.steps)
-        stitch = next((r for r in kernels if r["op"] == "stitch_argmax_colour"), None)
-        k_ms = stitch["avg_launch_ms"] if stitch else None
-        k_bytes = stitch["algorithmic_bytes_per_launch"] if stitch else None
     conf_resident = conf_dev.cpu().numpy()
     del resident
 
@@ -414,14 +443,7 @@ def run_ours(args, rank, world, local_rank):
                 "api": "pylc_b200.pipeline.TiledSegmenter.run_host"},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"kernel": "stitch_kernel (pylc_stitch_argmax_colour)", "bound": "hbm",
-                     "achieved": (k_bytes / (k_ms * 1e-3) / 1e9) if k_ms else None, "peak": peak, "peak_kind": peak_kind,
-                     "unit": "GB/s", "frac": (k_bytes / (k_ms * 1e-3) / 1e9 / peak) if k_ms else None,
-                     "avg_launch_ms": k_ms, "algorithmic_bytes_per_launch": k_bytes,
-                     "traffic": ncu_traffic("stitch45" if TILES_PER_IMAGE == 45 else "stitch", "stitch_kernel"),
-                     "traffic_source": "profiles/traffic_r*.json: ncu --set full capture of this launch shape (%d tiles), dram read + write" % TILES_PER_IMAGE,
-                     "share_of_step": (k_ms * n_mine / ms) if k_ms else None,
-                     "why_this_kernel": "largest algorithmic HBM stream of the SURVEY 8a hot path; every custom launch of the step is listed under `kernels`"},
+        "roofline": roofline_of(kernels, peak, peak_kind, n_mine, ms),
         "kernels": kernels,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -447,6 +469,8 @@ def main():
     ap.add_argument("--host-fit", action="store_true", help="fit-resize on host threads with cv2 (the reference's call) "
                     "instead of the bit-exact device kernel")
     ap.add_argument("--no-fuse", action="store_true", help="run the eager nn.Module instead of the BN-folded cuDNN-fused plan")
+    ap.add_argument("--no-fuse-upsample", action="store_true", help="final x4 up-sample and stitch as two kernels instead of "
+                    "the fused stitch that reads the decoder output (same results, bit for bit)")
     ap.add_argument("--images", type=int, default=None, help="images per GPU per step (weak) or in total (strong); "
                     "default: the configuration's own count (profiling runs use fewer)")
     ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS), help="BASELINE.json configs index: 1 = the "

@@ -223,6 +223,19 @@ PYLC_API int pylc_stitch_argmax_colour(const float *logits, const float *const *
                               float *stitched, pylc_stream_t stream);
 
 /* tools.colourize (utils/tools.py:322-358) on a flat u8 label array: rgb[i] = lut_rgb[labels[i]]. */
+/*
+ * Fused form of the network's last step + the stitch: takes the decoder's output
+ * BEFORE the final x4 bilinear up-sample -- `decoder_batches`: device array of device pointers to
+ * channels-last [b, hs, ws, C] f32 batches, hs = ws = T/4 -- evaluates
+ * F.interpolate(..., size=T, mode='bilinear', align_corners=True) (models/architectures/deeplab.py:38) per
+ * output pixel with the arithmetic of pylc_upsample_nhwc_to_nchw_f32, and stitches as
+ * pylc_stitch_argmax_colour does.  Outputs are bit-identical to that two-call route.
+ * PYLC_ERR_GEOMETRY for C > 12 or a geometry other than the x4 up-sample of 512-class tile sizes: the
+ * caller keeps the two-call route.
+ */
+PYLC_API int pylc_stitch_upsample_argmax_colour(const float *const *decoder_batches, int tiles_per_batch, int nr, int nc,
+                                       int C, int T, int S, int hs, int ws, const uint8_t *lut_rgb, uint8_t *labels,
+                                       uint8_t *rgb, float *stitched, pylc_stream_t stream);
 PYLC_API int pylc_colourise_u8(const uint8_t *labels, int64_t n_px, const uint8_t *lut_rgb, int C,
                       uint8_t *rgb, pylc_stream_t stream);
 

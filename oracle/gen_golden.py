@@ -284,6 +284,20 @@ def gen_augment(ref, out):
         out["aug_%s_optim_probs" % name] = np.asarray(om['probs'])
 
 
+def gen_warp(ref, out):
+    """tools.augment_transform (utils/tools.py:452-594) on a formula-generated tile, with the dtypes the
+    reference's loader hands it (float32 image, int64 mask; db/dataset.py:62-63) and the RandomState(j) seeds
+    Augmentor.oversample uses (utils/augment.py:213-215)."""
+    import pylc_oracle as orc
+    for ch in (1, 3):
+        img, mask = orc.augment_fixture_tile(ch)
+        for seed in (0, 1, 3):
+            a, b = ref.tools.augment_transform(img.astype(np.float32), mask.astype(np.int64), np.random.RandomState(seed))
+            out["warp_ch%d_s%d_img" % (ch, seed)] = np.asarray(a).astype(np.uint8)
+            assert np.array_equal(np.asarray(b), np.asarray(b).astype(np.uint8))
+            out["warp_ch%d_s%d_mask" % (ch, seed)] = np.asarray(b).astype(np.uint8)
+
+
 def gen_model(ref, out):
     """Model-file boundary: the reference's DeepLabv3+/ResNet-101 state-dict keys and shapes, its output
     on a seeded input with deterministic weights (oracle.fill_state_dict), and a model file whose `meta` is
@@ -322,7 +336,7 @@ def main():
     for fname, fn in (("split", gen_split), ("encode", gen_encode), ("colourize", gen_colourize),
                       ("extract_profile", gen_extract_profile), ("fit", gen_fit),
                       ("reconstruct", gen_reconstruct), ("evaluate", gen_evaluate), ("loss", gen_loss),
-                      ("augment", gen_augment), ("model", gen_model)):
+                      ("augment", gen_augment), ("model", gen_model), ("warp", gen_warp)):
         out = {}
         fn(ref, out)
         path = os.path.join(OUT, fname + ".npz")

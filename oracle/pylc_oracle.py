@@ -668,3 +668,11 @@ def fill_state_dict(state_dict):
             fan_in = v[0].numel()
             out[k] = torch.randn(v.shape, generator=g) * (1.6 / fan_in) ** 0.5
     return out
+
+
+def augment_fixture_tile(ch, T=512):
+    """Formula-generated tile + label mask for the augment_transform golden vectors (smooth enough to compress)."""
+    yy, xx = np.mgrid[0:T, 0:T]
+    img = np.stack([(xx // 7 * 5 + yy // 11 * 3 + 40 * c) % 256 for c in range(ch)]).astype(np.uint8)[None]
+    mask = ((xx // 60 + yy // 45) % 9).astype(np.uint8)[None]
+    return img, mask

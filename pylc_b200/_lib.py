@@ -60,6 +60,8 @@ SIGNATURES = {
                                               POINTER(c_float), POINTER(c_float), c_float, _ptr, _ptr]),
     "pylc_stitch_argmax_colour": (c_int, [_ptr, _ptr, c_int, c_int, c_int, c_int, c_int, c_int,
                                           POINTER(c_uint8), _u8p, _u8p, _ptr, _ptr]),
+    "pylc_stitch_upsample_argmax_colour": (c_int, [_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                                   POINTER(c_uint8), _u8p, _u8p, _ptr, _ptr]),
     "pylc_colourise_u8": (c_int, [_u8p, c_int64, POINTER(c_uint8), c_int, _u8p, _ptr]),
     "pylc_resample_encode_confusion": (c_int, [_u8p, c_int, c_int, _ptr, _ptr, c_int, c_int, _u8p, c_size_t,
                                                POINTER(c_uint8), POINTER(c_uint8), c_int, c_int, _ptr,

@@ -251,6 +251,208 @@ __global__ void __launch_bounds__(kThreads, 2) stitch_kernel(StitchArgs a, const
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// Fused form: stitch straight from the decoder's [b, T/4, T/4, C] channels-last output.
+// The network's last step, F.interpolate(x, size=T, mode='bilinear', align_corners=True)
+// (models/architectures/deeplab.py:38), is evaluated here per output pixel instead of being written out
+// as [b, C, T, T] logits and read back: 16x less input (26.5 MB instead of 424.7 MB per 3000x2000 image)
+// and one kernel instead of two.  The bilinear arithmetic is the same, in the same order, as
+// upsample_to_nchw_staged_kernel (netglue.cu) -- rows blended first: v = fma(hl0, r0, hl1 * r1), then
+// res = fma(l, v_left, r * v_right) -- so the logits, and with them the stitched map and the labels, are
+// bit-identical to the two-kernel route.
+//
+// A CTA owns kUpR output rows of one S x S block.  For each of the (up to four) source tiles it copies the
+// few decoder rows / columns those output rows touch into shared memory, one 48-byte padded record per
+// decoder pixel (4-byte cp.async; a record is three 16-byte shared loads later); a thread then produces
+// 2-pixel units exactly as stitch_units does, with "load the logits" replaced by "blend them".
+constexpr int kUpR = 8;            // output rows per CTA
+constexpr int kUpSrcRows = 4;      // decoder rows staged per tile: kUpR * (hs-1)/(T-1) < 2, + the row below, + float rounding
+constexpr int kUpCpad = 12;        // floats per staged decoder pixel (C <= 12)
+
+struct StitchUpArgs {
+    const float *const *batches;   // device array of channels-last decoder outputs [b, hs, ws, C]
+    int tiles_per_batch;
+    int nr, nc, C, T, S, hs, ws;
+    int overlap, h, w, nbx, nby, slabs;
+    int cols_max;                  // staged decoder columns per tile (S * (ws-1)/(T-1) + 3)
+    uint8_t *labels;
+    uint8_t *rgb;
+    float *stitched;
+};
+
+template <int C_T, int CMAX, int NH, int NV>
+__device__ __forceinline__ void stitch_up_units(const StitchUpArgs &a, const uint32_t *s_lut, float *s_src, int ky, int kx, int row0) {
+    constexpr int PX = 2;
+    const int C = C_T > 0 ? C_T : a.C;
+    const int T = a.T, S = a.S, hs = a.hs, ws = a.ws;
+    const float rh = (float)(hs - 1) / (float)(T - 1), rw = (float)(ws - 1) / (float)(T - 1);
+    int ti[2], ty0[2], tj[2], tx0[2];
+    if (!a.overlap) {
+        ti[0] = ky; ty0[0] = 0; tj[0] = kx; tx0[0] = 0;
+    } else {
+        if (NV == 1) {
+            ti[0] = ky == 0 ? 0 : a.nr - 1;
+            ty0[0] = ky == 0 ? 0 : S;
+        } else {
+            ti[0] = ky - 1; ty0[0] = S;
+            ti[1] = ky;     ty0[1] = 0;
+        }
+        if (NH == 1) {
+            tj[0] = kx == 0 ? 0 : a.nc - 1;
+            tx0[0] = kx == 0 ? 0 : S;
+        } else {
+            tj[0] = kx - 1; tx0[0] = S;
+            tj[1] = kx;     tx0[1] = 0;
+        }
+    }
+    // ---- stage ---------------------------------------------------------------------------------------
+    int ys0[NV], xs0[NH], ncol[NH];
+#pragma unroll
+    for (int s = 0; s < NV; ++s) ys0[s] = (int)(rh * (float)(ty0[s] + row0));
+#pragma unroll
+    for (int q = 0; q < NH; ++q) {
+        xs0[q] = (int)(rw * (float)tx0[q]);
+        ncol[q] = min(ws - 1, (int)(rw * (float)(tx0[q] + S - 1)) + 1) - xs0[q] + 1;
+    }
+    const int tile_f = kUpSrcRows * a.cols_max * kUpCpad;          // floats per staged tile
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(s_src);
+#pragma unroll
+    for (int s = 0; s < NV; ++s) {
+        const int nrow = min(hs - 1, (int)(rh * (float)(ty0[s] + row0 + kUpR - 1)) + 1) - ys0[s] + 1;
+#pragma unroll
+        for (int q = 0; q < NH; ++q) {
+            const int k = ti[s] * a.nc + tj[q], b = k / a.tiles_per_batch;
+            const float *tile = a.batches[b] + (size_t)(k - b * a.tiles_per_batch) * hs * ws * C;
+            const int run = ncol[q] * C;                            // contiguous floats per staged row
+            const uint32_t dst0 = s0 + (uint32_t)((s * NH + q) * tile_f) * 4u;
+            for (int i = threadIdx.x; i < nrow * run; i += kThreads) {
+                const int r = i / run, e = i - r * run;
+                const int col = e / C, c = e - col * C;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst0 + (uint32_t)((r * a.cols_max + col) * kUpCpad + c) * 4u),
+                             "l"(tile + ((size_t)(ys0[s] + r) * ws + xs0[q]) * C + e)
+                             : "memory");
+            }
+        }
+    }
+    cp_async_commit();
+
+    // ---- per-thread column set-up (row-invariant): the pair (X, X+1) touches at most three decoder columns
+    const int u = threadIdx.x & (S / PX - 1), rsel = threadIdx.x / (S / PX);     // S/2 units per row (a power of two)
+    const int rstep = kThreads / (S / PX);
+    const int X = u * PX;
+    uint32_t coff[NH][3];
+    float cw[NH][PX][3];
+#pragma unroll
+    for (int q = 0; q < NH; ++q) {
+        int x1[PX], xr[PX];
+        float l0[PX], l1[PX];
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            const float w1r = rw * (float)(tx0[q] + X + j);
+            x1[j] = (int)w1r;
+            xr[j] = min(x1[j] + 1, ws - 1);
+            l1[j] = w1r - (float)x1[j];
+            l0[j] = 1.f - l1[j];
+        }
+        const int xa = x1[0] - xs0[q];
+        coff[q][0] = (uint32_t)(xa * kUpCpad) * 4u;
+        coff[q][1] = (uint32_t)(min(xa + 1, ncol[q] - 1) * kUpCpad) * 4u;
+        coff[q][2] = (uint32_t)(min(xa + 2, ncol[q] - 1) * kUpCpad) * 4u;
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            const bool first = x1[j] == x1[0], right_same = xr[j] == x1[j];
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+            if (first) { c0 = l0[j]; if (right_same) c0 += l1[j]; else c1 = l1[j]; }
+            else { c1 = l0[j]; if (right_same) c1 += l1[j]; else c2 = l1[j]; }
+            cw[q][j][0] = c0; cw[q][j][1] = c1; cw[q][j][2] = c2;
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const uint32_t row_b = (uint32_t)(a.cols_max * kUpCpad) * 4u;
+    for (int r = rsel; r < kUpR; r += rstep) {
+        const int yl = row0 + r;
+        float strip[NV][CMAX][PX];
+#pragma unroll
+        for (int s = 0; s < NV; ++s) {
+            const float h1r = rh * (float)(ty0[s] + yl);
+            const int y1 = (int)h1r, y1p = y1 < hs - 1 ? 1 : 0;
+            const float hl1 = h1r - (float)y1, hl0 = 1.f - hl1;
+            float v[NH][CMAX][PX];
+#pragma unroll
+            for (int q = 0; q < NH; ++q) {
+                const uint32_t p0 = s0 + (uint32_t)((s * NH + q) * tile_f) * 4u + (uint32_t)(y1 - ys0[s]) * row_b;
+                const uint32_t p1 = p0 + (uint32_t)y1p * row_b;
+                float col[3][CMAX];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+#pragma unroll
+                    for (int c4 = 0; c4 < (CMAX + 3) / 4; ++c4) {
+                        const uint4 t0 = lds128(p0 + coff[q][k] + 16u * c4), t1 = lds128(p1 + coff[q][k] + 16u * c4);
+                        const float a0[4] = {__uint_as_float(t0.x), __uint_as_float(t0.y), __uint_as_float(t0.z), __uint_as_float(t0.w)};
+                        const float a1[4] = {__uint_as_float(t1.x), __uint_as_float(t1.y), __uint_as_float(t1.z), __uint_as_float(t1.w)};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (c4 * 4 + i < CMAX) col[k][c4 * 4 + i] = fmaf(hl0, a0[i], hl1 * a1[i]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c)
+#pragma unroll
+                    for (int j = 0; j < PX; ++j)
+                        v[q][c][j] = fmaf(cw[q][j][0], col[0][c], fmaf(cw[q][j][1], col[1][c], cw[q][j][2] * col[2][c]));
+            }
+            if (NH == 2) {
+                float r0[PX], r1[PX];
+                exp_cls<CMAX, PX, true>(v[0], C, kLog2e, r0);
+                exp_cls<CMAX, PX, true>(v[NH - 1], C, kLog2e, r1);
+                combine_cls<CMAX, PX>(v[0], r0, v[NH - 1], r1, C, NV == 2 ? 1.f : 0.5f);
+            }
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c)
+#pragma unroll
+                for (int j = 0; j < PX; ++j) strip[s][c][j] = v[0][c][j];
+        }
+        if (NV == 2) {
+            float r0[PX], r1[PX];
+            if (NH == 2) {
+                exp_cls<CMAX, PX, false>(strip[0], C, 0.5f * kLog2e, r0);
+                exp_cls<CMAX, PX, false>(strip[NV - 1], C, 0.5f * kLog2e, r1);
+            } else {
+                exp_cls<CMAX, PX, true>(strip[0], C, kLog2e, r0);
+                exp_cls<CMAX, PX, true>(strip[NV - 1], C, kLog2e, r1);
+            }
+            combine_cls<CMAX, PX>(strip[0], r0, strip[NV - 1], r1, C, 0.5f);
+        }
+        StitchArgs e;                    // emit_unit only reads the output pointers and the map size
+        e.labels = a.labels; e.rgb = a.rgb; e.stitched = a.stitched; e.h = a.h; e.w = a.w;
+        emit_unit<CMAX, PX>(e, s_lut, C, strip[0], (size_t)(ky * S + yl) * a.w + (size_t)(kx * S + X));
+    }
+}
+
+template <int C_T, int CMAX>
+__global__ void __launch_bounds__(kThreads, 2) stitch_up_kernel(StitchUpArgs a, const __grid_constant__ ColourLut lut) {
+    extern __shared__ __align__(16) float s_up[];
+    __shared__ uint32_t s_lut[PYLC_MAX_CLASSES];
+    if (threadIdx.x < PYLC_MAX_CLASSES) s_lut[threadIdx.x] = lut.rgb[threadIdx.x];
+    // (the barrier inside stitch_up_units, after the staging copies, also covers s_lut)
+    int bid = blockIdx.x;
+    const int slab = bid % a.slabs;
+    bid /= a.slabs;
+    bid = a.nbx * a.nby - 1 - bid;       // last tile row first, as stitch_kernel does
+    const int kx = bid % a.nbx, ky = bid / a.nbx;
+    const bool two_h = a.overlap && kx > 0 && kx < a.nc;
+    const bool two_v = a.overlap && ky > 0 && ky < a.nr;
+    if (two_h) {
+        if (two_v) stitch_up_units<C_T, CMAX, 2, 2>(a, s_lut, s_up, ky, kx, slab * kUpR);
+        else stitch_up_units<C_T, CMAX, 2, 1>(a, s_lut, s_up, ky, kx, slab * kUpR);
+    } else {
+        if (two_v) stitch_up_units<C_T, CMAX, 1, 2>(a, s_lut, s_up, ky, kx, slab * kUpR);
+        else stitch_up_units<C_T, CMAX, 1, 1>(a, s_lut, s_up, ky, kx, slab * kUpR);
+    }
+}
+
 }  // namespace pylc
 
 using namespace pylc;
@@ -304,5 +506,48 @@ extern "C" int pylc_stitch_argmax_colour(const float *logits, const float *const
         else if (C <= 16) stitch_kernel<0, 16, 1><<<grid, kThreads, 0, st>>>(a, lut);
         else stitch_kernel<0, 32, 1><<<grid, kThreads, 0, st>>>(a, lut);
     }
+    return finish_launch();
+}
+
+extern "C" int pylc_stitch_upsample_argmax_colour(const float *const *decoder_batches, int tiles_per_batch, int nr, int nc, int C,
+                                                  int T, int S, int hs, int ws, const uint8_t *lut_rgb, uint8_t *labels,
+                                                  uint8_t *rgb, float *stitched, pylc_stream_t stream) {
+    if (!decoder_batches || tiles_per_batch < 1 || nr < 1 || nc < 1 || T < 1 || S < 1 || hs < 2 || ws < 2) return PYLC_ERR_ARG;
+    if (rgb && !lut_rgb) return PYLC_ERR_ARG;
+    if (C < 1 || C > PYLC_MAX_CLASSES) return PYLC_ERR_CLASSES;
+    if (!(S == T || 2 * S == T)) return PYLC_ERR_GEOMETRY;
+    // this form covers the network's geometry: a x4 up-sample, rows of 2-pixel units that fill a CTA evenly
+    if (C > kUpCpad || hs * 4 != T || ws * 4 != T || S % kUpR || (S / 2) > kThreads || kThreads % (S / 2) || (S & (S - 1))) return PYLC_ERR_GEOMETRY;
+    if ((stitched && (uintptr_t)stitched % 8) || (labels && (uintptr_t)labels % 2) || (rgb && (uintptr_t)rgb % 2)) return PYLC_ERR_ALIGN;
+    StitchUpArgs a;
+    a.batches = decoder_batches;
+    a.tiles_per_batch = tiles_per_batch;
+    a.nr = nr; a.nc = nc; a.C = C; a.T = T; a.S = S; a.hs = hs; a.ws = ws;
+    a.overlap = S < T;
+    a.nbx = a.overlap ? nc + 1 : nc;
+    a.nby = a.overlap ? nr + 1 : nr;
+    a.h = a.nby * S;
+    a.w = a.nbx * S;
+    a.slabs = S / kUpR;
+    a.cols_max = (int)((double)S * (ws - 1) / (T - 1)) + 4;
+    a.labels = labels; a.rgb = rgb; a.stitched = stitched;
+    ColourLut lut;
+    if (lut_rgb) build_colour_lut(lut_rgb, C, &lut);
+    else for (int i = 0; i < PYLC_MAX_CLASSES; ++i) lut.rgb[i] = 0;
+    const size_t smem = (size_t)4 * kUpSrcRows * a.cols_max * kUpCpad * sizeof(float);
+    const unsigned grid = (unsigned)((long long)a.nbx * a.nby * a.slabs);
+    cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_UP(CT, CM)                                                                                                  \
+    do {                                                                                                                   \
+        cudaError_t e = cudaFuncSetAttribute(stitch_up_kernel<CT, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return (int)e;                                                                               \
+        stitch_up_kernel<CT, CM><<<grid, kThreads, smem, st>>>(a, lut);                                                   \
+    } while (0)
+    if (C == 9) LAUNCH_UP(9, 9);
+    else if (C == 11) LAUNCH_UP(11, 11);
+    else if (C <= 4) LAUNCH_UP(0, 4);
+    else if (C <= 8) LAUNCH_UP(0, 8);
+    else LAUNCH_UP(0, 12);
+#undef LAUNCH_UP
     return finish_launch();
 }

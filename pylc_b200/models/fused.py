@@ -209,6 +209,18 @@ class FusedDeepLab(object):
         return self.dec_out(self.dec2(self.dec1(x)))
 
     @torch.no_grad()
+    def decoder_s2d(self, xs):
+        """The decoder's output [B, n_classes, T/4, T/4] (channels-last f32) from space-to-depth tiles: the
+        network WITHOUT its final x4 bilinear up-sample, which ops.stitch_upsample_argmax_colour evaluates."""
+        if self.stem_s2d is None:
+            raise ValueError("space-to-depth stem unavailable for this network / plan")
+        return self.features(xs, s2d=True).float().contiguous(memory_format=torch.channels_last)
+
+    @torch.no_grad()
+    def decoder(self, x):
+        return self.features(x).float().contiguous(memory_format=torch.channels_last)
+
+    @torch.no_grad()
     def forward_s2d(self, xs):
         """Logits [B, n_classes, T, T] from space-to-depth tiles (T = 2 * (xs.shape[2] - 3))."""
         if self.stem_s2d is None:

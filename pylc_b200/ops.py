@@ -279,6 +279,49 @@ def stitch_argmax_colour(logits, nr, nc, T, S, lut_rgb=None, want_labels=True, w
     return labels, rgb, stitched
 
 
+def stitch_upsample_argmax_colour(decoder_batches, nr, nc, T, S, lut_rgb=None, want_labels=True, want_rgb=False,
+                                  want_stitched=False, tiles_per_batch=None):
+    """pylc_stitch_upsample_argmax_colour: stitch straight from the decoder's channels-last outputs
+    [b, C, T/4, T/4] (one tensor per network batch), the final x4 bilinear up-sample evaluated in the kernel.
+    Returns (labels [h,w] u8, rgb [h,w,3] u8 or None, stitched [C,h,w] f32 or None), bit-identical to
+    stitch_argmax_colour(upsample_nhwc_to_nchw(batch) ...)."""
+    lib = _lib.load()
+    if torch.is_tensor(decoder_batches):
+        decoder_batches = [decoder_batches]
+    decoder_batches = list(decoder_batches)
+    _need_cuda(*decoder_batches)
+    dev = decoder_batches[0].device
+    C, hs, ws = decoder_batches[0].shape[1:]
+    tpb = tiles_per_batch or decoder_batches[0].shape[0]
+    for i, t in enumerate(decoder_batches):
+        if not _is_nhwc(t) or tuple(t.shape[1:]) != (C, hs, ws):
+            raise PylcError("decoder batches must be channels-last float32 CUDA tensors of one shape")
+        if i < len(decoder_batches) - 1 and t.shape[0] != tpb:
+            raise PylcError("all tile batches but the last must hold tiles_per_batch tiles")
+    if sum(t.shape[0] for t in decoder_batches) != nr * nc:
+        raise PylcError("expected %d tiles, got %d" % (nr * nc, sum(t.shape[0] for t in decoder_batches)))
+    batch_table = torch.tensor([t.data_ptr() for t in decoder_batches], dtype=torch.int64).to(dev, non_blocking=True)
+    h, w = stitch_dims(nr, nc, T, S)
+    labels = torch.empty((h, w), dtype=torch.uint8, device=dev) if want_labels else None
+    rgb = torch.empty((h, w, 3), dtype=torch.uint8, device=dev) if want_rgb else None
+    stitched = torch.empty((C, h, w), dtype=torch.float32, device=dev) if want_stitched else None
+    pal = None
+    if lut_rgb is not None:
+        pal, c2 = _lib.palette_array(lut_rgb)
+        if c2 != C:
+            raise PylcError("lut_rgb has %d colours, the decoder output has %d classes" % (c2, C))
+    check(lib.pylc_stitch_upsample_argmax_colour(_p(batch_table), tpb, nr, nc, C, T, S, hs, ws, pal, _p(labels), _p(rgb),
+                                                 _p(stitched), _stream()), "pylc_stitch_upsample_argmax_colour")
+    batch_table.record_stream(torch.cuda.current_stream())
+    return labels, rgb, stitched
+
+
+def stitch_upsample_supported(C, T, S, hs, ws):
+    """Geometry the fused stitch covers (else callers keep up-sample + stitch as two launches)."""
+    return C <= 12 and hs * 4 == T and ws * 4 == T and (S == T or 2 * S == T) and S % 8 == 0 and S // 2 <= 256 \
+        and 256 % (S // 2) == 0 and (S & (S - 1)) == 0
+
+
 def colourise_u8(labels, lut_rgb):
     _need_cuda(labels)
     labels = labels.contiguous()

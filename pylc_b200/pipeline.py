@@ -40,7 +40,7 @@ class FittedImage(object):
 
 class TiledSegmenter(object):
     def __init__(self, model, batch_tiles=32, channels_last=True, autocast_dtype=None, host_workers=4,
-                 n_inject=None, keep_masks=False, fuse_network=False, device_fit=True):
+                 n_inject=None, keep_masks=False, fuse_network=False, device_fit=True, fuse_upsample=True):
         self.model = model
         self.meta = model.meta
         self.net = model.net.eval()
@@ -64,6 +64,12 @@ class TiledSegmenter(object):
         self.mean, self.std, self.post_div, self.out_ch = model.norm_params()
         # space-to-depth stem: the gather writes the tiles in the layout of the rearranged 4x4 stem convolution
         self.s2d = self.fused is not None and self.fused.stem_s2d is not None and self.out_ch == 3 and self.T % 2 == 0
+        # with the inference plan the stitch kernel reads the decoder's [b, T/4, T/4, C] output
+        # and evaluates the network's final x4 bilinear up-sample itself (bit-identical to the two-kernel
+        # route, 16x less stitch input); `fuse_upsample=False` keeps up-sample and stitch as two launches
+        self.fuse_upsample = bool(fuse_upsample and self.fused is not None and self.fused.glue and channels_last
+                                  and autocast_dtype is None
+                                  and ops.stitch_upsample_supported(self.C, self.T, self.S, self.T // 4, self.T // 4))
         self.palette = self.meta.palette_rgb
         self.lut = tools.colourize_lut(self.C, self.palette)
         self.n_inject = min(len(defaults.class_codes), self.C) if n_inject is None else n_inject
@@ -135,18 +141,19 @@ class TiledSegmenter(object):
         return f
 
     # ---- device stage -------------------------------------------------------------------------
-    def forward_tiles(self, tiles, s2d=False):
+    def forward_tiles(self, tiles, s2d=False, decoder_only=False):
         """Network forward over [n,3,T,T] f32 tiles (or their space-to-depth form) in batches; returns
-        the list of logit batches."""
+        the list of logit batches [b,C,T,T] -- or, with `decoder_only` (inference plan), of the decoder
+        outputs [b,C,T/4,T/4] (channels-last) that the fused stitch up-samples itself."""
         outs = []
         with torch.no_grad():
             for lo in range(0, tiles.shape[0], self.batch_tiles):
                 x = tiles[lo:lo + self.batch_tiles]
                 if s2d:
-                    outs.append(self.fused.forward_s2d(x))
+                    outs.append(self.fused.decoder_s2d(x) if decoder_only else self.fused.forward_s2d(x))
                     continue
                 if self.fused is not None:
-                    outs.append(self.fused(x))
+                    outs.append(self.fused.decoder(x) if decoder_only else self.fused(x))
                     continue
                 if self.channels_last:
                     x = x.contiguous(memory_format=torch.channels_last)
@@ -173,9 +180,13 @@ class TiledSegmenter(object):
             tiles = ops.tile_gather_norm_f32(img, f.h, f.w, self.ch, pitch, self.T, self.S, self.mean, self.std,
                                              self.post_div, self.out_ch)
         nr, nc = f.h // self.S - 1, f.w // self.S - 1
-        logits = self.forward_tiles(tiles, s2d=self.s2d)
-        labels, _, _ = ops.stitch_argmax_colour(logits if len(logits) > 1 else logits[0], nr, nc, self.T, self.S,
-                                                tiles_per_batch=self.batch_tiles)
+        if self.fuse_upsample:
+            dec = self.forward_tiles(tiles, s2d=self.s2d, decoder_only=True)
+            labels, _, _ = ops.stitch_upsample_argmax_colour(dec, nr, nc, self.T, self.S, tiles_per_batch=self.batch_tiles)
+        else:
+            logits = self.forward_tiles(tiles, s2d=self.s2d)
+            labels, _, _ = ops.stitch_argmax_colour(logits if len(logits) > 1 else logits[0], nr, nc, self.T, self.S,
+                                                    tiles_per_batch=self.batch_tiles)
         n_inject = self.n_inject if inject is None else inject
         res = ops.resample_encode_confusion(
             labels, f.w_full, f.h_full, gt_rgb=f.gt, gt_pitch=f.gt_pitch, palette=self.palette, lut_rgb=self.lut,

@@ -10,9 +10,10 @@ over-sampling rates and the class histogram of the over-sampled dataset -- is ON
 (pylc_sample_rate_grid, exact int64), and the O(grid x C) tail (probabilities, M2, JSD, argmin)
 is the reference's float64 NumPy again.
 
-Out of scope here: `oversample()` -- the perspective / brightness
-warps of tools.augment_transform are OpenCV calls on host arrays in the reference and are not part
-of the accelerated path.
+`oversample()` (reference augment.py:184-239) copies every tile and appends `rates[i]` warped copies of
+tile i.  The warps (tools.augment_transform: perspective jitter + brightness shift) are the reference's own
+OpenCV calls on host arrays -- same library, same arguments, same bytes (pinned by a golden vector from the
+reference) -- and the profile of the augmented set runs on the device kernels (utils/profile.py).
 """
 import numpy as np
 import torch
@@ -102,6 +103,44 @@ class Augmentor(object):
         self.rates = self.optim_meta['rates']
         return self
 
-    def oversample(self):
-        raise NotImplementedError("Augmentor.oversample (OpenCV warps on host arrays, reference augment.py:189-250) is "
-                                  "outside the accelerated path; use the optimised .rates with the reference's own augment step")
+    def oversample(self, shuffle=True):
+        """Originals + `rates[i]` augmented copies of tile i (reference augment.py:184-239): copy j of a tile is
+        tools.augment_transform with RandomState(j), exactly as the reference seeds it.  Sets .output_imgs,
+        .output_masks, .output_meta (profiled on the device)."""
+        from ..config import Parameters
+        from ..db.dataset import MLPDataset
+        from .profile import get_profile
+        from .tools import augment_transform, coshuffle
+        assert self.input_dset is not None and self.input_dset.size > 0, "Loaded input dataset is empty."
+        assert len(self.rates) == self.input_dset.size, "Run optimize() first: one rate per input tile."
+        db = self.input_dset.db
+        src_imgs, src_masks = db.data['img'][db.start:db.end], db.data['mask'][db.start:db.end]
+        if torch.is_tensor(src_imgs):
+            src_imgs, src_masks = src_imgs.cpu().numpy(), src_masks.cpu().numpy()
+        n_out = int(self.input_dset.size + np.sum(self.rates))
+        imgs = np.empty((n_out,) + tuple(src_imgs.shape[1:]), dtype=np.uint8)
+        masks = np.empty((n_out,) + tuple(src_masks.shape[1:]), dtype=np.uint8)
+        idx = 0
+        for i in range(self.input_dset.size):
+            img, mask = np.asarray(src_imgs[i:i + 1]), np.asarray(src_masks[i:i + 1])
+            imgs[idx], masks[idx] = img[0], mask[0]
+            idx += 1
+            # the loader hands the reference float32 images and int64 masks (db/dataset.py:62-63)
+            img_f, mask_l = img.astype(np.float32), mask.astype(np.int64)
+            for j in range(int(self.rates[i])):
+                inp, tgt = augment_transform(img_f, mask_l, np.random.RandomState(j))
+                imgs[idx] = np.asarray(torch.as_tensor(inp, dtype=torch.uint8).numpy()).reshape(imgs.shape[1:])
+                masks[idx] = torch.as_tensor(tgt, dtype=torch.uint8).numpy()
+                idx += 1
+        assert idx == n_out
+        if shuffle:
+            imgs, masks = coshuffle(imgs, masks)
+        self.output_imgs, self.output_masks = imgs, masks
+        self.output_meta = Parameters().update(vars(self.input_meta))
+        self.output_meta = get_profile(self.get_data())
+        self.output_meta.id = '_aug' + str(self.input_meta.id)
+        return self
+
+    def get_data(self):
+        from ..db.dataset import MLPDataset
+        return MLPDataset(input_data={'img': self.output_imgs, 'mask': self.output_masks, 'meta': self.output_meta})

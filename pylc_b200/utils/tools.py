@@ -248,3 +248,49 @@ def confirm_write_file(file_path):
     return True if not os.path.exists(file_path) or \
         input("\nFile {} exists.\n\tOverwrite?  (Enter 'Y' or 'y' for yes): ".format(file_path)) in ['Y', 'y'] \
         else False
+
+
+# ---- augmentation warps (reference tools.py:452-594) ---------------------------------------------------
+# Host OpenCV calls, kept call for call: the same library on the same arguments gives the same bytes as the
+# reference (random_state drives both the corner jitter and the brightness shift).  Outside the accelerated
+# path: a tile is 256 KB and the reference applies at most four warps per tile.
+
+def channel_shift(img, random_state):
+    """Random brightness: + int(U(10, 20)), clipped to u8 (reference tools.py:528-553)."""
+    shift_val = int(random_state.uniform(10, 20))
+    return np.uint8(np.clip(np.int16(img) + shift_val, 0, 255))
+
+
+def perspective_shift(img, mask, random_state):
+    """Random perspective jitter of four fixed control points, reflect-101 border, 30-px crop and resize
+    back to the tile size; masks use nearest-neighbour throughout (reference tools.py:556-594)."""
+    w = mask.shape[0]
+    h = mask.shape[1]
+    alpha = 0.06 * w
+    pts1 = np.float32([[56, 65], [368, 52], [28, 387], [389, 390]])
+    pts2 = pts1 + random_state.uniform(-alpha, alpha, size=pts1.shape).astype(np.float32)
+    m_trans = cv2.getPerspectiveTransform(pts1, pts2)
+    img = cv2.warpPerspective(img, m_trans, (w, h), flags=cv2.INTER_AREA, borderMode=cv2.BORDER_REFLECT_101)
+    mask = cv2.warpPerspective(mask, m_trans, (w, h), flags=cv2.INTER_NEAREST, borderMode=cv2.BORDER_REFLECT_101)
+    img = img[30:w - 30, 30:h - 30]
+    img = cv2.resize(img.astype('float32'), (w, h), interpolation=cv2.INTER_AREA)
+    mask = mask[30:w - 30, 30:h - 30]
+    mask = cv2.resize(mask.astype('float32'), (w, h), interpolation=cv2.INTER_NEAREST)
+    return img, mask
+
+
+def augment_transform(img, mask, random_state=None):
+    """img [1,ch,T,T], mask [1,T,T] -> (img [ch,T,T] or [T,T], mask [T,T]), perspective shift then brightness
+    shift (reference tools.py:452-492)."""
+    assert img.shape[2:] == mask.shape[1:], \
+        "Image dimensions {} must match mask shape {}.".format(img.shape, mask.shape[:2])
+    if random_state is None:
+        random_state = np.random.RandomState(None)
+    nch = img.shape[1]
+    img = np.squeeze(np.moveaxis(img, 1, -1), axis=0)
+    mask = np.squeeze(mask, axis=0)
+    img, mask = perspective_shift(img, mask, random_state)
+    img = channel_shift(img, random_state)
+    if nch == 3:
+        img = np.moveaxis(img, -1, 0)
+    return img, mask

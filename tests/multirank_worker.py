@@ -120,16 +120,45 @@ def main():
     crit_a(z_loc2, t_all[rank * B:(rank + 1) * B]).backward()
     out["grad_ddp_rel"] = (z_loc2.grad / world - g_one).abs().max().item() / den
 
+    # ---- (4) one data-parallel training step: DDP + MultiLoss(distributed, ddp_average) ---------------
+    # parameter gradients after DDP's averaging == gradients of the single large batch on one rank
+    # (BatchNorm in eval mode so that batch statistics do not depend on the shard; fp32 convolutions)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from pylc_b200.models.deeplab import DeepLab
+    torch.manual_seed(1)
+    net = DeepLab(n_classes=C).to(device).eval()
+    import copy
+    net_ref = copy.deepcopy(net)            # the single-rank reference runs on an unwrapped copy
+    gx = torch.Generator().manual_seed(21)
+    x_all = torch.randn(2 * world, 3, 96, 96, generator=gx).to(device)
+    y_all = torch.randint(0, C, (2 * world, 96, 96), generator=gx).to(device)
+    ddp = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local])
+    crit_t = MultiLoss(lw, schema, distributed=True, ddp_average=True)
+    crit_t.weights = crit_t.weights.to(device)
+    ddp.zero_grad()
+    crit_t(ddp(x_all[rank * 2:(rank + 1) * 2]), y_all[rank * 2:(rank + 1) * 2]).backward()
+    g_ddp = [p.grad.detach().clone() for p in net.parameters() if p.grad is not None]
+    crit_s = MultiLoss(lw, schema, distributed=False)
+    crit_s.weights = crit_s.weights.to(device)
+    crit_s(net_ref(x_all), y_all).backward()
+    g_one = [p.grad.detach().clone() for p in net_ref.parameters() if p.grad is not None]
+    num = torch.sqrt(sum(((a - b) ** 2).sum() for a, b in zip(g_ddp, g_one)))
+    den2 = torch.sqrt(sum((b ** 2).sum() for b in g_one))
+    out["param_grad_rel"] = float(num / den2)
+    out["n_param_grads"] = len(g_one)
+
     # every rank must agree: reduce the boolean verdicts (min) and the errors (max)
     flags = torch.tensor([float(out[k]) for k in ("conf_equal", "conf_contig_equal", "hist_equal", "probs_equal",
                                                   "mean_std_close")], device=device)
     torch.distributed.all_reduce(flags, op=torch.distributed.ReduceOp.MIN)
-    errs = torch.tensor([out["loss_rel"], out["grad_rel"], out["grad_ddp_rel"]], device=device, dtype=torch.float64)
+    errs = torch.tensor([out["loss_rel"], out["grad_rel"], out["grad_ddp_rel"], out["param_grad_rel"]], device=device,
+                        dtype=torch.float64)
     torch.distributed.all_reduce(errs, op=torch.distributed.ReduceOp.MAX)
     if rank == 0:
         for k, v in zip(("conf_equal", "conf_contig_equal", "hist_equal", "probs_equal", "mean_std_close"), flags.tolist()):
             out[k] = bool(v)
-        out["loss_rel"], out["grad_rel"], out["grad_ddp_rel"] = errs.tolist()
+        out["loss_rel"], out["grad_rel"], out["grad_ddp_rel"], out["param_grad_rel"] = errs.tolist()
         out["launches"] = int(ops._lib.launch_count())
         print(json.dumps(out), flush=True)
     torch.distributed.destroy_process_group()

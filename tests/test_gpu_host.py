@@ -318,6 +318,27 @@ def test_pipeline_matches_reference_sequence(ops, palettes, fuse):
     assert s["iou"] == orc.metrics_port(yt, yp, model.meta.class_codes)["iou"]
 
 
+def test_pipeline_fused_upsample_flag_changes_nothing(ops, palettes):
+    """TiledSegmenter(fuse_upsample=True) (the default with the inference plan: the stitch reads the decoder
+    output) and fuse_upsample=False (up-sample kernel + stitch kernel) give the same label
+    map, full-size prediction and confusion matrix, bit for bit."""
+    from pylc_b200.pipeline import TiledSegmenter
+    model = _tiny_model(3)
+    pal = palettes["a"]
+    W, H = 1600, 1200
+    img = orc.synth_image(31, W, H, 3)
+    gt = orc.synth_mask(31, W, H, pal, skew=True)
+    seg_a = TiledSegmenter(model, batch_tiles=8, keep_masks=True, fuse_network=True, fuse_upsample=True)
+    seg_b = TiledSegmenter(model, batch_tiles=8, keep_masks=True, fuse_network=True, fuse_upsample=False)
+    assert seg_a.fuse_upsample and not seg_b.fuse_upsample
+    seg_b.fused = seg_a.fused            # one plan (one set of per-layer route choices) for both
+    conf_a, res_a = seg_a.run_host([img], [gt])
+    conf_b, res_b = seg_b.run_host([img], [gt])
+    assert torch.equal(res_a[0]["labels"], res_b[0]["labels"])
+    assert torch.equal(res_a[0]["pred_full"], res_b[0]["pred_full"])
+    assert np.array_equal(conf_a, conf_b)
+
+
 @pytest.mark.parametrize("fuse", [False, True])
 def test_pipeline_grayscale_image(ops, palettes, fuse):
     """ch = 1 (historic photographs, BASELINE configs[0] / configs[4]): the gather replicates the gray
@@ -386,6 +407,40 @@ def test_augmentor_optimize_golden(ops, golden, name):
     for a, b in zip(aug.profile_data, data):
         assert a["jsd"] == b["jsd"] and a["m2"] == b["m2"] and a["aug_n_samples"] == b["aug_n_samples"]
         assert np.array_equal(a["probs"], b["probs"])
+
+
+def test_augmentor_oversample(ops, golden, palettes):
+    """Augmentor.oversample (reference augment.py:184-239): every input tile once, plus rates[i] warped copies
+    whose bytes are the reference's (golden warp vectors, RandomState(j)); the augmented set is profiled on the
+    device and its histogram is the bincount of the output masks."""
+    from pylc_b200.config import Parameters
+    from pylc_b200.db.dataset import MLPDataset
+    from pylc_b200.utils.augment import Augmentor
+    g = golden("warp")
+    img, mask = orc.augment_fixture_tile(3)
+    rng = np.random.default_rng(2)
+    other_img = rng.integers(0, 256, size=img.shape, dtype=np.uint8)
+    other_mask = orc.synth_labels(6, 512, 512, 9)[None]
+    meta = Parameters()
+    meta.update({"ch": 3})
+    dset = MLPDataset(input_data={"img": np.concatenate([img, other_img]), "mask": np.concatenate([mask, other_mask]),
+                                  "meta": meta})
+    aug = Augmentor().load(dset)
+    aug.rates = np.array([2, 0])                      # two warped copies of tile 0, none of tile 1
+    aug.oversample(shuffle=False)
+    assert aug.output_imgs.shape == (4, 3, 512, 512) and aug.output_masks.shape == (4, 512, 512)
+    assert np.array_equal(aug.output_imgs[0], img[0]) and np.array_equal(aug.output_masks[0], mask[0])
+    for j in (0, 1):
+        assert np.array_equal(aug.output_imgs[1 + j], g["warp_ch3_s%d_img" % j])
+        assert np.array_equal(aug.output_masks[1 + j], g["warp_ch3_s%d_mask" % j])
+    assert np.array_equal(aug.output_imgs[3], other_img[0]) and np.array_equal(aug.output_masks[3], other_mask[0])
+    m = aug.output_meta
+    assert m.n_samples == 4 and m.id.startswith("_aug")
+    assert m.dset_px_dist == np.bincount(aug.output_masks.ravel(), minlength=9).tolist()
+    shuffled = Augmentor().load(dset)
+    shuffled.rates = np.array([1, 1])
+    shuffled.oversample()
+    assert shuffled.output_imgs.shape[0] == 4
 
 
 def test_sample_rate_grid_wide_classes(ops):

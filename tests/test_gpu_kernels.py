@@ -328,6 +328,36 @@ def test_stitch_fitted_3000x2000(ops, palettes):
     assert mism <= total * 1e-5
 
 
+@pytest.mark.parametrize("C,nr,nc,T,S,tpb", [(9, 3, 5, 512, 256, 8), (11, 2, 2, 512, 256, 4), (5, 2, 3, 512, 512, 6),
+                                             (12, 1, 2, 512, 256, 2), (9, 2, 2, 256, 128, 3)])
+def test_stitch_fused_upsample_equals_two_kernel_route(ops, palettes, C, nr, nc, T, S, tpb):
+    """the stitch that reads the decoder's [b, T/4, T/4, C] channels-last output and evaluates
+    the network's final x4 bilinear up-sample itself (models/architectures/deeplab.py:38) is BIT-identical to
+    up-sample-to-logits followed by the stitch -- stitched map, labels and RGB -- and within the north-star
+    tolerances of the reference sequence F.interpolate -> tools.reconstruct evaluated by the oracle."""
+    n, hs = nr * nc, T // 4
+    g = torch.Generator().manual_seed(C * 100 + n)
+    dec_all = (torch.randn(n, C, hs, hs, generator=g) * 3).cuda().contiguous(memory_format=torch.channels_last)
+    batches = [dec_all[i:i + tpb].contiguous(memory_format=torch.channels_last) for i in range(0, n, tpb)]
+    lut = (palettes["a"] + palettes["b"])[:C]
+    logits = [ops.upsample_nhwc_to_nchw(b, (T, T)) for b in batches]
+    lab2, rgb2, map2 = ops.stitch_argmax_colour(logits if len(logits) > 1 else logits[0], nr, nc, T, S, lut_rgb=lut,
+                                                want_rgb=True, want_stitched=True, tiles_per_batch=tpb)
+    lab1, rgb1, map1 = ops.stitch_upsample_argmax_colour(batches, nr, nc, T, S, lut_rgb=lut, want_rgb=True,
+                                                         want_stitched=True, tiles_per_batch=tpb)
+    assert torch.equal(map1, map2)
+    assert torch.equal(lab1, lab2) and torch.equal(rgb1, rgb2)
+    # labels only (the pipeline's call)
+    lab0, _, _ = ops.stitch_upsample_argmax_colour(batches, nr, nc, T, S, tiles_per_batch=tpb)
+    assert torch.equal(lab0, lab1)
+    if n * T * T <= 4 * 512 * 512 and S < T:
+        up = torch.nn.functional.interpolate(dec_all.cpu().contiguous(), size=(T, T), mode="bilinear", align_corners=True)
+        ref_map = orc.stitch_map(up.numpy(), nr, nc, T, S)
+        np.testing.assert_allclose(map1.cpu().numpy(), ref_map, rtol=1e-5, atol=2e-6)
+        bad = lab1.cpu().numpy() != orc.stitch_labels(ref_map)
+        assert not (bad & (orc.top2_margin(ref_map) > 1e-5)).any()
+
+
 def test_colourise(ops, golden, palettes):
     g = golden("colourize")
     for name in ("a", "b"):

@@ -34,4 +34,6 @@ def test_sharded_path_equals_single_rank(world):
     # floating point: loss within 1e-4 relative (north_star), gradient of the local logits likewise
     assert res["loss_rel"] <= 1e-4
     assert res["grad_rel"] <= 2e-3 and res["grad_ddp_rel"] <= 2e-3
+    # one DDP training step: averaged parameter gradients == the single large batch's (fp32 convolutions)
+    assert res["n_param_grads"] > 300 and res["param_grad_rel"] <= 1e-3
     assert res["launches"] > 0

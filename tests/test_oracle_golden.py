@@ -235,3 +235,22 @@ def test_model_load_reads_reference_pickled_meta(tmp_path, monkeypatch):
     fresh = Parameters()
     fresh.update(vars(meta))                                  # Model.load: self.meta.update(model_data["meta"])
     assert fresh.class_codes == meta.class_codes
+
+
+# ---------------------------------------------------------------------------------------------
+# augmentation warps (utils/tools.py:452-594) -- host OpenCV calls in the reference and here
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("ch", [1, 3])
+@pytest.mark.parametrize("seed", [0, 1, 3])
+def test_augment_transform_equals_reference(golden, ch, seed):
+    """pylc_b200.utils.tools.augment_transform gives the bytes the reference's own function gave for the same
+    tile, dtypes and RandomState seed (perspective jitter, reflect border, crop + resize, brightness shift)."""
+    from pylc_b200.utils import tools
+    g = golden("warp")
+    img, mask = orc.augment_fixture_tile(ch)
+    a, b = tools.augment_transform(img.astype(np.float32), mask.astype(np.int64), np.random.RandomState(seed))
+    want_img, want_mask = g["warp_ch%d_s%d_img" % (ch, seed)], g["warp_ch%d_s%d_mask" % (ch, seed)]
+    assert np.asarray(a).dtype == np.uint8 and np.array_equal(np.asarray(a), want_img)
+    assert np.array_equal(np.asarray(b).astype(np.uint8), want_mask)
+    assert not np.array_equal(want_img.reshape(img.shape[1:] if ch == 3 else img.shape[2:]), img[0] if ch == 3 else img[0, 0])
