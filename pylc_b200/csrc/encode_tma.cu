@@ -43,17 +43,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     if (n <= 0) return;
 
     const uint32_t in0 = smem_u32(s_dyn), out0 = in0 + kStages * kBoxIn, bar0 = smem_u32(s_bar);
-    s_tab[tid] = ph.tab[tid];
-    if (tid < PYLC_MAX_CLASSES) s_hist[tid] = 0;
-    if (tid == 0) {
-        tma_prefetch_desc(&tm_src);
-        tma_prefetch_desc(&tm_dst);
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8u * s, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
     // boxes are walked row-major; box `item` covers pixels [bx*256, +256) x rows [by*32, +32)
     auto issue_load = [&](int item, int stage) {
         const int by = item / g.nbx, bx = item - by * g.nbx;
@@ -61,8 +50,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
         mbar_arrive_expect_tx(bar, kBoxIn);       // out-of-bounds parts of an edge box are zero-filled and still counted
         tma_load_2d(in0 + (uint32_t)stage * kBoxIn, &tm_src, bx * (kBoxPx * 3 / 4), by * kBoxRows, bar);
     };
-    if (tid == 0)
+    // thread 0 puts the first boxes in flight before the table copy and the barrier (see gather_tma.cu)
+    if (tid == 0) {
+        tma_prefetch_desc(&tm_src);
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8u * s, 1);
+        mbar_fence_init();
         for (int k = 0; k < kStages && k < n; ++k) issue_load(first + k, k);
+        tma_prefetch_desc(&tm_dst);
+    }
+    s_tab[tid] = ph.tab[tid];
+    if (tid < PYLC_MAX_CLASSES) s_hist[tid] = 0;
+    __syncthreads();
 
     const uint32_t mul = ph.mul, tab = smem_u32(s_tab);
     const uint32_t miss_e = 1u << 24;             // unmatched colours are class 1 (utils/tools.py:437)

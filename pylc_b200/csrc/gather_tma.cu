@@ -106,28 +106,28 @@ __global__ void __launch_bounds__(kThreads, kMaskCtasPerSm)
     if (n <= 0) return;
 
     const uint32_t in0 = smem_u32(s_dyn), out0 = in0 + kStages * kBoxIn, bar0 = smem_u32(s_bar);
-    s_tab[tid] = ph.tab[tid];
-    if (tid == 0) {
-        tma_prefetch_desc(&tm_src);
-        tma_prefetch_desc(&tm_dst);
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8u * s, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
     auto issue_load = [&](const BoxPos &p, int stage) {   // source coordinates in 32-bit elements / rows
         const uint32_t bar = bar0 + 8u * stage;
         mbar_arrive_expect_tx(bar, kBoxIn);
         tma_load_2d(in0 + (uint32_t)stage * kBoxIn, &tm_src, (p.bx * g.S + p.xp * kBoxPx) * 3 / 4, p.by * g.S + p.rg * kBoxRows, bar);
     };
+    // thread 0 puts the first boxes in flight before anything else happens in the CTA: the table copy and
+    // the barrier below overlap the loads' latency (the other threads only need the barriers initialised
+    // before they WAIT on them, which the __syncthreads guarantees)
     BoxPos pl = box_decode(g, first);       // next box to load (thread 0 only)
     if (tid == 0) {
+        tma_prefetch_desc(&tm_src);
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8u * s, 1);
+        mbar_fence_init();
         for (int k = 0; k < kStages && k < n; ++k) {
             issue_load(pl, k);
             pl = box_next(g, pl);
         }
+        tma_prefetch_desc(&tm_dst);
     }
+    s_tab[tid] = ph.tab[tid];
+    __syncthreads();
 
     const uint32_t mul = ph.mul, tab = smem_u32(s_tab);
     const uint32_t miss_e = 1u << 24;       // unmatched colours are class 1 (utils/tools.py:437)

@@ -230,7 +230,7 @@ __device__ __forceinline__ void loss_reduce_pass(const LossArgs &a, double *part
 
     // an out-of-range target poisons the CE numerator: every loss value and every gradient of this batch
     // becomes NaN instead of silently using another class's weight (the host mirror turns it into an error)
-    if (bad) ce_num = __int_as_float(0x7FC00000);
+    if (bad) ce_num = ce_den = __int_as_float(0x7FC00000);      // ce_den reaches every gradient through 1 / sum(w_t)
     // block reduction: warp shuffles in f32, cross-warp in f64 shared atomics
     const int lane = threadIdx.x & 31;
 #pragma unroll

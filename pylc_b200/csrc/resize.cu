@@ -142,9 +142,9 @@ constexpr int kArea2NE = kArea2Elems / kAreaThreads;
 template <int CN>
 __global__ void __launch_bounds__(kAreaThreads) area_resize_lt2_kernel(AreaArgs a) {
     extern __shared__ __align__(16) uint8_t s_dyn2[];
-    // layout: [stage_rows + 1][kArea2Elems] float sums | [rows_cta] uint4 {r0, beta0, beta1, beta2} | staged bytes
+    // layout: [stage_rows + 2][kArea2Elems] float sums | [rows_cta] uint4 {r0, beta0, beta1, beta2} | staged bytes
     float *s_buf = reinterpret_cast<float *>(s_dyn2);
-    uint4 *s_row = reinterpret_cast<uint4 *>(s_dyn2 + (size_t)(a.stage_rows + 1) * kArea2Elems * 4);
+    uint4 *s_row = reinterpret_cast<uint4 *>(s_dyn2 + (size_t)(a.stage_rows + 2) * kArea2Elems * 4);
     uint8_t *s_src = reinterpret_cast<uint8_t *>(s_row + a.rows_cta);
     const int dx0 = blockIdx.x * a.cols_cta, dx1 = min(a.dw, dx0 + a.cols_cta);
     const int dy0 = blockIdx.y * a.rows_cta, dy1 = min(a.dh, dy0 + a.rows_cta);
@@ -196,11 +196,12 @@ __global__ void __launch_bounds__(kAreaThreads) area_resize_lt2_kernel(AreaArgs 
     }
     __syncthreads();
 
-    // ---- H: one horizontal sum per (staged row, element); row `nrows` is a finite don't-care for 0-weight taps
+    // ---- H: one horizontal sum per (staged row, element); rows `nrows`, `nrows + 1` are finite don't-cares for the
+    //      0-weight vertical taps of the last destination rows (a 1:1 resize has ONE live tap per row)
     const uint32_t lo0 = (uint32_t)((src0 + (size_t)s_lo * a.src_pitch + (size_t)x_lo * CN) & 15), plo = (uint32_t)(a.src_pitch & 15);
     const uint32_t src_s = (uint32_t)__cvta_generic_to_shared(s_src), buf_s = (uint32_t)__cvta_generic_to_shared(s_buf);
 #pragma unroll 2
-    for (int r = 0; r <= nrows; ++r) {
+    for (int r = 0; r <= nrows + 1; ++r) {
         const uint32_t row = src_s + (uint32_t)r * (uint32_t)a.row_stride + ((lo0 + (uint32_t)r * plo) & 15u);
 #pragma unroll
         for (int i = 0; i < kArea2NE; ++i) {
@@ -322,7 +323,7 @@ extern "C" int pylc_fit_resize_area_u8(const uint8_t *src, int H, int W, int ch,
         a.rows_cta = 16;
         a.row_stride = (((int)ceil(a.cols_cta * sx) + 2) * ch + 30 + 15) & ~15;
         a.stage_rows = (int)ceil(a.rows_cta * sy) + 2;
-        const size_t smem = (size_t)(a.stage_rows + 1) * kArea2Elems * 4 + (size_t)a.rows_cta * 16 + (size_t)(a.stage_rows + 1) * a.row_stride + 64;   // + slack: 0-weight taps read a few bytes past the last row
+        const size_t smem = (size_t)(a.stage_rows + 2) * kArea2Elems * 4 + (size_t)a.rows_cta * 16 + (size_t)(a.stage_rows + 2) * a.row_stride + 64;   // + slack: 0-weight taps read a few bytes past the last row
         const dim3 grid((unsigned)((w + a.cols_cta - 1) / a.cols_cta), (unsigned)((h + a.rows_cta - 1) / a.rows_cta));
         cudaError_t e = ch == 1 ? cudaFuncSetAttribute(area_resize_lt2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                 : cudaFuncSetAttribute(area_resize_lt2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

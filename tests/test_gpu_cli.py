@@ -57,7 +57,7 @@ def test_cli_extract_profile_test_on_files(tmp_path, palettes):
     key = lambda a, b: (a.tobytes(), b.tobytes())               # noqa: E731
     assert sorted(key(a, b) for a, b in zip(got_img, got_mask)) == sorted(key(a, b) for a, b in zip(want_img, want_mask))
     meta = data["meta"]
-    ref = orc.profile_port(want_img, want_mask, C)
+    ref = orc.profile_port(want_img, want_mask, C, T)
     assert meta.n_samples == 6 and meta.ch == 1 and meta.n_classes == C
     assert meta.dset_px_dist == [int(v) for v in ref["dset_px_dist"]]
     assert sorted(map(tuple, meta.px_dist)) == sorted(map(tuple, np.asarray(ref["px_dist"]).tolist()))
@@ -108,6 +108,7 @@ def test_cli_extract_profile_test_on_files(tmp_path, palettes):
     # and the label map itself is the reference's reconstruct of THIS network's logits (near-ties aside)
     from pylc_b200.models.model import Model
     model = Model().load(model_file)
+    model.net.eval()                                                   # test.py:41
     fitted = cv2.resize(img, (w_fit, h_fit), interpolation=cv2.INTER_AREA)
     tiles = torch.from_numpy(orc.split_tiles(fitted, T, T // 2))
     logits = torch.cat([model.test(tiles[i:i + 8])[0] for i in range(0, len(tiles), 8)]).cpu().numpy()

@@ -237,6 +237,14 @@ def main():
     report("stitch_argmax_colour 45 tiles C9 labels (bench.py image)", 45 * C * T * T * 4 + 2560 * 1536,
            lambda: ops.stitch_argmax_colour(logits[:45], 5, 9, T, 256), "every logit once + 1 B label")
     del logits
+    # §8f-1: the same image stitched straight from the decoder's [45, 9, 128, 128] channels-last output, the
+    # final x4 bilinear up-sample evaluated in the kernel (no 424 MB logits round trip)
+    dec = (torch.randn((45, C, T // 4, T // 4), generator=g, device="cuda") * 3).contiguous(memory_format=torch.channels_last)
+    report("stitch_upsample_argmax_colour 45 tiles C9 labels (bench.py image)", dec.numel() * 4 + 2560 * 1536,
+           lambda: ops.stitch_upsample_argmax_colour(dec, 5, 9, T, 256),
+           "decoder output once + 1 B label; replaces upsample_nhwc_to_nchw + stitch_argmax_colour (2 x 424.7 MB + 26.5 MB of traffic); "
+           "exp- and blend-bound, not HBM-bound: compare its time with the sum of those two rows")
+    del dec
 
     # ---- evaluation --------------------------------------------------------------------------
     maps = (torch.from_numpy(ops.nn_index_map(Wf, W)).cuda(), torch.from_numpy(ops.nn_index_map(Hf, H)).cuda())
