@@ -15,10 +15,11 @@ only collective is the all-reduce of the [9,9] i64 confusion matrix.
 
     value   Mpx/s with the fitted images and ground truths already resident in HBM
     e2e     Mpx/s through pylc_b200.pipeline.TiledSegmenter.run_host: decoded images in pinned
-            host memory -> host fit-resize (OpenCV, as the reference) -> H2D -> GPU -> D2H of the
-            confusion matrix; every byte of every step's input crosses PCIe inside the timed region
-    roofline   the dominant custom kernel (fused stitch+softmax+argmax), timed live with CUDA
-            events on its stream inside the timed steps
+            host memory -> pitched H2D on the copy engine -> device fit-resize (bit-exact INTER_AREA)
+            -> gather -> network -> stitch -> resample + confusion -> D2H of the confusion matrix;
+            every byte of every step's input crosses PCIe inside the timed region
+    roofline   the custom kernel with the largest share of the timed step, timed live with CUDA
+            events on its stream inside the timed steps; `kernels` lists every custom launch
     cpu_baseline / --impl reference   the reference's CPU path (oracle port: same per-class
             passes, band-merge loops, scikit-learn calls; torch CPU network) on the host cores
 """
@@ -317,8 +318,8 @@ KERNEL_OF = {
     "upsample_nhwc_to_nchw": ("upsample_to_nchw_staged_kernel", "upnchw", "hbm"),
     "tile_gather_norm_s2d": ("gather_norm_s2d_staged_kernel", "gather_s2d", "hbm"),
     "tile_gather_norm_f32": ("gather_norm_staged_kernel", "gather_norm", "hbm"),
-    "fit_resize_area": ("area_resize_lt2_kernel", "resize", "issue (OpenCV's float sequence replayed exactly)"),
-    "resample_encode_confusion": ("resample_confusion_kernel", "resample", "issue (exact palette look-up + counters)"),
+    "fit_resize_area": ("area_resize_x2_kernel", "resize", "issue (OpenCV's float sequence replayed exactly, two elements per FFMA2 / FADD2)"),
+    "resample_encode_confusion": ("resample_confusion_tma_kernel", "resample", "hbm in the steady state; set-up and flush of a 15 us launch"),
 }
 
 

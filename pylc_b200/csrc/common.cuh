@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -44,6 +45,15 @@ int launch_mask_gather_tma(const uint8_t *src, int H, int W, size_t pitch, int T
                            uint8_t *dst, long long *px_dist, cudaStream_t st);
 int launch_class_encode_tma(const uint8_t *rgb, long long rows, long long cols, size_t pitch, const PaletteHash &ph, int C,
                             uint8_t *out, long long *hist, cudaStream_t st);
+
+// PYLC_NO_TMA=1 in the environment keeps every entry point on its per-thread kernel (A/B measurements, tests)
+inline bool tma_disabled() {
+    const char *e = getenv("PYLC_NO_TMA");
+    return e && e[0] == '1';
+}
+int launch_resample_confusion_tma(const uint8_t *labels, int h, int w, const int32_t *x_ofs, const int32_t *y_ofs, int h_full, int w_full,
+                                  const uint8_t *gt_rgb, size_t gt_pitch, const PaletteHash &ph, int C, int n_inject, long long *conf,
+                                  cudaStream_t st);
 
 #ifdef __CUDACC__
 

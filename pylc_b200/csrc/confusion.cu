@@ -474,6 +474,12 @@ extern "C" int pylc_resample_encode_confusion(const uint8_t *labels, int h, int 
         for (int i = 0; i < 256; ++i) ph.tab[i] = 1u << 24;
         ph.mul = 1;
     }
+    // counts only, aligned rows, C <= 11: the TMA form (confusion_tma.cu); PYLC_NO_TMA=1 keeps the per-thread kernel
+    if (conf && gt_rgb && !pred_full && !pred_rgb && !gt_full && !tma_disabled()) {
+        const int rc = launch_resample_confusion_tma(labels, h, w, x_ofs, y_ofs, h_full, w_full, gt_rgb, gt_pitch, ph, C, n_inject,
+                                                     reinterpret_cast<long long *>(conf), (cudaStream_t)stream);
+        if (rc >= 0) return rc;
+    }
     ColourLut lut;
     if (lut_rgb) build_colour_lut(lut_rgb, C, &lut);
     else for (int i = 0; i < PYLC_MAX_CLASSES; ++i) lut.rgb[i] = 0;

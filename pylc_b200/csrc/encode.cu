@@ -321,7 +321,7 @@ extern "C" int pylc_class_encode(const uint8_t *rgb, int n_img, int rows, int co
     const long long per_cta = (long long)kThreads * kUnitsPerThread;
     const unsigned grid = (unsigned)((a.total_units + per_cta - 1) / per_cta);
     cudaStream_t st = (cudaStream_t)stream;
-    if (layout == 0) {   // TMA form: 16-byte aligned rows, whole 16-pixel units per output row
+    if (layout == 0 && !tma_disabled()) {   // TMA form: 16-byte aligned rows, whole 16-pixel units per output row
         rc = launch_class_encode_tma(rgb, a.rows, a.cols, pitch, ph, C, out, a.hist, st);
         if (rc != -1) return rc;
     }

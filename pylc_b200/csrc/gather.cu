@@ -1084,7 +1084,7 @@ extern "C" int pylc_mask_gather_encode_hist(const uint8_t *src, int H, int W, si
     const bool al = aligned16(src, src_pitch);
     auto *pd = reinterpret_cast<long long *>(px_dist);
     // TMA form (16-byte aligned rows, S a multiple of 256, T/S <= 2): the reference's two geometries
-    rc = launch_mask_gather_tma(src, H, W, src_pitch, T, S, g.nH, g.nW, ph, C, dst, pd, st);
+    rc = tma_disabled() ? -1 : launch_mask_gather_tma(src, H, W, src_pitch, T, S, g.nH, g.nW, ph, C, dst, pd, st);
     if (rc != -1) return rc;
 #define LAUNCH(AL, NG, HS)                                                                                         \
     gather_mask_kernel<AL, NG, HS><<<persistent_ctas(gather_mask_kernel<AL, NG, HS>, g.items), kThreads, 0, st>>>( \

@@ -22,6 +22,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace pylc {
 
@@ -254,6 +255,241 @@ __global__ void __launch_bounds__(kAreaThreads) area_resize_lt2_kernel(AreaArgs 
     }
 }
 
+
+// ---- TMA + packed-f32x2 form for scale factors below 1.9 (sm_100a) -----------------------------------------
+// The fit-resize proper: what tools.adjust_to_tile asks for on 16-byte pitched device images.
+//   * A CTA owns 512 destination BYTES of a row (elements e = (dx, c); 128 threads x 4 consecutive elements, so
+//     a thread's store is one 32-bit word and a warp's a 128-byte line) and `rb` destination rows.
+//   * Its source patch arrives by cp.async.bulk.tensor.2d loads of 8-row boxes of the [H][pitch/4] source
+//     tensor, every box on its own mbarrier, all issued by one thread at kernel entry: the patch origin comes
+//     from the closed form of computeResizeAreaTab (area_start), not from a dependent table load.  No thread
+//     executes a staging instruction or a bounds check; out-of-image parts are zero-filled by the copy engine
+//     and only ever meet zero weights.
+//   * A thread walks DOWN the source rows: H(r) = the horizontal sums of its four elements on source row r
+//     (12 byte loads from the staged row; S*a as one FFMA on the bit pattern 2^23+S, two elements per
+//     instruction: fma.rn.f32x2 / add.rn.f32x2 -- SASS FFMA2 / FADD2 -- round each half exactly like the scalar
+//     FMUL / FADD of OpenCV's sequence).  The last three H rows live in registers; the row loop is unrolled by
+//     three so the ring rotates by renaming, without moves.  Destination row i is emitted when source row
+//     ys[i] + 2 has been summed (destination rows start on strictly increasing source rows for any down-scale):
+//     V = ((b0*H0) + b1*H1) + b2*H2 with the products as FFMA2 against an opaque zero, so the assembler cannot
+//     contract a product into the following add (ptxas does fuse mul.rn.f32x2 + add.rn.f32x2).
+//   Every horizontal sum is computed exactly once per CTA and never leaves registers.
+constexpr int kA3Elems = 512, kA3BoxRows = 8, kA3MaxBoxes = 16;
+
+struct Area3Args {
+    uint8_t *dst;
+    size_t dst_pitch;
+    int dst_row_bytes, dh;           // w * ch, h
+    int W, H, w, h;                  // source / destination sizes in pixels (area_start)
+    int rb, bw, nbox;                // destination rows per CTA; staged bytes per source row (multiple of 16); boxes per CTA
+    const int32_t *xs, *ys;
+    const float *xa, *ya;
+    float zero;                      // 0.0f the compiler cannot see
+    bool dst_words;                  // destination rows are 4-byte aligned
+};
+
+// start[d] of pylc_area_table, in closed form (same double arithmetic on the host and on the device)
+__host__ __device__ inline int area_start(int d, int ssize, int dsize) {
+    const double inv_scale = (double)dsize / ssize;
+    const double scale = 1. / inv_scale;
+    const double fsx1 = d * scale, fsx2 = fsx1 + scale;
+    int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+    sx2 = sx2 < ssize - 1 ? sx2 : ssize - 1;
+    sx1 = sx1 < sx2 ? sx1 : sx2;
+    return (sx1 - fsx1 > 1e-3) ? sx1 - 1 : sx1;
+}
+
+__device__ __forceinline__ unsigned long long f2_pack(uint32_t lo, uint32_t hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t b;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(addr));
+    return b;
+}
+__device__ __forceinline__ uint32_t cvt_u8_sat(float v) {      // saturate_cast<uchar>(cvRound(v))
+    uint32_t o;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(o) : "f"(v));
+    return o;
+}
+
+template <int CN>
+__global__ void __launch_bounds__(kAreaThreads) area_resize_x2_kernel(const __grid_constant__ CUtensorMap tm_src, const Area3Args a) {
+    extern __shared__ __align__(128) uint8_t s_dyn3[];        // nbox boxes of 8 rows x bw bytes | rb x uint4 {r0, beta0, beta1, beta2}
+    __shared__ __align__(8) unsigned long long s_bar[kA3MaxBoxes];
+    const int tid = threadIdx.x;
+    const int e0 = blockIdx.x * kA3Elems, dy0 = blockIdx.y * a.rb;
+    const int nd = min(a.rb, a.dh - dy0);
+    const uint32_t src_s = smem_u32(s_dyn3), bar0 = smem_u32(s_bar);
+    const uint32_t row_s = src_s + (uint32_t)a.nbox * kA3BoxRows * (uint32_t)a.bw;
+
+    // patch origin: source byte of the block's first element, source row of its first destination row
+    int byte0 = 0, s_lo = 0;
+    if (tid == 0) {
+        byte0 = area_start(e0 / CN, a.W, a.w) * CN;
+        s_lo = area_start(dy0, a.H, a.h);
+        tma_prefetch_desc(&tm_src);
+        for (int j = 0; j < a.nbox; ++j) mbar_init(bar0 + 8u * j, 1);
+        mbar_fence_init();
+        for (int j = 0; j < a.nbox; ++j) {
+            mbar_arrive_expect_tx(bar0 + 8u * j, (uint32_t)(kA3BoxRows * a.bw));
+            tma_load_2d(src_s + (uint32_t)(j * kA3BoxRows * a.bw), &tm_src, byte0 >> 2, s_lo + j * kA3BoxRows, bar0 + 8u * j);
+        }
+    }
+    // tables: the thread's four elements (clamped to the row) and the CTA's destination rows
+    const int x_lo = __ldg(a.xs + e0 / CN), y_lo = __ldg(a.ys + dy0);
+    uint32_t sb[4];
+    unsigned long long al2[2][3], ad2[2][3];
+    {
+        uint32_t alw[4][3];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = min(e0 + 4 * tid + i, a.dst_row_bytes - 1);
+            const int dx = e / CN, c = e - dx * CN;
+            sb[i] = (uint32_t)((__ldg(a.xs + dx) * CN + c) - ((x_lo * CN) & ~3));
+#pragma unroll
+            for (int k = 0; k < 3; ++k) alw[i][k] = __float_as_uint(__ldg(a.xa + (size_t)dx * PYLC_AREA_TAPS + k));
+        }
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                al2[p][k] = f2_pack(alw[2 * p][k], alw[2 * p + 1][k]);
+                ad2[p][k] = f2_pack(__float_as_uint(-8388608.f * __uint_as_float(alw[2 * p][k])),       // exact: power-of-two multiples
+                                    __float_as_uint(-8388608.f * __uint_as_float(alw[2 * p + 1][k])));
+            }
+    }
+    for (int i = tid; i < nd; i += kAreaThreads) {
+        const float *wv = a.ya + (size_t)(dy0 + i) * PYLC_AREA_TAPS;
+        sts128(row_s + 16u * i, make_uint4((uint32_t)(__ldg(a.ys + dy0 + i) - y_lo), __float_as_uint(__ldg(wv)), __float_as_uint(__ldg(wv + 1)),
+                                           __float_as_uint(__ldg(wv + 2))));
+    }
+    // the tables must be the ones area_start restates (pylc_area_table's): the patch was fetched for them
+    if (tid == 0 && (x_lo * CN != byte0 || y_lo != s_lo)) __trap();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (sb[i] + 2u * CN >= (uint32_t)a.bw) __trap();      // the host sizes the patch; never taken
+    __syncthreads();                                           // barriers initialised, row table written
+
+    const unsigned long long z2 = f2_pack(__float_as_uint(a.zero), __float_as_uint(a.zero));
+    const uint32_t bw = (uint32_t)a.bw;
+    auto hsum = [&](int r, unsigned long long &o0, unsigned long long &o1) {
+        if ((r & (kA3BoxRows - 1)) == 0) mbar_wait(bar0 + 8u * (uint32_t)(r / kA3BoxRows), 0);
+        const uint32_t row = src_s + (uint32_t)r * bw;
+        uint32_t p[4][3];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) p[i][k] = 0x4B000000u | lds_u8(row + sb[i] + (uint32_t)(k * CN));
+        o0 = f2_fma(f2_pack(p[0][0], p[1][0]), al2[0][0], ad2[0][0]);
+        o1 = f2_fma(f2_pack(p[2][0], p[3][0]), al2[1][0], ad2[1][0]);
+#pragma unroll
+        for (int k = 1; k < 3; ++k) {
+            o0 = f2_add(o0, f2_fma(f2_pack(p[0][k], p[1][k]), al2[0][k], ad2[0][k]));
+            o1 = f2_add(o1, f2_fma(f2_pack(p[2][k], p[3][k]), al2[1][k], ad2[1][k]));
+        }
+    };
+    const int n_valid = max(0, min(4, a.dst_row_bytes - (e0 + 4 * tid)));
+    uint8_t *d = a.dst + (size_t)dy0 * a.dst_pitch + (size_t)(e0 + 4 * tid);
+    uint4 rw = lds128(row_s);
+    int i = 0;
+    // emits destination row i from the H rows (h0: source row r0, h1: r0 + 1, h2: r0 + 2); true when it was the last one
+    auto emit = [&](unsigned long long h00, unsigned long long h01, unsigned long long h10, unsigned long long h11, unsigned long long h20,
+                    unsigned long long h21) -> bool {
+        const unsigned long long b0 = f2_pack(rw.y, rw.y), b1 = f2_pack(rw.z, rw.z), b2 = f2_pack(rw.w, rw.w);
+        unsigned long long s0 = f2_fma(h00, b0, z2), s1 = f2_fma(h01, b0, z2);
+        s0 = f2_add(s0, f2_fma(h10, b1, z2));
+        s1 = f2_add(s1, f2_fma(h11, b1, z2));
+        s0 = f2_add(s0, f2_fma(h20, b2, z2));
+        s1 = f2_add(s1, f2_fma(h21, b2, z2));
+        float v0, v1, v2, v3;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(s0));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(v2), "=f"(v3) : "l"(s1));
+        const uint32_t o0 = cvt_u8_sat(v0), o1 = cvt_u8_sat(v1), o2 = cvt_u8_sat(v2), o3 = cvt_u8_sat(v3);
+        if (n_valid == 4 && a.dst_words) {
+            *reinterpret_cast<uint32_t *>(d) = __byte_perm(__byte_perm(o0, o1, 0x0040), __byte_perm(o2, o3, 0x0040), 0x5410);
+        } else {
+            if (n_valid > 0) d[0] = (uint8_t)o0;
+            if (n_valid > 1) d[1] = (uint8_t)o1;
+            if (n_valid > 2) d[2] = (uint8_t)o2;
+            if (n_valid > 3) d[3] = (uint8_t)o3;
+        }
+        d += a.dst_pitch;
+        if (++i == nd) return true;
+        rw = lds128(row_s + 16u * (uint32_t)i);
+        return false;
+    };
+    unsigned long long A0 = 0, A1 = 0, B0 = 0, B1 = 0, C0 = 0, C1 = 0;
+    for (int r = 0;; r += 3) {
+        hsum(r, A0, A1);
+        if ((int)rw.x + 2 == r && emit(B0, B1, C0, C1, A0, A1)) break;
+        hsum(r + 1, B0, B1);
+        if ((int)rw.x + 2 == r + 1 && emit(C0, C1, A0, A1, B0, B1)) break;
+        hsum(r + 2, C0, C1);
+        if ((int)rw.x + 2 == r + 2 && emit(A0, A1, B0, B1, C0, C1)) break;
+    }
+}
+
+// Returns PYLC_OK / a CUDA error after launching, or -1 when the form does not apply (alignment, scale >= 1.9,
+// no tensor-map support): the caller falls through to the per-thread kernels.
+static int launch_area_resize_x2(const uint8_t *src, int H, int W, int ch, size_t src_pitch, uint8_t *dst, int h, int w, size_t dst_pitch,
+                                 const int32_t *xs, const float *xa, const int32_t *ys, const float *ya, cudaStream_t st) {
+    if (((uintptr_t)src % 16) || (src_pitch % 16) || tma_disabled()) return -1;
+    const double sx = (double)W / w, sy = (double)H / h;
+    if (sx >= 1.9 || sy >= 2.0) return -1;
+    Area3Args a;
+    a.dst = dst; a.dst_pitch = dst_pitch; a.dst_row_bytes = w * ch; a.dh = h; a.W = W; a.H = H; a.w = w; a.h = h;
+    a.xs = xs; a.ys = ys; a.xa = xa; a.ya = ya; a.zero = 0.f;
+    a.dst_words = ((uintptr_t)dst % 4 == 0) && (dst_pitch % 4 == 0);
+    a.bw = (((int)ceil((kA3Elems / ch + 2) * sx) + 2) * ch + 4 + 15) & ~15;
+    if (a.bw > 1024) return -1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int col_blocks = (a.dst_row_bytes + kA3Elems - 1) / kA3Elems;
+    auto kern = ch == 1 ? area_resize_x2_kernel<1> : area_resize_x2_kernel<3>;
+    // destination rows per CTA: the largest band that keeps the grid at a full wave or more, else the smallest
+    size_t smem = 0;
+    bool found = false;
+    const int cand[3] = {64, 32, 16};
+    for (int ci = 0; ci < 3; ++ci) {
+        const int rb = cand[ci];
+        const int nbox = ((int)ceil(rb * sy) + 4 + kA3BoxRows - 1) / kA3BoxRows;
+        const size_t sm = (size_t)nbox * kA3BoxRows * a.bw + (size_t)rb * 16;
+        if (nbox > kA3MaxBoxes || sm > 100 * 1024) continue;
+        a.rb = rb; a.nbox = nbox; smem = sm;
+        found = true;
+        if ((long long)col_blocks * ((h + rb - 1) / rb) >= (long long)sms * 2) break;
+    }
+    if (!found) return -1;
+    CUtensorMap tm;
+    {
+        const uint64_t dims[2] = {(uint64_t)(src_pitch / 4), (uint64_t)H};
+        const uint64_t strides[1] = {(uint64_t)src_pitch};
+        const uint32_t box[2] = {(uint32_t)(a.bw / 4), (uint32_t)kA3BoxRows};
+        if (!tma_encode_u32(&tm, src, 2, dims, strides, box)) return -1;
+    }
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    const dim3 grid((unsigned)col_blocks, (unsigned)((h + a.rb - 1) / a.rb));
+    kern<<<grid, kAreaThreads, smem, st>>>(tm, a);
+    return finish_launch();
+}
+
 }  // namespace pylc
 
 using namespace pylc;
@@ -317,6 +553,11 @@ extern "C" int pylc_fit_resize_area_u8(const uint8_t *src, int H, int W, int ch,
     a.dst = dst; a.dst_pitch = dst_pitch; a.dw = w; a.dh = h;
     a.xs = x_start; a.xn = x_count; a.xa = x_weights; a.ys = y_start; a.yn = y_count; a.ya = y_weights;
     const double sx = (double)W / w, sy = (double)H / h;
+    {
+        const int rc = launch_area_resize_x2(src, H, W, ch, src_pitch, dst, h, w, dst_pitch, x_start, x_weights, y_start, y_weights,
+                                             (cudaStream_t)stream);
+        if (rc != -1) return rc;
+    }
     if (sx < 2.0 && sy < 2.0) {
         // two-pass form: 384 destination bytes per row and CTA, up to 16 destination rows
         a.cols_cta = kArea2Elems / ch;

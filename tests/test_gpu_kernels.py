@@ -477,6 +477,40 @@ def test_resample_confusion_counts_only(ops, C, h, w, h_full, w_full, pitched):
     assert np.array_equal(conf.cpu().numpy(), 2 * orc.confusion_counts(yt, yp, C))
 
 
+@pytest.mark.parametrize("C,h,w,h_full,w_full,block,noise", [
+    (9, 1536, 2560, 2000, 3000, 50, False),   # the bench geometry: 12 column blocks, ragged last unit (3000 = 187.5 units)
+    (9, 1536, 2560, 2000, 3000, 50, True),    # per-pixel noise predictions: every group mixed (the dense branch)
+    (11, 256, 512, 301, 777, 23, False),      # ragged width (777 % 4 = 1: a partial group), 301 rows = 18.8 boxes
+    (9, 64, 160, 50, 100, 9, False),          # down-sampling by < 2: window lanes and per-pixel lanes in one warp
+    (9, 304, 400, 100, 130, 7, False),        # down-sampling by ~3: every lane gathers from global memory
+    (11, 512, 1024, 7, 2050, 3, False),       # fewer rows than one box, width just past a column block
+    (9, 1024, 1536, 1500, 2000, 200, False),  # configs[0]: large uniform regions (anchor path almost everywhere)
+    (2, 16, 16, 16, 16, 4, True),             # identity maps, two classes
+])
+def test_resample_confusion_tma_route(ops, monkeypatch, C, h, w, h_full, w_full, block, noise):
+    """Counts-only calls with 16-byte aligned rows take the TMA kernel (confusion_tma.cu): bit-exact against
+    the oracle's sklearn-equivalent counts, and equal to the per-thread kernel (PYLC_NO_TMA=1)."""
+    rng = np.random.default_rng(C * 1000 + w_full)
+    pal = rng.permutation(256 ** 3)[:C]
+    pal = [[int(v) & 255, (int(v) >> 8) & 255, int(v) >> 16] for v in pal]
+    labels = rng.integers(0, C, size=(h, w), dtype=np.uint8) if noise else orc.synth_labels(5, w, h, C, block=block)
+    gt = orc.synth_mask(6, w_full, h_full, pal, skew=False, off_palette=0.01)
+    d_gt, pitch = ops.upload_image(gt)
+    pred_full = orc.resample_labels(labels, w_full, h_full)
+    gt_lab = orc.class_encode_hwc(gt, pal)
+    for n_inject in (min(C, w_full), 0):
+        yt, yp = orc.inject_coverage(gt_lab, pred_full, n_inject)
+        want = orc.confusion_counts(yt, yp, C)
+        got = {}
+        for no_tma in ("0", "1"):
+            monkeypatch.setenv("PYLC_NO_TMA", no_tma)
+            res = ops.resample_encode_confusion(dev(labels), w_full, h_full, gt_rgb=d_gt, gt_pitch=pitch, palette=pal, n_inject=n_inject)
+            got[no_tma] = res["conf"].cpu().numpy()
+        assert np.array_equal(got["0"], want)
+        assert np.array_equal(got["1"], want)
+        assert int(got["0"].sum()) == h_full * w_full
+
+
 def test_resample_confusion_uniform_tall_image(ops, palettes):
     """A single (truth, prediction) pair over a tall narrow image: every lane counter of one code
     column carries the whole count, and ragged 48-px rows take the byte-wise ground-truth loads."""

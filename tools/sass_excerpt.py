@@ -16,7 +16,8 @@ R = sys.argv[1] if len(sys.argv) > 1 else "r2"
 PAT = collections.OrderedDict([
     ("UTMALDG", r"\bUTMALDG"), ("UTMASTG", r"\bUTMASTG"), ("UTMAPF (prefetch.tensormap)", r"\bUTMAPF|UTMACCTL"),
     ("UTMACMDFLUSH (bulk commit)", r"\bUTMACMDFLUSH"), ("SYNCS (mbarrier)", r"\bSYNCS\."), ("LDGSTS (cp.async)", r"\bLDGSTS"),
-    ("DEPBAR (wait_group)", r"\bDEPBAR"), ("REDUX", r"\bREDUX"), ("MUFU.EX2", r"MUFU\.EX2"), ("ATOMS", r"\bATOMS"),
+    ("DEPBAR (wait_group)", r"\bDEPBAR"), ("FFMA2 / FADD2 (f32x2, sm_100+)", r"\bFFMA2|\bFADD2|\bFMUL2"), ("REDUX", r"\bREDUX"),
+    ("MUFU.EX2", r"MUFU\.EX2"), ("ATOMS", r"\bATOMS"),
 ])
 
 
