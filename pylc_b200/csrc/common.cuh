@@ -12,9 +12,20 @@ namespace pylc {
 
 extern std::atomic<int64_t> g_launches;
 
+// Launch errors are reported by the call itself.  A fault INSIDE a kernel is asynchronous and would surface in
+// a later CUDA call of the process; PYLC_SYNC_CHECK=1 in the environment makes every entry point wait for its
+// kernel and return that error from the call that caused it (debugging aid: serialises the stream).
+inline bool sync_check_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("PYLC_SYNC_CHECK");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
 inline int finish_launch() {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && sync_check_enabled()) e = cudaDeviceSynchronize();
     return e == cudaSuccess ? PYLC_OK : (int)e;
 }
 

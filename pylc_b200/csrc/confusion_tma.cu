@@ -91,9 +91,13 @@ __device__ __forceinline__ void count_queued(uint32_t entry, uint32_t my_col, ui
         if (jj < nv) bump16(my_col + __byte_perm(idx, 0, 0x4440u | jj) * 64u, 1u);
 }
 
+#ifdef PYLC_CF_DEBUG      // per-CTA timeline for tools/exp/cfdbg.py: make EXTRA=-DPYLC_CF_DEBUG (never in the shipped library)
 __device__ unsigned long long g_cf_dbg[8 * 512];
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define DBG(slot) do { if (tid == 0 && blockIdx.x < 512) { g_cf_dbg[blockIdx.x * 8 + (slot)] = gtime(); g_cf_dbg[blockIdx.x * 8 + 4 + (slot)] = clock64(); } } while (0)
+#else
+#define DBG(slot) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(kCfThreads, kCfCtasPerSm)
     resample_confusion_tma_kernel(const __grid_constant__ CUtensorMap tm_gt, const __grid_constant__ CUtensorMap tm_lab, const CfArgs a,
@@ -385,4 +389,6 @@ int launch_resample_confusion_tma(const uint8_t *labels, int h, int w, const int
 }
 
 }  // namespace pylc
+#ifdef PYLC_CF_DEBUG
 extern "C" __attribute__((visibility("default"))) int pylc_debug_read(void *dst, size_t bytes) { return (int)cudaMemcpyFromSymbol(dst, pylc::g_cf_dbg, bytes); }
+#endif

@@ -261,42 +261,49 @@ __global__ void __launch_bounds__(kAreaThreads) area_resize_lt2_kernel(AreaArgs 
 //   * A CTA owns 512 destination BYTES of a row (elements e = (dx, c); 128 threads x 4 consecutive elements, so
 //     a thread's store is one 32-bit word and a warp's a 128-byte line) and `rb` destination rows.
 //   * Its source patch arrives by cp.async.bulk.tensor.2d loads of 8-row boxes of the [H][pitch/4] source
-//     tensor, every box on its own mbarrier, all issued by one thread at kernel entry: the patch origin comes
-//     from the closed form of computeResizeAreaTab (area_start), not from a dependent table load.  No thread
-//     executes a staging instruction or a bounds check; out-of-image parts are zero-filled by the copy engine
-//     and only ever meet zero weights.
-//   * A thread walks DOWN the source rows: H(r) = the horizontal sums of its four elements on source row r
-//     (12 byte loads from the staged row; S*a as one FFMA on the bit pattern 2^23+S, two elements per
-//     instruction: fma.rn.f32x2 / add.rn.f32x2 -- SASS FFMA2 / FADD2 -- round each half exactly like the scalar
-//     FMUL / FADD of OpenCV's sequence).  The last three H rows live in registers; the row loop is unrolled by
-//     three so the ring rotates by renaming, without moves.  Destination row i is emitted when source row
-//     ys[i] + 2 has been summed (destination rows start on strictly increasing source rows for any down-scale):
-//     V = ((b0*H0) + b1*H1) + b2*H2 with the products as FFMA2 against an opaque zero, so the assembler cannot
-//     contract a product into the following add (ptxas does fuse mul.rn.f32x2 + add.rn.f32x2).
+//     tensor, every box on its own mbarrier, requested by one thread two boxes ahead of the row walk.  The patch
+//     origin comes from the closed form of computeResizeAreaTab (area_start, a dozen double operations), not
+//     from a dependent table load, so the copy engine starts ~1 us into the kernel.  No thread executes a
+//     staging instruction or a bounds check; out-of-image parts are zero-filled and only ever meet zero weights.
+//   * A thread walks DOWN the source rows: H(r) = the horizontal sums of its four elements on source row r.  Its
+//     twelve tap bytes come from 3-4 aligned shared-memory words and byte permutes (see `words` below), and S*a is
+//     one FFMA on the bit pattern 2^23+S, two elements per instruction: fma.rn.f32x2 / add.rn.f32x2 -- SASS
+//     FFMA2 / FADD2 -- round each half exactly like the scalar FMUL / FADD of OpenCV's sequence.  The last three
+//     H rows live in registers; the row loop is unrolled by three so the ring rotates by renaming, without
+//     moves.  Destination row i is emitted when source row ys[i] + 2 has been summed (destination rows start on
+//     strictly increasing source rows for any down-scale): V = ((b0*H0) + b1*H1) + b2*H2 with the products as
+//     FFMA2 against an opaque zero, so the assembler cannot contract a product into the following add (ptxas
+//     does fuse mul.rn.f32x2 + add.rn.f32x2, which would round once instead of twice).
+//   Measured per-CTA timeline (3000x2000 colour, 720 CTAs in one wave): copy engine started 0.9 us after kernel
+//   entry, tables in registers at 1.3 us, first source row summed at 2.7 us (median), last CTA done at 17.6 us;
+//   the row walk issues at ~64 % of the SM's slots -- the kernel is bound by its ~75 instructions per source row
+//   and quad, not by DRAM (18 MB read, 12 MB written).
 //   Every horizontal sum is computed exactly once per CTA and never leaves registers.
-constexpr int kA3Elems = 512, kA3BoxRows = 8, kA3MaxBoxes = 16;
+constexpr int kA3Elems = 512, kA3BoxRows = 8, kA3MaxBoxes = 16, kA3Ahead = 2;
 
 struct Area3Args {
     uint8_t *dst;
     size_t dst_pitch;
     int dst_row_bytes, dh;           // w * ch, h
-    int W, H, w, h;                  // source / destination sizes in pixels (area_start)
+    int W, H, w, h;                  // source / destination sizes in pixels
+    double scale_x, scale_y;         // 1. / ((double)w / W), 1. / ((double)h / H): computeResizeAreaTab's `scale`, evaluated on the host
     int rb, bw, nbox;                // destination rows per CTA; staged bytes per source row (multiple of 16); boxes per CTA
     const int32_t *xs, *ys;
     const float *xa, *ya;
     float zero;                      // 0.0f the compiler cannot see
+    int org_mask;                    // patch origin = first source byte & org_mask (16-byte aligned box start in global memory)
     bool dst_words;                  // destination rows are 4-byte aligned
 };
 
-// start[d] of pylc_area_table, in closed form (same double arithmetic on the host and on the device)
-__host__ __device__ inline int area_start(int d, int ssize, int dsize) {
-    const double inv_scale = (double)dsize / ssize;
-    const double scale = 1. / inv_scale;
-    const double fsx1 = d * scale, fsx2 = fsx1 + scale;
+// start[d] of pylc_area_table in closed form: the same double operations in the same order, every one rounded on
+// its own (the intrinsics keep the device compiler from contracting d * scale + scale into an FMA, which the host
+// build never does), so the host table and the device agree bit for bit.  `scale` = 1. / ((double)dsize / ssize).
+__device__ __forceinline__ int area_start(int d, double scale, int ssize) {
+    const double fsx1 = __dmul_rn((double)d, scale), fsx2 = __dadd_rn(fsx1, scale);
     int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
     sx2 = sx2 < ssize - 1 ? sx2 : ssize - 1;
     sx1 = sx1 < sx2 ? sx1 : sx2;
-    return (sx1 - fsx1 > 1e-3) ? sx1 - 1 : sx1;
+    return (__dsub_rn((double)sx1, fsx1) > 1e-3) ? sx1 - 1 : sx1;
 }
 
 __device__ __forceinline__ unsigned long long f2_pack(uint32_t lo, uint32_t hi) {
@@ -325,74 +332,138 @@ __device__ __forceinline__ uint32_t cvt_u8_sat(float v) {      // saturate_cast<
     return o;
 }
 
+#ifdef PYLC_CF_DEBUG
+__device__ unsigned long long g_rs_dbg[8 * 2048];
+__device__ __forceinline__ unsigned long long rs_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define RDBG(slot) do { const int b_ = blockIdx.y * gridDim.x + blockIdx.x; if (threadIdx.x == 0 && b_ < 2048) g_rs_dbg[b_ * 8 + (slot)] = rs_gtime(); } while (0)
+#else
+#define RDBG(slot) do { } while (0)
+#endif
+
 template <int CN>
-__global__ void __launch_bounds__(kAreaThreads) area_resize_x2_kernel(const __grid_constant__ CUtensorMap tm_src, const Area3Args a) {
+__global__ void __launch_bounds__(kAreaThreads, 6) area_resize_x2_kernel(const __grid_constant__ CUtensorMap tm_src, const Area3Args a) {
     extern __shared__ __align__(128) uint8_t s_dyn3[];        // nbox boxes of 8 rows x bw bytes | rb x uint4 {r0, beta0, beta1, beta2}
     __shared__ __align__(8) unsigned long long s_bar[kA3MaxBoxes];
     const int tid = threadIdx.x;
+    RDBG(0);
     const int e0 = blockIdx.x * kA3Elems, dy0 = blockIdx.y * a.rb;
     const int nd = min(a.rb, a.dh - dy0);
     const uint32_t src_s = smem_u32(s_dyn3), bar0 = smem_u32(s_bar);
     const uint32_t row_s = src_s + (uint32_t)a.nbox * kA3BoxRows * (uint32_t)a.bw;
 
-    // patch origin: source byte of the block's first element, source row of its first destination row
-    int byte0 = 0, s_lo = 0;
+    // table loads first (one round trip to L2 / DRAM, consumed after the copy engine has been started)
+    int xs_v[4];
+    uint32_t alw[4][3], cc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int e = min(e0 + 4 * tid + i, a.dst_row_bytes - 1);
+        const int dx = e / CN;
+        cc[i] = (uint32_t)(e - dx * CN);
+        xs_v[i] = __ldg(a.xs + dx);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) alw[i][k] = __float_as_uint(__ldg(a.xa + (size_t)dx * PYLC_AREA_TAPS + k));
+    }
+    const int x_tab = __ldg(a.xs + e0 / CN), y_tab = __ldg(a.ys + dy0);      // only for the consistency check below
+    int ys_v = 0;
+    uint32_t yw[3] = {0u, 0u, 0u};
+    if (tid < nd) {                  // rb <= 64 < kAreaThreads: one destination row per thread
+        const float *wv = a.ya + (size_t)(dy0 + tid) * PYLC_AREA_TAPS;
+        ys_v = __ldg(a.ys + dy0 + tid);
+        yw[0] = __float_as_uint(__ldg(wv)), yw[1] = __float_as_uint(__ldg(wv + 1)), yw[2] = __float_as_uint(__ldg(wv + 2));
+    }
+    // patch origin (every thread: a dozen double operations): source byte of the block's first element, source row of
+    // its first destination row
+    const int x_lo = area_start(e0 / CN, a.scale_x, a.W), y_lo = area_start(dy0, a.scale_y, a.H);
+    const int byte0 = x_lo * CN, s_lo = y_lo;
+    // Boxes are requested in the order they are consumed, kA3Ahead boxes ahead of the row walk: with every box of
+    // every CTA requested at kernel entry, first boxes queued behind other CTAs' last ones and some CTAs saw their
+    // first row 7 us into a 17 us kernel.
+    auto issue_box = [&](int j) {
+        mbar_arrive_expect_tx(bar0 + 8u * j, (uint32_t)(kA3BoxRows * a.bw));
+        tma_load_2d(src_s + (uint32_t)(j * kA3BoxRows * a.bw), &tm_src, (byte0 & a.org_mask) >> 2, s_lo + j * kA3BoxRows, bar0 + 8u * j);
+    };
     if (tid == 0) {
-        byte0 = area_start(e0 / CN, a.W, a.w) * CN;
-        s_lo = area_start(dy0, a.H, a.h);
         tma_prefetch_desc(&tm_src);
         for (int j = 0; j < a.nbox; ++j) mbar_init(bar0 + 8u * j, 1);
         mbar_fence_init();
-        for (int j = 0; j < a.nbox; ++j) {
-            mbar_arrive_expect_tx(bar0 + 8u * j, (uint32_t)(kA3BoxRows * a.bw));
-            tma_load_2d(src_s + (uint32_t)(j * kA3BoxRows * a.bw), &tm_src, byte0 >> 2, s_lo + j * kA3BoxRows, bar0 + 8u * j);
-        }
+        for (int j = 0; j < kA3Ahead && j < a.nbox; ++j) issue_box(j);
     }
-    // tables: the thread's four elements (clamped to the row) and the CTA's destination rows
-    const int x_lo = __ldg(a.xs + e0 / CN), y_lo = __ldg(a.ys + dy0);
+    RDBG(1);
     uint32_t sb[4];
     unsigned long long al2[2][3], ad2[2][3];
-    {
-        uint32_t alw[4][3];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int e = min(e0 + 4 * tid + i, a.dst_row_bytes - 1);
-            const int dx = e / CN, c = e - dx * CN;
-            sb[i] = (uint32_t)((__ldg(a.xs + dx) * CN + c) - ((x_lo * CN) & ~3));
+    for (int i = 0; i < 4; ++i) sb[i] = (uint32_t)((xs_v[i] * CN + (int)cc[i]) - (byte0 & a.org_mask));
 #pragma unroll
-            for (int k = 0; k < 3; ++k) alw[i][k] = __float_as_uint(__ldg(a.xa + (size_t)dx * PYLC_AREA_TAPS + k));
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            al2[p][k] = f2_pack(alw[2 * p][k], alw[2 * p + 1][k]);
+            ad2[p][k] = f2_pack(__float_as_uint(-8388608.f * __uint_as_float(alw[2 * p][k])),       // exact: power-of-two multiples
+                                __float_as_uint(-8388608.f * __uint_as_float(alw[2 * p + 1][k])));
         }
-#pragma unroll
-        for (int p = 0; p < 2; ++p)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                al2[p][k] = f2_pack(alw[2 * p][k], alw[2 * p + 1][k]);
-                ad2[p][k] = f2_pack(__float_as_uint(-8388608.f * __uint_as_float(alw[2 * p][k])),       // exact: power-of-two multiples
-                                    __float_as_uint(-8388608.f * __uint_as_float(alw[2 * p + 1][k])));
-            }
-    }
-    for (int i = tid; i < nd; i += kAreaThreads) {
-        const float *wv = a.ya + (size_t)(dy0 + i) * PYLC_AREA_TAPS;
-        sts128(row_s + 16u * i, make_uint4((uint32_t)(__ldg(a.ys + dy0 + i) - y_lo), __float_as_uint(__ldg(wv)), __float_as_uint(__ldg(wv + 1)),
-                                           __float_as_uint(__ldg(wv + 2))));
-    }
+    if (tid < nd) sts128(row_s + 16u * tid, make_uint4((uint32_t)(ys_v - y_lo), yw[0], yw[1], yw[2]));
     // the tables must be the ones area_start restates (pylc_area_table's): the patch was fetched for them
-    if (tid == 0 && (x_lo * CN != byte0 || y_lo != s_lo)) __trap();
+    if (tid == 0 && (x_tab != x_lo || y_tab != y_lo)) __trap();
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-        if (sb[i] + 2u * CN >= (uint32_t)a.bw) __trap();      // the host sizes the patch; never taken
-    __syncthreads();                                           // barriers initialised, row table written
+        if (sb[i] + 2u * CN + 16u > (uint32_t)a.bw) __trap(); // the host sizes the patch (incl. the word form's 16-byte window); never taken
 
+    // Keep the loop invariants in registers: left alone, the compiler re-derives the addends (an FMUL each), the
+    // shared-memory base (S2R + LEA) and the parameters inside every horizontal sum to save registers.
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) asm volatile("" : "+l"(al2[p][k]), "+l"(ad2[p][k]));
+    uint32_t src_b = src_s, bar_b = bar0, bw = (uint32_t)a.bw;
+    asm volatile("" : "+r"(src_b), "+r"(bar_b), "+r"(bw));
     const unsigned long long z2 = f2_pack(__float_as_uint(a.zero), __float_as_uint(a.zero));
-    const uint32_t bw = (uint32_t)a.bw;
+    // Word form of the tap fetch.  The twelve bytes of a quad lie within 16 bytes of its first tap (elements of one
+    // pixel are adjacent, a pixel boundary inside the quad adds 0 or CN bytes; gray: consecutive columns start 1 or 2
+    // bytes apart), so 3-4 aligned words per source row replace 12 byte loads -- the byte loads, two wavefronts each
+    // because a warp's taps span more than 128 bytes, kept the LSU pipe busier than the issue slots.  The words are
+    // funnel-shifted to the quad's first byte (thread-constant amount), tap k's four bytes d_i + k*CN are picked by
+    // ONE byte permute with a thread-constant selector (nibble i = d_i), and a second permute with a literal selector
+    // drops each byte into the 2^23 + S bit pattern.  Needs d_3 + 2 <= 7 (gray) / d_3 <= 6 (colour): voted per CTA.
+    const uint32_t d1 = sb[1] - sb[0], d2 = sb[2] - sb[0], d3 = sb[3] - sb[0];
+    const bool quad_ok = d1 <= d2 && d2 <= d3 && d3 <= (CN == 1 ? 5u : 6u);
+    const bool words = __syncthreads_and(quad_ok) != 0;          // (also the barrier: mbarriers initialised, row table written)
+    RDBG(2);
+    uint32_t sel = d1 << 4 | d2 << 8 | d3 << 12, wofs = sb[0] & ~3u, wsh = (sb[0] & 3u) * 8u;
+    asm volatile("" : "+r"(sel), "+r"(wofs), "+r"(wsh));
     auto hsum = [&](int r, unsigned long long &o0, unsigned long long &o1) {
-        if ((r & (kA3BoxRows - 1)) == 0) mbar_wait(bar0 + 8u * (uint32_t)(r / kA3BoxRows), 0);
-        const uint32_t row = src_s + (uint32_t)r * bw;
+        if ((r & (kA3BoxRows - 1)) == 0) {
+            const int jn = r / kA3BoxRows + kA3Ahead;
+            if (tid == 0 && jn < a.nbox) issue_box(jn);
+            mbar_wait(bar_b + (uint32_t)r, 0);       // 8 bytes per barrier, 8 rows per box
+        }
+        const uint32_t row = src_b + (uint32_t)r * bw;
         uint32_t p[4][3];
+        if (words) {
+            uint32_t t[3];
+            const uint32_t wa = row + wofs;
+            if (CN == 1) {
+                const uint32_t w0 = lds32(wa), w1 = lds32(wa + 4), w2 = lds32(wa + 8);
+                const uint32_t a0 = __funnelshift_r(w0, w1, wsh), a1 = __funnelshift_r(w1, w2, wsh);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+                for (int k = 0; k < 3; ++k) t[k] = __byte_perm(a0, a1, sel + 0x1111u * k);
+            } else {
+                const uint32_t w0 = lds32(wa), w1 = lds32(wa + 4), w2 = lds32(wa + 8), w3 = lds32(wa + 12);
+                const uint32_t a0 = __funnelshift_r(w0, w1, wsh), a1 = __funnelshift_r(w1, w2, wsh), a2 = __funnelshift_r(w2, w3, wsh),
+                               a3 = __funnelshift_r(w3, w3, wsh);
+                t[0] = __byte_perm(a0, a1, sel);
+                t[1] = __byte_perm(__funnelshift_r(a0, a1, 24), __funnelshift_r(a1, a2, 24), sel);
+                t[2] = __byte_perm(__funnelshift_r(a1, a2, 16), __funnelshift_r(a2, a3, 16), sel);
+            }
 #pragma unroll
-            for (int k = 0; k < 3; ++k) p[i][k] = 0x4B000000u | lds_u8(row + sb[i] + (uint32_t)(k * CN));
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) p[i][k] = __byte_perm(t[k], 0x4B000000u, 0x7440u + i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) p[i][k] = 0x4B000000u | lds_u8(row + sb[i] + (uint32_t)(k * CN));
+        }
         o0 = f2_fma(f2_pack(p[0][0], p[1][0]), al2[0][0], ad2[0][0]);
         o1 = f2_fma(f2_pack(p[2][0], p[3][0]), al2[1][0], ad2[1][0]);
 #pragma unroll
@@ -434,12 +505,14 @@ __global__ void __launch_bounds__(kAreaThreads) area_resize_x2_kernel(const __gr
     unsigned long long A0 = 0, A1 = 0, B0 = 0, B1 = 0, C0 = 0, C1 = 0;
     for (int r = 0;; r += 3) {
         hsum(r, A0, A1);
+        if (r == 0) RDBG(3);
         if ((int)rw.x + 2 == r && emit(B0, B1, C0, C1, A0, A1)) break;
         hsum(r + 1, B0, B1);
         if ((int)rw.x + 2 == r + 1 && emit(C0, C1, A0, A1, B0, B1)) break;
         hsum(r + 2, C0, C1);
         if ((int)rw.x + 2 == r + 2 && emit(A0, A1, B0, B1, C0, C1)) break;
     }
+    RDBG(4);
 }
 
 // Returns PYLC_OK / a CUDA error after launching, or -1 when the form does not apply (alignment, scale >= 1.9,
@@ -452,26 +525,51 @@ static int launch_area_resize_x2(const uint8_t *src, int H, int W, int ch, size_
     Area3Args a;
     a.dst = dst; a.dst_pitch = dst_pitch; a.dst_row_bytes = w * ch; a.dh = h; a.W = W; a.H = H; a.w = w; a.h = h;
     a.xs = xs; a.ys = ys; a.xa = xa; a.ya = ya; a.zero = 0.f;
+    a.scale_x = 1. / ((double)w / W);      // pylc_area_table's `scale`, the same expression
+    a.scale_y = 1. / ((double)h / H);
     a.dst_words = ((uintptr_t)dst % 4 == 0) && (dst_pitch % 4 == 0);
-    a.bw = (((int)ceil((kA3Elems / ch + 2) * sx) + 2) * ch + 4 + 15) & ~15;
+    // the box of a tensor load must START on a 16-byte boundary of global memory (measured: a 4-byte aligned start
+    // faults with "illegal instruction"), so the patch origin is the first source byte rounded down to 16
+    a.org_mask = ~15;
+    a.bw = (((int)ceil((kA3Elems / ch + 2) * sx) + 2) * ch + 16 + 16 + 15) & ~15;     // + origin round-down + the word form's window
     if (a.bw > 1024) return -1;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int col_blocks = (a.dst_row_bytes + kA3Elems - 1) / kA3Elems;
     auto kern = ch == 1 ? area_resize_x2_kernel<1> : area_resize_x2_kernel<3>;
-    // destination rows per CTA: the largest band that keeps the grid at a full wave or more, else the smallest
+    // Destination rows per CTA.  A taller band re-computes fewer boundary rows (a band needs ~rb*sy + 4 source
+    // rows) but costs shared memory and resident CTAs; what hurts most is a grid slightly larger than one wave.
+    // Model: a wave of n resident CTAs per SM takes (rb*sy + 4) * max(1, n / 6) row times (about six 4-warp CTAs
+    // saturate the issue slots); pick the band height with the smallest modelled total.
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
     size_t smem = 0;
+    double best = 0;
     bool found = false;
-    const int cand[3] = {64, 32, 16};
-    for (int ci = 0; ci < 3; ++ci) {
+    const int cand[5] = {64, 48, 32, 24, 16};
+    for (int ci = 0; ci < 5; ++ci) {
         const int rb = cand[ci];
         const int nbox = ((int)ceil(rb * sy) + 4 + kA3BoxRows - 1) / kA3BoxRows;
         const size_t sm = (size_t)nbox * kA3BoxRows * a.bw + (size_t)rb * 16;
         if (nbox > kA3MaxBoxes || sm > 100 * 1024) continue;
-        a.rb = rb; a.nbox = nbox; smem = sm;
-        found = true;
-        if ((long long)col_blocks * ((h + rb - 1) / rb) >= (long long)sms * 2) break;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kAreaThreads, sm) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            continue;
+        }
+        const long long ctas = (long long)col_blocks * ((h + rb - 1) / rb), slots = (long long)sms * per_sm;
+        const double unit = rb * sy + 4.0;
+        const long long full = ctas / slots, rem = ctas % slots;
+        double t = (double)full * unit * fmax(1.0, per_sm / 6.0);
+        if (rem) t += unit * fmax(1.0, (double)((rem + sms - 1) / sms) / 6.0);
+        if (!found || t < best) {
+            best = t;
+            a.rb = rb; a.nbox = nbox; smem = sm;
+            found = true;
+        }
     }
     if (!found) return -1;
     CUtensorMap tm;
@@ -481,16 +579,15 @@ static int launch_area_resize_x2(const uint8_t *src, int H, int W, int ch, size_
         const uint32_t box[2] = {(uint32_t)(a.bw / 4), (uint32_t)kA3BoxRows};
         if (!tma_encode_u32(&tm, src, 2, dims, strides, box)) return -1;
     }
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        cudaGetLastError();
-        return -1;
-    }
     const dim3 grid((unsigned)col_blocks, (unsigned)((h + a.rb - 1) / a.rb));
     kern<<<grid, kAreaThreads, smem, st>>>(tm, a);
     return finish_launch();
 }
 
 }  // namespace pylc
+#ifdef PYLC_CF_DEBUG
+extern "C" __attribute__((visibility("default"))) int pylc_debug_read_rs(void *dst, size_t bytes) { return (int)cudaMemcpyFromSymbol(dst, pylc::g_rs_dbg, bytes); }
+#endif
 
 using namespace pylc;
 

@@ -51,7 +51,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
-// global -> shared box load; completion is signalled on `bar` as transaction bytes
+// global -> shared box load; completion is signalled on `bar` as transaction bytes.  The box must start on a
+// 16-byte boundary of global memory: c0 (in 32-bit elements) a multiple of 4 -- an unaligned start faults with
+// "illegal instruction" (measured on B200); its bytes beyond the tensor are zero-filled and still counted.
 __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
                  "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)

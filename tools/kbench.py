@@ -213,13 +213,13 @@ def main():
     # ---- test-time fit resize -----------------------------------------------------------------
     for (Wr, Hr, chr_) in ((3000, 2000, 3), (6000, 4000, 1)):
         wr, hr = orc.fit_dims(Wr, Hr, T)
-        raw = torch.from_numpy(orc.synth_image(2, Wr, Hr, chr_)).cuda()
+        raw, rp = ops.upload_image(orc.synth_image(2, Wr, Hr, chr_))      # 16-byte pitched rows, as TiledSegmenter uploads them
         fitted = torch.empty((hr, ops.pitch_for(wr * chr_)), dtype=torch.uint8, device="cuda")
-        ops.fit_resize_area(raw, Hr, Wr, chr_, Wr * chr_, hr, wr, out=fitted)      # builds + caches the tables
+        ops.fit_resize_area(raw, Hr, Wr, chr_, rp, hr, wr, out=fitted)      # builds + caches the tables
         report("fit_resize_area %dx%d ch%d -> %dx%d" % (Wr, Hr, chr_, wr, hr), (Wr * Hr + wr * hr) * chr_,
-               lambda raw=raw, fitted=fitted, Wr=Wr, Hr=Hr, chr_=chr_, wr=wr, hr=hr:
-               ops.fit_resize_area(raw, Hr, Wr, chr_, Wr * chr_, hr, wr, out=fitted),
-               "source read once + fitted image written once")
+               lambda raw=raw, rp=rp, fitted=fitted, Wr=Wr, Hr=Hr, chr_=chr_, wr=wr, hr=hr:
+               ops.fit_resize_area(raw, Hr, Wr, chr_, rp, hr, wr, out=fitted),
+               "source read once + fitted image written once; 16-byte pitched source rows")
         del raw, fitted
 
     # ---- stitch ------------------------------------------------------------------------------
