@@ -44,18 +44,22 @@ def fold_conv_bn(conv, bn):
     return w.float(), b.float()
 
 
-# Per layer and input shape, the plan times its two library routes once and keeps the faster:
+# Per layer and input shape, the plan times its library routes once and keeps the fastest:
 #   0  torch.cudnn_convolution_relu / _add_relu: one fused cuDNN call, engine chosen by cuDNN's heuristic
 #   1  F.conv2d (engine chosen by torch.backends.cudnn.benchmark when that is on) + in-place add / ReLU
-# Measured on B200 (round 1 launch list): the heuristic of route 0 puts one ASPP dilated 3x3 branch on an
-# sm80 implicit-GEMM kernel with two layout conversions (1.94 ms against 0.53 ms for its sibling branches);
-# route 1 finds the sm100 kernel.  Both are stock library convolutions on the same folded weights.
+#   2  tap split (3x3, stride 1, padding == dilation >= 6 only): the convolution as cuBLAS GEMMs over the windows
+#      that do not fall into the zero padding (`_Conv._tap_split`)
+# Measured on B200 (tools/exp/dilated_conv.py, 45 tiles): cuDNN has an sm100 kernel for the ASPP branches with
+# dilation 6 and 12 (0.54 ms) but none for dilation 18 on a 32 x 32 map -- routes 0 and 1, NHWC or NCHW, padded
+# by hand or not, all land on `sm80_xmma_fprop_implicit_gemm_tf32...` (1.73 ms) plus two layout conversions
+# (0.2 ms): 10 % of the whole network.  With dilation 18 > 32 / 2 every output pixel sees at most two taps per
+# axis, i.e. 39 % of the dense products, and route 2 computes only those, on the TF32 tensor cores through cuBLAS.
 AUTOTUNE = os.environ.get("PYLC_CONV_AUTOTUNE", "1") != "0"
 
 
 class _Conv(object):
     """One folded convolution with an optional fused ReLU / residual add."""
-    __slots__ = ("w", "b", "stride", "padding", "dilation", "relu", "choice")
+    __slots__ = ("w", "b", "stride", "padding", "dilation", "relu", "choice", "taps")
 
     def __init__(self, conv, bn, relu, channels_last):
         w, b = fold_conv_bn(conv, bn)
@@ -63,11 +67,54 @@ class _Conv(object):
         self.b = b.contiguous()
         self.stride, self.padding, self.dilation, self.relu = conv.stride, conv.padding, conv.dilation, relu
         self.choice = {}
+        self.taps = None
 
     def to(self, dtype):
         self.w = self.w.to(dtype)
         self.b = self.b.to(dtype) if self.b is not None else None
+        self.taps = None
         return self
+
+    def _tap_split_applies(self, x, residual):
+        d = self.dilation[0]
+        return (residual is None and self.relu and self.b is not None and x.dtype == torch.float32 and tuple(self.w.shape[2:]) == (3, 3)
+                and tuple(self.stride) == (1, 1) and tuple(self.dilation) == (d, d) and tuple(self.padding) == (d, d) and d >= 6
+                and d < min(x.shape[2], x.shape[3]) and x.is_contiguous(memory_format=torch.channels_last))
+
+    def _tap_split(self, x, residual=None):
+        """3x3 convolution with padding == dilation == d as GEMMs over the windows that miss the zero padding.
+        out[y, x] = sum_t W_t . in[y + ty*d, x + tx*d]; tap (ty, tx) contributes only where its source pixel
+        exists, a (H - d|ty|) x (W - d|tx|) window.  Windows spanning whole rows are contiguous in the
+        channels-last activation ([B, H, W, C]); the others are contiguous in ONE transposed copy ([B, W, H, C]),
+        where the three taps of a column offset share their GEMM (N = 3 * out_channels) and the rows a tap
+        cannot reach are dropped when its slice is added.  TF32 products, fp32 accumulation -- cuDNN's numerics."""
+        B, C, H, W = x.shape
+        d, O = self.dilation[0], self.w.shape[0]
+        if self.taps is None:           # [C, O] matrices per tap; the three row taps of a column offset side by side
+            wt = self.w.permute(2, 3, 1, 0).contiguous()                 # [3, 3, C, O]
+            self.taps = (wt, [torch.cat([wt[0, kx], wt[1, kx], wt[2, kx]], dim=1).contiguous() for kx in (0, 2)])
+        wt, wt3 = self.taps
+        ny, nx = H - d, W - d
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32      # the convolution's own precision class
+        try:
+            xn = x.permute(0, 2, 3, 1)                                   # [B, H, W, C]: the channels-last storage itself
+            out = torch.addmm(self.b, xn.reshape(B * H * W, C), wt[1, 1]).view(B, H, W, O)
+            for ky, (i0, o0) in ((0, (0, d)), (2, (d, 0))):              # tap rows -d / +d, column offset 0: whole rows
+                out[:, o0:o0 + ny].reshape(B, ny * W, O).baddbmm_(xn[:, i0:i0 + ny].reshape(B, ny * W, C), wt[ky, 1].expand(B, C, O))
+            xt = xn.transpose(1, 2).contiguous()                         # [B, W, H, C]
+            acc = torch.zeros((B, W, H, O), dtype=x.dtype, device=x.device)
+            for j, (i0, o0) in enumerate(((0, d), (d, 0))):              # column offsets -d / +d
+                # batched over the images: the column window is contiguous per image only (a 2-D reshape would copy it)
+                z = torch.bmm(xt[:, i0:i0 + nx].reshape(B, nx * H, C), wt3[j].expand(B, C, 3 * O)).view(B, nx, H, 3 * O)
+                dst = acc[:, o0:o0 + nx]
+                dst += z[..., O:2 * O]                                   # tap row 0
+                dst[:, :, d:] += z[:, :, :ny, :O]                        # tap row -d: source row y - d
+                dst[:, :, :ny] += z[:, :, d:, 2 * O:]                    # tap row +d: source row y + d
+            out += acc.transpose(1, 2)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        return out.relu_().permute(0, 3, 1, 2)                           # [B, O, H, W], channels-last strides
 
     def _fused(self, x, residual):
         if residual is not None:
@@ -84,7 +131,8 @@ class _Conv(object):
     def _pick(self, x, residual):
         """Time both routes on this very input (CUDA events, after a warm-up each)."""
         best, best_ms = 0, None
-        for route, fn in enumerate((self._fused, self._plain)):
+        routes = (self._fused, self._plain) + ((self._tap_split,) if self._tap_split_applies(x, residual) else ())
+        for route, fn in enumerate(routes):
             try:
                 for _ in range(2):
                     fn(x, residual)
@@ -109,7 +157,7 @@ class _Conv(object):
             route = self.choice.get(key)
             if route is None:
                 route = self.choice[key] = self._pick(x, residual)
-            return self._fused(x, residual) if route == 0 else self._plain(x, residual)
+            return (self._fused, self._plain, self._tap_split)[route](x, residual)
         return self._plain(x, residual)
 
 

@@ -794,3 +794,36 @@ def test_s2d_stem_equals_7x7_stem(ops):
     ya, yb = plan(planar), plan.forward_s2d(s2d)
     assert ya.shape == yb.shape == (planar.shape[0], 9, 256, 256)
     assert (ya - yb).abs().max() <= 5e-3 * ya.abs().max()
+
+
+@pytest.mark.parametrize("H,W,d,cin,cout,B", [(32, 32, 18, 2048, 256, 5), (32, 32, 12, 256, 64, 3), (24, 40, 6, 64, 32, 2), (32, 32, 24, 128, 16, 1)])
+def test_tap_split_route_equals_cudnn_convolution(ops, H, W, d, cin, cout, B):
+    """The inference plan's third convolution route (models/fused.py::_Conv._tap_split): a 3x3 convolution with
+    padding == dilation as cuBLAS GEMMs over the tap windows that miss the zero padding.  Same TF32 products and
+    fp32 sums as the cuDNN convolution of the same folded weights, in another order: equal to TF32 rounding."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from pylc_b200.models.fused import _Conv
+    torch.manual_seed(d)
+    conv = nn.Conv2d(cin, cout, 3, padding=d, dilation=d, bias=False).cuda()
+    bn = nn.BatchNorm2d(cout).cuda().eval()
+    with torch.no_grad():
+        bn.running_mean.normal_()
+        bn.running_var.uniform_(0.5, 2.0)
+        bn.weight.normal_()
+        bn.bias.normal_()
+    c = _Conv(conv, bn, True, True)
+    x = torch.randn(B, cin, H, W, device="cuda").contiguous(memory_format=torch.channels_last)
+    assert c._tap_split_applies(x, None)
+    with torch.no_grad():
+        want = F.relu(F.conv2d(x, c.w, c.b, 1, d, d))
+        exact = F.relu(F.conv2d(x.double(), c.w.double(), c.b.double(), 1, d, d))
+        got = c._tap_split(x)
+    assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+    scale = float(exact.abs().max())
+    err_split, err_cudnn = float((got - exact).abs().max()), float((want - exact).abs().max())
+    assert err_split <= 3e-3 * scale                       # TF32 inputs (10-bit mantissa), fp32 accumulation
+    assert err_split <= 4 * err_cudnn + 1e-6 * scale       # no worse than the library convolution it replaces
+    # and the plan's autotuned call returns the same thing whichever route it keeps
+    y = c(x)
+    assert float((y - exact).abs().max()) <= 3e-3 * scale

@@ -4,6 +4,9 @@ kernels each route launches, so the plan can pick a route that stays on sm100 ke
 import torch
 import torch.nn.functional as F
 from torch.profiler import ProfilerActivity, profile
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from pylc_b200.models.fused import _Conv
 
 torch.backends.cudnn.benchmark = True
 B = 45
@@ -52,12 +55,16 @@ def tap_split(x, w, b, d):
     return out.relu_()
 
 
-for name, cin, cout, d in [("layer4 d2", 512, 512, 2), ("layer4 d4", 512, 512, 4), ("layer4 d8", 512, 512, 8),
-                           ("aspp d6", 2048, 256, 6), ("aspp d12", 2048, 256, 12), ("aspp d18", 2048, 256, 18)]:
+for name, cin, cout, d in [("layer4 d8", 512, 512, 8), ("aspp d6", 2048, 256, 6), ("aspp d12", 2048, 256, 12), ("aspp d18", 2048, 256, 18)]:
     x = torch.randn(B, cin, 32, 32, device="cuda").contiguous(memory_format=cl)
     w = (torch.randn(cout, cin, 3, 3, device="cuda") * 0.01).contiguous(memory_format=cl)
     b = torch.randn(cout, device="cuda")
     xn, wn = x.contiguous(), w.contiguous()
+    conv_m = torch.nn.Conv2d(cin, cout, 3, padding=d, dilation=d, bias=True).cuda()
+    with torch.no_grad():
+        conv_m.weight.copy_(w)
+        conv_m.bias.copy_(b)
+    plan_conv = _Conv(conv_m, None, True, True)
     xp = F.pad(x, (d, d, d, d)).contiguous(memory_format=cl)
     routes = {
         "fused cudnn_convolution_relu (NHWC)": lambda: torch.cudnn_convolution_relu(x, w, b, (1, 1), (d, d), (d, d), 1),
@@ -66,6 +73,7 @@ for name, cin, cout, d in [("layer4 d2", 512, 512, 2), ("layer4 d4", 512, 512, 4
         "explicit zero pad + conv pad 0 (NHWC)": lambda: F.conv2d(F.pad(x, (d, d, d, d)), w, b, 1, 0, d).relu_(),
         "conv pad 0 on a pre-padded input": lambda: F.conv2d(xp, w, b, 1, 0, d).relu_(),
         "tap split (9 x 1x1 on valid windows)": lambda: tap_split(x, w, b, d),
+        "plan route 2: GEMM tap split": lambda: plan_conv._tap_split(x),
     }
     ref = routes["F.conv2d + relu_ (NCHW, benchmark)"]()
     print("== %s  %d->%d" % (name, cin, cout))
