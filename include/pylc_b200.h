@@ -325,6 +325,30 @@ PYLC_API int pylc_multiloss_fwd_bwd(const float *logits, const void *target, int
                            float *grad, float *out4, uint8_t *target_u8_ws, pylc_stream_t stream);
 PYLC_API int pylc_scale_unless_one_f32(float *data, int64_t n, const float *scale_dev, pylc_stream_t stream);
 
+/*
+ * The same single launch for a DATA-PARALLEL training step (one process per GPU): reduce pass -> grid barrier ->
+ * all-reduce of the 2C+3 partials INSIDE the kernel, over peer-addressable memory (NVLink / NVSwitch loads and
+ * stores; no NCCL call, no second launch) -> grid barrier -> loss values -> gradient pass.  The result is the loss
+ * of the single large batch of all ranks and d(that loss)/d(local logits); `partials` returns the global sums,
+ * identical to the last bit on every rank (added in rank order); n_px_total is B*HW*world.
+ * Replaces the reference's loss of one training step (models/model.py:317-325, models/modules/loss.py:71-194)
+ * under data parallelism, which the reference does not have (models/model.py:185-188).
+ *
+ *   peer_ws  DEVICE array [world]: pointer to every rank's exchange workspace as addressable from THIS process, in
+ *            rank order (torch.distributed._symmetric_memory: rendezvous(...).buffer_ptrs_dev).  A workspace is
+ *            PYLC_DP_WS_BYTES bytes, zero-initialised once; only these calls write it.
+ *   epoch    call counter, the same on every rank, 1, 2, 3, ... per workspace.
+ * Every rank of the group must make the call; a rank that does not arrive within ~1 s turns the results into NaN.
+ */
+#define PYLC_DP_MAX_RANKS 16
+#define PYLC_DP_MAX_PARTIALS 80 /* >= 2 * PYLC_MAX_CLASSES + 3 */
+#define PYLC_DP_WS_BYTES 2048
+PYLC_API int pylc_multiloss_fwd_bwd_dp(const float *logits, const void *target, int target_is_i64, int B, int C,
+                              int64_t HW, const float *class_w, const pylc_loss_cfg *cfg,
+                              double *partials, float grad_scale, const float *grad_scale_dev,
+                              float *grad, float *out4, uint8_t *target_u8_ws,
+                              double *const *peer_ws, int rank, int world, uint64_t epoch, pylc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,8 @@ SIGNATURES = {
                                     _ptr, c_int64, c_float, _ptr, _ptr, _ptr]),
     "pylc_multiloss_fwd_bwd": (c_int, [_ptr, _ptr, c_int, c_int, c_int, c_int64, _ptr, POINTER(LossCfg),
                                        _ptr, c_float, _ptr, _ptr, _ptr, _u8p, _ptr]),
+    "pylc_multiloss_fwd_bwd_dp": (c_int, [_ptr, _ptr, c_int, c_int, c_int, c_int64, _ptr, POINTER(LossCfg),
+                                          _ptr, c_float, _ptr, _ptr, _ptr, _u8p, _ptr, c_int, c_int, ctypes.c_uint64, _ptr]),
     "pylc_scale_unless_one_f32": (c_int, [_ptr, c_int64, _ptr, _ptr]),
 }
 

@@ -375,13 +375,86 @@ __global__ void loss_finalize_kernel(const double *partials, int C, long long n_
 // barrier, loss values written by one thread, gradient pass in reverse order.  Co-residency of the
 // whole grid is what cudaLaunchCooperativeKernel guarantees; the grid is the same one-wave
 // persistent grid the two-launch path uses.
+// ---- in-kernel all-reduce of the partials over peer memory (data-parallel training step) -------------------
+// Every rank owns one exchange workspace in memory its peers can address (symmetric memory: the same virtual
+// allocation mapped into every process over NVLink / NVSwitch); `peer_ws[r]` is rank r's, seen from here.  Two
+// slots alternate by call parity; a slot holds one arrival flag per rank and the rank's 2C+3 sums:
+//     struct { uint64 flag[PYLC_DP_MAX_RANKS]; double part[PYLC_DP_MAX_PARTIALS]; } slot[2];
+// Protocol of call number `epoch` (the same on every rank, starting at 1), run by CTA 0 after the grid has
+// finished the local reduction:
+//   1. publish the local sums in the own slot, fence at system scope;
+//   2. thread p stores `epoch` into flag[rank] of peer p's slot (st.release.sys -- a store over the fabric);
+//   3. thread p spins on the own slot's flag[p] (ld.acquire.sys) until it reads `epoch`: rank p's sums are visible;
+//   4. thread t adds the ranks' part[t] in rank order (the same order everywhere: bit-identical results on every
+//      rank) and writes the total over the local partials.
+// A rank can run at most one call ahead of its slowest peer (it needs that peer's flag of the current call), so
+// two slots are enough.  The spin is bounded: a peer that never arrives (a crashed rank, mismatched epochs) turns
+// the partials into NaN after ~1 s instead of hanging the device.
+struct DpArgs {
+    double *const *peer_ws;     // DEVICE array [world] of workspace pointers (every rank's, in rank order)
+    int rank, world;
+    unsigned long long epoch;
+};
+constexpr int kDpSlotDoubles = PYLC_DP_MAX_RANKS + PYLC_DP_MAX_PARTIALS;
+static_assert(2 * kDpSlotDoubles * 8 <= PYLC_DP_WS_BYTES, "workspace size in the header");
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double *p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// called by every thread of ONE CTA; n = 2C+3
+__device__ __forceinline__ void dp_all_reduce_partials(const DpArgs &dp, double *partials, int n) {
+    const int t = threadIdx.x;
+    const size_t slot = (size_t)(dp.epoch & 1ull) * kDpSlotDoubles;
+    double *mine = dp.peer_ws[dp.rank] + slot;
+    if (t < n) mine[PYLC_DP_MAX_RANKS + t] = __ldcg(partials + t);
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_ok;
+    if (t == 0) s_ok = 1;
+    __syncthreads();
+    if (t < dp.world) {
+        st_release_sys_u64(reinterpret_cast<unsigned long long *>(dp.peer_ws[t] + slot) + dp.rank, dp.epoch);
+        const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(mine) + t;
+        long long spins = 0;
+        while (ld_acquire_sys_u64(flag) != dp.epoch) {
+            if (++spins > (1ll << 24)) {        // ~1 s with the sleep below
+                s_ok = 0;
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (t < n) {
+        double sum = 0.0;
+        for (int r = 0; r < dp.world; ++r) sum += ld_relaxed_sys_f64(dp.peer_ws[r] + slot + PYLC_DP_MAX_RANKS + t);
+        partials[t] = s_ok ? sum : __longlong_as_double(0x7FF8000000000000ll);
+    }
+    __threadfence();
+}
+
 template <int C_T, int CMAX, int PX>
 __global__ void __launch_bounds__(kThreads, (PX == 4 || CMAX > 9) ? 2 : 3)
     loss_fused_kernel(LossArgs a, double *partials, long long n_px_total, float grad_scale, const float *grad_scale_dev,
-                      float *grad, float *out4) {
+                      float *grad, float *out4, DpArgs dp) {
     loss_reduce_pass<C_T, CMAX, PX>(a, partials);
     __threadfence();
     cooperative_groups::this_grid().sync();
+    if (dp.world > 1) {          // data parallel: the sums of the single large batch, exchanged inside the launch
+        if (blockIdx.x == 0) dp_all_reduce_partials(dp, partials, 2 * (C_T > 0 ? C_T : a.C) + 3);
+        cooperative_groups::this_grid().sync();
+    }
     if (out4 && blockIdx.x == 0 && threadIdx.x == 0) loss_finalize(partials, C_T > 0 ? C_T : a.C, n_px_total, a.cfg, out4);
     if (a.t8_out) {            // the gradient pass reads the 1-byte targets the reduce pass left behind
         a.target = a.t8_out;
@@ -505,10 +578,10 @@ extern "C" int pylc_multiloss_finalize(const double *partials, int C, int64_t n_
     return finish_launch();
 }
 
-extern "C" int pylc_multiloss_fwd_bwd(const float *logits, const void *target, int target_is_i64, int B, int C, int64_t HW,
-                                      const float *class_w, const pylc_loss_cfg *cfg, double *partials, float grad_scale,
-                                      const float *grad_scale_dev, float *grad, float *out4, uint8_t *target_u8_ws,
-                                      pylc_stream_t stream) {
+static int launch_loss_fused(const float *logits, const void *target, int target_is_i64, int B, int C, int64_t HW,
+                             const float *class_w, const pylc_loss_cfg *cfg, double *partials, float grad_scale,
+                             const float *grad_scale_dev, float *grad, float *out4, uint8_t *target_u8_ws, DpArgs dp,
+                             pylc_stream_t stream) {
     if (!partials || !grad) return PYLC_ERR_ARG;
     if ((uintptr_t)grad % 16) return PYLC_ERR_ALIGN;
     LossArgs a;
@@ -516,8 +589,8 @@ extern "C" int pylc_multiloss_fwd_bwd(const float *logits, const void *target, i
     int rc = fill_args(logits, target, target_is_i64, B, C, HW, class_w, cfg, &a, &px, target_u8_ws);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    long long n_px_total = (long long)B * HW;
-    void *args[] = {&a, &partials, &n_px_total, &grad_scale, &grad_scale_dev, &grad, &out4};
+    long long n_px_total = (long long)B * HW * dp.world;
+    void *args[] = {&a, &partials, &n_px_total, &grad_scale, &grad_scale_dev, &grad, &out4, &dp};
     cudaError_t e = cudaSuccess;
 #define LAUNCH_FUSED(K) e = cudaLaunchCooperativeKernel((void *)K, dim3(loss_grid(K, a.total_units)), dim3(kThreads), args, 0, st)
     if (px == 4) {
@@ -536,6 +609,28 @@ extern "C" int pylc_multiloss_fwd_bwd(const float *logits, const void *target, i
 #undef LAUNCH_FUSED
     if (e != cudaSuccess) return (int)e;
     return finish_launch();
+}
+
+extern "C" int pylc_multiloss_fwd_bwd(const float *logits, const void *target, int target_is_i64, int B, int C, int64_t HW,
+                                      const float *class_w, const pylc_loss_cfg *cfg, double *partials, float grad_scale,
+                                      const float *grad_scale_dev, float *grad, float *out4, uint8_t *target_u8_ws,
+                                      pylc_stream_t stream) {
+    DpArgs dp;
+    dp.peer_ws = nullptr; dp.rank = 0; dp.world = 1; dp.epoch = 0;
+    return launch_loss_fused(logits, target, target_is_i64, B, C, HW, class_w, cfg, partials, grad_scale, grad_scale_dev, grad, out4,
+                             target_u8_ws, dp, stream);
+}
+
+extern "C" int pylc_multiloss_fwd_bwd_dp(const float *logits, const void *target, int target_is_i64, int B, int C, int64_t HW,
+                                         const float *class_w, const pylc_loss_cfg *cfg, double *partials, float grad_scale,
+                                         const float *grad_scale_dev, float *grad, float *out4, uint8_t *target_u8_ws,
+                                         double *const *peer_ws, int rank, int world, uint64_t epoch, pylc_stream_t stream) {
+    if (!peer_ws || world < 1 || world > PYLC_DP_MAX_RANKS || rank < 0 || rank >= world || epoch == 0) return PYLC_ERR_ARG;
+    if (2 * C + 3 > PYLC_DP_MAX_PARTIALS) return PYLC_ERR_CLASSES;
+    DpArgs dp;
+    dp.peer_ws = peer_ws; dp.rank = rank; dp.world = world; dp.epoch = epoch;
+    return launch_loss_fused(logits, target, target_is_i64, B, C, HW, class_w, cfg, partials, grad_scale, grad_scale_dev, grad, out4,
+                             target_u8_ws, dp, stream);
 }
 
 extern "C" int pylc_scale_unless_one_f32(float *data, int64_t n, const float *scale_dev, pylc_stream_t stream) {

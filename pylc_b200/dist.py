@@ -77,6 +77,55 @@ def barrier():
         td.barrier()
 
 
+# ---- peer-addressable exchange workspace of the fused data-parallel loss ------------------------------------
+_exchange = {"state": None}
+
+
+def loss_exchange():
+    """The symmetric-memory workspace pylc_multiloss_fwd_bwd_dp exchanges its partials through, created on first
+    use (a COLLECTIVE: every rank must call it at the same point).  Returns a dict {ptrs_dev, rank, world,
+    next_epoch()} or None when the group has no peer-addressable memory (gloo, one rank, torch without symmetric
+    memory, PYLC_DP_FUSED=0): callers then use the two-launch route with an NCCL all-reduce in between.  All ranks
+    agree on the outcome (one MIN all-reduce of the success flags)."""
+    st = _exchange["state"]
+    if st is not None:
+        return st or None
+    ok, st = 0, {}
+    if world_size() > 1 and td.get_backend() == "nccl" and os.environ.get("PYLC_DP_FUSED", "1") != "0" and world_size() <= 16:
+        try:
+            import torch.distributed._symmetric_memory as symm
+            dev = torch.device("cuda", torch.cuda.current_device())
+            group = td.group.WORLD
+            if hasattr(symm, "enable_symm_mem_for_group"):
+                try:
+                    symm.enable_symm_mem_for_group(group.group_name)
+                except Exception:
+                    pass
+            buf = symm.empty(2048 // 8, dtype=torch.float64, device=dev)        # ops.DP_WS_BYTES
+            buf.zero_()
+            torch.cuda.synchronize()
+            hdl = symm.rendezvous(buf, group)
+            st = {"buf": buf, "hdl": hdl, "ptrs_dev": int(hdl.buffer_ptrs_dev), "rank": rank(), "world": world_size(), "epoch": 0}
+            ok = 1
+        except Exception as ex:       # noqa: BLE001 -- any failure means: no peer memory, use NCCL
+            st = {"error": repr(ex)}
+    if world_size() > 1:
+        flag = torch.tensor([ok], dtype=torch.int32, device=_comm_device())
+        td.all_reduce(flag, op=td.ReduceOp.MIN)
+        ok = int(flag.item())         # also orders every rank's zero-fill before anybody's first exchange
+    if not ok:
+        _exchange["state"] = False
+        _exchange["error"] = st.get("error")
+        return None
+
+    def next_epoch():
+        st["epoch"] += 1
+        return st["epoch"]
+    st["next_epoch"] = next_epoch
+    _exchange["state"] = st
+    return st
+
+
 def max_over_ranks(value):
     """Max of a python float across ranks (timing: the slowest rank defines the step)."""
     if world_size() == 1:

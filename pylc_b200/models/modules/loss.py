@@ -9,9 +9,11 @@ over the logits (2C+3 partial sums) and the backward ONE more (closed-form gradi
 terms); Dice needs the batch-global sums before any gradient exists, so two passes
 over the logits is the minimum.  On one GPU both passes run in a single cooperative launch
 (pylc_multiloss_fwd_bwd: grid-wide barrier between them, gradient pass back to front so it starts
-in L2) whenever the logits require a gradient; under data parallelism (`distributed=True`) they are
-two launches (pylc_multiloss_reduce / pylc_multiloss_grad) with the all-reduce of the partials in
-between, which makes the loss and gradient those of the single large batch.
+in L2) whenever the logits require a gradient.  Under data parallelism (`distributed=True`) the 2C+3
+partials are all-reduced between the passes, which makes the loss and gradient those of the single large
+batch: inside the same single launch, over peer-addressable memory (pylc_multiloss_fwd_bwd_dp, when the
+process group has symmetric memory), else as two launches (pylc_multiloss_reduce / pylc_multiloss_grad)
+with an NCCL all-reduce in between.
 
 Interface kept: MultiLoss(loss_weights, schema); .forward(pred, target); .ce_loss / .dice_loss /
 .focal_loss callable on their own (models/model.py:360-362); .ce / .dsc / .fl hold the last
@@ -47,6 +49,18 @@ class _MultiLossFn(torch.autograd.Function):
             ctx.save_for_backward(pred, target, partials)
             ctx.mark_non_differentiable(target)
             return out
+        if ctx.needs_input_grad[0] and distributed and pdist.world_size() > 1:
+            ex = pdist.loss_exchange()
+            if ex is not None:
+                # data-parallel training step, still ONE cooperative launch: the 2C+3 partials are all-reduced inside
+                # the kernel over peer-addressable memory (NVLink / NVSwitch), between the two passes
+                out, grad, partials = ops.multiloss_fwd_bwd_dp(pred, target, cfg, ex["ptrs_dev"], ex["rank"], ex["world"],
+                                                               ex["next_epoch"](), class_w)
+                ctx.fused_grad = grad
+                ctx.n_px = target.numel() * ex["world"]
+                ctx.save_for_backward(pred, target, partials)
+                ctx.mark_non_differentiable(target)
+                return out
         # int64 targets (the reference dtype) are copied to one byte per pixel by the reduce pass; the
         # gradient pass, and autograd's saved tensors, keep the 8x smaller copy
         t8 = None

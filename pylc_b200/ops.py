@@ -477,6 +477,31 @@ def multiloss_fwd_bwd(logits, target, cfg, class_w=None, grad_scale=1.0, out=Non
     return out4, grad, partials
 
 
+DP_WS_BYTES = 2048          # PYLC_DP_WS_BYTES
+
+
+def multiloss_fwd_bwd_dp(logits, target, cfg, peer_ws_dev, rank, world, epoch, class_w=None, grad_scale=1.0, out=None,
+                         partials=None, target_u8_ws=None):
+    """pylc_multiloss_fwd_bwd_dp: the data-parallel training step's loss in one cooperative launch -- the 2C+3
+    partials are all-reduced inside the kernel over peer-addressable memory.  `peer_ws_dev`: device address of the
+    [world] array of workspace pointers (dist.loss_exchange()); `epoch`: 1, 2, 3, ... the same on every rank.
+    Returns (out4, grad, partials) where partials are the global sums."""
+    logits, target, is_i64, B, C, HW = _loss_inputs(logits, target)
+    grad = out if out is not None else torch.empty_like(logits)
+    if partials is None:
+        partials = torch.zeros((2 * C + 3,), dtype=torch.float64, device=logits.device)
+    if is_i64 and target_u8_ws is None:
+        target_u8_ws = torch.empty((B * HW,), dtype=torch.uint8, device=logits.device)
+    if not is_i64:
+        target_u8_ws = None
+    out4 = torch.empty((4,), dtype=torch.float32, device=logits.device)
+    check(_lib.load().pylc_multiloss_fwd_bwd_dp(_p(logits), _p(target), is_i64, B, C, HW, _p(class_w), ctypes.byref(cfg),
+                                                _p(partials), float(grad_scale), None, _p(grad), _p(out4), _p(target_u8_ws),
+                                                ctypes.c_void_p(int(peer_ws_dev)), int(rank), int(world), int(epoch), _stream()),
+          "pylc_multiloss_fwd_bwd_dp")
+    return out4, grad, partials
+
+
 def scale_unless_one_(data, scale_dev):
     """In place data *= scale_dev (CUDA f32 scalar) unless it equals 1; no host sync."""
     _need_cuda(data, scale_dev)

@@ -120,6 +120,29 @@ def main():
     crit_a(z_loc2, t_all[rank * B:(rank + 1) * B]).backward()
     out["grad_ddp_rel"] = (z_loc2.grad / world - g_one).abs().max().item() / den
 
+    # ---- (3b) the two data-parallel routes agree: in-kernel exchange over peer memory vs NCCL between launches ----
+    ex = pdist.loss_exchange()               # the MultiLoss calls above already created it (or found none)
+    out["dp_fused_available"] = ex is not None
+    out["dp_partials_rel"] = out["dp_grad_rel"] = out["dp_loss_rel"] = 0.0
+    out["dp_partials_same_on_all_ranks"] = True
+    if ex is not None:
+        cfg = crit_d._cfg(0.5, 0.5, 0.5)
+        zl, tl = z_all[rank * B:(rank + 1) * B].contiguous(), t_all[rank * B:(rank + 1) * B].contiguous()
+        n_total = tl.numel() * world
+        part = ops.multiloss_reduce(zl, tl, cfg, crit_d.weights)
+        pdist.all_reduce_(part)
+        vals_n = ops.multiloss_finalize(part, C, n_total, cfg)
+        grad_n = ops.multiloss_grad(zl, tl, cfg, part, n_total, crit_d.weights)
+        for _ in range(3):                   # consecutive calls: both slots of the workspace, epochs in step
+            vals_f, grad_f, part_f = ops.multiloss_fwd_bwd_dp(zl, tl, cfg, ex["ptrs_dev"], ex["rank"], ex["world"], ex["next_epoch"](),
+                                                              crit_d.weights)
+        out["dp_partials_rel"] = float(((part_f - part).abs() / part.abs().clamp_min(1e-300)).max())
+        out["dp_loss_rel"] = float((vals_f - vals_n).abs().max() / vals_n.abs().max())
+        out["dp_grad_rel"] = float((grad_f - grad_n).abs().max() / grad_n.abs().max())
+        gathered = [torch.empty_like(part_f) for _ in range(world)]
+        torch.distributed.all_gather(gathered, part_f)
+        out["dp_partials_same_on_all_ranks"] = all(torch.equal(gathered[0], q) for q in gathered)
+
     # ---- (4) one data-parallel training step: DDP + MultiLoss(distributed, ddp_average) ---------------
     # parameter gradients after DDP's averaging == gradients of the single large batch on one rank
     # (BatchNorm in eval mode so that batch statistics do not depend on the shard; fp32 convolutions)
@@ -152,13 +175,14 @@ def main():
     flags = torch.tensor([float(out[k]) for k in ("conf_equal", "conf_contig_equal", "hist_equal", "probs_equal",
                                                   "mean_std_close")], device=device)
     torch.distributed.all_reduce(flags, op=torch.distributed.ReduceOp.MIN)
-    errs = torch.tensor([out["loss_rel"], out["grad_rel"], out["grad_ddp_rel"], out["param_grad_rel"]], device=device,
-                        dtype=torch.float64)
+    errs = torch.tensor([out["loss_rel"], out["grad_rel"], out["grad_ddp_rel"], out["param_grad_rel"], out["dp_partials_rel"],
+                         out["dp_loss_rel"], out["dp_grad_rel"]], device=device, dtype=torch.float64)
     torch.distributed.all_reduce(errs, op=torch.distributed.ReduceOp.MAX)
     if rank == 0:
         for k, v in zip(("conf_equal", "conf_contig_equal", "hist_equal", "probs_equal", "mean_std_close"), flags.tolist()):
             out[k] = bool(v)
-        out["loss_rel"], out["grad_rel"], out["grad_ddp_rel"], out["param_grad_rel"] = errs.tolist()
+        (out["loss_rel"], out["grad_rel"], out["grad_ddp_rel"], out["param_grad_rel"], out["dp_partials_rel"], out["dp_loss_rel"],
+         out["dp_grad_rel"]) = errs.tolist()
         out["launches"] = int(ops._lib.launch_count())
         print(json.dumps(out), flush=True)
     torch.distributed.destroy_process_group()

@@ -37,3 +37,8 @@ def test_sharded_path_equals_single_rank(world):
     # one DDP training step: averaged parameter gradients == the single large batch's (fp32 convolutions)
     assert res["n_param_grads"] > 300 and res["param_grad_rel"] <= 1e-3
     assert res["launches"] > 0
+    # the single-launch data-parallel loss (partials all-reduced inside the kernel over peer memory) equals the
+    # NCCL route: f64 sums in another order, identical bits on every rank
+    if res["dp_fused_available"]:
+        assert res["dp_partials_rel"] <= 1e-12 and res["dp_loss_rel"] <= 1e-6 and res["dp_grad_rel"] <= 1e-5
+        assert res["dp_partials_same_on_all_ranks"]

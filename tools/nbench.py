@@ -80,11 +80,28 @@ def config2(args, rank, world, rows):
             ops.multiloss_grad(z, t, cfg, part, n, class_w=w, out=grad)
         ms_dp = timed(lambda: step(True), args.steps)
         ms_local = timed(lambda: step(False), args.steps)
+        # the same step as ONE cooperative launch with the exchange inside the kernel (peer memory), and the
+        # single-GPU single launch it is to be compared with
+        ex = pdist.loss_exchange() if world > 1 else None
+        ms_fused_dp = None
+        if ex is not None:
+            def fused_dp():
+                part = torch.zeros((2 * C + 3,), dtype=torch.float64, device="cuda")
+                ops.multiloss_fwd_bwd_dp(z, t, cfg, ex["ptrs_dev"], ex["rank"], ex["world"], ex["next_epoch"](), w, out=grad, partials=part)
+            ms_fused_dp = timed(fused_dp, args.steps)
+
+        def fused_local():
+            part = torch.zeros((2 * C + 3,), dtype=torch.float64, device="cuda")
+            ops.multiloss_fwd_bwd(z, t, cfg, w, out=grad, partials=part)
+        ms_fused_local = timed(fused_local, args.steps)
         alg = npx * (8 * C + 8)
         if rank == 0:
             rows.append({"config": "configs[2]: multi-loss fwd+bwd, 512x512 tiles, batch 64/GPU, C=%d, weighted CE" % C,
                          "n_gpus": world, "ms_per_step": round(ms_dp, 4), "ms_per_step_without_allreduce": round(ms_local, 4),
                          "allreduce_share": round(max(0.0, ms_dp - ms_local) / ms_dp, 4),
+                         "ms_per_step_fused_exchange_in_kernel": None if ms_fused_dp is None else round(ms_fused_dp, 4),
+                         "ms_per_step_fused_single_gpu_launch": round(ms_fused_local, 4),
+                         "in_kernel_exchange_cost_ms": None if ms_fused_dp is None else round(ms_fused_dp - ms_fused_local, 4),
                          "tiles_per_s_all_gpus": round(B * world / (ms_dp * 1e-3), 1),
                          "alg_bytes_per_gpu": alg, "achieved_gbs_per_gpu": round(alg / (ms_dp * 1e-3) / 1e9, 1),
                          "frac_of_peak_per_gpu": round(alg / (ms_dp * 1e-3) / 1e9 / peak, 4), "peak_gbs": peak, "peak_kind": kind,
