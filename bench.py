@@ -312,10 +312,10 @@ def ncu_traffic(tag, kernel_prefix):
 # op of the pipeline -> (kernel it launches, tag of its ncu capture in profiles/traffic_r*.json, bound)
 KERNEL_OF = {
     "stitch_argmax_colour": ("stitch_kernel", "stitch45", "hbm"),
-    "stitch_upsample_argmax_colour": ("stitch_up_kernel", "stitchup45", "issue (exp + FMA per class; reads 16x fewer bytes than the logits)"),
-    "upsample_concat_nhwc": ("upsample_concat_staged_kernel", "upcat", "hbm"),
-    "maxpool3x3s2_nhwc": ("maxpool3x3s2_kernel", "maxpool", "hbm"),
-    "upsample_nhwc_to_nchw": ("upsample_to_nchw_staged_kernel", "upnchw", "hbm"),
+    "stitch_upsample_argmax_colour": ("stitch_up_kernel", "stitchup", "issue (exp + FMA per class; reads 16x fewer bytes than the logits)"),
+    "upsample_concat_nhwc": ("upsample_concat_staged_kernel", "netglue", "hbm"),
+    "maxpool3x3s2_nhwc": ("maxpool3x3s2_kernel", "netglue", "hbm"),
+    "upsample_nhwc_to_nchw": ("upsample_to_nchw_staged_kernel", "netglue", "hbm"),
     "tile_gather_norm_s2d": ("gather_norm_s2d_staged_kernel", "gather_s2d", "hbm"),
     "tile_gather_norm_f32": ("gather_norm_staged_kernel", "gather_norm", "hbm"),
     "fit_resize_area": ("area_resize_x2_kernel", "resize", "issue (OpenCV's float sequence replayed exactly, two elements per FFMA2 / FADD2)"),

@@ -74,6 +74,9 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
         : "memory");
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kCfWarps * 32) : "memory"); }
+// producer warp and consumer warps meet once, from different program points: a named barrier with an explicit
+// thread count (the warp-specialisation idiom; __syncthreads() is only defined for one convergent call site)
+__device__ __forceinline__ void cta_sync_all() { asm volatile("bar.sync 2, %0;" ::"n"(kCfThreads) : "memory"); }
 
 // lane-private 16-bit counter += w
 __device__ __forceinline__ void bump16(uint32_t saddr, uint32_t w) {
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(kCfThreads, kCfCtasPerSm)
             if (1 < n) tma_load_2d(st0 + kCfStage + kCfBoxIn, &tm_lab, wbase / 4, sy1, full0 + 8u);
             if (2 < n) tma_load_2d(st0 + 2 * kCfStage + kCfBoxIn, &tm_lab, wbase / 4, sy2, full0 + 16u);
         }
-        __syncthreads();                 // the consumers' set-up; barriers are initialised before any consumer waits on them
+        cta_sync_all();                  // the consumers' set-up; barriers are initialised before any consumer waits on them
         if (lane == 0) {
             int stage = 0;
             uint32_t round = 1;          // refill `round` of a stage waits for the consumers' release `round - 1`
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(kCfThreads, kCfCtasPerSm)
     const uint32_t my_tab = cnt0 + (uint32_t)(warp * CC) * 64u, my_col = my_tab + (uint32_t)lane * 2u;
     for (int i = lane; i < CC * 4; i += 32) sts128(my_tab + 16u * i, make_uint4(0u, 0u, 0u, 0u));
     const uint32_t q_warp = cnt0 + (uint32_t)(kCfWarps * CC) * 64u + (uint32_t)warp * (kCfQueue * 16u);
-    __syncthreads();                     // (with the producer warp) barriers + table ready
+    cta_sync_all();                      // (with the producer warp) barriers + table ready
     DBG(1);
     if (n <= 0) return;
     const uint32_t mul = ph.mul, tab = smem_u32(s_tab);

@@ -119,6 +119,14 @@ def main():
         rows.append(row)
         print(json.dumps(row), flush=True)
 
+    # ---- the harness's floor: what this timer reads for a launch that does (almost) nothing -------------
+    one = torch.ones((4,), dtype=torch.float32, device="cuda")
+    unit = torch.ones((1,), dtype=torch.float32, device="cuda")
+    report("launch floor: pylc_scale_unless_one_f32 on 4 floats (reads one scalar, returns)", 16,
+           lambda: ops.scale_unless_one_(one, unit),
+           "events around ONE launch after an L2 flush: every single-launch row above ~10 us of kernel time contains about this much "
+           "launch latency; the `sweep` rows (one CUDA graph of back-to-back launches) do not")
+
     # ---- extraction ------------------------------------------------------------------------
     W, H = 6000, 4000
     mask = orc.synth_mask(0, W, H, pal, skew=True)
@@ -276,6 +284,16 @@ def main():
     report("resample_encode_confusion 3000x2000 C9 (bench.py image)", Hb * Wb * 4,
            lambda: ops.resample_encode_confusion(lab_b, Wb, Hb, gt_rgb=dmb, gt_pitch=dpb, palette=pal, n_inject=C,
                                                  conf=conf, maps=maps_b), "3 B GT + 1 B label per full-res px")
+    if not only or any("sweep" in o or "resample" in o for o in only):
+        sets_b = []
+        for i in range(12):                      # 12 x (18 MB + 3.9 MB) of distinct inputs > L2
+            dm, dp = ops.upload_image(orc.synth_mask(40 + i, Wb, Hb, pal, skew=True))
+            sets_b.append((dm, dp, torch.from_numpy(orc.synth_labels(60 + i, wb, hb, C, skew=True, block=37)).cuda()))
+        report_sweep("resample_encode_confusion 3000x2000 C9 (bench.py image), sweep", Hb * Wb * 4,
+                     [lambda d=d, q=q, l=l: ops.resample_encode_confusion(l, Wb, Hb, gt_rgb=d, gt_pitch=q, palette=pal, n_inject=C,
+                                                                         conf=conf, maps=maps_b) for d, q, l in sets_b],
+                     "3 B GT + 1 B label per full-res px; back-to-back launches as inside an evaluation sweep")
+        del sets_b
     pred_full = torch.empty((H, W), dtype=torch.uint8, device="cuda")
     gt_full = torch.empty((H, W), dtype=torch.uint8, device="cuda")
 
