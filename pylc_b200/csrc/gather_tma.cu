@@ -27,11 +27,21 @@
 
 namespace pylc {
 
-constexpr int kBoxPx = 256, kBoxRows = 32;           // a box: 32 rows x 256 pixels; a lane owns two 16-pixel units of it
+#ifndef PYLC_GT_ROWS
+#define PYLC_GT_ROWS 32
+#endif
+#ifndef PYLC_GT_CTAS
+#define PYLC_GT_CTAS 3
+#endif
+#ifndef PYLC_GT_STAGES
+#define PYLC_GT_STAGES 2
+#endif
+constexpr int kBoxPx = 256, kBoxRows = PYLC_GT_ROWS; // a box: 32 rows x 256 pixels; a lane owns two 16-pixel units of it
+constexpr int kNU = kBoxRows / 16;
 constexpr int kUnitIn = 16 * kBoxPx * 3, kUnitOut = 16 * kBoxPx;      // the units of one lane are 16 rows apart
 constexpr int kBoxIn = kBoxRows * kBoxPx * 3, kBoxOut = kBoxRows * kBoxPx;
-constexpr int kStages = 2, kOutBufs = 2;
-constexpr int kMaskCtasPerSm = 3;
+constexpr int kStages = PYLC_GT_STAGES, kOutBufs = 2;
+constexpr int kMaskCtasPerSm = PYLC_GT_CTAS;
 
 struct TmaGeom {
     int T, S, nH, nW, m;
@@ -147,13 +157,13 @@ __global__ void __launch_bounds__(kThreads, kMaskCtasPerSm)
     for (int k = 0; k < n; ++k) {
         mbar_wait(bar0 + 8u * stage, parity);
         const uint32_t in_s = (uint32_t)stage * kBoxIn, out_s = (uint32_t)obuf * kBoxOut;
-        warp_encode_units<2, GROUPS>(in_warp0 + in_s, kUnitIn, out_warp0 + out_s, kUnitOut, q_warp, tab, mul, miss_e, gc);
+        warp_encode_units<kNU, GROUPS>(in_warp0 + in_s, kUnitIn, out_warp0 + out_s, kUnitOut, q_warp, tab, mul, miss_e, gc, (1u << kNU) - 1u);
         const BoxPos pn = box_next(g, p);
         const bool chg = pn.blk != p.blk || k + 1 == n;
         if (HIST && NG == 0) {              // wide palettes: count the finished units byte by byte
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < kNU; ++j) {
                 const uint4 r = lds128(out0 + out_s + (uint32_t)j * kUnitOut + (uint32_t)tid * 16u);
                 bc.add16(r.x, r.y, r.z, r.w);
             }

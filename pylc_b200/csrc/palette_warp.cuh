@@ -2,8 +2,9 @@
 //
 // The exact per-pixel look-up (key extract, hash multiply, slot, LDS, compare, select, pack) costs ~9
 // instructions per pixel, which is what bound the round-1 palette kernels (ncu: 59 % issue, 29 % DRAM).
-// Label masks are piecewise constant, so this form looks up ONE pixel per 4-pixel group and proves the
-// other three equal to it with three byte permutes and three compares on the group's 12 bytes:
+// Label masks are piecewise constant, so this form looks up ONE pixel per pair of 4-pixel groups and proves the
+// other seven equal to it with byte permutes and compares on the pair's 24 bytes (three per group, plus one
+// compare of the groups' first words):
 //
 //   phase A  every lane: NU units of 16 pixels = 4 NU groups; per group the anchor pixel's table entry is
 //            broadcast to four class bytes and a flag says whether the 12 bytes are NOT one repeated
@@ -129,15 +130,17 @@ __device__ __forceinline__ void warp_encode_units(uint32_t in_warp, uint32_t in_
         const uint4 q0 = lds128(in_lane), q1 = lds128(in_lane + 16), q2 = lds128(in_lane + 32);
         const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
         uint32_t ow[4], e[4];
+        const bool ok = (unit_ok >> j) & 1u;
+        // two 4-pixel groups share ONE look-up: both are uniform and their first words agree <=> the 8 pixels are
+        // one colour; otherwise BOTH groups go to the fix-up (the exact per-pixel path decides each of them)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t a = w[3 * k], b = w[3 * k + 1], c = w[3 * k + 2];
-            e[k] = lookup_entry_s(a, tab, mul, miss_e);
-            ow[k] = __byte_perm(e[k], 0, 0x3333);
-            const bool ok = (unit_ok >> j) & 1u;
-            const bool mixed = ok && group_spread(a, b, c) != 0;
-            flags |= mixed ? (1u << (4 * j + k)) : 0u;
-            if (COUNT) e[k] = (mixed || !ok) ? (kVoidId << 24) : e[k];
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t a = w[6 * h], b = w[6 * h + 1], c = w[6 * h + 2], d = w[6 * h + 3], f = w[6 * h + 4], g = w[6 * h + 5];
+            const uint32_t ent = lookup_entry_s(a, tab, mul, miss_e);
+            ow[2 * h] = ow[2 * h + 1] = __byte_perm(ent, 0, 0x3333);
+            const bool mixed = ok && (group_spread(a, b, c) | group_spread(d, f, g) | (a ^ d)) != 0;
+            flags |= mixed ? (3u << (4 * j + 2 * h)) : 0u;
+            if (COUNT) e[2 * h] = e[2 * h + 1] = (mixed || !ok) ? (kVoidId << 24) : ent;
         }
         sts128(out_warp + (uint32_t)j * out_stride + lane * 16u, make_uint4(ow[0], ow[1], ow[2], ow[3]));
         if (COUNT) aw[j] = pack_top_bytes(e[0], e[1], e[2], e[3]);

@@ -827,3 +827,25 @@ def test_tap_split_route_equals_cudnn_convolution(ops, H, W, d, cin, cout, B):
     # and the plan's autotuned call returns the same thing whichever route it keeps
     y = c(x)
     assert float((y - exact).abs().max()) <= 3e-3 * scale
+
+
+@pytest.mark.parametrize("W,H", [(1300, 1100), (2000, 1500)])
+def test_tma_and_per_thread_routes_agree(ops, palettes, monkeypatch, W, H):
+    """Every entry point with a TMA form (16-byte pitched rows) returns the same bytes from its per-thread kernels
+    (PYLC_NO_TMA=1): mask gather + encode + histogram, class_encode, fit-resize."""
+    pal = palettes["b"]
+    mask = orc.synth_mask(21, W, H, pal, skew=True, off_palette=0.01)
+    img = orc.synth_image(22, W, H, 3)
+    d_mask, mp = ops.upload_image(mask)
+    d_img, ip = ops.upload_image(img)
+    w, h = orc.fit_dims(W, H, 512)
+    got = {}
+    for no_tma in ("0", "1"):
+        monkeypatch.setenv("PYLC_NO_TMA", no_tma)
+        tiles, hist = ops.mask_gather_encode_hist(d_mask, H, W, mp, 512, 512, pal)
+        enc = ops.class_encode_hwc(d_mask, H, W, mp, pal, hist=True)
+        fit, _ = ops.fit_resize_area(d_img, H, W, 3, ip, h, w)
+        got[no_tma] = (tiles.clone(), hist.clone(), enc[0].clone(), enc[1].clone(), fit[:, :w * 3].clone())
+    for a, b in zip(got["0"], got["1"]):
+        assert torch.equal(a, b)
+    assert np.array_equal(got["0"][0].cpu().numpy(), orc.class_encode(orc.split_tiles(mask, 512, 512), pal))
