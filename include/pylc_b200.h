@@ -189,6 +189,22 @@ PYLC_API int pylc_upsample_nhwc_to_nchw_f32(const float *in, int B, int h, int w
                                    pylc_stream_t stream);
 
 /*
+ * Reduction step of the inference plan's tap-split route for a dilated 3x3 convolution the library has no
+ * sm_100 kernel for (models/modules/aspp.py: the dilation-18 branch on a 32x32 map, reference aspp.py:40-60).
+ * The plan computes every tap's product as a cuBLAS GEMM over a contiguous run of flat pixels of the
+ * channels-last activation, shifted by dy*W + dx pixels; this kernel adds them where the tap's source pixel
+ * lies inside the map and applies the ReLU:
+ *     out[b,y,x,:] = relu(out[b,y,x,:] + sum_t [0 <= y+dy_t < H and 0 <= x+dx_t < W] z_t[b, y*W + x - p0_t, :])
+ *   out  [B,H,W,O] f32 in/out (holds the centre tap's product + bias on entry), O % 4 == 0
+ *   z    HOST array [ntaps] of DEVICE pointers, z_t = [B, m_t, O] f32; p0 / m / dy / dx: HOST arrays [ntaps]
+ *        (flat range [p0_t, p0_t + m_t) of output pixels tap t was computed for; must cover every pixel the mask
+ *        lets through, else PYLC_ERR_GEOMETRY); ntaps <= 8.
+ */
+PYLC_API int pylc_tap_combine_relu_f32(float *out, int B, int H, int W, int O, const float *const *z,
+                              const int32_t *p0, const int32_t *m, const int32_t *dy, const int32_t *dx,
+                              int ntaps, pylc_stream_t stream);
+
+/*
  * pylc_tile_gather_norm_f32 in the layout the space-to-depth form of the ResNet stem wants (the 7x7
  * stride-2 convolution over 3 channels == a 4x4 stride-1 convolution over the 2x2 space-to-depth
  * image with the kernel zero-extended to 8x8; models/fused.py rearranges the weights):

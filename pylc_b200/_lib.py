@@ -55,6 +55,8 @@ SIGNATURES = {
     "pylc_upload_pitched": (c_int, [_ptr, c_size_t, _ptr, c_size_t, c_size_t, c_size_t, _ptr]),
     "pylc_upsample_concat_nhwc_f32": (c_int, [_ptr, c_int, c_int, c_int, c_int, _ptr, c_int, c_int, c_int, _ptr, _ptr]),
     "pylc_maxpool3x3s2_nhwc_f32": (c_int, [_ptr, c_int, c_int, c_int, c_int, _ptr, _ptr]),
+    "pylc_tap_combine_relu_f32": (c_int, [_ptr, c_int, c_int, c_int, c_int, POINTER(ctypes.c_void_p), POINTER(ctypes.c_int32),
+                                          POINTER(ctypes.c_int32), POINTER(ctypes.c_int32), POINTER(ctypes.c_int32), c_int, _ptr]),
     "pylc_upsample_nhwc_to_nchw_f32": (c_int, [_ptr, c_int, c_int, c_int, c_int, _ptr, c_int, c_int, _ptr]),
     "pylc_tile_gather_norm_s2d_f32": (c_int, [_u8p, c_int, c_int, c_int, c_size_t, c_int, c_int,
                                               POINTER(c_float), POINTER(c_float), c_float, _ptr, _ptr]),

@@ -404,6 +404,71 @@ extern "C" int pylc_upsample_concat_nhwc_f32(const float *x, int B, int h, int w
     return finish_launch();
 }
 
+// ---- tap combine: the reduction step of the plan's tap-split convolution -------------------------------
+// out[b, y, x, :] = relu(out[b, y, x, :] + sum over taps t whose source pixel (y + dy_t, x + dx_t) lies inside the
+// map of z_t[b, p - p0_t, :]), p = y*W + x.  z_t holds the product of tap t for the flat pixel range
+// [p0_t, p0_t + m_t) of every image (a GEMM over a contiguous run of the channels-last activation shifted by
+// dy_t*W + dx_t pixels; rows whose source wrapped into the neighbouring image row are the ones masked out here).
+// One streaming pass: every float4 of `out` is read and written once, every valid float4 of the z_t once.
+constexpr int kMaxTaps = 8;
+struct TapArgs {
+    float *out;
+    const float *z[kMaxTaps];
+    int p0[kMaxTaps], m[kMaxTaps], dy[kMaxTaps], dx[kMaxTaps];
+    int ntaps, B, H, W, O4;          // O4 = channels / 4
+};
+
+__global__ void __launch_bounds__(kThreads) tap_combine_relu_kernel(const __grid_constant__ TapArgs a) {
+    const int HW = a.H * a.W;
+    const long long total = (long long)a.B * HW * a.O4;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        const int o4 = (int)(i % a.O4);
+        const long long bp = i / a.O4;
+        const int p = (int)(bp % HW), b = (int)(bp / HW);
+        const int y = p / a.W, x = p - y * a.W;
+        float4 v = reinterpret_cast<const float4 *>(a.out)[i];
+#pragma unroll
+        for (int t = 0; t < kMaxTaps; ++t) {
+            if (t < a.ntaps && (unsigned)(y + a.dy[t]) < (unsigned)a.H && (unsigned)(x + a.dx[t]) < (unsigned)a.W) {
+                const float4 z = ld_stream_f4(a.z[t] + (((long long)b * a.m[t] + (p - a.p0[t])) * a.O4 + o4) * 4);
+                v.x += z.x; v.y += z.y; v.z += z.z; v.w += z.w;
+            }
+        }
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        reinterpret_cast<float4 *>(a.out)[i] = v;
+    }
+}
+
+extern "C" int pylc_tap_combine_relu_f32(float *out, int B, int H, int W, int O, const float *const *z, const int32_t *p0,
+                                         const int32_t *m, const int32_t *dy, const int32_t *dx, int ntaps, pylc_stream_t stream) {
+    if (!out || B < 1 || H < 1 || W < 1 || ntaps < 0 || ntaps > kMaxTaps) return PYLC_ERR_ARG;
+    if (ntaps && (!z || !p0 || !m || !dy || !dx)) return PYLC_ERR_ARG;
+    if (O < 4 || O % 4) return PYLC_ERR_GEOMETRY;
+    if ((uintptr_t)out % 16) return PYLC_ERR_ALIGN;
+    TapArgs a;
+    a.out = out; a.ntaps = ntaps; a.B = B; a.H = H; a.W = W; a.O4 = O / 4;
+    for (int t = 0; t < kMaxTaps; ++t) {
+        const bool on = t < ntaps;
+        a.z[t] = on ? z[t] : nullptr;
+        a.p0[t] = on ? p0[t] : 0; a.m[t] = on ? m[t] : 0; a.dy[t] = on ? dy[t] : 0; a.dx[t] = on ? dx[t] : 0;
+        if (on) {
+            if (!z[t] || (uintptr_t)z[t] % 16) return PYLC_ERR_ALIGN;
+            // every pixel the mask lets through must lie inside [p0, p0 + m): source inside the map <=> p + dy*W + dx in [0, HW)
+            const long long s = (long long)dy[t] * W + dx[t];
+            const long long lo = s < 0 ? -s : 0, hi = (long long)H * W - (s > 0 ? s : 0);
+            if (p0[t] > lo || (long long)p0[t] + m[t] < hi) return PYLC_ERR_GEOMETRY;
+        }
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long total = (long long)B * H * W * a.O4;
+    long long want = (total + kThreads - 1) / kThreads;
+    if (want > (long long)sms * 8) want = (long long)sms * 8;
+    tap_combine_relu_kernel<<<(unsigned)want, kThreads, 0, (cudaStream_t)stream>>>(a);
+    return finish_launch();
+}
+
 extern "C" int pylc_maxpool3x3s2_nhwc_f32(const float *in, int B, int H, int W, int C, float *out, pylc_stream_t stream) {
     if (!in || !out || B < 1 || H < 1 || W < 1) return PYLC_ERR_ARG;
     if (C < 4 || C % 4) return PYLC_ERR_GEOMETRY;

@@ -47,13 +47,14 @@ def fold_conv_bn(conv, bn):
 # Per layer and input shape, the plan times its library routes once and keeps the fastest:
 #   0  torch.cudnn_convolution_relu / _add_relu: one fused cuDNN call, engine chosen by cuDNN's heuristic
 #   1  F.conv2d (engine chosen by torch.backends.cudnn.benchmark when that is on) + in-place add / ReLU
-#   2  tap split (3x3, stride 1, padding == dilation >= 6 only): the convolution as cuBLAS GEMMs over the windows
-#      that do not fall into the zero padding (`_Conv._tap_split`)
+#   2  tap split (3x3, stride 1, padding == dilation >= 6 only): the convolution as nine cuBLAS GEMMs over the flat
+#      pixel ranges that do not fall into the zero padding, summed by pylc_tap_combine_relu_f32 (`_Conv._tap_split`)
 # Measured on B200 (tools/exp/dilated_conv.py, 45 tiles): cuDNN has an sm100 kernel for the ASPP branches with
 # dilation 6 and 12 (0.54 ms) but none for dilation 18 on a 32 x 32 map -- routes 0 and 1, NHWC or NCHW, padded
 # by hand or not, all land on `sm80_xmma_fprop_implicit_gemm_tf32...` (1.73 ms) plus two layout conversions
 # (0.2 ms): 10 % of the whole network.  With dilation 18 > 32 / 2 every output pixel sees at most two taps per
-# axis, i.e. 39 % of the dense products, and route 2 computes only those, on the TF32 tensor cores through cuBLAS.
+# axis, i.e. 39 % of the dense products; route 2 computes 62 % (whole flat runs, so that no window is ever copied),
+# on the TF32 tensor cores through cuBLAS.
 AUTOTUNE = os.environ.get("PYLC_CONV_AUTOTUNE", "1") != "0"
 
 
@@ -77,44 +78,47 @@ class _Conv(object):
 
     def _tap_split_applies(self, x, residual):
         d = self.dilation[0]
-        return (residual is None and self.relu and self.b is not None and x.dtype == torch.float32 and tuple(self.w.shape[2:]) == (3, 3)
+        return (residual is None and self.relu and self.b is not None and x.dtype == torch.float32 and x.is_cuda
+                and tuple(self.w.shape[2:]) == (3, 3) and self.w.shape[0] % 4 == 0
                 and tuple(self.stride) == (1, 1) and tuple(self.dilation) == (d, d) and tuple(self.padding) == (d, d) and d >= 6
                 and d < min(x.shape[2], x.shape[3]) and x.is_contiguous(memory_format=torch.channels_last))
 
     def _tap_split(self, x, residual=None):
-        """3x3 convolution with padding == dilation == d as GEMMs over the windows that miss the zero padding.
-        out[y, x] = sum_t W_t . in[y + ty*d, x + tx*d]; tap (ty, tx) contributes only where its source pixel
-        exists, a (H - d|ty|) x (W - d|tx|) window.  Windows spanning whole rows are contiguous in the
-        channels-last activation ([B, H, W, C]); the others are contiguous in ONE transposed copy ([B, W, H, C]),
-        where the three taps of a column offset share their GEMM (N = 3 * out_channels) and the rows a tap
-        cannot reach are dropped when its slice is added.  TF32 products, fp32 accumulation -- cuDNN's numerics."""
+        """3x3 convolution with padding == dilation == d as GEMMs over the tap windows that miss the zero padding.
+        out[y, x] = sum_t W_t . in[y + ty*d, x + tx*d].  In the channels-last activation ([B, H*W, C] as flat
+        pixels) tap t reads the pixels of the output shifted by s_t = ty*d*W + tx*d, so its product for the flat
+        output range [max(0,-s_t), H*W - max(0,s_t)) is ONE strided-batch cuBLAS GEMM on a view -- no copy, no
+        transpose.  Rows whose source wrapped into the neighbouring image row (tx != 0) are computed and then
+        masked by pylc_tap_combine_relu_f32, which adds the eight tap products to the centre tap's, applies the
+        ReLU and writes the result in one streaming pass.  Dilation 18 on 32 x 32: 62 % of the dense products.
+        TF32 products, fp32 accumulation -- the library convolution's numerics, summed in another order."""
         B, C, H, W = x.shape
         d, O = self.dilation[0], self.w.shape[0]
-        if self.taps is None:           # [C, O] matrices per tap; the three row taps of a column offset side by side
-            wt = self.w.permute(2, 3, 1, 0).contiguous()                 # [3, 3, C, O]
-            self.taps = (wt, [torch.cat([wt[0, kx], wt[1, kx], wt[2, kx]], dim=1).contiguous() for kx in (0, 2)])
-        wt, wt3 = self.taps
-        ny, nx = H - d, W - d
+        if self.taps is None:                                            # [3, 3, C, O]: one [C, O] matrix per tap
+            self.taps = self.w.permute(2, 3, 1, 0).contiguous()
+        wt = self.taps
+        HW = H * W
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32      # the convolution's own precision class
         try:
-            xn = x.permute(0, 2, 3, 1)                                   # [B, H, W, C]: the channels-last storage itself
-            out = torch.addmm(self.b, xn.reshape(B * H * W, C), wt[1, 1]).view(B, H, W, O)
-            for ky, (i0, o0) in ((0, (0, d)), (2, (d, 0))):              # tap rows -d / +d, column offset 0: whole rows
-                out[:, o0:o0 + ny].reshape(B, ny * W, O).baddbmm_(xn[:, i0:i0 + ny].reshape(B, ny * W, C), wt[ky, 1].expand(B, C, O))
-            xt = xn.transpose(1, 2).contiguous()                         # [B, W, H, C]
-            acc = torch.zeros((B, W, H, O), dtype=x.dtype, device=x.device)
-            for j, (i0, o0) in enumerate(((0, d), (d, 0))):              # column offsets -d / +d
-                # batched over the images: the column window is contiguous per image only (a 2-D reshape would copy it)
-                z = torch.bmm(xt[:, i0:i0 + nx].reshape(B, nx * H, C), wt3[j].expand(B, C, 3 * O)).view(B, nx, H, 3 * O)
-                dst = acc[:, o0:o0 + nx]
-                dst += z[..., O:2 * O]                                   # tap row 0
-                dst[:, :, d:] += z[:, :, :ny, :O]                        # tap row -d: source row y - d
-                dst[:, :, :ny] += z[:, :, d:, 2 * O:]                    # tap row +d: source row y + d
-            out += acc.transpose(1, 2)
+            xf = x.permute(0, 2, 3, 1).reshape(B, HW, C)                 # the channels-last storage itself
+            out = torch.addmm(self.b, xf.reshape(B * HW, C), wt[1, 1]).view(B, H, W, O)
+            taps = []
+            for ky in range(3):
+                for kx in range(3):
+                    if ky == 1 and kx == 1:
+                        continue
+                    dy, dx = (ky - 1) * d, (kx - 1) * d
+                    s_ = dy * W + dx
+                    p0, p1 = max(0, -s_), HW - max(0, s_)
+                    if p1 <= p0 or abs(dy) >= H or abs(dx) >= W:
+                        continue
+                    z = torch.bmm(xf[:, p0 + s_:p1 + s_], wt[ky, kx].expand(B, C, O))
+                    taps.append((z, p0, dy, dx))
+            ops.tap_combine_relu_(out, taps)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
-        return out.relu_().permute(0, 3, 1, 2)                           # [B, O, H, W], channels-last strides
+        return out.permute(0, 3, 1, 2)                                   # [B, O, H, W], channels-last strides
 
     def _fused(self, x, residual):
         if residual is not None:
@@ -197,6 +201,7 @@ class FusedDeepLab(object):
         self.aspp = [mk(m.atrous_conv, m.bn, True) for m in (a.aspp1, a.aspp2, a.aspp3, a.aspp4)]
         self.aspp_pool = mk(a.global_avg_pool[1], a.global_avg_pool[2], True)
         self.aspp_out = mk(a.conv1, a.bn1, True)
+        self._aspp_fold = None
         d = net.decoder
         self.dec_low = mk(d.conv1, d.bn1, True)
         self.dec1 = mk(d.last_conv[0], d.last_conv[1], True)
@@ -226,6 +231,30 @@ class FusedDeepLab(object):
         s.b, s.stride, s.padding, s.dilation, s.relu, s.choice = stem.b, (1, 1), (0, 0), (1, 1), True, {}
         return s
 
+    def _aspp_out_folded(self, cat4, pooled):
+        """ASPP's 1x1 projection (reference aspp.py:88-100: conv1 over the concatenation of the four atrous
+        branches and the up-sampled image-pooling branch) without materialising the pooled branch: a bilinear
+        up-sample of a 1x1 map (align_corners=True) is that pixel everywhere, so its share of the projection is one
+        vector per image, W_p . pooled[b] + bias, added to the projection of the other four branches:
+            relu(W_a . cat4[b, :, y, x] + (W_p . pooled[b] + bias))
+        One strided-batch TF32 GEMM on the channels-last concatenation (the vector enters as its beta = 1 operand)
+        and an in-place ReLU; the up-sample kernel, a fifth of the concat and a fifth of the projection's K go."""
+        B, K, H, W = cat4.shape
+        conv = self.aspp_out
+        O = conv.w.shape[0]
+        if self._aspp_fold is None:
+            w = conv.w.reshape(O, -1)                                    # [O, 1280] folded 1x1 weights
+            self._aspp_fold = (w[:, :K].t().contiguous(), w[:, K:].t().contiguous())
+        wa, wp = self._aspp_fold
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
+        try:
+            v = torch.addmm(conv.b, pooled.reshape(B, -1), wp)           # [B, O]
+            out = torch.baddbmm(v.unsqueeze(1), cat4.permute(0, 2, 3, 1).reshape(B, H * W, K), wa.expand(B, K, O))
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        return out.relu_().view(B, H, W, O).permute(0, 3, 1, 2)
+
     def _cast(self, conv):
         return conv.to(self.dtype) if self.dtype is not None else conv
 
@@ -247,8 +276,11 @@ class FusedDeepLab(object):
             if si == 0:
                 low = x
         pooled = self.aspp_pool(F.adaptive_avg_pool2d(x, 1))
-        pooled = F.interpolate(pooled, size=x.shape[2:], mode='bilinear', align_corners=True)
-        x = self.aspp_out(torch.cat([br(x) for br in self.aspp] + [pooled], dim=1))
+        if glue:
+            x = self._aspp_out_folded(torch.cat([br(x) for br in self.aspp], dim=1), pooled)
+        else:
+            pooled = F.interpolate(pooled, size=x.shape[2:], mode='bilinear', align_corners=True)
+            x = self.aspp_out(torch.cat([br(x) for br in self.aspp] + [pooled], dim=1))
         low = self.dec_low(low)
         if glue:      # up-sample + concat in one pass (one write of the [B,304,H/4,W/4] tensor, nothing else)
             x = ops.upsample_concat_nhwc(x, low)

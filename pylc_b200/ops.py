@@ -556,6 +556,23 @@ def maxpool3x3s2_nhwc(x):
     return out
 
 
+def tap_combine_relu_(out_bhwo, taps):
+    """pylc_tap_combine_relu_f32, in place on `out_bhwo` [B,H,W,O] f32 (contiguous): adds the tap products
+    `taps` = [(z [B,m,O] contiguous f32, p0, dy, dx), ...] where their source pixel lies inside the map, then ReLU."""
+    _need_cuda(out_bhwo)
+    B, H, W, O = out_bhwo.shape
+    n = len(taps)
+    if not out_bhwo.is_contiguous() or any(not z.is_contiguous() or z.dtype != torch.float32 or z.shape[0] != B or z.shape[2] != O
+                                           for z, _, _, _ in taps):
+        raise PylcError("tap_combine_relu_ takes contiguous float32 tensors [B,H,W,O] and [B,m,O]")
+    zp = (ctypes.c_void_p * max(n, 1))(*[z.data_ptr() for z, _, _, _ in taps])
+    i32 = lambda vals: (ctypes.c_int32 * max(n, 1))(*vals)          # noqa: E731
+    check(_lib.load().pylc_tap_combine_relu_f32(_p(out_bhwo), B, H, W, O, zp, i32([t[1] for t in taps]), i32([t[0].shape[1] for t in taps]),
+                                                i32([t[2] for t in taps]), i32([t[3] for t in taps]), n, _stream()),
+          "pylc_tap_combine_relu_f32")
+    return out_bhwo
+
+
 def upsample_nhwc_to_nchw(x, size):
     """pylc_upsample_nhwc_to_nchw_f32: bilinear(align_corners=True) up-sample of a channels-last tensor to
     `size`, returned as a plain contiguous NCHW tensor (the stitch kernel's layout)."""
