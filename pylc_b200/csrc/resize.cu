@@ -531,7 +531,8 @@ static int launch_area_resize_x2(const uint8_t *src, int H, int W, int ch, size_
     // the box of a tensor load must START on a 16-byte boundary of global memory (measured: a 4-byte aligned start
     // faults with "illegal instruction"), so the patch origin is the first source byte rounded down to 16
     a.org_mask = ~15;
-    a.bw = (((int)ceil((kA3Elems / ch + 2) * sx) + 2) * ch + 16 + 16 + 15) & ~15;     // + origin round-down + the word form's window
+    a.bw = (((int)ceil((kA3Elems / ch + 2) * sx) + 2) * ch + 16 + 16 + 16 + 15) & ~15;     // + origin round-down + the word form's window + slack
+    // (fuzzed over 10 000 column blocks of 400 random geometries: the largest staged offset reaches this bound minus 16)
     if (a.bw > 1024) return -1;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

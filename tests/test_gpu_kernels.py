@@ -849,3 +849,44 @@ def test_tma_and_per_thread_routes_agree(ops, palettes, monkeypatch, W, H):
     for a, b in zip(got["0"], got["1"]):
         assert torch.equal(a, b)
     assert np.array_equal(got["0"][0].cpu().numpy(), orc.class_encode(orc.split_tiles(mask, 512, 512), pal))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fit_resize_random_geometries_bit_exact(ops, seed):
+    """Random down-scales with factors in [1, 1.9) on both axes, gray and colour, pitched rows (the TMA + f32x2
+    kernel, incl. its byte-load fallback for column blocks whose taps spread too far): every byte equals OpenCV's."""
+    import cv2
+    rng = np.random.default_rng(100 + seed)
+    for _ in range(4):
+        ch = int(rng.choice([1, 3]))
+        w, h = int(rng.integers(40, 900)), int(rng.integers(33, 700))
+        W, H = min(int(w * rng.uniform(1.0, 1.89)), int(w * 1.89)), min(int(h * rng.uniform(1.0, 1.95)), int(h * 1.95))
+        W, H = max(W, w), max(H, h)
+        if not ops.area_supported(W, H, w, h):
+            continue
+        img = rng.integers(0, 256, size=(H, W) if ch == 1 else (H, W, 3), dtype=np.uint8)
+        d_img, pitch = ops.upload_image(img)
+        out, po = ops.fit_resize_area(d_img, H, W, ch, pitch, h, w)
+        want = cv2.resize(img, (w, h), interpolation=cv2.INTER_AREA)
+        got = out.cpu().numpy()[:, :w * ch].reshape(want.shape)
+        assert np.array_equal(got, want), (W, H, w, h, ch)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_resample_confusion_tma_random_geometries(ops, seed):
+    """Random label-map / ground-truth geometries (up- and down-sampling, ragged widths, few rows) and class counts
+    through the counts-only route: equal to the oracle's counts."""
+    rng = np.random.default_rng(200 + seed)
+    for _ in range(4):
+        C = int(rng.integers(2, 12))
+        w, h = 16 * int(rng.integers(1, 40)), int(rng.integers(1, 300))
+        w_full, h_full = int(rng.integers(C, 900)), int(rng.integers(1, 500))
+        pal = rng.permutation(256 ** 3)[:C]
+        pal = [[int(v) & 255, (int(v) >> 8) & 255, int(v) >> 16] for v in pal]
+        labels = orc.synth_labels(int(rng.integers(1 << 20)), w, h, C, block=int(rng.integers(1, 40)))
+        gt = orc.synth_mask(int(rng.integers(1 << 20)), w_full, h_full, pal, skew=False, off_palette=0.02)
+        d_gt, pitch = ops.upload_image(gt)
+        n_inject = int(rng.integers(0, C + 1))
+        res = ops.resample_encode_confusion(dev(labels), w_full, h_full, gt_rgb=d_gt, gt_pitch=pitch, palette=pal, n_inject=n_inject)
+        yt, yp = orc.inject_coverage(orc.class_encode_hwc(gt, pal), orc.resample_labels(labels, w_full, h_full), n_inject)
+        assert np.array_equal(res["conf"].cpu().numpy(), orc.confusion_counts(yt, yp, C)), (C, w, h, w_full, h_full, n_inject)
