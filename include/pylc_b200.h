@@ -263,7 +263,9 @@ PYLC_API int pylc_colourise_u8(const uint8_t *labels, int64_t n_px, const uint8_
  * Evaluator.load's two class_encode passes, Evaluator.validate's coverage injection and every
  * scikit-learn confusion matrix (utils/tools.py:316-317, utils/evaluate.py:87-119,150-176,
  * utils/metrics.py:45-87).
- *   labels    [h, w] u8 fitted-resolution labels
+ *   labels    [h, w] u8 fitted-resolution labels, every value < C (what pylc_stitch_*_argmax_colour and
+ *             pylc_class_encode emit).  PRECONDITION, not checked: a per-pixel test costs 10-15 % of the kernel
+ *             (measured); a label >= C indexes the shared-memory counters out of range
  *   x_ofs     [w_full] i32, y_ofs [h_full] i32: OpenCV nearest source index per destination index
  *   gt_rgb    nullable [h_full, w_full, 3] u8 ground truth, pitch bytes (NULL: no confusion)
  *   palette   HOST [C, 3] u8 (class_encode rules as above) ; lut_rgb HOST [C,3] (for pred_rgb)

@@ -890,3 +890,4 @@ def test_resample_confusion_tma_random_geometries(ops, seed):
         res = ops.resample_encode_confusion(dev(labels), w_full, h_full, gt_rgb=d_gt, gt_pitch=pitch, palette=pal, n_inject=n_inject)
         yt, yp = orc.inject_coverage(orc.class_encode_hwc(gt, pal), orc.resample_labels(labels, w_full, h_full), n_inject)
         assert np.array_equal(res["conf"].cpu().numpy(), orc.confusion_counts(yt, yp, C)), (C, w, h, w_full, h_full, n_inject)
+
