@@ -76,7 +76,10 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kCfWarps * 32) : "memory"); }
 // producer warp and consumer warps meet once, from different program points: a named barrier with an explicit
 // thread count (the warp-specialisation idiom; __syncthreads() is only defined for one convergent call site)
-__device__ __forceinline__ void cta_sync_all() { asm volatile("bar.sync 2, %0;" ::"n"(kCfThreads) : "memory"); }
+__device__ __forceinline__ void cta_sync_all() {
+    __syncwarp();                 // bar.sync is the .aligned form: the warp must be converged when it arrives
+    asm volatile("bar.sync 2, %0;" ::"n"(kCfThreads) : "memory");
+}
 
 // lane-private 16-bit counter += w
 __device__ __forceinline__ void bump16(uint32_t saddr, uint32_t w) {
