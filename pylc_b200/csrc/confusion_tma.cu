@@ -74,11 +74,11 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
         : "memory");
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kCfWarps * 32) : "memory"); }
-// producer warp and consumer warps meet once, from different program points: a named barrier with an explicit
-// thread count (the warp-specialisation idiom; __syncthreads() is only defined for one convergent call site)
+// producer warp and consumer warps meet once after their set-up, at one call site (compute-sanitizer's synccheck
+// reports a barrier that the warps of a CTA reach from different program points)
 __device__ __forceinline__ void cta_sync_all() {
-    __syncwarp();                 // bar.sync is the .aligned form: the warp must be converged when it arrives
-    asm volatile("bar.sync 2, %0;" ::"n"(kCfThreads) : "memory");
+    __syncwarp();                 // the producer's lane 0 ran the prologue alone: converge before the aligned barrier
+    __syncthreads();
 }
 
 // lane-private 16-bit counter += w
@@ -121,9 +121,12 @@ __global__ void __launch_bounds__(kCfThreads, kCfCtasPerSm)
     const int X0 = cb * kCfBoxPx;
     const uint32_t st0 = smem_u32(s_dyn), full0 = smem_u32(s_full), empty0 = smem_u32(s_empty);
 
-    // ---- producer warp ------------------------------------------------------------------------------------
+    // ---- set-up: producer warp and consumer warps each do their part, then meet at ONE barrier ---------------
+    int wbase_p = 0;                     // producer: first byte column of the label window (16-byte aligned)
+    int X = 0, valid_x = 0, wbase = 0;   // consumers: the lane's first pixel, its valid pixels, the window origin
+    int sxs[16];
+    uint32_t cnt0 = 0, my_tab = 0, my_col = 0, q_warp = 0;
     if (warp == kCfWarps) {
-        int wbase = 0;
         if (lane == 0) {
             // the map entries the label-window coordinates depend on: requested first, used after the ground-truth
             // boxes (which depend on nothing) are in flight
@@ -147,12 +150,37 @@ __global__ void __launch_bounds__(kCfThreads, kCfCtasPerSm)
                     tma_load_2d(st0 + (uint32_t)s * kCfStage, &tm_gt, X0 * 3 / 4, (by0 + s) * kCfBoxRows, full0 + 8u * s);
                 }
             }
-            wbase = x_first & ~15;
-            if (0 < n) tma_load_2d(st0 + kCfBoxIn, &tm_lab, wbase / 4, sy0, full0);
-            if (1 < n) tma_load_2d(st0 + kCfStage + kCfBoxIn, &tm_lab, wbase / 4, sy1, full0 + 8u);
-            if (2 < n) tma_load_2d(st0 + 2 * kCfStage + kCfBoxIn, &tm_lab, wbase / 4, sy2, full0 + 16u);
+            wbase_p = x_first & ~15;
+            if (0 < n) tma_load_2d(st0 + kCfBoxIn, &tm_lab, wbase_p / 4, sy0, full0);
+            if (1 < n) tma_load_2d(st0 + kCfStage + kCfBoxIn, &tm_lab, wbase_p / 4, sy1, full0 + 8u);
+            if (2 < n) tma_load_2d(st0 + 2 * kCfStage + kCfBoxIn, &tm_lab, wbase_p / 4, sy2, full0 + 16u);
         }
-        cta_sync_all();                  // the consumers' set-up; barriers are initialised before any consumer waits on them
+    } else {
+        // column map of the lane's 16 pixels (constant for the CTA), issued before the set-up stores
+        X = X0 + (lane & 15) * 16;
+        valid_x = max(0, min(16, a.w_full - X));
+        if (valid_x == 16 && ((uintptr_t)a.x_ofs & 15) == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int4 v = __ldg(reinterpret_cast<const int4 *>(a.x_ofs + X) + k);
+                sxs[4 * k] = v.x, sxs[4 * k + 1] = v.y, sxs[4 * k + 2] = v.z, sxs[4 * k + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sxs[j] = __ldg(a.x_ofs + min(X + j, a.w_full - 1));
+        }
+        wbase = __ldg(a.x_ofs + X0) & ~15;
+        s_tab[tid] = (ph.tab[tid] & 0x00FFFFFFu) | (((ph.tab[tid] >> 24) * (uint32_t)a.C) << 24);   // class byte pre-multiplied by C
+        cnt0 = st0 + kCfStages * kCfStage;
+        my_tab = cnt0 + (uint32_t)(warp * CC) * 64u;
+        my_col = my_tab + (uint32_t)lane * 2u;
+        for (int i = lane; i < CC * 4; i += 32) sts128(my_tab + 16u * i, make_uint4(0u, 0u, 0u, 0u));
+        q_warp = cnt0 + (uint32_t)(kCfWarps * CC) * 64u + (uint32_t)warp * (kCfQueue * 16u);
+    }
+    cta_sync_all();                      // every thread of the CTA, one call site: mbarriers initialised, table and counters ready
+
+    // ---- producer warp: keeps the ring full ---------------------------------------------------------------
+    if (warp == kCfWarps) {
         if (lane == 0) {
             int stage = 0;
             uint32_t round = 1;          // refill `round` of a stage waits for the consumers' release `round - 1`
@@ -164,7 +192,7 @@ __global__ void __launch_bounds__(kCfThreads, kCfCtasPerSm)
                 const uint32_t bar = full0 + 8u * stage, dst = st0 + (uint32_t)stage * kCfStage;
                 mbar_arrive_expect_tx(bar, kCfStage);
                 tma_load_2d(dst, &tm_gt, X0 * 3 / 4, Y0, bar);
-                tma_load_2d(dst + kCfBoxIn, &tm_lab, wbase / 4, sy0, bar);
+                tma_load_2d(dst + kCfBoxIn, &tm_lab, wbase_p / 4, sy0, bar);
                 sy0 = sy0_next;
                 if (++stage == kCfStages) {
                     stage = 0;
@@ -176,28 +204,6 @@ __global__ void __launch_bounds__(kCfThreads, kCfCtasPerSm)
     }
 
     // ---- consumer warps -----------------------------------------------------------------------------------
-    // column map of the lane's 16 pixels (constant for the CTA), issued before the set-up stores
-    const int X = X0 + (lane & 15) * 16;
-    const int valid_x = max(0, min(16, a.w_full - X));
-    int sxs[16];
-    if (valid_x == 16 && ((uintptr_t)a.x_ofs & 15) == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int4 v = __ldg(reinterpret_cast<const int4 *>(a.x_ofs + X) + k);
-            sxs[4 * k] = v.x, sxs[4 * k + 1] = v.y, sxs[4 * k + 2] = v.z, sxs[4 * k + 3] = v.w;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) sxs[j] = __ldg(a.x_ofs + min(X + j, a.w_full - 1));
-    }
-    const int wbase = __ldg(a.x_ofs + X0) & ~15;
-
-    s_tab[tid] = (ph.tab[tid] & 0x00FFFFFFu) | (((ph.tab[tid] >> 24) * (uint32_t)a.C) << 24);   // class byte pre-multiplied by C
-    const uint32_t cnt0 = st0 + kCfStages * kCfStage;
-    const uint32_t my_tab = cnt0 + (uint32_t)(warp * CC) * 64u, my_col = my_tab + (uint32_t)lane * 2u;
-    for (int i = lane; i < CC * 4; i += 32) sts128(my_tab + 16u * i, make_uint4(0u, 0u, 0u, 0u));
-    const uint32_t q_warp = cnt0 + (uint32_t)(kCfWarps * CC) * 64u + (uint32_t)warp * (kCfQueue * 16u);
-    cta_sync_all();                      // (with the producer warp) barriers + table ready
     DBG(1);
     if (n <= 0) return;
     const uint32_t mul = ph.mul, tab = smem_u32(s_tab);
