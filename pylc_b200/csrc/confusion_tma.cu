@@ -21,9 +21,15 @@
 //   * counters are lane-private 16-bit columns in shared memory, tab[warp][t*C+p][lane]: one conflict-free
 //     load / add / store per update, no atomics; summed and flushed with <= C*C global atomics per CTA.
 // The coverage injection of Evaluator.validate (the first n_inject flat pixels count as (i, i),
-// utils/evaluate.py:172-174) is applied as a correction by one thread: -1 on the true pair, +1 on (i, i).
-// Lanes whose maps do not fit the staged window (down-sampling maps) gather their labels from global memory;
-// results are identical.
+// utils/evaluate.py:172-174) is applied as a correction, one lane per injected pixel: -1 on its true pair,
+// +1 on (i, i).  Lanes whose maps do not fit the staged window (down-sampling maps) gather their labels from
+// global memory; results are identical.  Precondition (not checked, see include/pylc_b200.h): labels < C.
+//
+// Measured (B200, 6000x4000, 288 CTAs in one wave; tools/exp/cfdbg.py with -DPYLC_CF_DEBUG): set-up done 1.8 us
+// after kernel entry, first box consumed at 4.8 us (every CTA requests three stages at once: 14 MB of fill),
+// 21 boxes per CTA in 18.3 us = 5.2 TB/s during the loop, flush 0.7 us.  The first version's producer spun on
+// the `empty` barriers without sleeping and issued 11 % of the kernel's instructions; its mixed groups were
+// counted box by box with ~9 of 32 lanes active, which was half of all instructions (hence the deferred queue).
 #include "palette_warp.cuh"
 
 namespace pylc {

@@ -161,10 +161,11 @@ total = pdist.all_reduce_i64(local)
 part = torch.tensor([0.5 * (rank + 1), 2.0], dtype=torch.float64)
 pdist.all_reduce_(part)
 t = pdist.max_over_ranks(1.0 + rank)
+ex = pdist.loss_exchange()          # collective; gloo has no peer-addressable memory: every rank agrees on None
 pdist.barrier()
 if rank == 0:
     print(json.dumps({"world": world, "mine": mine, "ok": bool(np.array_equal(total, conf_all.sum(axis=0))),
-                      "part": part.tolist(), "t": t}))
+                      "part": part.tolist(), "t": t, "exchange": ex is not None}))
 torch.distributed.destroy_process_group()
 """
 
@@ -180,7 +181,7 @@ def test_dist_gloo_two_ranks(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     res = json.loads(line)
-    assert res == {"world": 2, "mine": [0, 2, 4, 6], "ok": True, "part": [1.5, 4.0], "t": 2.0}
+    assert res == {"world": 2, "mine": [0, 2, 4, 6], "ok": True, "part": [1.5, 4.0], "t": 2.0, "exchange": False}
 
 
 def test_rank_steps_equal_on_every_rank():
