@@ -86,6 +86,22 @@ PYLC_API int pylc_mask_gather_encode_hist(const uint8_t *src, int H, int W, size
                                  pylc_stream_t stream);
 
 /*
+ * Extraction sweep over a STACK of n_img equally sized sources in one call (one launch on the staged / TMA
+ * forms): what the file loop of Extractor.extract (utils/extract.py:136-222) does image by image.
+ *   src        image i starts at src + i * img_stride (img_stride >= H * src_pitch; a multiple of 16 keeps
+ *              the vector / TMA forms), each [H, W(,3)] with row pitch `src_pitch`
+ *   dst        [n_img * nH*nW, ...]: the tiles of image i follow those of image i-1, as the reference's
+ *              tile buffers are filled (utils/extract.py:182,214)
+ *   stat / px_dist  nullable, [n_img * nH*nW, ...], same order; px_dist is added into
+ * Results are identical to n_img single-image calls.
+ */
+PYLC_API int pylc_tile_gather_u8_stack(const uint8_t *src, int n_img, size_t img_stride, int H, int W, int ch,
+                              size_t src_pitch, int T, int S, uint8_t *dst, uint64_t *stat, pylc_stream_t stream);
+PYLC_API int pylc_mask_gather_encode_hist_stack(const uint8_t *src, int n_img, size_t img_stride, int H, int W,
+                                       size_t src_pitch, int T, int S, const uint8_t *palette, int C, uint8_t *dst,
+                                       int64_t *px_dist, pylc_stream_t stream);
+
+/*
  * Standalone tools.class_encode (utils/tools.py:412-449).
  *   layout 0: rgb is [n_img, rows, cols, 3] interleaved with row pitch `pitch` (n_img images
  *             stored back to back, rows*pitch bytes each)          -> out [n_img, rows, cols]

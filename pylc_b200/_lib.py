@@ -42,6 +42,9 @@ SIGNATURES = {
     "pylc_tile_gather_u8": (c_int, [_u8p, c_int, c_int, c_int, c_size_t, c_int, c_int, _u8p, _ptr, _ptr]),
     "pylc_mask_gather_encode_hist": (c_int, [_u8p, c_int, c_int, c_size_t, c_int, c_int,
                                              POINTER(c_uint8), c_int, _u8p, _ptr, _ptr]),
+    "pylc_tile_gather_u8_stack": (c_int, [_u8p, c_int, c_size_t, c_int, c_int, c_int, c_size_t, c_int, c_int, _u8p, _ptr, _ptr]),
+    "pylc_mask_gather_encode_hist_stack": (c_int, [_u8p, c_int, c_size_t, c_int, c_int, c_size_t, c_int, c_int,
+                                                   POINTER(c_uint8), c_int, _u8p, _ptr, _ptr]),
     "pylc_class_encode": (c_int, [_u8p, c_int, c_int, c_int, c_size_t, c_int, POINTER(c_uint8), c_int,
                                   _u8p, _ptr, _ptr]),
     "pylc_profile_tiles": (c_int, [_u8p, c_int, _u8p, c_int, c_int64, c_int, _ptr, _ptr, _ptr]),

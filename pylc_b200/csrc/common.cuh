@@ -52,8 +52,8 @@ void build_colour_lut(const uint8_t *lut_rgb, int C, ColourLut *out);
 // TMA forms (gather_tma.cu).  Return PYLC_OK / a CUDA error after launching, or -1 when the form does not
 // apply to the arguments (alignment, geometry, driver without tensor maps): the caller then launches the
 // per-thread kernel.
-int launch_mask_gather_tma(const uint8_t *src, int H, int W, size_t pitch, int T, int S, int nH, int nW, const PaletteHash &ph, int C,
-                           uint8_t *dst, long long *px_dist, cudaStream_t st);
+int launch_mask_gather_tma(const uint8_t *src, int n_img, size_t img_stride, int H, int W, size_t pitch, int T, int S, int nH, int nW,
+                           const PaletteHash &ph, int C, uint8_t *dst, long long *px_dist, cudaStream_t st);
 int launch_class_encode_tma(const uint8_t *rgb, long long rows, long long cols, size_t pitch, const PaletteHash &ph, int C,
                             uint8_t *out, long long *hist, cudaStream_t st);
 

@@ -265,10 +265,17 @@ __global__ void __launch_bounds__(kThreads) gather_img_kernel(GatherGeom g, uint
 // are reduced and added to the block's tiles once per CTA.
 template <int CH, bool STATS>
 __global__ void __launch_bounds__(kThreads) gather_img_staged_kernel(GatherGeom g, uint8_t *__restrict__ dst,
-                                                                    unsigned long long *__restrict__ stat, int strip_rows, int spb) {
+                                                                    unsigned long long *__restrict__ stat, int strip_rows, int spb,
+                                                                    size_t img_stride) {
     __shared__ unsigned long long s_sum[CH * 2];
     extern __shared__ __align__(16) uint8_t s_src[];          // strip_rows rows of S * CH bytes
     if (STATS && threadIdx.x < CH * 2) s_sum[threadIdx.x] = 0;
+    {   // blockIdx.y: image of a stack of equally sized sources, its tiles follow the previous image's
+        const size_t img = blockIdx.y, tiles_img = (size_t)g.nH * g.nW;
+        g.src += img * img_stride;
+        dst += img * tiles_img * CH * ((size_t)g.T * g.T);
+        if (STATS) stat += img * tiles_img * CH * 2;
+    }
     const int blk = blockIdx.x / spb, y0 = (blockIdx.x - blk * spb) * strip_rows;
     const int nrow = min(strip_rows, g.S - y0);
     const int bx = blk % g.nbx, by = blk / g.nbx;
@@ -1025,9 +1032,10 @@ extern "C" int pylc_tile_grid(int H, int W, int T, int S, int *nH, int *nW) {
     return PYLC_OK;
 }
 
-extern "C" int pylc_tile_gather_u8(const uint8_t *src, int H, int W, int ch, size_t src_pitch, int T, int S,
-                                   uint8_t *dst, uint64_t *stat, pylc_stream_t stream) {
+extern "C" int pylc_tile_gather_u8_stack(const uint8_t *src, int n_img, size_t img_stride, int H, int W, int ch, size_t src_pitch,
+                                         int T, int S, uint8_t *dst, uint64_t *stat, pylc_stream_t stream) {
     if (ch != 1 && ch != 3) return PYLC_ERR_ARG;
+    if (n_img < 1 || (n_img > 1 && img_stride < (size_t)H * src_pitch)) return PYLC_ERR_ARG;
     GatherGeom g;
     int rc = make_geom(src, H, W, ch, src_pitch, T, S, &g);
     if (rc) return rc;
@@ -1035,42 +1043,67 @@ extern "C" int pylc_tile_gather_u8(const uint8_t *src, int H, int W, int ch, siz
     if (!dst) return PYLC_ERR_ARG;
     if ((uintptr_t)dst % 16) return PYLC_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool al = aligned16(src, src_pitch);
+    const bool al = aligned16(src, src_pitch) && (n_img == 1 || img_stride % 16 == 0);
     auto *sp = reinterpret_cast<unsigned long long *>(stat);
-    // staged form: strips of up to 32 KB (64 rows) of source rows per CTA
+    // staged form: strips of up to 32 KB (64 rows) of source rows per CTA, the stack in the grid's y dimension
     int strip_rows = 1;
     while (strip_rows * 2 <= S && (size_t)strip_rows * 2 * S * ch <= 32 * 1024 && strip_rows < 64) strip_rows *= 2;
     const size_t strip = (size_t)strip_rows * S * ch;
     const int spb = (S + strip_rows - 1) / strip_rows;
     if (al && g.m <= 2 && strip <= 32 * 1024 && (long long)g.nbx * g.nby * spb < 0x7FFFFFFF) {
-        const unsigned grid = (unsigned)(g.nbx * g.nby * spb);
-        if (ch == 1) {
-            if (stat) gather_img_staged_kernel<1, true><<<grid, kThreads, strip, st>>>(g, dst, sp, strip_rows, spb);
-            else gather_img_staged_kernel<1, false><<<grid, kThreads, strip, st>>>(g, dst, sp, strip_rows, spb);
-        } else {
-            if (stat) gather_img_staged_kernel<3, true><<<grid, kThreads, strip, st>>>(g, dst, sp, strip_rows, spb);
-            else gather_img_staged_kernel<3, false><<<grid, kThreads, strip, st>>>(g, dst, sp, strip_rows, spb);
+        for (int i0 = 0; i0 < n_img; i0 += 65535) {      // grid.y limit
+            const int ni = n_img - i0 < 65535 ? n_img - i0 : 65535;
+            const dim3 grid((unsigned)(g.nbx * g.nby * spb), (unsigned)ni);
+            GatherGeom gi = g;
+            gi.src = src + (size_t)i0 * img_stride;
+            uint8_t *d = dst + (size_t)i0 * g.nH * g.nW * ch * T * T;
+            unsigned long long *s = sp ? sp + (size_t)i0 * g.nH * g.nW * ch * 2 : nullptr;
+            if (ch == 1) {
+                if (stat) gather_img_staged_kernel<1, true><<<grid, kThreads, strip, st>>>(gi, d, s, strip_rows, spb, img_stride);
+                else gather_img_staged_kernel<1, false><<<grid, kThreads, strip, st>>>(gi, d, s, strip_rows, spb, img_stride);
+            } else {
+                if (stat) gather_img_staged_kernel<3, true><<<grid, kThreads, strip, st>>>(gi, d, s, strip_rows, spb, img_stride);
+                else gather_img_staged_kernel<3, false><<<grid, kThreads, strip, st>>>(gi, d, s, strip_rows, spb, img_stride);
+            }
+            rc = finish_launch();
+            if (rc) return rc;
         }
-        return finish_launch();
+        return PYLC_OK;
     }
+    // unaligned sources / T/S > 2: the persistent per-thread kernel, one launch per image of the stack
+    const bool al1 = aligned16(src, src_pitch) && (n_img == 1 || img_stride % 16 == 0);
 #define LAUNCH(CH, AL, ST) \
-    gather_img_kernel<CH, AL, ST><<<persistent_ctas(gather_img_kernel<CH, AL, ST>, g.items), kThreads, 0, st>>>(g, dst, sp)
-    if (ch == 1) {
-        if (al) { if (stat) LAUNCH(1, true, true); else LAUNCH(1, true, false); }
-        else    { if (stat) LAUNCH(1, false, true); else LAUNCH(1, false, false); }
-    } else {
-        if (al) { if (stat) LAUNCH(3, true, true); else LAUNCH(3, true, false); }
-        else    { if (stat) LAUNCH(3, false, true); else LAUNCH(3, false, false); }
+    gather_img_kernel<CH, AL, ST><<<persistent_ctas(gather_img_kernel<CH, AL, ST>, g.items), kThreads, 0, st>>>(gi, d, s)
+    for (int i = 0; i < n_img; ++i) {
+        GatherGeom gi = g;
+        gi.src = src + (size_t)i * img_stride;
+        uint8_t *d = dst + (size_t)i * g.nH * g.nW * ch * T * T;
+        unsigned long long *s = sp ? sp + (size_t)i * g.nH * g.nW * ch * 2 : nullptr;
+        if (ch == 1) {
+            if (al1) { if (stat) LAUNCH(1, true, true); else LAUNCH(1, true, false); }
+            else     { if (stat) LAUNCH(1, false, true); else LAUNCH(1, false, false); }
+        } else {
+            if (al1) { if (stat) LAUNCH(3, true, true); else LAUNCH(3, true, false); }
+            else     { if (stat) LAUNCH(3, false, true); else LAUNCH(3, false, false); }
+        }
+        rc = finish_launch();
+        if (rc) return rc;
     }
 #undef LAUNCH
-    return finish_launch();
+    return PYLC_OK;
 }
 
-extern "C" int pylc_mask_gather_encode_hist(const uint8_t *src, int H, int W, size_t src_pitch, int T, int S,
-                                            const uint8_t *palette, int C, uint8_t *dst, int64_t *px_dist,
-                                            pylc_stream_t stream) {
+extern "C" int pylc_tile_gather_u8(const uint8_t *src, int H, int W, int ch, size_t src_pitch, int T, int S,
+                                   uint8_t *dst, uint64_t *stat, pylc_stream_t stream) {
+    return pylc_tile_gather_u8_stack(src, 1, 0, H, W, ch, src_pitch, T, S, dst, stat, stream);
+}
+
+extern "C" int pylc_mask_gather_encode_hist_stack(const uint8_t *src, int n_img, size_t img_stride, int H, int W, size_t src_pitch,
+                                                  int T, int S, const uint8_t *palette, int C, uint8_t *dst, int64_t *px_dist,
+                                                  pylc_stream_t stream) {
     if (!palette) return PYLC_ERR_ARG;
     if (C < 1 || C > PYLC_MAX_CLASSES) return PYLC_ERR_CLASSES;
+    if (n_img < 1 || (n_img > 1 && img_stride < (size_t)H * src_pitch)) return PYLC_ERR_ARG;
     GatherGeom g;
     int rc = make_geom(src, H, W, 3, src_pitch, T, S, &g);
     if (rc) return rc;
@@ -1081,17 +1114,19 @@ extern "C" int pylc_mask_gather_encode_hist(const uint8_t *src, int H, int W, si
     if (!dst) return PYLC_ERR_ARG;
     if ((uintptr_t)dst % 16) return PYLC_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool al = aligned16(src, src_pitch);
-    auto *pd = reinterpret_cast<long long *>(px_dist);
-    // TMA form (16-byte aligned rows, S a multiple of 256, T/S <= 2): the reference's two geometries
-    rc = tma_disabled() ? -1 : launch_mask_gather_tma(src, H, W, src_pitch, T, S, g.nH, g.nW, ph, C, dst, pd, st);
+    const bool al = aligned16(src, src_pitch) && (n_img == 1 || img_stride % 16 == 0);
+    // TMA form (16-byte aligned rows, S a multiple of 256, T/S <= 2): the reference's two geometries; the whole
+    // stack is ONE launch (3-D tensor map over [n_img][H][pitch / 4])
+    rc = tma_disabled() ? -1
+                        : launch_mask_gather_tma(src, n_img, img_stride, H, W, src_pitch, T, S, g.nH, g.nW, ph, C, dst,
+                                                 reinterpret_cast<long long *>(px_dist), st);
     if (rc != -1) return rc;
 #define LAUNCH(AL, NG, HS)                                                                                         \
     gather_mask_kernel<AL, NG, HS><<<persistent_ctas(gather_mask_kernel<AL, NG, HS>, g.items), kThreads, 0, st>>>( \
-        g, ph, C, dst, pd)
+        gi, ph, C, d, pd)
 #define LAUNCH_CUR(AL, NG, HS)                                                                          \
     gather_mask_cursor_kernel<AL, NG, HS>                                                              \
-        <<<persistent_ctas(gather_mask_cursor_kernel<AL, NG, HS>, g.items), kThreads, 0, st>>>(g, ph, C, dst, pd)
+        <<<persistent_ctas(gather_mask_cursor_kernel<AL, NG, HS>, g.items), kThreads, 0, st>>>(gi, ph, C, d, pd)
 #define PICK(L, AL)                                                 \
     switch (px_dist ? counter_groups(C) : -1) {                     \
         case -1: L(AL, 5, false); break;                            \
@@ -1100,15 +1135,29 @@ extern "C" int pylc_mask_gather_encode_hist(const uint8_t *src, int H, int W, si
         case 7: L(AL, 7, true); break;                              \
         default: L(AL, 0, true); break;                             \
     }
-    if (g.m <= 2) {
-        if (al) { PICK(LAUNCH_CUR, true) } else { PICK(LAUNCH_CUR, false) }
-    } else {
-        if (al) { PICK(LAUNCH, true) } else { PICK(LAUNCH, false) }
+    for (int i = 0; i < n_img; ++i) {       // per-thread kernels: one launch per image of the stack
+        GatherGeom gi = g;
+        gi.src = src + (size_t)i * img_stride;
+        uint8_t *d = dst + (size_t)i * g.nH * g.nW * T * T;
+        long long *pd = px_dist ? reinterpret_cast<long long *>(px_dist) + (size_t)i * g.nH * g.nW * C : nullptr;
+        if (g.m <= 2) {
+            if (al) { PICK(LAUNCH_CUR, true) } else { PICK(LAUNCH_CUR, false) }
+        } else {
+            if (al) { PICK(LAUNCH, true) } else { PICK(LAUNCH, false) }
+        }
+        rc = finish_launch();
+        if (rc) return rc;
     }
 #undef PICK
 #undef LAUNCH_CUR
 #undef LAUNCH
-    return finish_launch();
+    return PYLC_OK;
+}
+
+extern "C" int pylc_mask_gather_encode_hist(const uint8_t *src, int H, int W, size_t src_pitch, int T, int S,
+                                            const uint8_t *palette, int C, uint8_t *dst, int64_t *px_dist,
+                                            pylc_stream_t stream) {
+    return pylc_mask_gather_encode_hist_stack(src, 1, 0, H, W, src_pitch, T, S, palette, C, dst, px_dist, stream);
 }
 
 extern "C" int pylc_tile_gather_norm_f32(const uint8_t *src, int H, int W, int ch, size_t src_pitch, int T, int S,

@@ -48,20 +48,27 @@ struct TmaGeom {
     int nbx, nby;          // S-blocks across / down
     int xparts, rgroups;   // boxes across / down one block
     int per_block;         // xparts * rgroups
-    int items;             // nbx * nby * per_block
+    int items_img;         // nbx * nby * per_block: boxes of one image
+    int tiles_img;         // nH * nW
+    int items;             // n_img * items_img (a stack of equally sized sources is one launch)
 };
 
 struct BoxPos {
-    int blk, bx, by, rg, xp;
+    int blk, bx, by, rg, xp;   // blk numbers the S-blocks of the whole stack (change detection only)
+    int img, tile0;            // source image of the stack and its first destination tile
 };
 __device__ __forceinline__ BoxPos box_decode(const TmaGeom &g, int item) {
     BoxPos p;
-    p.blk = item / g.per_block;
-    const int r = item - p.blk * g.per_block;
+    p.img = item / g.items_img;
+    const int li = item - p.img * g.items_img;
+    const int lb = li / g.per_block;
+    const int r = li - lb * g.per_block;
     p.rg = r / g.xparts;
     p.xp = r - p.rg * g.xparts;
-    p.by = p.blk / g.nbx;
-    p.bx = p.blk - p.by * g.nbx;
+    p.by = lb / g.nbx;
+    p.bx = lb - p.by * g.nbx;
+    p.blk = p.img * (g.nbx * g.nby) + lb;
+    p.tile0 = p.img * g.tiles_img;
     return p;
 }
 __device__ __forceinline__ BoxPos box_next(const TmaGeom &g, BoxPos p) {
@@ -72,7 +79,11 @@ __device__ __forceinline__ BoxPos box_next(const TmaGeom &g, BoxPos p) {
             ++p.blk;
             if (++p.bx == g.nbx) {
                 p.bx = 0;
-                ++p.by;
+                if (++p.by == g.nby) {
+                    p.by = 0;
+                    ++p.img;
+                    p.tile0 += g.tiles_img;
+                }
             }
         }
     }
@@ -96,12 +107,13 @@ __device__ __forceinline__ void flush_warp_hist_tma(const TmaGeom &g, const BoxP
         const int c_lo = max(0, p.bx - g.m + 1), c_hi = min(g.nW - 1, p.bx);
         for (int r = r_lo; r <= r_hi; ++r)
             for (int c = c_lo; c <= c_hi; ++c)
-                atomicAdd((unsigned long long *)&px_dist[(size_t)(r * g.nW + c) * C + lane], (unsigned long long)mine);
+                atomicAdd((unsigned long long *)&px_dist[(size_t)(p.tile0 + r * g.nW + c) * C + lane], (unsigned long long)mine);
     }
 }
 
 // NG > 0: GroupCounter<NG> histograms (C <= 14); NG = 0: ByteCounter over the finished box (C <= 32); HIST off: none
-template <int NG, bool HIST>
+// STACK: the source is a stack of equally sized images ([n_img][H][pitch/4] tensor map, 3-D box loads)
+template <int NG, bool HIST, bool STACK>
 __global__ void __launch_bounds__(kThreads, kMaskCtasPerSm)
     gather_mask_tma_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_dst,
                            const TmaGeom g, const __grid_constant__ PaletteHash ph, int C, long long *__restrict__ px_dist) {
@@ -119,7 +131,9 @@ __global__ void __launch_bounds__(kThreads, kMaskCtasPerSm)
     auto issue_load = [&](const BoxPos &p, int stage) {   // source coordinates in 32-bit elements / rows
         const uint32_t bar = bar0 + 8u * stage;
         mbar_arrive_expect_tx(bar, kBoxIn);
-        tma_load_2d(in0 + (uint32_t)stage * kBoxIn, &tm_src, (p.bx * g.S + p.xp * kBoxPx) * 3 / 4, p.by * g.S + p.rg * kBoxRows, bar);
+        const int c0 = (p.bx * g.S + p.xp * kBoxPx) * 3 / 4, c1 = p.by * g.S + p.rg * kBoxRows;
+        if (STACK) tma_load_3d(in0 + (uint32_t)stage * kBoxIn, &tm_src, c0, c1, p.img, bar);
+        else tma_load_2d(in0 + (uint32_t)stage * kBoxIn, &tm_src, c0, c1, bar);
     };
     // thread 0 puts the first boxes in flight before anything else happens in the CTA: the table copy and
     // the barrier below overlap the loads' latency (the other threads only need the barriers initialised
@@ -186,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, kMaskCtasPerSm)
             const int c_lo = max(0, p.bx - g.m + 1), c_hi = min(g.nW - 1, p.bx);
             for (int r = r_lo; r <= r_hi; ++r)
                 for (int c = c_lo; c <= c_hi; ++c)
-                    tma_store_3d(&tm_dst, ((p.bx - c) * g.S + p.xp * kBoxPx) / 4, (p.by - r) * g.S + p.rg * kBoxRows, r * g.nW + c, out0 + out_s);
+                    tma_store_3d(&tm_dst, ((p.bx - c) * g.S + p.xp * kBoxPx) / 4, (p.by - r) * g.S + p.rg * kBoxRows, p.tile0 + r * g.nW + c, out0 + out_s);
             tma_store_commit();
             if (k + kStages < n) {
                 issue_load(pl, stage);
@@ -204,28 +218,37 @@ __global__ void __launch_bounds__(kThreads, kMaskCtasPerSm)
 }
 
 // Returns PYLC_OK after launching, or -1 when this form does not apply (the caller falls back to the
-// per-thread kernels): needs 16-byte aligned rows, S a multiple of 256 and T/S <= 2.
-int launch_mask_gather_tma(const uint8_t *src, int H, int W, size_t pitch, int T, int S, int nH, int nW, const PaletteHash &ph, int C,
-                           uint8_t *dst, long long *px_dist, cudaStream_t st) {
+// per-thread kernels): needs 16-byte aligned rows, S a multiple of 256 and T/S <= 2.  n_img > 1: a stack of
+// equally sized sources `img_stride` bytes apart (a multiple of 16), tiles of image i at dst tile i * nH * nW.
+int launch_mask_gather_tma(const uint8_t *src, int n_img, size_t img_stride, int H, int W, size_t pitch, int T, int S, int nH, int nW,
+                           const PaletteHash &ph, int C, uint8_t *dst, long long *px_dist, cudaStream_t st) {
     if (((uintptr_t)src % 16) || (pitch % 16) || ((uintptr_t)dst % 16) || S % kBoxPx || S % kBoxRows || T % S || T / S > 2 || T % 16) return -1;
+    if (n_img < 1 || (n_img > 1 && (img_stride % 16 || img_stride < (size_t)H * pitch))) return -1;
     TmaGeom g;
     g.T = T, g.S = S, g.nH = nH, g.nW = nW, g.m = T / S;
     g.nbx = nW - 1 + g.m, g.nby = nH - 1 + g.m;
     g.xparts = S / kBoxPx, g.rgroups = S / kBoxRows;
     g.per_block = g.xparts * g.rgroups;
-    const long long items = (long long)g.nbx * g.nby * g.per_block;
-    if (items <= 0 || items > 0x7FFFFFFF || (long long)nH * nW > 0x7FFFFFFF) return -1;
+    const long long items = (long long)g.nbx * g.nby * g.per_block * n_img;
+    if (items <= 0 || items > 0x7FFFFFFF || (long long)nH * nW * n_img > 0x7FFFFFFF) return -1;
     g.items = (int)items;
+    g.items_img = (int)(items / n_img);
+    g.tiles_img = nH * nW;
 
     CUtensorMap tm_src, tm_dst;
-    {
+    if (n_img == 1) {
         const uint64_t dims[2] = {(uint64_t)(pitch / 4), (uint64_t)H};
         const uint64_t strides[1] = {(uint64_t)pitch};
         const uint32_t box[2] = {kBoxPx * 3 / 4, kBoxRows};
         if (!tma_encode_u32(&tm_src, src, 2, dims, strides, box)) return -1;
+    } else {
+        const uint64_t dims[3] = {(uint64_t)(pitch / 4), (uint64_t)H, (uint64_t)n_img};
+        const uint64_t strides[2] = {(uint64_t)pitch, (uint64_t)img_stride};
+        const uint32_t box[3] = {kBoxPx * 3 / 4, kBoxRows, 1};
+        if (!tma_encode_u32(&tm_src, src, 3, dims, strides, box)) return -1;
     }
     {
-        const uint64_t dims[3] = {(uint64_t)(T / 4), (uint64_t)T, (uint64_t)nH * nW};
+        const uint64_t dims[3] = {(uint64_t)(T / 4), (uint64_t)T, (uint64_t)nH * nW * n_img};
         const uint64_t strides[2] = {(uint64_t)T, (uint64_t)T * T};
         const uint32_t box[3] = {kBoxPx / 4, kBoxRows, 1};
         if (!tma_encode_u32(&tm_dst, dst, 3, dims, strides, box)) return -1;
@@ -237,7 +260,12 @@ int launch_mask_gather_tma(const uint8_t *src, int H, int W, size_t pitch, int T
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 #define LAUNCH(NG, HS)                                                                                         \
     do {                                                                                                       \
-        auto kern = gather_mask_tma_kernel<NG, HS>;                                                            \
+        if (n_img > 1) LAUNCH_K(NG, HS, true);                                                                 \
+        else LAUNCH_K(NG, HS, false);                                                                          \
+    } while (0)
+#define LAUNCH_K(NG, HS, STK)                                                                                  \
+    do {                                                                                                       \
+        auto kern = gather_mask_tma_kernel<NG, HS, STK>;                                                          \
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {   \
             cudaGetLastError();                                                                                \
             return -1;                                                                                         \
@@ -258,6 +286,7 @@ int launch_mask_gather_tma(const uint8_t *src, int H, int W, size_t pitch, int T
         default: LAUNCH(0, true); break;
     }
 #undef LAUNCH
+#undef LAUNCH_K
     return finish_launch();
 }
 

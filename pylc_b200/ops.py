@@ -152,6 +152,64 @@ def mask_gather_encode_hist(src, H, W, pitch, T, S, palette, hist=True, out=None
     return tiles, px_dist
 
 
+def upload_stack(images, device=None, staging=None):
+    """Equally sized u8 images [H,W] / [H,W,3] -> ONE device tensor [n, H, pitch] with 16-byte aligned rows
+    (the `src` of the *_stack entry points; image stride = H * pitch).  `staging`: a pinned [>= n, H, pitch] u8
+    tensor to reuse between calls.  Returns (stack, pitch, staging)."""
+    first = np.asarray(images[0])
+    H = first.shape[0]
+    row = first.shape[1] * (first.shape[2] if first.ndim == 3 else 1)
+    pitch = pitch_for(row)
+    n = len(images)
+    if staging is None or staging.shape[0] < n or tuple(staging.shape[1:]) != (H, pitch):
+        staging = torch.empty((n, H, pitch), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    elif torch.cuda.is_available():
+        torch.cuda.current_stream().synchronize()      # the previous upload may still be reading the buffer
+    view = staging.numpy()
+    for i, im in enumerate(images):
+        im = np.asarray(im)
+        if im.shape != first.shape or im.dtype != np.uint8:
+            raise PylcError("upload_stack takes equally sized u8 images")
+        view[i, :, :row] = im.reshape(H, row)
+    return staging[:n].to(device or torch.device("cuda"), non_blocking=True), pitch, staging
+
+
+def tile_gather_u8_stack(src, H, W, ch, pitch, T, S, stats=False, out=None, stat_out=None):
+    """pylc_tile_gather_u8_stack: `src` [n_img, H, pitch] u8 (equally sized images) -> tiles
+    [n_img*n, ch, T, T] u8 in image order (and stat [n_img*n, ch, 2] i64), one launch."""
+    _need_cuda(src)
+    if src.dim() != 3 or not src.is_contiguous():
+        raise PylcError("tile_gather_u8_stack takes a contiguous [n_img, H, pitch] u8 stack")
+    n_img, stride = src.shape[0], src.shape[1] * src.shape[2]
+    nH, nW = tile_grid(H, W, T, S)
+    n = nH * nW * n_img
+    tiles = out if out is not None else torch.empty((n, ch, T, T), dtype=torch.uint8, device=src.device)
+    stat = None
+    if stats:
+        stat = stat_out.zero_() if stat_out is not None else torch.zeros((n, ch, 2), dtype=torch.int64, device=src.device)
+    check(_lib.load().pylc_tile_gather_u8_stack(_p(src), n_img, stride, H, W, ch, pitch, T, S, _p(tiles), _p(stat), _stream()),
+          "pylc_tile_gather_u8_stack")
+    return (tiles, stat) if stats else tiles
+
+
+def mask_gather_encode_hist_stack(src, H, W, pitch, T, S, palette, hist=True, out=None, px_dist=None):
+    """pylc_mask_gather_encode_hist_stack: `src` [n_img, H, pitch] u8 RGB masks -> (tiles [n_img*n, T, T] u8,
+    px_dist [n_img*n, C] i64 or None) in image order, one launch.  `px_dist` given: added into."""
+    _need_cuda(src)
+    if src.dim() != 3 or not src.is_contiguous():
+        raise PylcError("mask_gather_encode_hist_stack takes a contiguous [n_img, H, pitch] u8 stack")
+    n_img, stride = src.shape[0], src.shape[1] * src.shape[2]
+    pal, C = _lib.palette_array(palette)
+    nH, nW = tile_grid(H, W, T, S)
+    n = nH * nW * n_img
+    tiles = out if out is not None else torch.empty((n, T, T), dtype=torch.uint8, device=src.device)
+    if px_dist is None:
+        px_dist = torch.zeros((n, C), dtype=torch.int64, device=src.device) if hist else None
+    check(_lib.load().pylc_mask_gather_encode_hist_stack(_p(src), n_img, stride, H, W, pitch, T, S, pal, C, _p(tiles),
+                                                         _p(px_dist), _stream()), "pylc_mask_gather_encode_hist_stack")
+    return tiles, px_dist
+
+
 def tile_gather_norm_f32(src, H, W, ch, pitch, T, S, mean, std, post_div=255.0, out_ch=3, out=None):
     """pylc_tile_gather_norm_f32: network-ready f32 tiles [n,out_ch,T,T]."""
     _need_cuda(src)

@@ -29,6 +29,9 @@ from .profile import finish_profile, get_profile, print_meta, tile_moments_to_st
 
 
 class Extractor(object):
+    STACK_MAX = 32             # images per extraction launch
+    STACK_BYTES = 1 << 30      # bound on one stack's device + pinned staging footprint (image + RGB mask)
+
     def __init__(self, params=None):
         self.meta = Parameters(params) if params is not None else defaults
         self.verbose = True
@@ -74,6 +77,30 @@ class Extractor(object):
         dev = utils._device()
         img_parts, mask_parts, dist_parts, stat_parts = [], [], [], []
         n_img = n_mask = 0
+        # Consecutive files of one size are extracted as a STACK: one upload and one launch per kernel for up to
+        # STACK_MAX images (pylc_tile_gather_u8_stack / pylc_mask_gather_encode_hist_stack), tiles in file order.
+        pending = []
+
+        def shape_of(a):
+            return None if a is None else a.shape
+
+        def flush():
+            if not pending:
+                return
+            imgs, masks = [p[0] for p in pending], [p[1] for p in pending]
+            H, W = imgs[0].shape[:2]
+            d_imgs, pitch, self._staging[0] = ops.upload_stack(imgs, dev, self._staging[0])
+            tiles, stat = ops.tile_gather_u8_stack(d_imgs, H, W, ch, pitch, T, S, stats=True)
+            img_parts.append(tiles)
+            stat_parts.append(stat)
+            if masks[0] is not None:
+                mh, mw = masks[0].shape[:2]
+                d_masks, mpitch, self._staging[1] = ops.upload_stack(masks, dev, self._staging[1])
+                m_tiles, px_dist = ops.mask_gather_encode_hist_stack(d_masks, mh, mw, mpitch, T, S, self.meta.palette_rgb)
+                mask_parts.append(m_tiles)
+                dist_parts.append(px_dist)
+            pending.clear()
+
         for scale in self.meta.scales:
             if self.verbose:
                 print('\nExtraction --- Scaling Factor: {}'.format(scale))
@@ -83,9 +110,8 @@ class Extractor(object):
                 img, w_fitted, h_fitted, offset = utils.adjust_to_tile(img, T, S, ch) \
                     if self.fit else (img, w_scaled, h_scaled, 0)
                 H, W = img.shape[:2]
-                d_img, pitch = ops.upload_image(img, dev)
-                tiles, stat = ops.tile_gather_u8(d_img, H, W, ch, pitch, T, S, stats=True)
-                n_tiles = tiles.shape[0]
+                nH, nW = ops.tile_grid(H, W, T, S)
+                n_tiles = nH * nW
                 self.meta.extract = {
                     'fid': os.path.basename(img_name.replace('.', '_')) + '_scale_' + str(scale),
                     'n': n_tiles, 'w_full': w_full, 'h_full': h_full, 'w_scaled': w_scaled, 'h_scaled': h_scaled,
@@ -95,22 +121,23 @@ class Extractor(object):
                 if n_tiles > self.imgs_capacity:
                     print('Data array reached capacity. Increase the number of tiles per image.')
                     exit(1)
-                img_parts.append(tiles)
-                stat_parts.append(stat)
                 n_img += n_tiles
                 if mask is not None:
                     assert mask.shape[1] == w_scaled and mask.shape[0] == h_scaled, \
                         "Dimensions do not match: \n\tImage {}\n\tMask {}.".format(img_name, mask_name)
-                    d_mask, mpitch = ops.upload_image(mask, dev)
-                    m_tiles, px_dist = ops.mask_gather_encode_hist(d_mask, mask.shape[0], mask.shape[1], mpitch, T, S,
-                                                                   self.meta.palette_rgb)
+                    # the mask is tiled at its own (scaled, unfitted) size, as in the reference (extract.py:189-195)
+                    mH, mW = ops.tile_grid(mask.shape[0], mask.shape[1], T, S)
                     if self.verbose:
-                        md = dict(self.meta.extract, n=m_tiles.shape[0],
+                        md = dict(self.meta.extract, n=mH * mW,
                                   fid=os.path.basename(mask_name.replace('.', '_')) + '_scale_' + str(scale))
                         self.print_result("Mask", mask_name, md)
-                    mask_parts.append(m_tiles)
-                    dist_parts.append(px_dist)
-                    n_mask += m_tiles.shape[0]
+                    n_mask += mH * mW
+                if pending and (pending[0][0].shape != img.shape or shape_of(pending[0][1]) != shape_of(mask)
+                                or len(pending) >= self.STACK_MAX
+                                or (len(pending) + 1) * img.size * 4 > self.STACK_BYTES):
+                    flush()
+                pending.append((img, mask))
+        flush()
         self.imgs = torch.cat(img_parts) if len(img_parts) > 1 else img_parts[0]
         self.img_idx = n_img
         self._stat = torch.cat(stat_parts) if len(stat_parts) > 1 else stat_parts[0]
@@ -145,6 +172,7 @@ class Extractor(object):
         self._px_dist = None
         self._stat = None
         self._perm = None
+        self._staging = [None, None]
         self.fit = False
         self.meta.id = '_db_pylc_' + self.meta.ch_label + '_' + str(int(time.time()))
         return self

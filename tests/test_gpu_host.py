@@ -65,6 +65,38 @@ def test_extractor_extract_profile(ops, palettes, ch, schema):
     np.testing.assert_allclose(m2.px_std, want["px_std"], rtol=1e-5)
 
 
+@pytest.mark.parametrize("stack_max", [32, 2])
+def test_extractor_stacks_equal_sized_files(ops, palettes, stack_max):
+    """Runs of equally sized files go through the *_stack entry points (one launch per kernel and stack);
+    file order, tiles, masks and the profile are what the per-file loop of extract.py:132-222 gives."""
+    from pylc_b200.config import Parameters
+    from pylc_b200.utils.extract import Extractor
+    pal = palettes["b"]
+    meta = Parameters({"schema": "./schemas/schema_b.json"})
+    meta.update({"ch": 1})
+    sizes = [(1300, 1100)] * 3 + [(1100, 1300)] + [(1300, 1100)] * 2       # two runs around an odd one out
+    imgs = [orc.synth_image(50 + i, w, h, 1) for i, (w, h) in enumerate(sizes)]
+    masks = [orc.synth_mask(50 + i, w, h, pal, skew=bool(i & 1)) for i, (w, h) in enumerate(sizes)]
+    ex = Extractor(meta)
+    ex.verbose = False
+    ex.STACK_MAX = stack_max
+    n0 = ops._lib.launch_count()
+    ex.load_arrays(imgs, masks).extract().profile()
+    launches = ops._lib.launch_count() - n0
+    assert launches == (6 if stack_max == 32 else 8)         # 2 kernels x stacks (3 | 1 | 2  or  2, 1 | 1 | 2)
+    ref_i = np.concatenate([orc.split_tiles(im, T, T) for im in imgs])
+    ref_m = np.concatenate([orc.class_encode_port(orc.split_tiles(m, T, T), pal) for m in masks])
+    got_i, got_m = ex.host()
+    assert np.array_equal(got_i, ref_i) and np.array_equal(got_m, ref_m)
+    want = orc.profile_port(ref_i, ref_m, len(pal), T)
+    m = ex.get_meta()
+    assert np.array_equal(np.array(m.px_dist), want["px_dist"])
+    assert np.array_equal(np.array(m.dset_px_dist), want["dset_px_dist"])
+    np.testing.assert_allclose(m.px_mean, want["px_mean"], rtol=1e-5)
+    np.testing.assert_allclose(m.px_std, want["px_std"], rtol=1e-5)
+    np.testing.assert_allclose(m.weights, want["weights"], rtol=1e-15)
+
+
 def test_extractor_coshuffle_is_one_permutation(ops, palettes):
     from pylc_b200.utils.extract import Extractor
     meta = _params(ch=1)

@@ -171,6 +171,80 @@ def test_mask_gather_wide_palette_duplicates_unaligned(ops):
     assert torch.equal(tiles, tiles2) and torch.equal(px_dist, px2)
 
 
+@pytest.mark.parametrize("pk,n_img,H,W,T,S,ch", [
+    ("b", 5, 1500, 2000, 512, 512, 1),     # configs[3]: gray image + schema_b mask pairs, one launch per stack (TMA form)
+    ("a", 3, 1024, 1536, 512, 256, 3),     # 50 % overlap: a box goes to up to four tiles of its own image only
+    ("b", 4, 80, 96, 32, 16, 1),           # small tiles: per-thread kernels, one launch per image inside the call
+    ("a", 2, 600, 1001, 512, 512, 3),      # ragged width
+    ("b", 1, 1100, 1300, 512, 512, 1),     # a stack of one
+])
+def test_extraction_stack_equals_per_image(ops, palettes, pk, n_img, H, W, T, S, ch):
+    """pylc_tile_gather_u8_stack / pylc_mask_gather_encode_hist_stack: the file loop of Extractor.extract
+    (utils/extract.py:136-222) over equally sized pairs as one call -- tiles, moments and histograms in file
+    order, bit-identical to the oracle and to per-image calls."""
+    pal = palettes[pk]
+    C = len(pal)
+    imgs = [orc.synth_image(20 + i, W, H, ch) for i in range(n_img)]
+    masks = [orc.synth_mask(20 + i, W, H, pal, skew=bool(i & 1), off_palette=0.002) for i in range(n_img)]
+    d_imgs, ip, staging = ops.upload_stack(imgs)
+    d_masks, mp, _ = ops.upload_stack(masks)
+    assert tuple(d_imgs.shape) == (n_img, H, ip) and tuple(d_masks.shape) == (n_img, H, mp)
+    tiles, stat = ops.tile_gather_u8_stack(d_imgs, H, W, ch, ip, T, S, stats=True)
+    m_tiles, px_dist = ops.mask_gather_encode_hist_stack(d_masks, H, W, mp, T, S, pal)
+    ref_i = np.concatenate([orc.split_tiles(im, T, S) for im in imgs])
+    ref_m = np.concatenate([orc.class_encode(orc.split_tiles(m, T, S), pal) for m in masks])
+    assert np.array_equal(tiles.cpu().numpy(), ref_i)
+    assert np.array_equal(m_tiles.cpu().numpy(), ref_m)
+    assert np.array_equal(px_dist.cpu().numpy(), orc.tile_histograms(ref_m, C))
+    x = ref_i.astype(np.int64).reshape(ref_i.shape[0], ch, -1)
+    assert np.array_equal(stat.cpu().numpy(), np.stack([x.sum(-1), (x * x).sum(-1)], axis=-1))
+    # the same through the single-image entry points
+    per = ref_i.shape[0] // n_img
+    for i in range(n_img):
+        t1, s1 = ops.tile_gather_u8(d_imgs[i], H, W, ch, ip, T, S, stats=True)
+        m1, p1 = ops.mask_gather_encode_hist(d_masks[i], H, W, mp, T, S, pal)
+        sl = slice(i * per, (i + 1) * per)
+        assert torch.equal(t1, tiles[sl]) and torch.equal(s1, stat[sl])
+        assert torch.equal(m1, m_tiles[sl]) and torch.equal(p1, px_dist[sl])
+    # histograms accumulate into a caller's buffer; the tile-only form writes no histogram
+    m2, p2 = ops.mask_gather_encode_hist_stack(d_masks, H, W, mp, T, S, pal, px_dist=px_dist.clone())
+    assert torch.equal(p2, 2 * px_dist) and torch.equal(m2, m_tiles)
+    m3, p3 = ops.mask_gather_encode_hist_stack(d_masks, H, W, mp, T, S, pal, hist=False)
+    assert p3 is None and torch.equal(m3, m_tiles)
+
+
+def test_extraction_stack_padded_image_stride(ops, palettes):
+    """The image stride of a stack may exceed H * pitch (a pool with slack rows between images)."""
+    pal = palettes["a"]
+    H, W, T, S, n_img = 1024, 1024, 512, 256, 3
+    masks = [orc.synth_mask(40 + i, W, H, pal) for i in range(n_img)]
+    imgs = [orc.synth_image(40 + i, W, H, 3) for i in range(n_img)]
+    pitch = ops.pitch_for(W * 3)
+    pool_m = torch.full((n_img, H + 7, pitch), 255, dtype=torch.uint8, device="cuda")
+    pool_i = torch.full((n_img, H + 7, pitch), 255, dtype=torch.uint8, device="cuda")
+    for i in range(n_img):
+        pool_m[i, :H, :W * 3] = dev(masks[i].reshape(H, W * 3))
+        pool_i[i, :H, :W * 3] = dev(imgs[i].reshape(H, W * 3))
+    lib = ops._lib.load()
+    pal_c, C = ops._lib.palette_array(pal)
+    n = 9 * n_img
+    tiles = torch.empty((n, T, T), dtype=torch.uint8, device="cuda")
+    px = torch.zeros((n, C), dtype=torch.int64, device="cuda")
+    ops.check(lib.pylc_mask_gather_encode_hist_stack(ops._p(pool_m), n_img, (H + 7) * pitch, H, W, pitch, T, S, pal_c, C,
+                                                     ops._p(tiles), ops._p(px), ops._stream()), "stack")
+    ref_m = np.concatenate([orc.class_encode(orc.split_tiles(m, T, S), pal) for m in masks])
+    assert np.array_equal(tiles.cpu().numpy(), ref_m)
+    assert np.array_equal(px.cpu().numpy(), orc.tile_histograms(ref_m, C))
+    it = torch.empty((n, 3, T, T), dtype=torch.uint8, device="cuda")
+    ops.check(lib.pylc_tile_gather_u8_stack(ops._p(pool_i), n_img, (H + 7) * pitch, H, W, 3, pitch, T, S, ops._p(it), None,
+                                            ops._stream()), "stack")
+    assert np.array_equal(it.cpu().numpy(), np.concatenate([orc.split_tiles(im, T, S) for im in imgs]))
+    # a stride shorter than one image is rejected
+    with pytest.raises(ops.PylcError):
+        ops.check(lib.pylc_tile_gather_u8_stack(ops._p(pool_i), n_img, H * pitch - 16, H, W, 3, pitch, T, S, ops._p(it), None,
+                                                ops._stream()), "stack")
+
+
 def test_class_encode_golden_and_layouts(ops, golden, palettes):
     g = golden("encode")
     for name in ("a", "b", "dup"):

@@ -116,11 +116,9 @@ def config3(args, rank, world, rows):
     meta = Parameters({"schema": "./schemas/schema_b.json"})
     pal, C = meta.palette_rgb, meta.n_classes
     assert C == 11
-    pool = []
-    for i in range(pool_n):                       # 24 x (3 MB + 9 MB) = 288 MB of distinct inputs (> L2)
-        d_img, ip = ops.upload_image(synth.image(rank * pool_n + i, W, H, 1))
-        d_mask, mp = ops.upload_image(synth.mask(rank * pool_n + i, W, H, pal, skew=True))
-        pool.append((d_img, ip, d_mask, mp))
+    # 24 x (3 MB + 9 MB) = 288 MB of distinct inputs (> L2), resident as two stacks [24, H, pitch]
+    d_imgs, ip, _ = ops.upload_stack([synth.image(rank * pool_n + i, W, H, 1) for i in range(pool_n)])
+    d_masks, mp, _ = ops.upload_stack([synth.mask(rank * pool_n + i, W, H, pal, skew=True) for i in range(pool_n)])
     mine = pdist.shard_indices(n_pairs, rank, world)
     nH, nW = ops.tile_grid(H, W, T, S)
     per = nH * nW
@@ -128,38 +126,67 @@ def config3(args, rank, world, rows):
     tiles = torch.empty((len(mine) * per, 1, T, T), dtype=torch.uint8, device="cuda")
     masks = torch.empty((len(mine) * per, T, T), dtype=torch.uint8, device="cuda")
     px_dist = torch.zeros((len(mine) * per, C), dtype=torch.int64, device="cuda")
+    stat = torch.zeros((len(mine) * per, 1, 2), dtype=torch.int64, device="cuda")
 
-    def sweep():
-        px_dist.zero_()
-        stats = []
-        for k, gi in enumerate(mine):
-            d_img, ip, d_mask, mp = pool[gi % pool_n]
-            _, st = ops.tile_gather_u8(d_img, H, W, 1, ip, T, S, stats=True, out=tiles[k * per:(k + 1) * per])
-            ops.mask_gather_encode_hist(d_mask, H, W, mp, T, S, pal, out=masks[k * per:(k + 1) * per],
-                                        px_dist=px_dist[k * per:(k + 1) * per])
-            stats.append(st)
+    def finish():
         hist = px_dist.sum(0)
-        mom = torch.stack(stats).sum((0, 1)).view(-1)
+        mom = stat.sum((0, 1)).view(-1)
         if world > 1:
             pdist.all_reduce_(hist)
             pdist.all_reduce_(mom)
         return hist, mom
-    ms = timed(sweep, max(1, args.steps // 4), warmup=1)
-    hist, _ = sweep()
+
+    def sweep_pairs():           # the reference's file loop: two launches per pair
+        px_dist.zero_()
+        for k, gi in enumerate(mine):
+            j = gi % pool_n
+            ops.tile_gather_u8_stack(d_imgs[j:j + 1], H, W, 1, ip, T, S, stats=True, out=tiles[k * per:(k + 1) * per],
+                                     stat_out=stat[k * per:(k + 1) * per])
+            ops.mask_gather_encode_hist(d_masks[j], H, W, mp, T, S, pal, out=masks[k * per:(k + 1) * per],
+                                        px_dist=px_dist[k * per:(k + 1) * per])
+        return finish()
+
+    def sweep_stacks():          # equally sized pairs as stacks of 24: two launches per 24 pairs
+        px_dist.zero_()
+        stat.zero_()
+        lib, pal_c = ops._lib.load(), ops._lib.palette_array(pal)[0]
+        st = ops._stream()
+        for k0 in range(0, len(mine), pool_n):
+            n = min(pool_n, len(mine) - k0)
+            lo, hi = k0 * per, (k0 + n) * per
+            ops.check(lib.pylc_tile_gather_u8_stack(ops._p(d_imgs), n, H * ip, H, W, 1, ip, T, S, ops._p(tiles[lo:hi]),
+                                                    ops._p(stat[lo:hi]), st), "pylc_tile_gather_u8_stack")
+            ops.check(lib.pylc_mask_gather_encode_hist_stack(ops._p(d_masks), n, H * mp, H, W, mp, T, S, pal_c, C,
+                                                             ops._p(masks[lo:hi]), ops._p(px_dist[lo:hi]), st),
+                      "pylc_mask_gather_encode_hist_stack")
+        return finish()
+
     total_px = n_pairs * per * T * T
-    ok = int(hist.sum()) == total_px
     alg = n_pairs * per * T * T * (2 + 4)          # gray gather 1+1 B, mask gather 3+1 B per tile pixel
     peak, kind = peak_gbs()
+    results = {}
+    for name, fn, launches in (("stacks", sweep_stacks, 2.0 / pool_n), ("pairs", sweep_pairs, 2.0)):
+        ms = timed(fn, max(1, args.steps // 4), warmup=1)
+        hist, mom = fn()
+        results[name] = (ms, hist.clone(), mom.clone(), tiles[:per * pool_n].clone(), masks[:per * pool_n].clone())
+        if rank == 0:
+            rows.append({"config": "configs[3]: extraction/profile sweep, %d synthetic 2000x1500 gray image + mask pairs, schema_b (11 classes)" % n_pairs,
+                         "form": {"stacks": "stacks of %d equally sized pairs per call (pylc_*_stack)" % pool_n,
+                                  "pairs": "one call per pair (the reference's file loop)"}[name],
+                         "n_gpus": world, "ms_per_sweep": round(ms, 2), "pairs_per_s_all_gpus": round(n_pairs / (ms * 1e-3), 1),
+                         "mpx_per_s_all_gpus": round(n_pairs * W * H / 1e6 / (ms * 1e-3), 1),
+                         "launches_per_pair": round(launches, 4), "us_per_pair_per_gpu": round(ms * 1e3 / len(mine), 2),
+                         "alg_bytes_all_gpus": alg, "achieved_gbs_all_gpus": round(alg / (ms * 1e-3) / 1e9, 1),
+                         "frac_of_peak_per_gpu": round(alg / world / (ms * 1e-3) / 1e9 / peak, 4), "peak_gbs": peak, "peak_kind": kind,
+                         "histogram_total_equals_pixel_count": int(hist.sum()) == total_px,
+                         "exchange": "one ncclAllReduce(sum) of the [11] i64 dataset histogram and one of the moment sums per sweep"})
+    a, b = results["stacks"], results["pairs"]
+    same = all(torch.equal(x, y) for x, y in zip(a[1:], b[1:]))
     if rank == 0:
-        rows.append({"config": "configs[3]: extraction/profile sweep, %d synthetic 2000x1500 gray image + mask pairs, schema_b (11 classes)" % n_pairs,
-                     "n_gpus": world, "ms_per_sweep": round(ms, 2), "pairs_per_s_all_gpus": round(n_pairs / (ms * 1e-3), 1),
-                     "mpx_per_s_all_gpus": round(n_pairs * W * H / 1e6 / (ms * 1e-3), 1),
-                     "launches_per_pair": 2, "us_per_pair_per_gpu": round(ms * 1e3 / len(mine), 2),
-                     "alg_bytes_all_gpus": alg, "achieved_gbs_all_gpus": round(alg / (ms * 1e-3) / 1e9, 1),
-                     "frac_of_peak_per_gpu": round(alg / world / (ms * 1e-3) / 1e9 / peak, 4), "peak_gbs": peak, "peak_kind": kind,
-                     "histogram_total_equals_pixel_count": ok,
-                     "exchange": "one ncclAllReduce(sum) of the [11] i64 dataset histogram and one of the moment sums per sweep",
-                     "bound": "two launches of ~10 us per pair, issued from Python: launch-bound, not bandwidth-bound"})
+        rows[-2]["identical_to_per_pair_calls"] = same
+        rows[-2]["speedup_over_per_pair_calls"] = round(b[0] / a[0], 2)
+    if not same:
+        raise SystemExit("configs[3]: stacked and per-pair sweeps disagree")
 
 
 def main():

@@ -42,6 +42,22 @@ for d, p, img, ch in ((d1, p1, img1, 1), (d3, p3, img3, 3)):
     g = ops.tile_gather_u8(d, H, W, ch, p, T, 256)
     assert np.array_equal(g.cpu().numpy(), orc.split_tiles(img, T, 256))
 
+# stacks of equally sized sources: one launch (3-D tensor map over the stack; grid.y = image)
+masks = [mask, orc.synth_mask(2, W, H, pal, off_palette=0.01), orc.synth_mask(3, W, H, pal, skew=True)]
+imgs = [img1, orc.synth_image(3, W, H, 1), orc.synth_image(4, W, H, 1)]
+d_ms, mps, _ = ops.upload_stack(masks)
+d_is, ips, _ = ops.upload_stack(imgs)
+ref_m = np.concatenate([orc.class_encode(orc.split_tiles(m, T, 256), pal) for m in masks])
+for no_tma in ("0", "1"):
+    os.environ["PYLC_NO_TMA"] = no_tma
+    tiles, hist = ops.mask_gather_encode_hist_stack(d_ms, H, W, mps, T, 256, pal)
+    assert np.array_equal(tiles.cpu().numpy(), ref_m) and np.array_equal(hist.cpu().numpy(), orc.tile_histograms(ref_m, C))
+os.environ["PYLC_NO_TMA"] = "0"
+g, st = ops.tile_gather_u8_stack(d_is, H, W, 1, ips, T, 256, stats=True)
+ref_i = np.concatenate([orc.split_tiles(im, T, 256) for im in imgs])
+assert np.array_equal(g.cpu().numpy(), ref_i)
+assert np.array_equal(st.cpu().numpy()[:, 0, 0], ref_i.astype(np.int64).reshape(len(ref_i), -1).sum(-1))
+
 # fit resize (TMA + f32x2) against cv2 via the oracle restatement
 import cv2  # noqa: E402
 for d, p, img, ch in ((d1, p1, img1, 1), (d3, p3, img3, 3)):
