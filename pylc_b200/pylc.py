@@ -156,10 +156,13 @@ def test(args):
     evaluator = Evaluator(model.meta)
     evaluator.aggregate_inject = 0 in mine           # the concatenated vectors carry ONE injection
     seg = TiledSegmenter(model, batch_tiles=getattr(args, 'batch_tiles', 32), keep_masks=True)
-    for i in mine:
+    def decode(i):
         fpair = files[i]
         img_file, mask_file = (fpair['img'], fpair['mask']) if isinstance(fpair, dict) else (fpair, None)
-        img, w_full, h_full, w_scaled, h_scaled = tools.get_image(img_file, model.meta.ch, scale=params.scale)
+        return (i, img_file, mask_file) + tuple(tools.get_image(img_file, model.meta.ch, scale=params.scale))
+
+    # the next files decode on host threads while the current image is on the GPU (file order kept)
+    for i, img_file, mask_file, img, w_full, h_full, w_scaled, h_scaled in tools.ordered_prefetch(decode, mine, depth=3):
         f = seg.stage(img, None, index=i)
         torch.cuda.current_stream().wait_event(f.ready)
         res = seg.segment_fitted(f, inject=0)         # stitch + argmax + colourise + resample on the GPU

@@ -104,11 +104,15 @@ class Extractor(object):
         for scale in self.meta.scales:
             if self.verbose:
                 print('\nExtraction --- Scaling Factor: {}'.format(scale))
-            for fpair in self.files:
+            def decode_fit(fpair, scale=scale):
                 img, mask, img_name, mask_name, dims = self._decode(fpair, scale)
+                fitted = utils.adjust_to_tile(img, T, S, ch) if self.fit else (img, dims[2], dims[3], 0)
+                return fitted, mask, img_name, mask_name, dims
+
+            # files are decoded (and fitted) on host threads ahead of the loop, in file order
+            for fitted, mask, img_name, mask_name, dims in utils.ordered_prefetch(decode_fit, self.files):
                 w_full, h_full, w_scaled, h_scaled = dims
-                img, w_fitted, h_fitted, offset = utils.adjust_to_tile(img, T, S, ch) \
-                    if self.fit else (img, w_scaled, h_scaled, 0)
+                img, w_fitted, h_fitted, offset = fitted
                 H, W = img.shape[:2]
                 nH, nW = ops.tile_grid(H, W, T, S)
                 n_tiles = nH * nW

@@ -12,7 +12,10 @@ per-pixel body replaced by an sm_100a kernel call through the C ABI (pylc_b200.o
 
 There is no CPU path for the kernels: without a CUDA device these functions raise PylcError.
 """
+import collections
+import itertools
 import os
+from concurrent.futures import ThreadPoolExecutor
 from math import ceil
 
 import cv2
@@ -28,6 +31,41 @@ def _device():
     if not torch.cuda.is_available():
         raise PylcError("pylc_b200 needs a CUDA device (B200); there is no CPU fallback")
     return torch.device("cuda", torch.cuda.current_device())
+
+
+def decode_threads():
+    """Host threads used to decode image files ahead of the GPU (`PYLC_DECODE_THREADS`; 0 or 1 = decode in the
+    calling thread, as the reference does).  OpenCV's decoders release the GIL, so files decode in parallel."""
+    env = os.environ.get("PYLC_DECODE_THREADS")
+    if env is not None:
+        return max(0, int(env))
+    return min(8, os.cpu_count() or 1)
+
+
+def ordered_prefetch(fn, items, workers=None, depth=None):
+    """Generator over fn(item) for every item IN ORDER, with up to `depth` results computed ahead on `workers`
+    host threads -- the file loop of Extractor.extract / test.py (reference extract.py:132-150, test.py:52-61)
+    decodes file k+1.. while file k is on the GPU.  An exception (or the reference's exit(1)) raised by fn
+    surfaces in the caller at that item's position; workers <= 1 degenerates to a plain sequential loop."""
+    items = list(items)
+    workers = decode_threads() if workers is None else int(workers)
+    if workers <= 1 or len(items) <= 1:
+        for it in items:
+            yield fn(it)
+        return
+    depth = max(1, int(depth) if depth else workers + 2)
+    todo = iter(items)
+    with ThreadPoolExecutor(max_workers=workers, thread_name_prefix="pylc-decode") as pool:
+        ahead = collections.deque(pool.submit(fn, it) for it in itertools.islice(todo, depth))
+        try:
+            while ahead:
+                res = ahead.popleft().result()
+                for it in itertools.islice(todo, 1):
+                    ahead.append(pool.submit(fn, it))
+                yield res
+        finally:
+            for fut in ahead:
+                fut.cancel()
 
 
 def is_grayscale(img):

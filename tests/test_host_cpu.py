@@ -111,6 +111,72 @@ def test_collate_pairs_by_basename(tmp_path):
 
 # ---- config / dataset ------------------------------------------------------------------------
 
+def test_get_image_decodes_files_like_the_reference(tmp_path, palettes):
+    """tools.get_image (reference tools.py:77-148) on real files: gray .tif, colour .png mask; channel order,
+    the grayscale check of colour requests, and the scale rule (INTER_AREA image / INTER_NEAREST mask)."""
+    import cv2
+    from pylc_b200.utils import tools
+    gray = orc.synth_image(3, 700, 600, 1)
+    mask = orc.synth_mask(3, 700, 600, palettes["a"])
+    cv2.imwrite(str(tmp_path / "g.tif"), gray)
+    cv2.imwrite(str(tmp_path / "m.png"), cv2.cvtColor(mask, cv2.COLOR_RGB2BGR))
+    img, w, h, ws, hs = tools.get_image(str(tmp_path / "g.tif"), 1)
+    assert (w, h, ws, hs) == (700, 600, 700, 600) and np.array_equal(img, gray)
+    m, w, h, ws, hs = tools.get_image(str(tmp_path / "m.png"), 3, interpolate=cv2.INTER_NEAREST)
+    assert np.array_equal(m, mask)                                   # RGB order restored
+    with pytest.raises(SystemExit):                                   # a gray file asked for as colour stops
+        tools.get_image(str(tmp_path / "g.tif"), 3)
+    img2, w, h, ws, hs = tools.get_image(str(tmp_path / "g.tif"), 1, scale=0.5)
+    assert np.array_equal(img2, cv2.resize(gray, (ws, hs), interpolation=cv2.INTER_AREA)) and (w, h) == (700, 600)
+
+
+def test_ordered_prefetch_keeps_order_and_surfaces_errors(tmp_path):
+    """The decode look-ahead of the file loops (Extractor.extract, pylc test): results in item order whatever
+    the completion order, bounded look-ahead, worker exceptions / exit(1) raised at the item's position."""
+    import threading
+    import time
+    import cv2
+    from pylc_b200.utils import tools
+    started = []
+    lock = threading.Lock()
+
+    def slow(i):
+        with lock:
+            started.append(i)
+        time.sleep(0.02 * ((7 - i) % 4))                              # later items finish first
+        return i * i
+
+    for workers in (0, 1, 4):
+        assert list(tools.ordered_prefetch(slow, range(12), workers=workers)) == [i * i for i in range(12)]
+    assert list(tools.ordered_prefetch(slow, [], workers=4)) == []
+    # bounded look-ahead: after taking the first result at most depth + 1 items have been started
+    del started[:]
+    gen = tools.ordered_prefetch(slow, range(40), workers=2, depth=3)
+    assert next(gen) == 0
+    with lock:
+        assert len(started) <= 5
+    gen.close()
+
+    def boom(i):
+        if i == 3:
+            exit(1)                                                   # the reference's error convention
+        if i == 5:
+            raise ValueError("bad file")
+        return i
+
+    got = []
+    with pytest.raises(SystemExit):
+        for v in tools.ordered_prefetch(boom, range(8), workers=4):
+            got.append(v)
+    assert got == [0, 1, 2]
+    # real files decode identically through the look-ahead
+    imgs = [orc.synth_image(10 + i, 320, 240, 1) for i in range(6)]
+    for i, im in enumerate(imgs):
+        cv2.imwrite(str(tmp_path / ("f%d.png" % i)), im)
+    out = list(tools.ordered_prefetch(lambda i: tools.get_image(str(tmp_path / ("f%d.png" % i)), 1)[0], range(6), workers=3))
+    assert all(np.array_equal(a, b) for a, b in zip(out, imgs))
+
+
 def test_parameters_schema_b_and_update():
     from pylc_b200.config import Parameters
     p = Parameters({"schema": "./schemas/schema_b.json", "ch": 1})
