@@ -18,6 +18,7 @@ import argparse
 import os
 import sys
 
+import cv2
 import torch
 
 from . import dist as pdist
@@ -159,10 +160,14 @@ def test(args):
     def decode(i):
         fpair = files[i]
         img_file, mask_file = (fpair['img'], fpair['mask']) if isinstance(fpair, dict) else (fpair, None)
-        return (i, img_file, mask_file) + tuple(tools.get_image(img_file, model.meta.ch, scale=params.scale))
+        gt = None
+        if mask_file:                                 # what Evaluator.load decodes (reference evaluate.py:87-91)
+            gt = tools.get_image(mask_file, ch=3, scale=params.scale, interpolate=cv2.INTER_NEAREST)[0]
+        return (i, img_file, mask_file, gt) + tuple(tools.get_image(img_file, model.meta.ch, scale=params.scale))
 
-    # the next files decode on host threads while the current image is on the GPU (file order kept)
-    for i, img_file, mask_file, img, w_full, h_full, w_scaled, h_scaled in tools.ordered_prefetch(decode, mine, depth=3):
+    # the next files (image + ground truth) decode on host threads while the current image is on the GPU
+    for i, img_file, mask_file, gt, img, w_full, h_full, w_scaled, h_scaled in \
+            tools.ordered_prefetch(decode, mine, depth=3):
         f = seg.stage(img, None, index=i)
         torch.cuda.current_stream().wait_event(f.ready)
         res = seg.segment_fitted(f, inject=0)         # stitch + argmax + colourise + resample on the GPU
@@ -171,7 +176,7 @@ def test(args):
         meta.extract = {'fid': os.path.basename(img_file.replace('.', '_')) + '_scale_' + str(params.scale),
                         'n': (f.h // seg.S - 1) * (f.w // seg.S - 1), 'w_full': w_full, 'h_full': h_full,
                         'w_scaled': w_scaled, 'h_scaled': h_scaled, 'w_fitted': f.w, 'h_fitted': f.h, 'offset': 0}
-        evaluator.load(res, meta, mask_true_path=mask_file, scale=params.scale).save_image()
+        evaluator.load(res, meta, mask_true_path=mask_file, scale=params.scale, mask_true=gt).save_image()
         if mask_file and not params.aggregate_metrics:
             print("\nStarting evaluation ... ")
             evaluator.evaluate().save_metrics()
