@@ -16,6 +16,8 @@
 // processed, so every thread keeps two units in flight.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace pylc {
 
 struct GatherGeom {
@@ -263,71 +265,74 @@ __global__ void __launch_bounds__(kThreads) gather_img_kernel(GatherGeom g, uint
 // CTA in flight at once), a thread takes its 16-pixel units from there with conflict-free 16-byte reads,
 // the destination tile bases are computed once per CTA, and the moments -- the strip lies in one block --
 // are reduced and added to the block's tiles once per CTA.
+// Grid: x = strip of the block, y = block column, z = image * nby + block row (a stack of equally sized
+// sources is one launch).  A CTA moves only ~8 units per thread, so its fixed cost is kept small: no
+// per-thread integer division (chunk -> row by a host-computed reciprocal), the <= 4 destination tiles as a
+// branch-free 2 x 2 table.  (The first version spent 60 % of its ~870 instructions per thread on set-up
+// and flush and ran at 75 % issue utilisation: ncu, profiles/ncu_r2c_summary.md.)
+#ifndef PYLC_IMG_STRIP_KB
+#define PYLC_IMG_STRIP_KB 32
+#endif
+constexpr int kImgStripKB = PYLC_IMG_STRIP_KB;
+struct StagedArgs {
+    int strip_rows;
+    uint32_t magic_cpr, magic_gpr;   // ceil(2^32 / d) for d = 16-byte chunks per strip row / 16-pixel units per row
+    size_t img_stride;
+};
+__device__ __forceinline__ int div_small(int q, int d, uint32_t magic) {   // q / d for q < 2^16
+    return d == 1 ? q : (int)__umulhi((uint32_t)q, magic);
+}
+
 template <int CH, bool STATS>
-__global__ void __launch_bounds__(kThreads) gather_img_staged_kernel(GatherGeom g, uint8_t *__restrict__ dst,
-                                                                    unsigned long long *__restrict__ stat, int strip_rows, int spb,
-                                                                    size_t img_stride) {
+__global__ void __launch_bounds__(kThreads) gather_img_staged_kernel(const GatherGeom g, uint8_t *__restrict__ dst,
+                                                                    unsigned long long *__restrict__ stat, const StagedArgs sa) {
     __shared__ unsigned long long s_sum[CH * 2];
     extern __shared__ __align__(16) uint8_t s_src[];          // strip_rows rows of S * CH bytes
-    if (STATS && threadIdx.x < CH * 2) s_sum[threadIdx.x] = 0;
-    {   // blockIdx.y: image of a stack of equally sized sources, its tiles follow the previous image's
-        const size_t img = blockIdx.y, tiles_img = (size_t)g.nH * g.nW;
-        g.src += img * img_stride;
-        dst += img * tiles_img * CH * ((size_t)g.T * g.T);
-        if (STATS) stat += img * tiles_img * CH * 2;
-    }
-    const int blk = blockIdx.x / spb, y0 = (blockIdx.x - blk * spb) * strip_rows;
-    const int nrow = min(strip_rows, g.S - y0);
-    const int bx = blk % g.nbx, by = blk / g.nbx;
-    const int row_bytes = g.S * CH, cpr = row_bytes / 16;
+    const int tid = threadIdx.x;
+    if (STATS && tid < CH * 2) s_sum[tid] = 0;
+    const int bx = blockIdx.y;
+    const int img = blockIdx.z / g.nby, by = blockIdx.z - img * g.nby;
+    const int y0 = blockIdx.x * sa.strip_rows;
+    const int nrow = min(sa.strip_rows, g.S - y0);
+    const int row_bytes = g.S * CH, cpr = row_bytes >> 4;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_src);
     {
-        const uint8_t *src0 = g.src + (size_t)(by * g.S + y0) * g.pitch + (size_t)bx * row_bytes;
-        int r = threadIdx.x / cpr, ck = threadIdx.x - r * cpr;
-        const int dr = kThreads / cpr, dck = kThreads - dr * cpr;
-        for (; r < nrow; r += dr, ck += dck) {
-            if (ck >= cpr) {
-                ck -= cpr;
-                if (++r >= nrow) break;
-            }
-            cp_async16(sbase + (uint32_t)(r * row_bytes + ck * 16), src0 + (size_t)r * g.pitch + ck * 16);
+        const uint8_t *src0 = g.src + (size_t)img * sa.img_stride + (size_t)(by * g.S + y0) * g.pitch + (size_t)bx * row_bytes;
+        const int nchunk = nrow * cpr;
+        for (int q = tid; q < nchunk; q += kThreads) {       // the strip is dense in shared memory: chunk q at q * 16
+            const int r = div_small(q, cpr, sa.magic_cpr), ck = q - r * cpr;
+            cp_async16(sbase + (uint32_t)q * 16u, src0 + (size_t)r * g.pitch + ck * 16);
         }
         cp_async_commit();
     }
+    // destination tiles of block (by, bx): tile (by - dr, bx - dc) holds it at rows dr * S, columns dc * S
     const size_t TT = (size_t)g.T * g.T;
-    const TileSpan ts = tile_span(g, by, bx);
+    const long long tile0 = (long long)img * g.nH * g.nW;
     uint8_t *tb[4];
-    int nt = 0;
+    bool ok[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) tb[i] = dst;
-    for (int r = ts.r_lo; r <= ts.r_hi; ++r)
-        for (int c = ts.c_lo; c <= ts.c_hi; ++c) {
-            uint8_t *b = dst + ((size_t)(r * g.nW + c) * CH) * TT + (size_t)((by - r) * g.S + y0) * g.T + (bx - c) * g.S;
-            if (nt == 0) tb[0] = b;
-            else if (nt == 1) tb[1] = b;
-            else if (nt == 2) tb[2] = b;
-            else if (nt == 3) tb[3] = b;
-            ++nt;
-        }
+    for (int i = 0; i < 4; ++i) {
+        const int dr = i >> 1, dc = i & 1;
+        const int r = by - dr, c = bx - dc;
+        ok[i] = dr < g.m && dc < g.m && r >= 0 && r < g.nH && c >= 0 && c < g.nW;
+        const long long tile = ok[i] ? tile0 + (long long)r * g.nW + c : tile0;
+        tb[i] = dst + (size_t)tile * CH * TT + (size_t)(dr * g.S + y0) * g.T + dc * g.S;
+    }
     cp_async_wait<0>();
     __syncthreads();
 
     uint32_t s1[CH], s2[CH];
 #pragma unroll
     for (int k = 0; k < CH; ++k) s1[k] = s2[k] = 0;
-    int row = threadIdx.x / g.gpr, grp = threadIdx.x - row * g.gpr;
-    const int d_row = kThreads / g.gpr, d_grp = kThreads - d_row * g.gpr;
-    for (; row < nrow; row += d_row, grp += d_grp) {
-        if (grp >= g.gpr) {
-            grp -= g.gpr;
-            if (++row >= nrow) break;
-        }
-        const uint32_t sa = sbase + (uint32_t)(row * row_bytes + grp * 16 * CH);
+    const int nunit = nrow * g.gpr;
+    for (int q = tid; q < nunit; q += kThreads) {             // unit q of the strip: shared-memory offset q * 16 * CH
+        const int row = div_small(q, g.gpr, sa.magic_gpr), grp = q - row * g.gpr;
+        const uint32_t sa_u = sbase + (uint32_t)q * (16u * CH);
         uint4 o[CH];
         if (CH == 1) {
-            o[0] = lds128(sa);
+            o[0] = lds128(sa_u);
         } else {
-            const uint4 q0 = lds128(sa), q1 = lds128(sa + 16), q2 = lds128(sa + 32);
+            const uint4 q0 = lds128(sa_u), q1 = lds128(sa_u + 16), q2 = lds128(sa_u + 32);
             const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
             uint32_t r[4], gg[4], b[4];
 #pragma unroll
@@ -350,7 +355,7 @@ __global__ void __launch_bounds__(kThreads) gather_img_staged_kernel(GatherGeom 
         const int off = row * g.T + grp * 16;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            if (i < nt) {
+            if (ok[i]) {
 #pragma unroll
                 for (int k = 0; k < CH; ++k) st_stream16(tb[i] + k * TT + off, o[k]);
             }
@@ -360,17 +365,17 @@ __global__ void __launch_bounds__(kThreads) gather_img_staged_kernel(GatherGeom 
         for (int k = 0; k < CH; ++k) {
             const uint32_t a = __reduce_add_sync(0xFFFFFFFFu, s1[k] & 0xFFFFu), ah = __reduce_add_sync(0xFFFFFFFFu, s1[k] >> 16);
             const uint32_t b = __reduce_add_sync(0xFFFFFFFFu, s2[k] & 0xFFFFu), bh = __reduce_add_sync(0xFFFFFFFFu, s2[k] >> 16);
-            if ((threadIdx.x & 31) == 0) {
+            if ((tid & 31) == 0) {
                 atomicAdd(&s_sum[k * 2], (unsigned long long)a + ((unsigned long long)ah << 16));
                 atomicAdd(&s_sum[k * 2 + 1], (unsigned long long)b + ((unsigned long long)bh << 16));
             }
         }
         __syncthreads();
-        const int nt_c = ts.c_hi - ts.c_lo + 1;
-        for (int i = threadIdx.x; i < nt * CH * 2; i += kThreads) {
-            const int t = i / (CH * 2), k = i - t * (CH * 2);
-            const int r = ts.r_lo + t / nt_c, c = ts.c_lo + t % nt_c;
-            atomicAdd(&stat[(size_t)(r * g.nW + c) * CH * 2 + k], s_sum[k]);
+        if (tid < 4 * CH * 2) {                                // one thread per (destination tile, channel, moment)
+            const int i = tid / (CH * 2), k = tid - i * (CH * 2);
+            const int r = by - (i >> 1), c = bx - (i & 1);
+            if ((i >> 1) < g.m && (i & 1) < g.m && r >= 0 && r < g.nH && c >= 0 && c < g.nW)
+                atomicAdd(&stat[(size_t)(tile0 + (long long)r * g.nW + c) * CH * 2 + k], s_sum[k]);
         }
     }
 }
@@ -1046,24 +1051,36 @@ extern "C" int pylc_tile_gather_u8_stack(const uint8_t *src, int n_img, size_t i
     const bool al = aligned16(src, src_pitch) && (n_img == 1 || img_stride % 16 == 0);
     auto *sp = reinterpret_cast<unsigned long long *>(stat);
     // staged form: strips of up to 32 KB (64 rows) of source rows per CTA, the stack in the grid's y dimension
+    static const size_t strip_cap = [] {       // PYLC_IMG_STRIP_KB: A/B knob for the strip size (1..32 KB)
+        const char *e = getenv("PYLC_IMG_STRIP_KB");
+        const long kb = e ? atol(e) : 0;
+        return (size_t)(kb >= 1 && kb <= 32 ? kb : kImgStripKB) * 1024;
+    }();
     int strip_rows = 1;
-    while (strip_rows * 2 <= S && (size_t)strip_rows * 2 * S * ch <= 32 * 1024 && strip_rows < 64) strip_rows *= 2;
+    while (strip_rows * 2 <= S && (size_t)strip_rows * 2 * S * ch <= strip_cap && strip_rows < 64) strip_rows *= 2;
     const size_t strip = (size_t)strip_rows * S * ch;
     const int spb = (S + strip_rows - 1) / strip_rows;
-    if (al && g.m <= 2 && strip <= 32 * 1024 && (long long)g.nbx * g.nby * spb < 0x7FFFFFFF) {
-        for (int i0 = 0; i0 < n_img; i0 += 65535) {      // grid.y limit
-            const int ni = n_img - i0 < 65535 ? n_img - i0 : 65535;
-            const dim3 grid((unsigned)(g.nbx * g.nby * spb), (unsigned)ni);
+    if (al && g.m <= 2 && strip <= 32 * 1024 && g.nbx <= 65535 && g.nby <= 65535 && S * ch / 16 >= 1) {
+        StagedArgs sa;
+        sa.strip_rows = strip_rows;
+        const uint32_t cpr = (uint32_t)(S * ch / 16), gpr = (uint32_t)(S / 16);
+        sa.magic_cpr = cpr > 1 ? (uint32_t)((0x100000000ull + cpr - 1) / cpr) : 0u;
+        sa.magic_gpr = gpr > 1 ? (uint32_t)((0x100000000ull + gpr - 1) / gpr) : 0u;
+        sa.img_stride = img_stride;
+        const int per_launch = 65535 / g.nby;                  // grid.z = image * nby + block row
+        for (int i0 = 0; i0 < n_img; i0 += per_launch) {
+            const int ni = n_img - i0 < per_launch ? n_img - i0 : per_launch;
+            const dim3 grid((unsigned)spb, (unsigned)g.nbx, (unsigned)(g.nby * ni));
             GatherGeom gi = g;
             gi.src = src + (size_t)i0 * img_stride;
             uint8_t *d = dst + (size_t)i0 * g.nH * g.nW * ch * T * T;
             unsigned long long *s = sp ? sp + (size_t)i0 * g.nH * g.nW * ch * 2 : nullptr;
             if (ch == 1) {
-                if (stat) gather_img_staged_kernel<1, true><<<grid, kThreads, strip, st>>>(gi, d, s, strip_rows, spb, img_stride);
-                else gather_img_staged_kernel<1, false><<<grid, kThreads, strip, st>>>(gi, d, s, strip_rows, spb, img_stride);
+                if (stat) gather_img_staged_kernel<1, true><<<grid, kThreads, strip, st>>>(gi, d, s, sa);
+                else gather_img_staged_kernel<1, false><<<grid, kThreads, strip, st>>>(gi, d, s, sa);
             } else {
-                if (stat) gather_img_staged_kernel<3, true><<<grid, kThreads, strip, st>>>(gi, d, s, strip_rows, spb, img_stride);
-                else gather_img_staged_kernel<3, false><<<grid, kThreads, strip, st>>>(gi, d, s, strip_rows, spb, img_stride);
+                if (stat) gather_img_staged_kernel<3, true><<<grid, kThreads, strip, st>>>(gi, d, s, sa);
+                else gather_img_staged_kernel<3, false><<<grid, kThreads, strip, st>>>(gi, d, s, sa);
             }
             rc = finish_launch();
             if (rc) return rc;

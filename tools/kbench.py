@@ -161,6 +161,38 @@ def main():
                      [lambda d=d, q=q, o=o: ops.mask_gather_encode_hist(d, H, W, q, T, 512, pal, out=o, px_dist=m_hist) for d, q, o in sets],
                      "3 B in + 1 B out per tile px")
         del sets
+    if not only or any("stack" in o for o in only):
+        # configs[3] geometry: 24 gray image + schema_b mask pairs of 2000x1500 as one stack per kernel
+        pal_b = Parameters({"schema": "./schemas/schema_b.json"}).palette_rgb
+        Ws, Hs, K = 2000, 1500, 24
+        d_ms, mps, _ = ops.upload_stack([orc.synth_mask(100 + i, Ws, Hs, pal_b, skew=True) for i in range(K)])
+        d_is, ips, _ = ops.upload_stack([orc.synth_image(100 + i, Ws, Hs, 1) for i in range(K)])
+        nHs, nWs = ops.tile_grid(Hs, Ws, T, 512)
+        n_t = nHs * nWs * K
+        s_m = torch.empty((n_t, T, T), dtype=torch.uint8, device="cuda")
+        s_i = torch.empty((n_t, 1, T, T), dtype=torch.uint8, device="cuda")
+        s_h = torch.zeros((n_t, len(pal_b)), dtype=torch.int64, device="cuda")
+        s_st = torch.zeros((n_t, 1, 2), dtype=torch.int64, device="cuda")
+        report("mask_gather_encode_hist stack of 24 x 2000x1500 S512 C11 (one launch)", n_t * T * T * 4,
+               lambda: ops.mask_gather_encode_hist_stack(d_ms, Hs, Ws, mps, T, 512, pal_b, out=s_m, px_dist=s_h),
+               "3 B in + 1 B out per tile px; pylc_mask_gather_encode_hist_stack")
+        report("tile_gather_u8 gray + moments stack of 24 x 2000x1500 S512 (one launch)", n_t * T * T * 2,
+               lambda: ops.tile_gather_u8_stack(d_is, Hs, Ws, 1, ips, T, 512, stats=True, out=s_i, stat_out=s_st),
+               "1 B in + 1 B out per tile px; pylc_tile_gather_u8_stack (the moments buffer is zeroed by a memset inside the timed region)")
+        if not only or any("sweep" in o or "stack" in o for o in only):
+            sets = []
+            for j in range(4):
+                dj, _, _ = ops.upload_stack([orc.synth_image(200 + 24 * j + i, Ws, Hs, 1) for i in range(K)])
+                sets.append((dj, torch.empty_like(s_i)))
+            lib = ops._lib.load()
+
+            def gray_stack(d, o):       # the C entry point directly: no memset of the moments between launches
+                ops.check(lib.pylc_tile_gather_u8_stack(ops._p(d), K, Hs * ips, Hs, Ws, 1, ips, T, 512, ops._p(o), ops._p(s_st),
+                                                        ops._stream()), "pylc_tile_gather_u8_stack")
+            report_sweep("tile_gather_u8 gray + moments stack of 24 x 2000x1500 S512, sweep", n_t * T * T * 2,
+                         [lambda d=d, o=o: gray_stack(d, o) for d, o in sets], "1 B in + 1 B out per tile px")
+            del sets
+        del d_ms, d_is, s_m, s_i, s_h, s_st
     enc_out = torch.empty((1, H, W), dtype=torch.uint8, device="cuda")
     palc0, _ = ops._lib.palette_array(pal)
     enc_hist = torch.zeros((C,), dtype=torch.int64, device="cuda")
