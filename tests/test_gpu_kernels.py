@@ -34,17 +34,21 @@ def dev(a):
     (75, 101, 1, 32, 32), (80, 96, 3, 32, 16), (70, 200, 1, 64, 16), (512, 512, 3, 512, 512),
     (300, 300, 1, 512, 512),
 ])
-def test_tile_gather(ops, H, W, ch, T, S):
+def test_tile_gather(ops, H, W, ch, T, S, monkeypatch):
     img = orc.synth_image(3, W, H, ch)
     d, pitch = ops.upload_image(img)
-    tiles, stat = ops.tile_gather_u8(d, H, W, ch, pitch, T, S, stats=True)
     ref = orc.split_tiles(img, T, S)
-    assert tuple(tiles.shape) == ref.shape
-    assert np.array_equal(tiles.cpu().numpy(), ref)
-    if ref.shape[0]:
-        x = ref.astype(np.int64).reshape(ref.shape[0], ch, -1)
-        want = np.stack([x.sum(-1), (x * x).sum(-1)], axis=-1)
-        assert np.array_equal(stat.cpu().numpy(), want)
+    for no_tma in ("0", "1"):       # the switch must not change anything here (the image gathers are cp.async forms)
+        monkeypatch.setenv("PYLC_NO_TMA", no_tma)
+        tiles, stat = ops.tile_gather_u8(d, H, W, ch, pitch, T, S, stats=True)
+        assert tuple(tiles.shape) == ref.shape
+        assert np.array_equal(tiles.cpu().numpy(), ref)
+        if ref.shape[0]:
+            x = ref.astype(np.int64).reshape(ref.shape[0], ch, -1)
+            want = np.stack([x.sum(-1), (x * x).sum(-1)], axis=-1)
+            assert np.array_equal(stat.cpu().numpy(), want)
+        plain = ops.tile_gather_u8(d, H, W, ch, pitch, T, S)          # the form without moments
+        assert np.array_equal(plain.cpu().numpy(), ref)
 
 
 def test_tile_gather_unaligned_source(ops):
@@ -178,7 +182,7 @@ def test_mask_gather_wide_palette_duplicates_unaligned(ops):
     ("a", 2, 600, 1001, 512, 512, 3),      # ragged width
     ("b", 1, 1100, 1300, 512, 512, 1),     # a stack of one
 ])
-def test_extraction_stack_equals_per_image(ops, palettes, pk, n_img, H, W, T, S, ch):
+def test_extraction_stack_equals_per_image(ops, palettes, pk, n_img, H, W, T, S, ch, monkeypatch):
     """pylc_tile_gather_u8_stack / pylc_mask_gather_encode_hist_stack: the file loop of Extractor.extract
     (utils/extract.py:136-222) over equally sized pairs as one call -- tiles, moments and histograms in file
     order, bit-identical to the oracle and to per-image calls."""
@@ -191,6 +195,12 @@ def test_extraction_stack_equals_per_image(ops, palettes, pk, n_img, H, W, T, S,
     assert tuple(d_imgs.shape) == (n_img, H, ip) and tuple(d_masks.shape) == (n_img, H, mp)
     tiles, stat = ops.tile_gather_u8_stack(d_imgs, H, W, ch, ip, T, S, stats=True)
     m_tiles, px_dist = ops.mask_gather_encode_hist_stack(d_masks, H, W, mp, T, S, pal)
+    monkeypatch.setenv("PYLC_NO_TMA", "1")          # the per-thread / cp.async twins give the same bytes
+    tiles_b, stat_b = ops.tile_gather_u8_stack(d_imgs, H, W, ch, ip, T, S, stats=True)
+    m_tiles_b, px_dist_b = ops.mask_gather_encode_hist_stack(d_masks, H, W, mp, T, S, pal)
+    monkeypatch.delenv("PYLC_NO_TMA")
+    assert torch.equal(tiles, tiles_b) and torch.equal(stat, stat_b)
+    assert torch.equal(m_tiles, m_tiles_b) and torch.equal(px_dist, px_dist_b)
     ref_i = np.concatenate([orc.split_tiles(im, T, S) for im in imgs])
     ref_m = np.concatenate([orc.class_encode(orc.split_tiles(m, T, S), pal) for m in masks])
     assert np.array_equal(tiles.cpu().numpy(), ref_i)
