@@ -138,8 +138,8 @@ def config3(args, rank, world, rows):
 
     def sweep_pairs():           # the reference's file loop: two launches per pair
         px_dist.zero_()
-        for k, gi in enumerate(mine):
-            j = gi % pool_n
+        for k in range(len(mine)):
+            j = k % pool_n                  # the rank's k-th pair: the same pool image the stacked sweep reads
             ops.tile_gather_u8_stack(d_imgs[j:j + 1], H, W, 1, ip, T, S, stats=True, out=tiles[k * per:(k + 1) * per],
                                      stat_out=stat[k * per:(k + 1) * per])
             ops.mask_gather_encode_hist(d_masks[j], H, W, mp, T, S, pal, out=masks[k * per:(k + 1) * per],
