@@ -5,13 +5,15 @@ Same chainable interface: Extractor(params).load(img, mask).extract(fit, stride,
 .coshuffle().profile().get_data(); same `meta.extract` dict, capacity check and messages.  The
 per-pixel work is done by the sm_100a kernels:
 
-    image tiles  Extractor.__split + np.copyto (extract.py:279-310,182)      -> pylc_tile_gather_u8
-    mask tiles   __split + tools.class_encode + np.copyto (extract.py:195-214) -> pylc_mask_gather_encode_hist
+    image tiles  Extractor.__split + np.copyto (extract.py:279-310,182)      -> pylc_tile_gather_u8[_stack]
+    mask tiles   __split + tools.class_encode + np.copyto (extract.py:195-214) -> pylc_mask_gather_encode_hist[_stack]
                  (the per-tile class histograms profile() needs fall out of the same pass)
 
-Decode and the optional fit-resize stay on the host (OpenCV, bit-identical by construction).
-Each decoded image is staged once through pinned memory; tiles are written straight into two
-device-resident buffers sized exactly (the reference pre-allocates n_files*700 host tiles).
+Decode and the optional fit-resize stay on the host (OpenCV, bit-identical by construction), on a few
+threads that run ahead of the loop in file order (tools.ordered_prefetch).  Consecutive files of one
+size form a STACK: one pinned staging copy, one upload and ONE launch per kernel for up to STACK_MAX
+files (pylc_tile_gather_u8_stack / pylc_mask_gather_encode_hist_stack); tiles are written straight
+into device-resident buffers sized exactly (the reference pre-allocates n_files*700 host tiles).
 `.imgs` / `.masks` are CUDA u8 tensors [N,ch,T,T] / [N,T,T]; `.host()` returns NumPy copies.
 """
 import os

@@ -177,6 +177,73 @@ def test_ordered_prefetch_keeps_order_and_surfaces_errors(tmp_path):
     assert all(np.array_equal(a, b) for a, b in zip(out, imgs))
 
 
+def test_extractor_stack_grouping_host_logic(monkeypatch, palettes):
+    """Host logic of Extractor.extract without a GPU: the device entry points are replaced by oracle stand-ins that
+    record their calls, so what is checked is the grouping of consecutive equally sized files into stacks
+    (STACK_MAX, size changes, images without masks), the file order of the tiles and the `meta.extract` record
+    (reference utils/extract.py:132-222)."""
+    from pylc_b200 import ops
+    from pylc_b200.config import Parameters
+    from pylc_b200.utils import extract as ex_mod
+    from pylc_b200.utils import tools
+    calls = []
+
+    def upload_stack(images, device=None, staging=None):
+        a = np.stack([np.asarray(im).reshape(im.shape[0], -1) for im in images])
+        return torch.from_numpy(a), a.shape[2], None
+
+    def tile_gather_u8_stack(src, H, W, ch, pitch, T, S, stats=False, out=None, stat_out=None):
+        calls.append(("img", src.shape[0], H, W))
+        tiles = np.concatenate([orc.split_tiles(im.numpy().reshape((H, W) if ch == 1 else (H, W, ch)), T, S) for im in src])
+        x = tiles.astype(np.int64).reshape(tiles.shape[0], ch, -1)
+        stat = torch.from_numpy(np.stack([x.sum(-1), (x * x).sum(-1)], axis=-1))
+        return (torch.from_numpy(tiles), stat) if stats else torch.from_numpy(tiles)
+
+    def mask_gather_encode_hist_stack(src, H, W, pitch, T, S, palette, hist=True, out=None, px_dist=None):
+        calls.append(("mask", src.shape[0], H, W))
+        enc = np.concatenate([orc.class_encode(orc.split_tiles(m.numpy().reshape(H, W, 3), T, S), palette) for m in src])
+        return torch.from_numpy(enc), torch.from_numpy(orc.tile_histograms(enc, len(palette)))
+
+    monkeypatch.setattr(ops, "upload_stack", upload_stack)
+    monkeypatch.setattr(ops, "tile_gather_u8_stack", tile_gather_u8_stack)
+    monkeypatch.setattr(ops, "mask_gather_encode_hist_stack", mask_gather_encode_hist_stack)
+    monkeypatch.setattr(ops, "tile_grid", lambda H, W, T, S: ((H - T) // S + 1 if H >= T else 0, (W - T) // S + 1 if W >= T else 0))
+    monkeypatch.setattr(tools, "_device", lambda: torch.device("cpu"))
+    monkeypatch.setenv("PYLC_DECODE_THREADS", "3")
+
+    pal = palettes["a"]
+    meta = Parameters()
+    meta.update({"ch": 1})
+    T = meta.tile_size
+    sizes = [(1100, 1050)] * 5 + [(1050, 1100)] + [(1100, 1050)] * 2
+    imgs = [orc.synth_image(70 + i, w, h, 1) for i, (w, h) in enumerate(sizes)]
+    masks = [orc.synth_mask(70 + i, w, h, pal) for i, (w, h) in enumerate(sizes)]
+    ex = ex_mod.Extractor(meta)
+    ex.verbose = False
+    ex.STACK_MAX = 3
+    ex.load_arrays(imgs, masks).extract()
+    # runs: 5 equal (3 + 2 by STACK_MAX) | 1 odd | 2 equal ; one image and one mask call per stack
+    assert [c[1] for c in calls if c[0] == "img"] == [3, 2, 1, 2]
+    assert [c[1] for c in calls if c[0] == "mask"] == [3, 2, 1, 2]
+    ref_i = np.concatenate([orc.split_tiles(im, T, T) for im in imgs])
+    ref_m = np.concatenate([orc.class_encode(orc.split_tiles(m, T, T), pal) for m in masks])
+    got_i, got_m = ex.host()
+    assert np.array_equal(got_i, ref_i) and np.array_equal(got_m, ref_m)          # file order kept across stacks
+    e = ex.get_meta().extract
+    assert (e["n"], e["w_full"], e["h_full"], e["w_fitted"], e["h_fitted"], e["offset"]) == (4, 1100, 1050, 1100, 1050, 0)
+    assert ex.get_meta().n_tiles == len(ref_i) == 32 and ex.mask_idx == 32
+    ex.profile()                                                                  # from the kernels' by-products
+    want = orc.profile_port(ref_i, ref_m, len(pal), T)
+    assert np.array_equal(np.array(ex.get_meta().px_dist), want["px_dist"])
+    np.testing.assert_allclose(ex.get_meta().px_mean, want["px_mean"], rtol=1e-5)
+    np.testing.assert_allclose(ex.get_meta().px_std, want["px_std"], rtol=1e-5)
+    # images only: no mask calls, a zero mask buffer of matching length (extract.py:96-102)
+    del calls[:]
+    ex.load_arrays(imgs[:4]).extract()
+    assert [c[0] for c in calls] == ["img", "img"] and [c[1] for c in calls] == [3, 1]
+    assert ex.masks.shape[0] == ex.imgs.shape[0] == 16 and int(ex.masks.sum()) == 0
+
+
 def test_parameters_schema_b_and_update():
     from pylc_b200.config import Parameters
     p = Parameters({"schema": "./schemas/schema_b.json", "ch": 1})
