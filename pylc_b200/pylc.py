@@ -6,13 +6,14 @@ train.py:22-174), same sub-commands and flags for the tiled-segmentation path:
     python -m pylc_b200.pylc extract --ch 3 --img DIR --mask DIR [--schema S] [--output DIR]
     python -m pylc_b200.pylc profile --db FILE            (documented by the reference README but
                                                           not wired there: preprocess.py:77-91 recurses)
+    python -m pylc_b200.pylc augment --db FILE            (sample-rate search + over-sampling of rare classes)
     python -m pylc_b200.pylc train   --db FILE [--batch_size N --n_epochs E --lr LR --weighted ...]
     python -m pylc_b200.pylc test    --model M --img I [--mask G] [--scale S] [--save_logits]
                                      [--aggregate_metrics]
 
 Launched under torchrun (WORLD_SIZE > 1), `extract`/`profile`/`test` shard images or tiles across
-the GPUs and all-reduce only histograms / confusion matrices (pylc_b200.dist).  `augment`, `merge`
-and `grayscale` are outside the accelerated path and are not provided.
+the GPUs and all-reduce only histograms / confusion matrices (pylc_b200.dist).  `merge` and `grayscale`
+are stubs in the reference itself (preprocess.py:94-122: commented-out body / bare return) and are not provided.
 """
 import argparse
 import os
@@ -65,6 +66,24 @@ def profile(args):
     meta = get_profile(dset)
     print_meta(meta)
     return meta
+
+
+def augment(args):
+    """Over-sample the rare classes of a tile database (reference preprocess.py:54-74): sample-rate search on
+    the device (pylc_sample_rate_grid), the reference's OpenCV warps on the host, profile of the result on the
+    device, `_aug<id>` database written next to the others."""
+    from .utils.augment import Augmentor
+    from .utils.profile import print_meta
+    print('\nStarting augmentation on database:\n\t{}'.format(args.db))
+    augmentor = Augmentor().load(args.db)
+    print_meta(augmentor.input_meta)
+    augmentor.optimize()
+    augmentor.oversample()
+    aug_dset = augmentor.print_settings().get_data()
+    print_meta(augmentor.output_meta)
+    path = aug_dset.save()
+    print('Augmentation done: {} tiles -> {}'.format(aug_dset.size, path))
+    return path
 
 
 def train(args):
@@ -213,6 +232,11 @@ def get_parser():
     p = sub.add_parser('profile', help='Profile an extraction database.')
     common(p)
     p.set_defaults(func=profile)
+    p.add_argument('--db', type=str, required=True, help='Path to database file.')
+
+    p = sub.add_parser('augment', help='Data augmentation for database.')
+    common(p)
+    p.set_defaults(func=augment)
     p.add_argument('--db', type=str, required=True, help='Path to database file.')
 
     p = sub.add_parser('train', help='Train model on an extraction database.')

@@ -141,6 +141,22 @@ class Augmentor(object):
         self.output_meta.id = '_aug' + str(self.input_meta.id)
         return self
 
+    def print_settings(self):
+        """Augmentation read-out: augmented against input sample counts, M2, JSD and the winning grid point
+        (reference augment.py:348-378)."""
+        rule = '_' * 70
+        row = ' {:30s}{:20s}{:20s}'.format
+        lines = ['', '', 'Augmentation Results', rule, row(' ', 'Augmented', 'Input'), rule,
+                 row('Total Samples', str(self.output_meta.n_samples), str(self.input_meta.n_samples)),
+                 row('Total Generated', str(len(self.output_imgs) - self.input_size), '-'),
+                 row('M2', str(round(self.output_meta.m2, 4)), str(round(self.input_meta.m2, 4))),
+                 row('JSD', str(round(self.output_meta.jsd, 4)), str(round(self.input_meta.jsd, 4))), rule,
+                 row('Threshold [Range]', str(self.optim_meta['threshold']), str(defaults.aug_threshold_range)),
+                 row('Rate Coefficient [Range]', str(self.optim_meta['rate_coef']), str(defaults.aug_rate_coef_range)),
+                 ' {:30s}{:20s}'.format('Max Rate', str(defaults.aug_oversample_rate_range[1])), rule, '']
+        print('\n'.join(lines))
+        return self
+
     def get_data(self):
         from ..db.dataset import MLPDataset
         return MLPDataset(input_data={'img': self.output_imgs, 'mask': self.output_masks, 'meta': self.output_meta})

@@ -119,3 +119,41 @@ def test_cli_extract_profile_test_on_files(tmp_path, palettes):
     clear = orc.top2_margin(ref_map) > 2e-2
     assert clear.mean() > 0.5
     assert (labels[clear] == ref_lab[clear]).mean() > 0.999
+
+
+def test_cli_augment_on_database(tmp_path, palettes):
+    """`pylc augment --db` (reference preprocess.py:54-74, utils/argparse.py:91-106): sample-rate search, over-sampling
+    and re-profiling of a tile database written by the extractor; the `_aug<id>` database it writes holds the input
+    tiles plus the warped copies Augmentor.oversample produces in-process for the same rates."""
+    from pylc_b200.config import Parameters
+    from pylc_b200.db.dataset import DB
+    from pylc_b200.utils.augment import Augmentor
+    from pylc_b200.utils.extract import Extractor
+    pal = palettes["a"]
+    meta = Parameters()
+    meta.update({"ch": 1})
+    os.makedirs(tmp_path / "db")
+    meta.output_dir = str(tmp_path / "db")
+    imgs = [orc.synth_image(30 + i, 1100, 1100, 1) for i in range(4)]
+    masks = [orc.synth_mask(30 + i, 1100, 1100, pal, skew=True) for i in range(4)]
+    ex = Extractor(meta)
+    ex.verbose = False
+    db_path = ex.load_arrays(imgs, masks).extract().profile().get_data().save()
+    n_in = 16
+
+    out = _cli(tmp_path, "augment", "--db", db_path)
+    assert "Augmentation Results" in out and "Augmentation done" in out
+    aug_files = [p for p in glob.glob(str(tmp_path / "db" / "_aug*")) if p != db_path]
+    assert len(aug_files) == 1
+    got = DB._read(aug_files[0])
+
+    want = Augmentor().load(db_path)
+    want.optimize().oversample(shuffle=False)
+    n_out = n_in + int(np.sum(want.rates))
+    assert got["img"].shape == (n_out, 1, T, T) and got["mask"].shape == (n_out, T, T)
+    key = lambda a, b: (a.tobytes(), b.tobytes())               # noqa: E731  (the CLI shuffles: compare as pairs)
+    assert sorted(key(a, b) for a, b in zip(got["img"], got["mask"])) == \
+        sorted(key(a, b) for a, b in zip(want.output_imgs, want.output_masks))
+    m = got["meta"]
+    assert m.n_samples == n_out and m.id == "_aug" + str(want.input_meta.id)
+    assert m.dset_px_dist == np.bincount(np.asarray(got["mask"]).ravel(), minlength=len(pal)).tolist()
