@@ -90,6 +90,8 @@ def train(args):
     """Training loop (reference train.py:22-174): validate at epoch 0, then train + validate."""
     from .db.dataset import MLPDataset
     from .models.model import Model
+    if getattr(args, 'weighted', None) is not None:      # the reference tests the option's truthiness
+        args.weighted = bool(args.weighted)
     params = Parameters(args)
     rank, world, local = pdist.init_from_env()
     tr_dset = MLPDataset(db_path=args.db, partition=(0, 1 - defaults.partition))
@@ -105,7 +107,8 @@ def train(args):
                        if getattr(args, k, None) is not None})
     model.meta.optim_type = getattr(args, 'optim', None) or model.meta.optim_type
     model.meta.sched_type = getattr(args, 'sched', None) or model.meta.sched_type
-    model.meta.pretrained = getattr(args, 'pretrained', None) or False
+    pretrained = getattr(args, 'pretrained', None)
+    model.meta.pretrained = (defaults.pretrained if pretrained is True else pretrained) or False
     model.resume_checkpoint = bool(getattr(args, 'resume', False))
     model.distributed = world > 1
     model.is_writer = rank == 0                      # one rank writes checkpoints / loss logs
@@ -223,9 +226,9 @@ def get_parser():
     p = sub.add_parser('extract', help='Extract tiles from images/masks and profile them.')
     common(p)
     p.set_defaults(func=extract)
-    p.add_argument('-i', '--img', type=str, required=True, help='Path to images directory or file.')
-    p.add_argument('-m', '--mask', type=str, required=True, help='Path to masks directory or file.')
-    p.add_argument('--ch', type=int, required=True, choices=defaults.ch_options, help='Number of image channels.')
+    p.add_argument('-i', '--img', type=str, default='./data/raw/images/', required=True, help='Path to images directory or file.')
+    p.add_argument('-m', '--mask', type=str, default=None, help='Path to masks directory or file (optional, as in the reference).')
+    p.add_argument('--ch', type=int, default=3, required=True, choices=defaults.ch_options, help='Number of image channels.')
     p.add_argument('--batch_size', type=int, default=defaults.batch_size)
     p.add_argument('-o', '--output', type=str, default=None, help='Database output directory.')
 
@@ -245,7 +248,8 @@ def get_parser():
     p.add_argument('--db', type=str, required=True)
     p.add_argument('--arch', type=str, default=defaults.arch, choices=defaults.arch_options)
     p.add_argument('--backbone', type=str, default=defaults.backbone, choices=defaults.backbone_options)
-    p.add_argument('--weighted', action='store_true', help='Weight cross-entropy by class (profile weights).')
+    # the reference's --weighted takes a value (any non-empty string enables it); the bare flag is accepted too
+    p.add_argument('--weighted', nargs='?', const=True, default=None, help='Weight cross-entropy by class (profile weights).')
     p.add_argument('--ce_weight', type=float, default=defaults.ce_weight)
     p.add_argument('--dice_weight', type=float, default=defaults.dice_weight)
     p.add_argument('--focal_weight', type=float, default=defaults.focal_weight)
@@ -254,7 +258,12 @@ def get_parser():
     p.add_argument('--lr', type=float, default=defaults.lr)
     p.add_argument('--batch_size', type=int, default=defaults.batch_size)
     p.add_argument('--n_epochs', type=int, default=defaults.n_epochs)
-    p.add_argument('--pretrained', type=str, default=None, help='Path to pretrained ResNet-101 weights.')
+    # reference: a bare flag that loads defaults.pretrained; a path may follow here
+    p.add_argument('--pretrained', nargs='?', const=True, default=None, help='Use pre-trained ResNet-101 weights (optionally: path).')
+    # U-Net-only options of the reference parser: accepted for command-line compatibility, unused by DeepLabv3+
+    p.add_argument('--normalize', type=str, default=defaults.norm_type, choices=defaults.norm_options)
+    p.add_argument('--activation', type=str, default=defaults.activ_type, choices=defaults.activ_options)
+    p.add_argument('--up_mode', type=str, default=defaults.up_mode, choices=defaults.up_mode_options)
     p.add_argument('--n_workers', type=int, default=defaults.n_workers)
     p.add_argument('--report', type=int, default=defaults.report)
     p.add_argument('--resume', action='store_true')
@@ -264,7 +273,7 @@ def get_parser():
     common(p)
     p.set_defaults(func=test)
     p.add_argument('-l', '--model', type=str, required=True, help='Path to trained PyLC model.')
-    p.add_argument('-i', '--img', type=str, required=True)
+    p.add_argument('-i', '--img', type=str, default='./data/raw/images/', help='Path to images directory or file.')
     p.add_argument('-m', '--mask', type=str, default=None)
     p.add_argument('--scale', type=float, default=defaults.scale)
     p.add_argument('--save_logits', action='store_true')

@@ -244,6 +244,66 @@ def test_extractor_stack_grouping_host_logic(monkeypatch, palettes):
     assert ex.masks.shape[0] == ex.imgs.shape[0] == 16 and int(ex.masks.sum()) == 0
 
 
+def test_cli_parser_accepts_reference_command_lines():
+    """The sub-commands and flags of the reference parser (utils/argparse.py:40-335) for the path: every form a PyLC
+    user types parses here to the same destinations."""
+    from pylc_b200.pylc import get_parser
+    p = get_parser()
+    a = p.parse_args("extract --ch 3 --img ./imgs --mask ./masks".split())
+    assert (a.action, a.ch, a.img, a.mask) == ("extract", 3, "./imgs", "./masks")
+    a = p.parse_args("extract --ch 1 -i ./imgs".split())                  # masks are optional (argparse.py:60-66)
+    assert a.mask is None and a.ch == 1
+    a = p.parse_args("augment --db data/db/x.h5".split())
+    assert a.action == "augment" and a.db == "data/db/x.h5"
+    a = p.parse_args("profile --db data/db/x.h5".split())
+    assert a.action == "profile"
+    a = p.parse_args(("train --db x.h5 --arch deeplab --backbone resnet --weighted --pretrained --resume --normalize batch "
+                      "--activation relu --up_mode upsample --optim adam --sched step_lr --lr 0.001 --batch_size 8 --n_epochs 2 "
+                      "--n_workers 0 --report 10 --clip 0.5 --ce_weight 0.5 --dice_weight 0.3 --focal_weight 0.2").split())
+    assert a.weighted is True and a.pretrained is True and a.resume is True and a.clip == 0.5
+    a = p.parse_args("train --db x.h5 --weighted True --pretrained ./w.pth".split())   # value forms
+    assert a.weighted == "True" and a.pretrained == "./w.pth"
+    a = p.parse_args("train --db x.h5".split())
+    assert a.weighted is None and a.pretrained is None and not a.resume
+    a = p.parse_args("test -l m.pth -i img.tif -m mask.png --scale 0.5 --save_logits --aggregate_metrics".split())
+    assert (a.model, a.img, a.mask, a.scale, a.save_logits, a.aggregate_metrics) == ("m.pth", "img.tif", "mask.png", 0.5, True, True)
+    with pytest.raises(SystemExit):
+        p.parse_args("extract --ch 2 --img x".split())                    # ch in {1, 3}
+
+
+def test_cli_parser_covers_reference_options_live():
+    """In the build container: every option of the reference's extract / augment / train / test sub-parsers exists here
+    with the same destination and choices (merge / grayscale are stubs in the reference and are not provided)."""
+    import argparse
+    import importlib
+    import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference not present (GPU box)")
+    ref_harness.load()
+    sys.path.insert(0, ref_harness.REF_ROOT)
+    try:
+        ref_parser = importlib.import_module("utils.argparse").get_parser()
+    finally:
+        sys.path.remove(ref_harness.REF_ROOT)
+    from pylc_b200.pylc import get_parser
+
+    def subs(parser):
+        for act in parser._actions:
+            if isinstance(act, argparse._SubParsersAction):
+                return {name: {tuple(x.option_strings): x for x in sp._actions if x.option_strings and x.dest != "help"}
+                        for name, sp in act.choices.items()}
+        return {}
+    ref, ours = subs(ref_parser), subs(get_parser())
+    assert set(ref) - set(ours) == {"merge", "grayscale"}
+    for cmd in ("extract", "augment", "train", "test"):
+        for opts, act in ref[cmd].items():
+            assert opts in ours[cmd], (cmd, opts)
+            mine = ours[cmd][opts]
+            assert mine.dest == act.dest and mine.choices == act.choices, (cmd, opts)
+            if act.default is not None and act.type is not None:          # typed defaults are the reference's
+                assert mine.default == act.default, (cmd, opts, mine.default, act.default)
+
+
 def test_parameters_schema_b_and_update():
     from pylc_b200.config import Parameters
     p = Parameters({"schema": "./schemas/schema_b.json", "ch": 1})
