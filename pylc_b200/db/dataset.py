@@ -145,8 +145,17 @@ class MLPDataset(torch.utils.data.IterableDataset):
 
     def loader(self, batch_size=1, n_workers=0, drop_last=False):
         return (torch.utils.data.DataLoader(self, batch_size=batch_size, num_workers=n_workers,
+                                            worker_init_fn=self.init_worker,
                                             pin_memory=torch.cuda.is_available(), drop_last=drop_last),
                 self.size // batch_size)
+
+    def init_worker(self, worker_id):
+        """DataLoader worker hook: each worker process iterates its own slice of the partition
+        (reference dataset.py:109-115)."""
+        info = torch.utils.data.get_worker_info()
+        if info is not None and not getattr(self, "_worker_ready", False):
+            self.db.init_worker(worker_id, info.num_workers)
+            self._worker_ready = True
 
     def device_batches(self, batch_size, device=None, drop_last=False):
         """u8 (img [b,ch,T,T], mask [b,T,T]) batches as CUDA tensors.  GPU-resident tiles are sliced

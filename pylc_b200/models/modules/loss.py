@@ -200,3 +200,12 @@ class MultiLoss(torch.nn.Module):
         for i, w in enumerate(self.weights):
             print('{:8s}{:22s}{:<10f}'.format(self.codes[i], self.categories[i], w))
         print()
+
+
+def __getattr__(name):
+    """`RunningLoss` is importable from here as in the reference (models/modules/loss.py:218-327); it is defined next
+    to Model (models/model.py), which imports this module, hence the lazy look-up."""
+    if name == "RunningLoss":
+        from ..model import RunningLoss
+        return RunningLoss
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

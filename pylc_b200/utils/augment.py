@@ -34,11 +34,11 @@ class Augmentor(object):
         self.profile_data = []
         self.rates = []
 
-    def load(self, source):
-        """`source`: a database path, or an MLPDataset (reference augment.py:45-76 takes a path)."""
+    def load(self, db_path):
+        """`db_path`: a database path (reference augment.py:45-76) or, as an extension, an MLPDataset."""
         from ..db.dataset import MLPDataset
-        self.input_dset = source if isinstance(source, MLPDataset) else MLPDataset(source)
-        self.input_path = source if isinstance(source, str) else None
+        self.input_dset = db_path if isinstance(db_path, MLPDataset) else MLPDataset(db_path)
+        self.input_path = db_path if isinstance(db_path, str) else None
         self.input_meta = self.input_dset.get_meta()
         self.input_size = self.input_dset.size
         return self

@@ -68,6 +68,38 @@ def ordered_prefetch(fn, items, workers=None, depth=None):
                 fut.cancel()
 
 
+def rgb2hex(color):
+    """[R, G, B] -> '#rrggbb' (reference tools.py:24-39)."""
+    return "#{:02x}{:02x}{:02x}".format(int(color[0]), int(color[1]), int(color[2]))
+
+
+def grayscale(img):
+    """[H,W,3] -> channel mean [H,W]; other channel counts are reported and left alone (reference tools.py:59-74)."""
+    if img.shape[2] == 3:
+        return np.mean(img, axis=2)
+    print("Grayscaling skipped: Image is already single-channel." if img.shape[2] == 1
+          else "Grayscaling stopped: Image channel is invalid.")
+
+
+def map_palette(img_array, key):
+    """Re-map class indices through `key` (new value per old index), reference tools.py:388-409."""
+    index = np.digitize(img_array.numpy().ravel(), range(len(key)), right=True)
+    return torch.tensor(np.asarray(key)[index].reshape(img_array.shape))
+
+
+def add_noise(img, w, h):
+    """Gaussian noise (variance 10) added to every channel, min-max normalised back to u8 (reference tools.py:496-533)."""
+    gaussian = np.random.normal(0, 10 ** 0.5, (w, h))
+    if img.ndim == 2:
+        noisy = img + gaussian
+    else:
+        noisy = np.zeros(img.shape, np.float32)
+        for k in range(3):
+            noisy[:, :, k] = img[:, :, k] + gaussian
+    cv2.normalize(noisy, noisy, 0, 255, cv2.NORM_MINMAX, dtype=-1)
+    return noisy.astype(np.uint8)
+
+
 def is_grayscale(img):
     """True when all three channels are identical (reference tools.py:27-43)."""
     if img.ndim < 3 or img.shape[2] == 1:
