@@ -357,6 +357,32 @@ def test_python_surface_covers_reference_live():
     assert not problems, problems
 
 
+@pytest.mark.parametrize("schema", ["schema_a", "schema_b"])
+def test_parameters_table_equals_reference_live(schema):
+    """`json.dumps(vars(Parameters))` is the metadata record of database and model files (reference database.py:216-235,
+    checkpoint.py:53-66): attribute names and default values must be the reference's, key for key."""
+    import importlib
+    import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference not present (GPU box)")
+    ref_harness.load()
+    sys.path.insert(0, ref_harness.REF_ROOT)
+    try:
+        ref_cfg = importlib.import_module("config")
+    finally:
+        sys.path.remove(ref_harness.REF_ROOT)
+    from pylc_b200.config import Parameters
+    import argparse
+    # a Namespace, as the CLI passes it: the reference ignores a dict's "schema" key at construction (config.py:108 tests
+    # hasattr), which this package accepts as an extension
+    args = argparse.Namespace(schema="./schemas/%s.json" % schema)
+    want, got = vars(ref_cfg.Parameters(args)), vars(Parameters(args))
+    assert set(want) == set(got)
+    for k in want:
+        if k != "seed":                     # np.random seed of the process, different by construction
+            assert want[k] == got[k], k
+
+
 def test_parameters_schema_b_and_update():
     from pylc_b200.config import Parameters
     p = Parameters({"schema": "./schemas/schema_b.json", "ch": 1})
