@@ -4,7 +4,7 @@
  * This is the drop-in boundary.  The PyLC reference has no FFI layer (it is pure Python); each
  * entry point below replaces the NumPy / Torch-CPU / scikit-learn body of one reference function
  * (cited per function, paths relative to the PyLC source root).  The Python host layer
- * (pylc_b200/utils/*.py, pylc_b200/models/modules/loss.py) binds these with ctypes and keeps the
+ * (the modules under pylc_b200/utils and pylc_b200/models/modules/loss.py) binds these with ctypes and keeps the
  * reference's own signatures; INTEGRATION.md shows the stub a PyLC maintainer would add.
  *
  * Conventions
