@@ -255,6 +255,24 @@ def test_extraction_stack_padded_image_stride(ops, palettes):
                                                 ops._stream()), "stack")
 
 
+def test_extraction_stack_unaligned_rows(ops, palettes):
+    """A stack whose rows are not 16-byte aligned (tightly packed 1001-pixel rows): the byte-wise per-thread kernels
+    run once per image inside the one call; results as for aligned stacks."""
+    pal = palettes["b"]
+    H, W, T, S, n_img = 600, 1001, 512, 512, 3
+    masks = np.stack([orc.synth_mask(60 + i, W, H, pal, off_palette=0.01) for i in range(n_img)])
+    imgs = np.stack([orc.synth_image(60 + i, W, H, 1) for i in range(n_img)])
+    d_m, d_i = dev(masks.reshape(n_img, H, W * 3)), dev(imgs.reshape(n_img, H, W))
+    m_tiles, px_dist = ops.mask_gather_encode_hist_stack(d_m, H, W, W * 3, T, S, pal)
+    tiles, stat = ops.tile_gather_u8_stack(d_i, H, W, 1, W, T, S, stats=True)
+    ref_m = np.concatenate([orc.class_encode(orc.split_tiles(m, T, S), pal) for m in masks])
+    ref_i = np.concatenate([orc.split_tiles(im, T, S) for im in imgs])
+    assert np.array_equal(m_tiles.cpu().numpy(), ref_m) and np.array_equal(tiles.cpu().numpy(), ref_i)
+    assert np.array_equal(px_dist.cpu().numpy(), orc.tile_histograms(ref_m, len(pal)))
+    x = ref_i.astype(np.int64).reshape(ref_i.shape[0], 1, -1)
+    assert np.array_equal(stat.cpu().numpy(), np.stack([x.sum(-1), (x * x).sum(-1)], axis=-1))
+
+
 def test_class_encode_golden_and_layouts(ops, golden, palettes):
     g = golden("encode")
     for name in ("a", "b", "dup"):
