@@ -676,3 +676,127 @@ def augment_fixture_tile(ch, T=512):
     img = np.stack([(xx // 7 * 5 + yy // 11 * 3 + 40 * c) % 256 for c in range(ch)]).astype(np.uint8)[None]
     mask = ((xx // 60 + yy // 45) % 9).astype(np.uint8)[None]
     return img, mask
+
+
+# ---------------------------------------------------------------------------------------------
+# Augmentation warps: tools.augment_transform (reference utils/tools.py:452-594) restated without
+# OpenCV's image functions.  The reference calls cv2.warpPerspective / cv2.resize (OpenCV is not
+# vendored; requirements.txt:8 pins cv2 >= 3.4); their published algorithms are restated here and
+# pinned three ways: the golden vectors the reference produced (tests/golden/warp.npz), the
+# reference's own function on other seeds (tests/test_oracle_golden.py, build container) and the
+# installed cv2 run on the same inputs.  Only cv2.getPerspectiveTransform / cv2.invert (an 8x8 and
+# a 3x3 solve on the host) are still OpenCV calls, as in the product.
+# ---------------------------------------------------------------------------------------------
+
+def _reflect101(p, n):
+    """cv2.BORDER_REFLECT_101 for |overshoot| < n: ... 2 1 | 0 1 2 ... n-2 n-1 | n-2 n-3 ..."""
+    p = np.where(p < 0, -p, p)
+    return np.where(p >= n, 2 * (n - 1) - p, p)
+
+
+def warp_fixed_coords(m_inv, w, h, tab):
+    """Source coordinates of cv2.warpPerspective for every destination pixel, as OpenCV computes them
+    (imgproc/imgwarp.cpp WarpPerspectiveInvoker): double precision, per block of bw0 columns the
+    numerators / denominator at the block's first column plus M * x1 inside it, scaled by tab / W
+    (tab = 32 sub-pixel steps for INTER_LINEAR, 1 for INTER_NEAREST), rounded half-to-even."""
+    bh0 = min(16, h)
+    bw0 = min(1024 // bh0, w)
+    xb = (np.arange(w) // bw0 * bw0).astype(np.float64)[None, :]
+    x1 = (np.arange(w) % bw0).astype(np.float64)[None, :]
+    y = np.arange(h, dtype=np.float64)[:, None]
+    M = np.asarray(m_inv, dtype=np.float64)
+    X0 = M[0, 0] * xb + M[0, 1] * y + M[0, 2]
+    Y0 = M[1, 0] * xb + M[1, 1] * y + M[1, 2]
+    W0 = M[2, 0] * xb + M[2, 1] * y + M[2, 2]
+    W = W0 + M[2, 0] * x1
+    W = np.where(W != 0, tab / np.where(W != 0, W, 1.0), 0.0)
+    fX = np.clip((X0 + M[0, 0] * x1) * W, -2.0 ** 31, 2.0 ** 31 - 1)
+    fY = np.clip((Y0 + M[1, 0] * x1) * W, -2.0 ** 31, 2.0 ** 31 - 1)
+    return np.rint(fX).astype(np.int64), np.rint(fY).astype(np.int64)
+
+
+def warp_perspective_linear_f32(img, m_inv):
+    """cv2.warpPerspective(img f32, M, (w, h), INTER_LINEAR, BORDER_REFLECT_101) given inv(M) (what the
+    reference's flags=INTER_AREA resolves to): 1/32-pixel coordinates, float bilinear table
+    (1-fy)(1-fx), (1-fy)fx, fy(1-fx), fy*fx.  For 8-bit valued inputs every product and sum is exact."""
+    h, w = img.shape[:2]
+    X, Y = warp_fixed_coords(m_inv, w, h, 32.0)
+    sx, sy = X >> 5, Y >> 5
+    one = np.float32(1)
+    fx, fy = ((X & 31) / 32.0).astype(np.float32), ((Y & 31) / 32.0).astype(np.float32)
+    wts = [(one - fy) * (one - fx), (one - fy) * fx, fy * (one - fx), fy * fx]
+    if img.ndim == 3:
+        wts = [t[..., None] for t in wts]
+    x0, x1, y0, y1 = _reflect101(sx, w), _reflect101(sx + 1, w), _reflect101(sy, h), _reflect101(sy + 1, h)
+    im = img.astype(np.float32)
+    return im[y0, x0] * wts[0] + im[y0, x1] * wts[1] + im[y1, x0] * wts[2] + im[y1, x1] * wts[3]
+
+
+def warp_perspective_nearest(mask, m_inv):
+    """cv2.warpPerspective(mask, M, (w, h), INTER_NEAREST, BORDER_REFLECT_101) given inv(M)."""
+    h, w = mask.shape[:2]
+    X, Y = warp_fixed_coords(m_inv, w, h, 1.0)
+    return mask[_reflect101(Y, h), _reflect101(X, w)]
+
+
+def area_upscale_tab(ssize, dsize):
+    """Tap table of cv2.resize(f32, INTER_AREA) when ENLARGING (imgproc/resize.cpp, area_mode with the linear
+    kernel): first tap sx = floor(dx * ssize/dsize), second-tap weight fx = frac((dx+1) - (sx+1) * dsize/ssize)
+    as f32 (0 when not positive), taps clamped to the last source sample."""
+    scale, inv = ssize / dsize, dsize / ssize
+    sx, fx = np.zeros(dsize, np.int64), np.zeros(dsize, np.float32)
+    for dx in range(dsize):
+        s = int(np.floor(dx * scale))
+        f = np.float32((dx + 1) - (s + 1) * inv)
+        f = np.float32(0) if f <= 0 else np.float32(f - np.floor(f))
+        if s >= ssize - 1:
+            f, s = np.float32(0), ssize - 1
+        sx[dx], fx[dx] = s, f
+    return sx, fx
+
+
+def resize_area_upscale_f32(src, dsize):
+    """cv2.resize(src f32 [S,S(,C)], (dsize, dsize), INTER_AREA) for dsize > S: rows first, then columns, every
+    product and sum rounded to f32 separately (no fused multiply-add), as the installed OpenCV does."""
+    S = src.shape[0]
+    sx, fx = area_upscale_tab(S, dsize)
+    one = np.float32(1)
+    a0, a1 = one - fx, fx
+    if src.ndim == 3:
+        a0, a1 = a0[None, :, None], a1[None, :, None]
+    rows = src[:, sx] * a0 + src[:, np.minimum(sx + 1, S - 1)] * a1
+    b0 = (one - fx).reshape((-1,) + (1,) * (src.ndim - 1))
+    b1 = fx.reshape(b0.shape)
+    return (rows[sx] * b0 + rows[np.minimum(sx + 1, S - 1)] * b1).astype(np.float32)
+
+
+def augment_params(random_state, w):
+    """The random draws of perspective_shift + channel_shift in the reference's order (tools.py:577-580, 550):
+    returns (inverse perspective matrix 3x3 f64, brightness shift int)."""
+    import cv2
+    pts1 = np.float32([[56, 65], [368, 52], [28, 387], [389, 390]])
+    pts2 = pts1 + random_state.uniform(-0.06 * w, 0.06 * w, size=pts1.shape).astype(np.float32)
+    m_inv = cv2.invert(cv2.getPerspectiveTransform(pts1, pts2))[1]
+    return m_inv, int(random_state.uniform(10, 20))
+
+
+def augment_transform_port(img, mask, random_state):
+    """tools.augment_transform (reference utils/tools.py:452-594): img [1,ch,T,T], mask [1,T,T] ->
+    (img u8 [ch,T,T] or [T,T], mask f32 [T,T]).  Perspective jitter (bilinear image / nearest mask, reflect-101),
+    30-px crop, resize back to T (INTER_AREA image / INTER_NEAREST mask), brightness shift through int16."""
+    nch = img.shape[1]
+    im = np.squeeze(np.moveaxis(np.asarray(img, dtype=np.float32), 1, -1), axis=0)
+    if nch == 1:
+        im = im[..., 0]
+    mk = np.squeeze(np.asarray(mask), axis=0)
+    w = mk.shape[0]
+    m_inv, shift = augment_params(random_state, w)
+    wim = np.ascontiguousarray(warp_perspective_linear_f32(im, m_inv)[30:w - 30, 30:w - 30])
+    wmk = warp_perspective_nearest(mk, m_inv)[30:w - 30, 30:w - 30]
+    rim = resize_area_upscale_f32(wim, w)
+    idx = np.minimum(np.floor(np.arange(w) * ((w - 60) / w)).astype(np.int64), w - 61)   # cv2 INTER_NEAREST
+    rmk = wmk[idx][:, idx].astype(np.float32)
+    out = np.uint8(np.clip(np.int16(rim) + shift, 0, 255))                              # channel_shift, tools.py:550-555
+    if nch == 3:
+        out = np.moveaxis(out, -1, 0)
+    return out, rmk

@@ -254,3 +254,40 @@ def test_augment_transform_equals_reference(golden, ch, seed):
     assert np.asarray(a).dtype == np.uint8 and np.array_equal(np.asarray(a), want_img)
     assert np.array_equal(np.asarray(b).astype(np.uint8), want_mask)
     assert not np.array_equal(want_img.reshape(img.shape[1:] if ch == 3 else img.shape[2:]), img[0] if ch == 3 else img[0, 0])
+
+
+@pytest.mark.parametrize("ch", [1, 3])
+@pytest.mark.parametrize("seed", [0, 1, 3])
+def test_augment_transform_port_equals_reference_golden(golden, ch, seed):
+    """The OpenCV-free restatement (oracle.augment_transform_port: fixed-point warp coordinates, float bilinear
+    table, reflect-101, the enlarging INTER_AREA taps without FMA, int16 brightness shift) reproduces the
+    reference's bytes."""
+    g = golden("warp")
+    img, mask = orc.augment_fixture_tile(ch)
+    a, b = orc.augment_transform_port(img.astype(np.float32), mask.astype(np.int64), np.random.RandomState(seed))
+    assert a.dtype == np.uint8 and np.array_equal(a, g["warp_ch%d_s%d_img" % (ch, seed)])
+    assert np.array_equal(b.astype(np.uint8), g["warp_ch%d_s%d_mask" % (ch, seed)])
+
+
+@pytest.mark.parametrize("ch,seed", [(1, 4), (1, 7), (3, 5), (3, 11)])
+def test_augment_transform_port_equals_opencv_chain(ch, seed):
+    """Same restatement against the OpenCV call chain itself (tools.augment_transform = the reference's calls,
+    pinned above) on noise tiles and other seeds: every rounding decision of cv2.warpPerspective and cv2.resize."""
+    from pylc_b200.utils import tools
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, size=(1, ch, 512, 512), dtype=np.uint8)
+    mask = rng.integers(0, 11, size=(1, 512, 512))
+    a, b = tools.augment_transform(img.astype(np.float32), mask.astype(np.int64), np.random.RandomState(seed))
+    c, d = orc.augment_transform_port(img.astype(np.float32), mask.astype(np.int64), np.random.RandomState(seed))
+    assert np.array_equal(np.asarray(a), c) and np.array_equal(np.asarray(b), d)
+    # the pieces on their own
+    import cv2
+    m_inv, _ = orc.augment_params(np.random.RandomState(seed), 512)
+    m = cv2.invert(m_inv)[1]
+    hwc = np.moveaxis(img[0], 0, -1).astype(np.float32)
+    hwc = hwc[..., 0] if ch == 1 else hwc
+    want = cv2.warpPerspective(hwc, m, (512, 512), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+    got = orc.warp_perspective_linear_f32(hwc, cv2.invert(m)[1])
+    assert np.array_equal(want, got)
+    crop = np.ascontiguousarray(want[30:482, 30:482])
+    assert np.array_equal(cv2.resize(crop, (512, 512), interpolation=cv2.INTER_AREA), orc.resize_area_upscale_f32(crop, 512))
