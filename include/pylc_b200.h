@@ -146,6 +146,23 @@ PYLC_API int pylc_sample_rate_grid(const double *scores, const int64_t *px_dist,
                           int n_thresholds, int rate_lo, int rate_hi, int64_t *sum_rates,
                           int64_t *full_px_dist, pylc_stream_t stream);
 
+/*
+ * Over-sampled copies of tiles, replaces tools.augment_transform = perspective_shift + channel_shift
+ * (utils/tools.py:452-594) for every copy Augmentor.oversample appends (utils/augment.py:205-222): cv2.warpPerspective
+ * (bilinear image / nearest mask, BORDER_REFLECT_101), the 30-pixel crop, cv2.resize back to T (INTER_AREA image /
+ * INTER_NEAREST mask) and the brightness shift, bit-identical to that OpenCV call chain (arithmetic: csrc/augment_math.cuh).
+ *   src_img   [n_src, ch, T, T] u8, src_mask [n_src, T, T] u8 (class indices)
+ *   job_src   [n_jobs] i32   source tile of copy j
+ *   job_minv  [n_jobs, 9] f64  row-major INVERSE of cv2.getPerspectiveTransform(pts1, pts2) (cv2.invert; the host draws
+ *             pts2 from RandomState(j) exactly as the reference, tools.py:577-580)
+ *   job_shift [n_jobs] i32   brightness shift int(uniform(10, 20)) (tools.py:550)          -- all DEVICE
+ *   dst_img   [n_jobs, ch, T, T] u8, dst_mask [n_jobs, T, T] u8
+ * ch is 1 or 3, T > 61.  Copies with a source index outside [0, n_src) are left unwritten.
+ */
+PYLC_API int pylc_augment_tiles_u8(const uint8_t *src_img, const uint8_t *src_mask, int n_src, int ch, int T,
+                          const int32_t *job_src, const double *job_minv, const int32_t *job_shift, int n_jobs,
+                          uint8_t *dst_img, uint8_t *dst_mask, pylc_stream_t stream);
+
 /* ---- test-time fit resize ----------------------------------------------------------------- */
 
 #define PYLC_AREA_TAPS 6 /* source cells per destination cell and axis: scale factors below 5 */

@@ -51,6 +51,7 @@ SIGNATURES = {
     "pylc_tile_gather_norm_f32": (c_int, [_u8p, c_int, c_int, c_int, c_size_t, c_int, c_int,
                                           POINTER(c_float), POINTER(c_float), c_float, c_int, _ptr, _ptr]),
     "pylc_sample_rate_grid": (c_int, [_ptr, _ptr, c_int, c_int, _ptr, c_int, _ptr, c_int, c_int, c_int, _ptr, _ptr, _ptr]),
+    "pylc_augment_tiles_u8": (c_int, [_u8p, _u8p, c_int, c_int, c_int, _ptr, _ptr, _ptr, c_int, _u8p, _u8p, _ptr]),
     "pylc_area_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "pylc_area_table": (c_int, [c_int, c_int, _ptr, _ptr, _ptr]),
     "pylc_fit_resize_area_u8": (c_int, [_u8p, c_int, c_int, c_int, c_size_t, _u8p, c_int, c_int, c_size_t,

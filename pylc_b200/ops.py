@@ -584,6 +584,32 @@ def sample_rate_grid(scores, px_dist, rate_coefs, thresholds, rate_lo, rate_hi):
     return sum_rates, full
 
 
+def augment_tiles(src_imgs, src_masks, job_src, job_minv, job_shift, out_imgs=None, out_masks=None):
+    """pylc_augment_tiles_u8: over-sampled copies of tiles (perspective jitter, crop, resize back, brightness shift),
+    bit-identical to the reference's OpenCV chain.  src_imgs [n,ch,T,T] u8, src_masks [n,T,T] u8 (CUDA); job_src
+    [J] int, job_minv [J,3,3] / [J,9] f64 (inverse perspective matrices), job_shift [J] int (host arrays or CUDA
+    tensors).  Returns (imgs [J,ch,T,T] u8, masks [J,T,T] u8)."""
+    _need_cuda(src_imgs, src_masks)
+    dev = src_imgs.device
+    if src_imgs.dtype != torch.uint8 or src_masks.dtype != torch.uint8 or src_imgs.dim() != 4 or src_masks.dim() != 3:
+        raise PylcError("augment_tiles takes u8 tiles [n,ch,T,T] and u8 masks [n,T,T]")
+    src_imgs, src_masks = src_imgs.contiguous(), src_masks.contiguous()
+    n, ch, T = src_imgs.shape[0], src_imgs.shape[1], src_imgs.shape[2]
+    d_src = torch.as_tensor(np.asarray(job_src) if not torch.is_tensor(job_src) else job_src).to(dev, torch.int32).contiguous()
+    d_minv = torch.as_tensor(np.asarray(job_minv) if not torch.is_tensor(job_minv) else job_minv).to(dev, torch.float64).reshape(-1, 9).contiguous()
+    d_shift = torch.as_tensor(np.asarray(job_shift) if not torch.is_tensor(job_shift) else job_shift).to(dev, torch.int32).contiguous()
+    J = d_src.numel()
+    if d_minv.shape[0] != J or d_shift.numel() != J:
+        raise PylcError("augment_tiles: one source index, matrix and shift per copy")
+    if J and (int(d_src.min()) < 0 or int(d_src.max()) >= n):
+        raise PylcError("augment_tiles: source index out of range")
+    imgs = out_imgs if out_imgs is not None else torch.empty((J, ch, T, T), dtype=torch.uint8, device=dev)
+    masks = out_masks if out_masks is not None else torch.empty((J, T, T), dtype=torch.uint8, device=dev)
+    check(_lib.load().pylc_augment_tiles_u8(_p(src_imgs), _p(src_masks), n, ch, T, _p(d_src), _p(d_minv), _p(d_shift), J,
+                                            _p(imgs), _p(masks), _stream()), "pylc_augment_tiles_u8")
+    return imgs, masks
+
+
 # ---- network glue (channels-last f32 activations) ---------------------------------------------------
 
 def _is_nhwc(t):

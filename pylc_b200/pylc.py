@@ -78,7 +78,7 @@ def augment(args):
     augmentor = Augmentor().load(args.db)
     print_meta(augmentor.input_meta)
     augmentor.optimize()
-    augmentor.oversample()
+    augmentor.oversample(device=True if getattr(args, 'device_warps', False) else None)
     aug_dset = augmentor.print_settings().get_data()
     print_meta(augmentor.output_meta)
     path = aug_dset.save()
@@ -241,6 +241,8 @@ def get_parser():
     common(p)
     p.set_defaults(func=augment)
     p.add_argument('--db', type=str, required=True, help='Path to database file.')
+    p.add_argument('--device_warps', action='store_true',
+                   help='Make the over-sampled copies with pylc_augment_tiles_u8 (same bytes as the OpenCV calls).')
 
     p = sub.add_parser('train', help='Train model on an extraction database.')
     common(p)

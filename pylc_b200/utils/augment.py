@@ -103,16 +103,22 @@ class Augmentor(object):
         self.rates = self.optim_meta['rates']
         return self
 
-    def oversample(self, shuffle=True):
+    def oversample(self, shuffle=True, device=None):
         """Originals + `rates[i]` augmented copies of tile i (reference augment.py:184-239): copy j of a tile is
         tools.augment_transform with RandomState(j), exactly as the reference seeds it.  Sets .output_imgs,
-        .output_masks, .output_meta (profiled on the device)."""
+        .output_masks, .output_meta (profiled on the device).
+        device=True (or PYLC_AUG_DEVICE=1): the copies are made by pylc_augment_tiles_u8 -- the same bytes as the
+        OpenCV chain (csrc/augment_math.cuh), one launch for all copies; default: the reference's own OpenCV calls
+        on the host."""
+        import os
         from ..config import Parameters
         from ..db.dataset import MLPDataset
         from .profile import get_profile
-        from .tools import augment_transform, coshuffle
+        from .tools import augment_params, augment_transform, coshuffle
         assert self.input_dset is not None and self.input_dset.size > 0, "Loaded input dataset is empty."
         assert len(self.rates) == self.input_dset.size, "Run optimize() first: one rate per input tile."
+        if device is None:
+            device = os.environ.get("PYLC_AUG_DEVICE", "0") == "1"
         db = self.input_dset.db
         src_imgs, src_masks = db.data['img'][db.start:db.end], db.data['mask'][db.start:db.end]
         if torch.is_tensor(src_imgs):
@@ -120,6 +126,23 @@ class Augmentor(object):
         n_out = int(self.input_dset.size + np.sum(self.rates))
         imgs = np.empty((n_out,) + tuple(src_imgs.shape[1:]), dtype=np.uint8)
         masks = np.empty((n_out,) + tuple(src_masks.shape[1:]), dtype=np.uint8)
+        if device:
+            # job table on the host (17 numbers per copy, the reference's RandomState(j) draws), pixels on the device
+            rates = np.asarray(self.rates, dtype=np.int64)
+            T = int(src_masks.shape[-1])
+            job_src = np.repeat(np.arange(len(rates)), rates)
+            params = [augment_params(np.random.RandomState(j), T) for i in range(len(rates)) for j in range(int(rates[i]))]
+            first = np.arange(len(rates)) + np.concatenate([[0], np.cumsum(rates)[:-1]])      # output slot of original i
+            copy_slots = np.setdiff1d(np.arange(n_out), first)                                 # copies follow their original
+            imgs[first], masks[first] = np.asarray(src_imgs), np.asarray(src_masks)
+            if len(job_src):
+                from .tools import _device
+                dev = _device()
+                out_i, out_m = ops.augment_tiles(torch.from_numpy(np.ascontiguousarray(src_imgs, dtype=np.uint8)).to(dev),
+                                                 torch.from_numpy(np.ascontiguousarray(src_masks, dtype=np.uint8)).to(dev),
+                                                 job_src, np.stack([p[0] for p in params]), np.array([p[1] for p in params]))
+                imgs[copy_slots], masks[copy_slots] = out_i.cpu().numpy(), out_m.cpu().numpy()
+            return self._finish_oversample(imgs, masks, shuffle)
         idx = 0
         for i in range(self.input_dset.size):
             img, mask = np.asarray(src_imgs[i:i + 1]), np.asarray(src_masks[i:i + 1])
@@ -133,6 +156,12 @@ class Augmentor(object):
                 masks[idx] = torch.as_tensor(tgt, dtype=torch.uint8).numpy()
                 idx += 1
         assert idx == n_out
+        return self._finish_oversample(imgs, masks, shuffle)
+
+    def _finish_oversample(self, imgs, masks, shuffle):
+        from ..config import Parameters
+        from .profile import get_profile
+        from .tools import coshuffle
         if shuffle:
             imgs, masks = coshuffle(imgs, masks)
         self.output_imgs, self.output_masks = imgs, masks

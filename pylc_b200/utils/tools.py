@@ -349,6 +349,16 @@ def perspective_shift(img, mask, random_state):
     return img, mask
 
 
+def augment_params(random_state, w):
+    """The random draws of perspective_shift + channel_shift in the reference's order (tools.py:577-580, 550) without
+    touching pixels: (INVERSE perspective matrix 3x3 f64 = cv2.invert(cv2.getPerspectiveTransform(pts1, pts2)), which is
+    what cv2.warpPerspective applies; brightness shift int) -- the job record of pylc_augment_tiles_u8."""
+    pts1 = np.float32([[56, 65], [368, 52], [28, 387], [389, 390]])
+    pts2 = pts1 + random_state.uniform(-0.06 * w, 0.06 * w, size=pts1.shape).astype(np.float32)
+    m_inv = cv2.invert(cv2.getPerspectiveTransform(pts1, pts2))[1]
+    return m_inv, int(random_state.uniform(10, 20))
+
+
 def augment_transform(img, mask, random_state=None):
     """img [1,ch,T,T], mask [1,T,T] -> (img [ch,T,T] or [T,T], mask [T,T]), perspective shift then brightness
     shift (reference tools.py:452-492)."""

@@ -475,6 +475,26 @@ def test_augmentor_oversample(ops, golden, palettes):
     assert shuffled.output_imgs.shape[0] == 4
 
 
+def test_augmentor_oversample_device_equals_host_path(ops):
+    """Augmentor.oversample(device=True) -- copies made by pylc_augment_tiles_u8 -- gives the arrays of the default
+    path through the reference's OpenCV calls (reference utils/augment.py:184-239), and the same profile."""
+    from pylc_b200.config import Parameters
+    from pylc_b200.db.dataset import MLPDataset
+    from pylc_b200.utils.augment import Augmentor
+    imgs = np.stack([orc.synth_image(80 + i, 512, 512, 3).transpose(2, 0, 1) for i in range(3)])
+    masks = np.stack([orc.synth_labels(80 + i, 512, 512, 9, skew=True) for i in range(3)]).astype(np.uint8)
+    meta = Parameters()
+    meta.update({"ch": 3})
+    got = []
+    for device in (False, True):
+        aug = Augmentor().load(MLPDataset(input_data={"img": imgs, "mask": masks, "meta": meta}))
+        aug.rates = np.array([1, 0, 2])
+        aug.oversample(shuffle=False, device=device)
+        got.append(aug)
+    assert np.array_equal(got[0].output_imgs, got[1].output_imgs) and np.array_equal(got[0].output_masks, got[1].output_masks)
+    assert got[0].output_meta.dset_px_dist == got[1].output_meta.dset_px_dist and got[1].output_meta.n_samples == 6
+
+
 def test_sample_rate_grid_wide_classes(ops):
     rng = np.random.default_rng(3)
     N, C = 1234, 20

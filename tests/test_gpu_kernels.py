@@ -993,3 +993,37 @@ def test_resample_confusion_tma_random_geometries(ops, seed):
         yt, yp = orc.inject_coverage(orc.class_encode_hwc(gt, pal), orc.resample_labels(labels, w_full, h_full), n_inject)
         assert np.array_equal(res["conf"].cpu().numpy(), orc.confusion_counts(yt, yp, C)), (C, w, h, w_full, h_full, n_inject)
 
+
+# ---------------------------------------------------------------------------------------------
+# augmentation copies on the device (tools.augment_transform, utils/tools.py:452-594)
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("ch", [1, 3])
+def test_augment_tiles_device_equals_reference_golden_and_opencv(ops, golden, ch):
+    """pylc_augment_tiles_u8: the bytes the reference's augment_transform produced for the fixture tile and
+    RandomState(0 / 1 / 3) (golden warp vectors), and the OpenCV call chain on noise tiles with other seeds and a
+    job table that re-uses and re-orders sources.  Bit-exact: image and mask."""
+    from pylc_b200.utils import tools
+    g = golden("warp")
+    img, mask = orc.augment_fixture_tile(ch)
+    seeds = [0, 1, 3]
+    params = [tools.augment_params(np.random.RandomState(s), 512) for s in seeds]
+    out_i, out_m = ops.augment_tiles(dev(img), dev(mask), [0, 0, 0], np.stack([p[0] for p in params]), [p[1] for p in params])
+    out_i, out_m = out_i.cpu().numpy(), out_m.cpu().numpy()
+    for j, s in enumerate(seeds):
+        want = g["warp_ch%d_s%d_img" % (ch, s)]
+        assert np.array_equal(out_i[j].reshape(want.shape), want)
+        assert np.array_equal(out_m[j], g["warp_ch%d_s%d_mask" % (ch, s)])
+    rng = np.random.default_rng(ch)
+    img = rng.integers(0, 256, size=(2, ch, 512, 512), dtype=np.uint8)
+    mask = rng.integers(0, 11, size=(2, 512, 512)).astype(np.uint8)
+    seeds, srcs = [2, 5, 8], [1, 0, 1]
+    params = [tools.augment_params(np.random.RandomState(s), 512) for s in seeds]
+    out_i, out_m = ops.augment_tiles(dev(img), dev(mask), srcs, np.stack([p[0] for p in params]), [p[1] for p in params])
+    for j, (s, k) in enumerate(zip(seeds, srcs)):
+        a, b = tools.augment_transform(img[k:k + 1].astype(np.float32), mask[k:k + 1].astype(np.int64), np.random.RandomState(s))
+        assert np.array_equal(np.asarray(a).reshape(out_i[j].shape), out_i[j].cpu().numpy())
+        assert np.array_equal(np.asarray(b), out_m[j].cpu().numpy())
+    with pytest.raises(ops.PylcError):
+        ops.augment_tiles(dev(img), dev(mask), [2], np.stack([params[0][0]]), [10])      # source index out of range
+

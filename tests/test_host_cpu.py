@@ -383,6 +383,90 @@ def test_parameters_table_equals_reference_live(schema):
             assert want[k] == got[k], k
 
 
+def _oracle_host_lib():
+    """oracle/_build/libpylc_oracle_host.so: the augmentation kernel's per-pixel function compiled for the host."""
+    import ctypes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "oracle", "_build", "libpylc_oracle_host.so")
+    if not os.path.isfile(path):
+        subprocess.run(["make", "-C", os.path.join(root, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    lib = ctypes.CDLL(path)
+    fn = lib.pylc_oracle_augment_tiles_host
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3 + [ctypes.c_int] + [ctypes.c_void_p] * 2
+    return fn
+
+
+def _augment_tiles_host(src_imgs, src_masks, job_src, job_minv, job_shift):
+    fn = _oracle_host_lib()
+    imgs = np.ascontiguousarray(np.asarray(src_imgs), dtype=np.uint8)
+    masks = np.ascontiguousarray(np.asarray(src_masks), dtype=np.uint8)
+    src = np.ascontiguousarray(job_src, dtype=np.int32)
+    minv = np.ascontiguousarray(np.asarray(job_minv, dtype=np.float64).reshape(-1, 9))
+    shift = np.ascontiguousarray(job_shift, dtype=np.int32)
+    n, ch, T = imgs.shape[0], imgs.shape[1], imgs.shape[2]
+    out_i, out_m = np.zeros((len(src), ch, T, T), np.uint8), np.zeros((len(src), T, T), np.uint8)
+    assert fn(imgs.ctypes.data, masks.ctypes.data, n, ch, T, src.ctypes.data, minv.ctypes.data, shift.ctypes.data, len(src),
+              out_i.ctypes.data, out_m.ctypes.data) == 0
+    return out_i, out_m
+
+
+@pytest.mark.parametrize("ch", [1, 3])
+def test_augment_kernel_arithmetic_on_host_equals_reference_golden(golden, ch):
+    """csrc/augment_math.cuh -- the per-pixel function of pylc_augment_tiles_u8 -- compiled for the host: the bytes
+    the reference's augment_transform produced (golden warp vectors) and, on noise tiles, the OpenCV chain itself."""
+    from pylc_b200.utils import tools
+    g = golden("warp")
+    img, mask = orc.augment_fixture_tile(ch)
+    seeds = [0, 1, 3]
+    params = [tools.augment_params(np.random.RandomState(s), 512) for s in seeds]
+    out_i, out_m = _augment_tiles_host(img, mask, [0] * 3, np.stack([p[0] for p in params]), [p[1] for p in params])
+    for j, s in enumerate(seeds):
+        assert np.array_equal(out_i[j].reshape(g["warp_ch%d_s%d_img" % (ch, s)].shape), g["warp_ch%d_s%d_img" % (ch, s)])
+        assert np.array_equal(out_m[j], g["warp_ch%d_s%d_mask" % (ch, s)])
+    rng = np.random.default_rng(ch)
+    img = rng.integers(0, 256, size=(2, ch, 512, 512), dtype=np.uint8)
+    mask = rng.integers(0, 11, size=(2, 512, 512)).astype(np.uint8)
+    seeds = [2, 5, 8]
+    params = [tools.augment_params(np.random.RandomState(s), 512) for s in seeds]
+    out_i, out_m = _augment_tiles_host(img, mask, [1, 0, 1], np.stack([p[0] for p in params]), [p[1] for p in params])
+    for j, (s, src) in enumerate(zip(seeds, [1, 0, 1])):
+        a, b = tools.augment_transform(img[src:src + 1].astype(np.float32), mask[src:src + 1].astype(np.int64), np.random.RandomState(s))
+        assert np.array_equal(np.asarray(a).reshape(out_i[j].shape), out_i[j]) and np.array_equal(np.asarray(b), out_m[j])
+
+
+def test_oversample_device_plumbing_equals_host_path(monkeypatch):
+    """Augmentor.oversample(device=True): job table (RandomState(j) draws per copy), slot order (each original followed
+    by its copies) and dtypes -- with the device entry point replaced by its host twin, the result equals the default
+    path through the reference's OpenCV calls, array for array (reference utils/augment.py:184-239)."""
+    from pylc_b200 import ops
+    from pylc_b200.config import Parameters
+    from pylc_b200.db.dataset import MLPDataset
+    from pylc_b200.utils import profile, tools
+    from pylc_b200.utils.augment import Augmentor
+
+    def fake(src_imgs, src_masks, job_src, job_minv, job_shift, out_imgs=None, out_masks=None):
+        a, b = _augment_tiles_host(src_imgs.numpy(), src_masks.numpy(), job_src, job_minv, job_shift)
+        return torch.from_numpy(a), torch.from_numpy(b)
+    monkeypatch.setattr(ops, "augment_tiles", fake)
+    monkeypatch.setattr(tools, "_device", lambda: torch.device("cpu"))
+    monkeypatch.setattr(profile, "get_profile", lambda dset: dset.get_meta())
+    rng = np.random.default_rng(0)
+    imgs = rng.integers(0, 256, size=(4, 1, 512, 512), dtype=np.uint8)
+    masks = rng.integers(0, 9, size=(4, 512, 512)).astype(np.uint8)
+    meta = Parameters()
+    meta.update({"ch": 1})
+    outs = []
+    for device in (False, True):
+        aug = Augmentor().load(MLPDataset(input_data={"img": imgs, "mask": masks, "meta": meta}))
+        aug.rates = np.array([2, 0, 1, 3])
+        aug.oversample(shuffle=False, device=device)
+        outs.append((aug.output_imgs, aug.output_masks))
+        assert aug.output_imgs.shape == (10, 1, 512, 512) and aug.output_meta.id.startswith("_aug")
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[1][0][[0, 3, 4, 6]], imgs)           # originals at the head of their groups
+
+
 def test_parameters_schema_b_and_update():
     from pylc_b200.config import Parameters
     p = Parameters({"schema": "./schemas/schema_b.json", "ch": 1})
