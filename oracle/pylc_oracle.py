@@ -689,9 +689,18 @@ def augment_fixture_tile(ch, T=512):
 # ---------------------------------------------------------------------------------------------
 
 def _reflect101(p, n):
-    """cv2.BORDER_REFLECT_101 for |overshoot| < n: ... 2 1 | 0 1 2 ... n-2 n-1 | n-2 n-3 ..."""
-    p = np.where(p < 0, -p, p)
-    return np.where(p >= n, 2 * (n - 1) - p, p)
+    """cv2.BORDER_REFLECT_101 (borderInterpolate): ... 2 1 | 0 1 2 ... n-2 n-1 | n-2 n-3 ..., reflected until inside
+    (closed form: the pattern has period 2(n-1))."""
+    p = np.asarray(p)
+    if n == 1:
+        return np.zeros_like(p)
+    q = np.mod(p, 2 * (n - 1))
+    return np.where(q < n, q, 2 * (n - 1) - q)
+
+
+def _sat_short(v):
+    """saturate_cast<short>: warpPerspective hands remap its integer coordinates as 16-bit values."""
+    return np.clip(v, -32768, 32767)
 
 
 def warp_fixed_coords(m_inv, w, h, tab):
@@ -721,7 +730,7 @@ def warp_perspective_linear_f32(img, m_inv):
     (1-fy)(1-fx), (1-fy)fx, fy(1-fx), fy*fx.  For 8-bit valued inputs every product and sum is exact."""
     h, w = img.shape[:2]
     X, Y = warp_fixed_coords(m_inv, w, h, 32.0)
-    sx, sy = X >> 5, Y >> 5
+    sx, sy = _sat_short(X >> 5), _sat_short(Y >> 5)
     one = np.float32(1)
     fx, fy = ((X & 31) / 32.0).astype(np.float32), ((Y & 31) / 32.0).astype(np.float32)
     wts = [(one - fy) * (one - fx), (one - fy) * fx, fy * (one - fx), fy * fx]
@@ -736,7 +745,7 @@ def warp_perspective_nearest(mask, m_inv):
     """cv2.warpPerspective(mask, M, (w, h), INTER_NEAREST, BORDER_REFLECT_101) given inv(M)."""
     h, w = mask.shape[:2]
     X, Y = warp_fixed_coords(m_inv, w, h, 1.0)
-    return mask[_reflect101(Y, h), _reflect101(X, w)]
+    return mask[_reflect101(_sat_short(Y), h), _reflect101(_sat_short(X), w)]
 
 
 def area_upscale_tab(ssize, dsize):

@@ -45,6 +45,10 @@ PYLC_HD int round_even(double v) { return (int)lrint(v); }      // default round
 
 constexpr int kCrop = 30;            // tools.py:584,587
 
+// saturate_cast<short>: warpPerspective hands remap its integer coordinates as 16-bit values (this also bounds the
+// reflection loop below when a denominator crosses zero and the coordinate saturates)
+PYLC_HD int sat_short(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
+
 PYLC_HD int reflect101(int p, int n) {
     if ((unsigned)p < (unsigned)n) return p;
     if (n == 1) return 0;
@@ -86,7 +90,7 @@ struct WarpTaps {
 PYLC_HD WarpTaps warp_taps(const double *M, int x, int y, int T, int bw0) {
     int X, Y;
     warp_xy(M, x, y, bw0, 32.0, X, Y);
-    const int sx = X >> 5, sy = Y >> 5;                      // arithmetic shifts: floor for negative coordinates
+    const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);   // arithmetic shifts: floor for negative coordinates
     const float fx = (float)(X & 31) * 0.03125f, fy = (float)(Y & 31) * 0.03125f;
     const float gx = fadd(1.0f, -fx), gy = fadd(1.0f, -fy);
     const int x0 = reflect101(sx, T), x1 = reflect101(sx + 1, T), y0 = reflect101(sy, T), y1 = reflect101(sy + 1, T);
@@ -102,7 +106,7 @@ PYLC_HD float warp_value(const uint8_t *plane, const WarpTaps &t) {
 PYLC_HD int warp_nearest_offset(const double *M, int x, int y, int T, int bw0) {
     int X, Y;
     warp_xy(M, x, y, bw0, 1.0, X, Y);
-    return reflect101(Y, T) * T + reflect101(X, T);
+    return reflect101(sat_short(Y), T) * T + reflect101(sat_short(X), T);
 }
 
 // enlarging INTER_AREA tap of destination index d: first source sample s (second = min(s + 1, ssize - 1)) and the

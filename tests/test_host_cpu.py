@@ -435,6 +435,24 @@ def test_augment_kernel_arithmetic_on_host_equals_reference_golden(golden, ch):
         assert np.array_equal(np.asarray(a).reshape(out_i[j].shape), out_i[j]) and np.array_equal(np.asarray(b), out_m[j])
 
 
+@pytest.mark.parametrize("T,ch,seed", [(62, 1, 0), (128, 3, 7), (384, 1, 7), (1024, 1, 7)])
+def test_augment_kernel_arithmetic_other_tile_sizes(T, ch, seed):
+    """The same host-compiled kernel function and the NumPy restatement against the OpenCV chain at other tile sizes.
+    The control points are fixed for 512-pixel tiles (tools.py:576), so at 1024 the jitter is a strong perspective whose
+    denominator crosses zero inside the tile: coordinates saturate to 16 bits, as OpenCV's remap receives them, and the
+    reflect-101 border is applied many times over."""
+    from pylc_b200.utils import tools
+    rng = np.random.default_rng(T + ch)
+    img = rng.integers(0, 256, size=(1, ch, T, T), dtype=np.uint8)
+    mask = rng.integers(0, 9, size=(1, T, T)).astype(np.uint8)
+    m_inv, shift = tools.augment_params(np.random.RandomState(seed), T)
+    out_i, out_m = _augment_tiles_host(img, mask, [0], m_inv[None], [shift])
+    a, b = tools.augment_transform(img.astype(np.float32), mask.astype(np.int64), np.random.RandomState(seed))
+    assert np.array_equal(np.asarray(a).reshape(out_i[0].shape), out_i[0]) and np.array_equal(np.asarray(b), out_m[0])
+    c, d = orc.augment_transform_port(img.astype(np.float32), mask.astype(np.int64), np.random.RandomState(seed))
+    assert np.array_equal(np.asarray(a), c) and np.array_equal(np.asarray(b), d)
+
+
 def test_oversample_device_plumbing_equals_host_path(monkeypatch):
     """Augmentor.oversample(device=True): job table (RandomState(j) draws per copy), slot order (each original followed
     by its copies) and dtypes -- with the device entry point replaced by its host twin, the result equals the default
